@@ -1,0 +1,132 @@
+/* omchat_b200 — C-ABI of the B200-native OmChat multimodal forward pass.
+ *
+ * The reference (om-ai-lab/OmChat) has no FFI: its hot path is Python calling torch.nn modules. This header is the
+ * boundary a maintainer would bind instead (ctypes stub in INTEGRATION.md). Every entry point replaces one group of
+ * reference call sites (cited per function, paths relative to the reference root). Conventions:
+ *   - plain device pointers + sizes, no torch types; bf16 = raw uint16 storage; row-major; leading dims in ELEMENTS
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises, never allocates
+ *     device memory, never frees caller memory; outputs go to caller-allocated buffers
+ *   - returns 0 on success or a negative OMC_ERR_* code; omc_last_error() gives the message (thread-local)
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns OMC_ERR_CUDA
+ */
+#ifndef OMCHAT_B200_H_
+#define OMCHAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMC_OK 0
+#define OMC_ERR_ARG (-1)    /* invalid argument / unsupported mode */
+#define OMC_ERR_SHAPE (-2)  /* shape constraint violated (cf. ValueError in modeling_intern_vit.py:329-338) */
+#define OMC_ERR_ALIGN (-3)  /* pointer / leading-dimension alignment */
+#define OMC_ERR_CUDA (-4)   /* CUDA runtime error (message holds cudaGetErrorString) */
+#define OMC_ERR_DRIVER (-5) /* driver entry point (tensor-map encode) unavailable/failed */
+
+/* GEMM epilogues */
+#define OMC_EPI_NONE 0   /* Y = X W^T (+ bias) */
+#define OMC_EPI_GELU 1   /* Y = gelu_erf(X W^T + bias) */
+#define OMC_EPI_RES 2    /* Y = res + scale * (X W^T + bias)   (scale, bias optional) */
+#define OMC_EPI_SWIGLU 3 /* W rows interleaved [128 gate | 128 up] per 256: Y[:, N/2] = silu(gate) * up */
+
+const char* omc_last_error(void);
+int omc_version(void);
+/* number of SMs of the current device (148 on B200), <0 on error */
+int omc_num_sms(void);
+
+/* ---- dense linear layers: tcgen05/TMEM/TMA GEMM -------------------------------------------------------------------
+ * Y[M,N] = X[M,K] W[N,K]^T with fused epilogue. Replaces nn.Linear at intern_vit_6b/modeling_intern_vit.py:124
+ * (qkv), :136 (proj, with ls1+residual of :218), :183-190 (fc1+GELU, fc2 with ls2+residual of :220), the conv
+ * patch-embed :73-75,92 after omc_vit_im2col, multimodal_projector/builder.py:57-61, and the Qwen2 q/k/v/o/gate/up/down
+ * projections (transformers models/qwen2/modeling_qwen2.py:46-48,219-221,245).
+ * tile_cfg: 0 = auto; else (BN) | (cta_group << 16) | (max_ctas << 20). out_is_f32: write fp32 (EPI_NONE only). */
+int omc_gemm_bf16(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M, int N,
+                  int K, const void* bias, const void* scale, const void* res, long long ldr, int epi, int out_is_f32,
+                  int tile_cfg, void* stream);
+
+/* ---- decode-time linear layers: split-K GEMV, 128-bit loads, warp-shuffle reductions ---------------------------
+ * out[B,N] = epi( norm(x)[B,K] W[N,K]^T ), B <= 8. If norm_w != NULL the input is RMS-normalised first
+ * (Qwen2RMSNorm modeling_qwen2.py:258-263 fused in). epi: NONE (+bias), RES (+res), SWIGLU (interleaved W).
+ * out_is_f32 selects fp32 output (lm_head logits, modeling_qwen2.py:470-472). */
+int omc_gemv_bf16(const void* x, long long ldx, const void* W, long long ldw, void* out, long long ldo, int B, int N,
+                  int K, const void* norm_w, float eps, const void* bias, const void* res, long long ldr, int epi,
+                  int out_is_f32, void* stream);
+
+/* ---- row ops --------------------------------------------------------------------------------------------------
+ * InternRMSNorm / Qwen2RMSNorm: out = w * cast_bf16(x * rsqrt(mean(x^2) + eps)), statistics in fp32
+ * (modeling_intern_vit.py:39-44, modeling_qwen2.py:258-263). Also used in place with ldx=3*C for the full-width
+ * QK-norm of modeling_intern_vit.py:143-146,161-165. */
+int omc_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, int rows, int C, float eps,
+                void* stream);
+
+/* ---- vision tower glue -----------------------------------------------------------------------------------------
+ * im2col for the 14x14/stride-14 patch conv (modeling_intern_vit.py:73-75,92): pixels [B,3,H,W] (fp32 if
+ * pixels_are_f32 else bf16) -> cols [B*(H/14)*(W/14), ldc] bf16, column index = c*196 + ky*14 + kx (the conv weight's
+ * own flattening), zero padded to ldc. */
+int omc_vit_im2col(const void* pixels, int pixels_are_f32, void* cols, long long ldc, int B, int H, int W,
+                   void* stream);
+/* hidden[b,0,:] = cls + pos[0]; hidden[b,1+i,:] = patch[b*P+i,:] + pos[1+i]  (modeling_intern_vit.py:94-101;
+ * the bicubic resize of :82-88 is the identity at the native grid and is not re-applied). */
+int omc_vit_assemble(const void* patch, const void* cls, const void* pos, void* hidden, int B, int P, int C,
+                     void* stream);
+/* feature select 'patch' (internVIT_encoder.py:35-43: drop CLS) fused with InternVL-style pixel shuffle.
+ * hidden [B, 1+G*G, C] -> out [B, (G*r)^2, C/(r*r)] with r = 1/down (down = 1: plain CLS drop, down = 2: ratio 0.5).
+ * Pure gather: bit-exact. */
+int omc_select_pixel_shuffle(const void* hidden, void* out, int B, int G, int C, int down, void* stream);
+
+/* ---- attention ---------------------------------------------------------------------------------------------------
+ * Flash-style softmax(Q K^T * scale) V with head_dim 128, fp32 softmax, over packed variable-length sequences.
+ * q rows [total, Hq, 128] with row stride ldq (elements), k/v rows [total, Hkv, 128] with strides ldk/ldv, out row
+ * stride ldo. Sequence s covers rows cu_seqlens[s]..cu_seqlens[s+1] (int32, device). causal=0: ViT attention
+ * (modeling_intern_vit.py:148-152 / flash_attention.py:43-55); causal=1 with Hq = 7*Hkv: Qwen2 GQA prefill
+ * (modeling_qwen2.py:161-184,229-243). */
+int omc_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                      void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int Hq,
+                      int Hkv, int causal, float scale, void* stream);
+
+/* ---- Qwen2 decoder glue ----------------------------------------------------------------------------------------
+ * RoPE (rotate-half, pairs (i, i+64), theta, fp32 angles: modeling_qwen2.py:102-113,124-146) applied in place to the
+ * q and k slices of qkv [T, (Hq+2*Hkv)*128] (inv_freq: 64 fp32 on device, computed by the host exactly as
+ * Qwen2RotaryEmbedding does), then K and V of every token are appended to the paged cache
+ * (replaces DynamicCache.update, modeling_qwen2.py:227). kv_pool: [num_pages, 2, Hkv, page_size, 128] bf16 for ONE
+ * layer; token t of sequence seq_ids[t] at position pos[t] goes to page block_table[seq_ids[t]*max_pages +
+ * pos[t]/page_size], slot pos[t]%page_size. */
+int omc_rope_kv_store(void* qkv, long long ldqkv, const int32_t* pos, const int32_t* seq_ids, int T, int Hq, int Hkv,
+                      const float* inv_freq, void* kv_pool, const int32_t* block_table, int max_pages, int page_size,
+                      void* stream);
+/* One decode step of GQA attention over the paged cache, with the new token's RoPE + cache append fused in.
+ * qkv [B, (Hq+2*Hkv)*128]: the new token's q|k|v projections BEFORE RoPE (inv_freq != NULL), or q already rotated with
+ * K/V already in the cache (inv_freq == NULL). ctx_lens[B] int32 on device = context length INCLUDING the new token.
+ * Keys are split over `splits` CTAs per (sequence, kv head) and merged by the last CTA to finish (log-sum-exp).
+ * workspace: omc_decode_attn_workspace_bytes() bytes, zero-initialised once by the caller (self-resetting counters).
+ * page_size must be a multiple of 16, Hq/Hkv <= 8. */
+int omc_decode_attn_splits(int B, int Hkv, int max_ctx);
+long long omc_decode_attn_workspace_bytes(int B, int Hq, int Hkv, int splits);
+int omc_paged_decode_attn(const void* qkv, long long ldq, const float* inv_freq, void* kv_pool,
+                          const int32_t* block_table, int max_pages, int page_size, const int32_t* ctx_lens, int B,
+                          int Hq, int Hkv, int splits, float scale, void* out, long long ldo, void* workspace,
+                          void* stream);
+/* embed_tokens gather (omchat_arch.py:139): out[t,:] = table[ids[t],:]; ids int64. */
+int omc_embed_lookup(const int64_t* ids, int T, const void* table, int C, void* out, long long ldo, void* stream);
+/* Image-token splice (omchat_arch.py:115-195), integer placement on device, bit-exact.
+ * ids: packed int64 [S_total]; seq_offsets int32 [n_seq+1] into ids; every id == image_token (-200) is replaced,
+ * in batch-major order, by the L rows of the next image feature block feats[img, L, C]; all other ids gather
+ * table rows. Outputs: embeds [T_total, C] packed, pos_ids int32 [T_total] (0..len-1 per sequence), seq_ids int32
+ * [T_total], out_offsets int32 [n_seq+1]. max_len > 0 truncates each spliced sequence (omchat_arch.py:161-164).
+ * A sequence without placeholders still consumes one feature block (omchat_arch.py:122-129).
+ * workspace: int32 [S_total + n_seq + 2]. T_capacity is the row capacity of the outputs
+ * (S_total + n_img*(L-1) always suffices). */
+int omc_splice(const int64_t* ids, const int32_t* seq_offsets, int n_seq, int S_total, long long image_token,
+               const void* table, const void* feats, int n_img, int L, int C, int max_len, void* embeds,
+               int32_t* pos_ids, int32_t* seq_ids, int32_t* out_offsets, int32_t* workspace, int T_capacity,
+               void* stream);
+/* greedy sampling (HF GenerationMixin argmax as driven by cli.py:60-70): next[b] = argmax_v logits[b, v]
+ * (lowest index on ties), logits fp32 [B, V] with row stride ldl. workspace: 128*B floats. */
+int omc_argmax(const float* logits, long long ldl, int B, int V, int64_t* next, float* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMCHAT_B200_H_ */
