@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import torch
+    return torch.load(os.path.join(ROOT, "tests", "golden", "golden_tiny.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def tiny_sd():
+    from tiny import tiny_state_dict
+    return tiny_state_dict(0)

@@ -1,0 +1,82 @@
+"""Deterministic tiny OmChat configuration + weights shared by the golden generator and the parity tests.
+
+head_dim stays 128 (ViT 2 heads x 128, LLM 2 q heads / 1 kv head x 128) because the CUDA attention kernels are
+specialised for the real models' head_dim; everything else is shrunk so the CPU oracle runs in seconds.
+"""
+from __future__ import annotations
+
+import torch
+
+TINY = dict(
+    vit_hidden=256, vit_heads=2, vit_inter=512, vit_layers=2, image_size=224, patch_size=14,
+    hidden=256, heads=2, kv_heads=1, inter=512, layers=2, vocab=1000, rope_theta=1e6,
+)
+
+
+def tiny_state_dict(seed: int = 0) -> dict:
+    """Random weights under the reference's state-dict names. Norm / layer-scale weights are perturbed away from their
+    init values (ones / 0.1) so that every parameter influences the outputs."""
+    g = torch.Generator().manual_seed(seed)
+    c = TINY
+    sd = {}
+
+    def rn(*shape, std=0.02, mean=0.0):
+        return torch.randn(*shape, generator=g) * std + mean
+
+    vt = "model.vision_tower.vision_tower."
+    C, I = c["vit_hidden"], c["vit_inter"]
+    npos = (c["image_size"] // c["patch_size"]) ** 2 + 1
+    sd[vt + "embeddings.class_embedding"] = rn(1, 1, C, std=1.0)
+    sd[vt + "embeddings.position_embedding"] = rn(1, npos, C, std=1.0)
+    sd[vt + "embeddings.patch_embedding.weight"] = rn(C, 3, 14, 14, std=0.05)
+    sd[vt + "embeddings.patch_embedding.bias"] = rn(C, std=0.1)
+    for li in range(c["vit_layers"]):
+        p = f"{vt}encoder.layers.{li}."
+        sd[p + "ls1"] = rn(C, std=0.03, mean=0.1)
+        sd[p + "ls2"] = rn(C, std=0.03, mean=0.1)
+        sd[p + "attn.qkv.weight"] = rn(3 * C, C, std=0.05)
+        sd[p + "attn.q_norm.weight"] = rn(C, std=0.1, mean=1.0)
+        sd[p + "attn.k_norm.weight"] = rn(C, std=0.1, mean=1.0)
+        sd[p + "attn.proj.weight"] = rn(C, C, std=0.05)
+        sd[p + "attn.proj.bias"] = rn(C, std=0.1)
+        sd[p + "mlp.fc1.weight"] = rn(I, C, std=0.05)
+        sd[p + "mlp.fc1.bias"] = rn(I, std=0.1)
+        sd[p + "mlp.fc2.weight"] = rn(C, I, std=0.05)
+        sd[p + "mlp.fc2.bias"] = rn(C, std=0.1)
+        sd[p + "norm1.weight"] = rn(C, std=0.1, mean=1.0)
+        sd[p + "norm2.weight"] = rn(C, std=0.1, mean=1.0)
+    H = c["hidden"]
+    sd["model.mm_projector.0.weight"] = rn(H, C, std=0.05)
+    sd["model.mm_projector.0.bias"] = rn(H, std=0.1)
+    sd["model.mm_projector.2.weight"] = rn(H, H, std=0.05)
+    sd["model.mm_projector.2.bias"] = rn(H, std=0.1)
+    sd["model.embed_tokens.weight"] = rn(c["vocab"], H, std=0.5)
+    D = H // c["heads"]
+    for li in range(c["layers"]):
+        p = f"model.layers.{li}."
+        sd[p + "self_attn.q_proj.weight"] = rn(c["heads"] * D, H, std=0.05)
+        sd[p + "self_attn.q_proj.bias"] = rn(c["heads"] * D, std=0.1)
+        sd[p + "self_attn.k_proj.weight"] = rn(c["kv_heads"] * D, H, std=0.05)
+        sd[p + "self_attn.k_proj.bias"] = rn(c["kv_heads"] * D, std=0.1)
+        sd[p + "self_attn.v_proj.weight"] = rn(c["kv_heads"] * D, H, std=0.05)
+        sd[p + "self_attn.v_proj.bias"] = rn(c["kv_heads"] * D, std=0.1)
+        sd[p + "self_attn.o_proj.weight"] = rn(H, c["heads"] * D, std=0.05)
+        sd[p + "mlp.gate_proj.weight"] = rn(c["inter"], H, std=0.05)
+        sd[p + "mlp.up_proj.weight"] = rn(c["inter"], H, std=0.05)
+        sd[p + "mlp.down_proj.weight"] = rn(H, c["inter"], std=0.05)
+        sd[p + "input_layernorm.weight"] = rn(H, std=0.1, mean=1.0)
+        sd[p + "post_attention_layernorm.weight"] = rn(H, std=0.1, mean=1.0)
+    sd["model.norm.weight"] = rn(H, std=0.1, mean=1.0)
+    sd["lm_head.weight"] = rn(c["vocab"], H, std=0.05)
+    return sd
+
+
+def weights_checksum(sd: dict) -> float:
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+def tiny_inputs(seed: int = 1):
+    g = torch.Generator().manual_seed(seed)
+    pixels = torch.randn(4, 3, TINY["image_size"], TINY["image_size"], generator=g)
+    ids = torch.randint(0, TINY["vocab"] - 10, (3, 24), generator=g)
+    return pixels, ids
