@@ -1,4 +1,4 @@
-"""In-tree build of the C-ABI CUDA library (sm_100a) and of the oracle's C helpers.
+"""In-tree build of the C-ABI CUDA library (sm_100a).
 
 `python -m omchat_b200.build` or `__graft_entry__.build()`; nvcc cross-compiles without a GPU. The resulting
 `omchat_b200/_lib/libomchat_b200.so` is git-ignored but travels to the GPU box with the repo snapshot.

@@ -1,0 +1,244 @@
+"""ctypes binding of libomchat_b200.so (the C-ABI declared in include/omchat_b200.h) + thin torch-tensor wrappers.
+
+There is no fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "_lib" / "libomchat_b200.so"
+
+EPI_NONE, EPI_GELU, EPI_RES, EPI_SWIGLU = 0, 1, 2, 3
+
+# every symbol include/omchat_b200.h declares: name -> (restype, argtypes)
+_P, _I, _L, _F = c_void_p, c_int, c_longlong, c_float
+SIGNATURES = {
+    "omc_last_error": (c_char_p, []),
+    "omc_version": (_I, []),
+    "omc_num_sms": (_I, []),
+    "omc_gemm_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _L, _I, _I, _I, _P]),
+    "omc_gemv_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _L, _I, _I, _P]),
+    "omc_rmsnorm": (_I, [_P, _L, _P, _P, _L, _I, _I, _F, _P]),
+    "omc_vit_im2col": (_I, [_P, _I, _P, _L, _I, _I, _I, _P]),
+    "omc_vit_assemble": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "omc_select_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "omc_attention_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "omc_rope_kv_store": (_I, [_P, _L, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
+    "omc_decode_attn_splits": (_I, [_I, _I, _I]),
+    "omc_decode_attn_workspace_bytes": (_L, [_I, _I, _I, _I]),
+    "omc_paged_decode_attn": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _F, _P, _L, _P, _P]),
+    "omc_embed_lookup": (_I, [_P, _I, _P, _I, _P, _L, _P]),
+    "omc_splice": (_I, [_P, _P, _I, _I, _L, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P]),
+    "omc_argmax": (_I, [_P, _L, _I, _I, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class OmcError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (building is __graft_entry__.build()'s job; a missing library is a hard error)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.environ.get("OMCHAT_B200_LIB", str(LIB_PATH))
+    if not os.path.exists(path):
+        raise OmcError(f"{path} not found: run `python -m omchat_b200.build` (there is no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().omc_last_error().decode(errors="replace")
+        raise OmcError(f"{what} failed ({rc}): {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise OmcError("omchat_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+# ----------------------------------------------------------------------------------------------- wrappers
+def gemm(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, scale=None, res=None,
+         epi: int = EPI_NONE, out_f32: bool = False, tile_cfg: int = 0) -> torch.Tensor:
+    """out[M,N] = epi(x[M,K] @ w[N,K]^T). x/out may be row-strided 2-D views (last dim contiguous)."""
+    _need_cuda(x, w)
+    assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1] and x.stride(1) == 1 and w.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[0]
+    n_out = N // 2 if epi == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty(M, n_out, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    rc = load().omc_gemm_bf16(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
+                              _ptr(bias), _ptr(scale), _ptr(res), res.stride(0) if res is not None else 0, epi,
+                              1 if out_f32 else 0, tile_cfg, _stream())
+    _check(rc, "omc_gemm_bf16")
+    return out
+
+
+def gemv(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, norm_w=None, eps: float = 1e-6,
+         bias=None, res=None, epi: int = EPI_NONE, out_f32: bool = False) -> torch.Tensor:
+    _need_cuda(x, w)
+    B, K = x.shape
+    N = w.shape[0]
+    n_out = N // 2 if epi == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty(B, n_out, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    rc = load().omc_gemv_bf16(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), B, N, K,
+                              _ptr(norm_w), eps, _ptr(bias), _ptr(res), res.stride(0) if res is not None else 0, epi,
+                              1 if out_f32 else 0, _stream())
+    _check(rc, "omc_gemv_bf16")
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, w)
+    assert x.dim() == 2 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    rc = load().omc_rmsnorm(_ptr(x), x.stride(0), _ptr(w), _ptr(out), out.stride(0), x.shape[0], x.shape[1], eps,
+                            _stream())
+    _check(rc, "omc_rmsnorm")
+    return out
+
+
+def vit_im2col(pixels: torch.Tensor, ldc: int = 640) -> torch.Tensor:
+    _need_cuda(pixels)
+    assert pixels.dim() == 4 and pixels.shape[1] == 3 and pixels.is_contiguous()
+    assert pixels.dtype in (torch.float32, torch.bfloat16)
+    B, _, H, W = pixels.shape
+    cols = torch.empty(B * (H // 14) * (W // 14), ldc, device=pixels.device, dtype=torch.bfloat16)
+    rc = load().omc_vit_im2col(_ptr(pixels), 1 if pixels.dtype == torch.float32 else 0, _ptr(cols), ldc, B, H, W,
+                               _stream())
+    _check(rc, "omc_vit_im2col")
+    return cols
+
+
+def vit_assemble(patch: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, B: int) -> torch.Tensor:
+    _need_cuda(patch, cls, pos)
+    P = patch.shape[0] // B
+    C = patch.shape[1]
+    hidden = torch.empty(B * (P + 1), C, device=patch.device, dtype=torch.bfloat16)
+    rc = load().omc_vit_assemble(_ptr(patch), _ptr(cls), _ptr(pos), _ptr(hidden), B, P, C, _stream())
+    _check(rc, "omc_vit_assemble")
+    return hidden
+
+
+def select_pixel_shuffle(hidden: torch.Tensor, B: int, G: int, down: int) -> torch.Tensor:
+    _need_cuda(hidden)
+    C = hidden.shape[-1]
+    out = torch.empty(B * (G // down) ** 2, C * down * down, device=hidden.device, dtype=torch.bfloat16)
+    rc = load().omc_select_pixel_shuffle(_ptr(hidden), _ptr(out), B, G, C, down, _stream())
+    _check(rc, "omc_select_pixel_shuffle")
+    return out
+
+
+def attention(q, k, v, out, cu_seqlens: torch.Tensor, max_seqlen: int, Hq: int, Hkv: int, causal: bool, scale: float):
+    """q/k/v/out: 2-D row views [total, H*128] (possibly slices of a packed qkv buffer: row stride = parent's)."""
+    _need_cuda(q, k, v, out, cu_seqlens)
+    assert cu_seqlens.dtype == torch.int32
+    rc = load().omc_attention_fwd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                  out.stride(0), _ptr(cu_seqlens), cu_seqlens.numel() - 1, max_seqlen, Hq, Hkv,
+                                  1 if causal else 0, scale, _stream())
+    _check(rc, "omc_attention_fwd")
+    return out
+
+
+def rope_kv_store(qkv, pos, seq_ids, Hq, Hkv, inv_freq, kv_pool, block_table, page_size):
+    _need_cuda(qkv, pos, inv_freq, kv_pool, block_table)
+    assert pos.dtype == torch.int32 and block_table.dtype == torch.int32 and inv_freq.dtype == torch.float32
+    rc = load().omc_rope_kv_store(_ptr(qkv), qkv.stride(0), _ptr(pos), _ptr(seq_ids), qkv.shape[0], Hq, Hkv,
+                                  _ptr(inv_freq), _ptr(kv_pool), _ptr(block_table), block_table.shape[1], page_size,
+                                  _stream())
+    _check(rc, "omc_rope_kv_store")
+
+
+def decode_attn_splits(B: int, Hkv: int, max_ctx: int) -> int:
+    return load().omc_decode_attn_splits(B, Hkv, max_ctx)
+
+
+def decode_attn_workspace(B: int, Hq: int, Hkv: int, splits: int, device) -> torch.Tensor:
+    n = load().omc_decode_attn_workspace_bytes(B, Hq, Hkv, splits)
+    return torch.zeros((n + 3) // 4, device=device, dtype=torch.int32)
+
+
+def paged_decode_attn(qkv, inv_freq, kv_pool, block_table, page_size, ctx_lens, Hq, Hkv, splits, scale, out, workspace):
+    _need_cuda(qkv, kv_pool, block_table, ctx_lens, out, workspace)
+    assert ctx_lens.dtype == torch.int32 and block_table.dtype == torch.int32
+    rc = load().omc_paged_decode_attn(_ptr(qkv), qkv.stride(0), _ptr(inv_freq), _ptr(kv_pool), _ptr(block_table),
+                                      block_table.shape[1], page_size, _ptr(ctx_lens), qkv.shape[0], Hq, Hkv, splits,
+                                      scale, _ptr(out), out.stride(0), _ptr(workspace), _stream())
+    _check(rc, "omc_paged_decode_attn")
+    return out
+
+
+def embed_lookup(ids: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(ids, table)
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    T, C = ids.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty(T, C, device=table.device, dtype=torch.bfloat16)
+    rc = load().omc_embed_lookup(_ptr(ids), T, _ptr(table), C, _ptr(out), out.stride(0), _stream())
+    _check(rc, "omc_embed_lookup")
+    return out
+
+
+def splice(ids: torch.Tensor, seq_offsets: torch.Tensor, table: torch.Tensor, feats: Optional[torch.Tensor],
+           image_token: int, max_len: int, T_capacity: int):
+    """Returns (embeds [T_capacity, C], pos_ids, seq_ids, out_offsets [n_seq+1]) — rows beyond out_offsets[-1] are
+    unspecified."""
+    _need_cuda(ids, seq_offsets, table)
+    assert ids.dtype == torch.int64 and seq_offsets.dtype == torch.int32
+    n_seq, S = seq_offsets.numel() - 1, ids.numel()
+    C = table.shape[1]
+    n_img, L = (feats.shape[0], feats.shape[1]) if feats is not None else (0, 1)
+    dev = table.device
+    embeds = torch.empty(T_capacity, C, device=dev, dtype=torch.bfloat16)
+    pos_ids = torch.empty(T_capacity, device=dev, dtype=torch.int32)
+    seq_ids = torch.empty(T_capacity, device=dev, dtype=torch.int32)
+    out_off = torch.empty(n_seq + 1, device=dev, dtype=torch.int32)
+    ws = torch.empty(S + n_seq + 2, device=dev, dtype=torch.int32)
+    rc = load().omc_splice(_ptr(ids), _ptr(seq_offsets), n_seq, S, image_token, _ptr(table), _ptr(feats), n_img, L, C,
+                           max_len, _ptr(embeds), _ptr(pos_ids), _ptr(seq_ids), _ptr(out_off), _ptr(ws), T_capacity,
+                           _stream())
+    _check(rc, "omc_splice")
+    return embeds, pos_ids, seq_ids, out_off
+
+
+def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    _need_cuda(logits)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    B, V = logits.shape
+    if out is None:
+        out = torch.empty(B, device=logits.device, dtype=torch.int64)
+    if workspace is None:
+        workspace = torch.empty(128 * B, device=logits.device, dtype=torch.float32)
+    rc = load().omc_argmax(_ptr(logits), logits.stride(0), B, V, _ptr(out), _ptr(workspace), _stream())
+    _check(rc, "omc_argmax")
+    return out
