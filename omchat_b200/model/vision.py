@@ -1,0 +1,137 @@
+"""InternViT-6B vision tower + mm_projector on the C-ABI kernels.
+
+Mirrors InternVITVisionTower (omchat/model/multimodal_encoder/internVIT_encoder.py:10-56) and the projector of
+omchat/model/multimodal_projector/builder.py:54-61. Per layer (intern_vit_6b/modeling_intern_vit.py:218-220):
+    rmsnorm -> QKV GEMM -> full-width q/k RMSNorm (in place) -> flash attention -> proj GEMM (+bias, *ls1, +residual)
+    rmsnorm -> fc1 GEMM (+bias, GELU) -> fc2 GEMM (+bias, *ls2, +residual)
+All activations are bf16 [rows, C] with rows = crops * (patches + 1); the residual stream is updated in place.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .. import lib
+from ..config import OmChatQwen2Config
+from .weights import ProjW, VitW
+
+
+class InternVITVisionTower:
+    """Same surface the reference callers touch: .is_loaded, .load_model(), .image_processor, .hidden_size,
+    .num_patches, __call__(images) -> [n, P, C] (feature_select 'patch' drops CLS, internVIT_encoder.py:35-43)."""
+
+    def __init__(self, cfg: OmChatQwen2Config, weights: Optional[VitW]):
+        self.cfg = cfg
+        self.vc = cfg.vision_config
+        self.w = weights
+        self.is_loaded = weights is not None
+        self.select_layer = cfg.mm_vision_select_layer
+        self.select_feature = cfg.mm_vision_select_feature
+        self.image_processor = None  # CPU preprocessing (CLIPImageProcessor) is outside the hot path
+        self.max_crops_per_pass = 64
+        self._cu_cache = {}
+
+    def load_model(self):
+        if self.w is None:
+            raise RuntimeError("vision tower weights were not provided")
+        self.is_loaded = True
+
+    @property
+    def hidden_size(self) -> int:
+        return self.vc.hidden_size
+
+    @property
+    def num_patches(self) -> int:
+        return self.vc.num_patches
+
+    def num_layers_to_run(self) -> int:
+        L = self.vc.num_hidden_layers
+        k = self.select_layer if self.select_layer >= 0 else L + 1 + self.select_layer
+        if not 0 <= k <= L:
+            raise ValueError(f"mm_vision_select_layer {self.select_layer} out of range")
+        return k
+
+    def _cu_seqlens(self, n: int, S: int, device) -> torch.Tensor:
+        key = (n, S, str(device))
+        if key not in self._cu_cache:
+            self._cu_cache[key] = (torch.arange(n + 1, dtype=torch.int32) * S).to(device)
+        return self._cu_cache[key]
+
+    @torch.no_grad()
+    def hidden_states(self, pixels: torch.Tensor, n_layers: Optional[int] = None, collect: bool = False):
+        """Run embeddings + the first n_layers blocks. Returns hidden [n*(P+1), C] (and the per-layer list if collect)."""
+        w, vc = self.w, self.vc
+        if pixels.dim() != 4 or pixels.shape[1] != 3:
+            raise ValueError(f"wrong pixel_values size: {tuple(pixels.shape)}")  # modeling_intern_vit.py:338
+        if pixels.shape[2] != vc.image_size or pixels.shape[3] != vc.image_size:
+            raise ValueError(f"expected {vc.image_size}x{vc.image_size} crops, got {tuple(pixels.shape[2:])}")
+        n = pixels.shape[0]
+        if pixels.dtype not in (torch.float32, torch.bfloat16):
+            pixels = pixels.float()
+        pixels = pixels.contiguous()
+        C, H = vc.hidden_size, vc.num_attention_heads
+        S = vc.num_patches + 1
+        n_layers = self.num_layers_to_run() if n_layers is None else n_layers
+        cols = lib.vit_im2col(pixels, w.patch_w.shape[1])
+        patch = lib.gemm(cols, w.patch_w, bias=w.patch_b)
+        h = lib.vit_assemble(patch, w.cls, w.pos, n)
+        del cols, patch
+        states = [h.clone()] if collect else None
+        cu = self._cu_seqlens(n, S, h.device)
+        rows = n * S
+        xn = torch.empty(rows, C, device=h.device, dtype=torch.bfloat16)
+        qkv = torch.empty(rows, 3 * C, device=h.device, dtype=torch.bfloat16)
+        attn = torch.empty(rows, C, device=h.device, dtype=torch.bfloat16)
+        act = torch.empty(rows, vc.intermediate_size, device=h.device, dtype=torch.bfloat16)
+        scale = (C // H) ** -0.5
+        eps = vc.layer_norm_eps
+        for li in range(n_layers):
+            l = w.layers[li]
+            lib.rmsnorm(h, l.norm1, eps, out=xn)
+            lib.gemm(xn, l.qkv, out=qkv)
+            if vc.qk_normalization:
+                lib.rmsnorm(qkv[:, :C], l.q_norm, eps, out=qkv[:, :C])
+                lib.rmsnorm(qkv[:, C:2 * C], l.k_norm, eps, out=qkv[:, C:2 * C])
+            lib.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], attn, cu, S, H, H, False, scale)
+            lib.gemm(attn, l.proj_w, out=h, bias=l.proj_b, scale=l.ls1, res=h, epi=lib.EPI_RES)
+            lib.rmsnorm(h, l.norm2, eps, out=xn)
+            lib.gemm(xn, l.fc1_w, out=act, bias=l.fc1_b, epi=lib.EPI_GELU)
+            lib.gemm(act, l.fc2_w, out=h, bias=l.fc2_b, scale=l.ls2, res=h, epi=lib.EPI_RES)
+            if collect:
+                states.append(h.clone())
+        return (h, states) if collect else h
+
+    @torch.no_grad()
+    def __call__(self, images: torch.Tensor, pixel_shuffle_down: int = 1) -> torch.Tensor:
+        """images [n,3,S,S] -> features [n, L, C*down^2]; CLS dropped ('patch') then optional pixel shuffle."""
+        if isinstance(images, (list, tuple)):
+            images = torch.stack([im for im in images])
+        if self.select_feature not in ("patch",):
+            raise ValueError(f"Unexpected select feature: {self.select_feature}")
+        vc = self.vc
+        G = vc.image_size // vc.patch_size
+        outs = []
+        for i in range(0, images.shape[0], self.max_crops_per_pass):
+            chunk = images[i:i + self.max_crops_per_pass]
+            h = self.hidden_states(chunk)
+            f = lib.select_pixel_shuffle(h, chunk.shape[0], G, pixel_shuffle_down)
+            outs.append(f.view(chunk.shape[0], (G // pixel_shuffle_down) ** 2, -1))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    forward = __call__
+
+
+class MMProjector:
+    """mlp2x_gelu projector (multimodal_projector/builder.py:54-61): Linear + GELU + Linear on [n*L, Cin]."""
+
+    def __init__(self, weights: ProjW):
+        self.w = weights
+
+    @torch.no_grad()
+    def __call__(self, feats: torch.Tensor) -> torch.Tensor:
+        shp = feats.shape
+        x = feats.reshape(-1, shp[-1])
+        h = lib.gemm(x, self.w.w0, bias=self.w.b0, epi=lib.EPI_GELU)
+        y = lib.gemm(h, self.w.w2, bias=self.w.b2)
+        return y.view(*shp[:-1], y.shape[-1])

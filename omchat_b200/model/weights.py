@@ -1,0 +1,235 @@
+"""Device-resident bf16 weights in the layouts the kernels consume, built from a state dict that uses the reference's own
+parameter names (`model.vision_tower.vision_tower.*`, `model.mm_projector.{0,2}.*`, `model.layers.*`, `model.norm.weight`,
+`model.embed_tokens.weight`, `lm_head.weight`; HF-hub layout names are remapped with the table of
+convert_omchat_to_hf.py:26-35 read backwards), or random-initialised directly on the device for benchmarks.
+
+Layout decisions (all K-major = nn.Linear's own [out, in] layout, so no transposes):
+  - patch-embed conv weight [C,3,14,14] -> [C, 640] (K = 588 zero-padded to a TMA-legal row pitch)
+  - Qwen2 q/k/v -> one [Hq*128 + 2*Hkv*128, hidden] matrix + one bias vector
+  - Qwen2 gate/up -> one [2*I, hidden] matrix, rows interleaved [128 gate | 128 up] per 256 so a single N-tile of the
+    GEMM (or a warp of the GEMV) holds matching gate/up columns for the fused SwiGLU epilogue
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from ..config import OmChatQwen2Config
+
+VT = "model.vision_tower.vision_tower."
+PATCH_K = 640
+
+# convert_omchat_to_hf.py:26-35 (omchat name fragment -> HF-hub name fragment)
+KEYS_TO_MODIFY_MAPPING = {
+    "model.vision_tower.vision_tower.": "vision_tower.",
+    "model.mm_projector.0": "multi_modal_projector.linear_1",
+    "model.mm_projector.2": "multi_modal_projector.linear_2",
+    "model.": "language_model.model.",
+    "lm_head.": "language_model.lm_head.",
+}
+
+
+def from_hf_names(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Map an HF-hub style state dict (OmChatForConditionalGeneration) back to the omchat names used here."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("vision_tower."):
+            k = VT + k[len("vision_tower."):]
+        elif k.startswith("multi_modal_projector.linear_1"):
+            k = "model.mm_projector.0" + k[len("multi_modal_projector.linear_1"):]
+        elif k.startswith("multi_modal_projector.linear_2"):
+            k = "model.mm_projector.2" + k[len("multi_modal_projector.linear_2"):]
+        elif k.startswith("language_model.model."):
+            k = "model." + k[len("language_model.model."):]
+        elif k.startswith("language_model.lm_head."):
+            k = "lm_head." + k[len("language_model.lm_head."):]
+        out[k] = v
+    return out
+
+
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    I, K = gate.shape
+    assert I % 128 == 0, "intermediate size must be a multiple of 128 for the fused SwiGLU layout"
+    return torch.stack([gate.view(I // 128, 128, K), up.view(I // 128, 128, K)], dim=1).reshape(2 * I, K)
+
+
+@dataclass
+class VitLayerW:
+    norm1: torch.Tensor
+    qkv: torch.Tensor
+    q_norm: torch.Tensor
+    k_norm: torch.Tensor
+    proj_w: torch.Tensor
+    proj_b: torch.Tensor
+    ls1: torch.Tensor
+    norm2: torch.Tensor
+    fc1_w: torch.Tensor
+    fc1_b: torch.Tensor
+    fc2_w: torch.Tensor
+    fc2_b: torch.Tensor
+    ls2: torch.Tensor
+
+
+@dataclass
+class VitW:
+    patch_w: torch.Tensor  # [C, 640]
+    patch_b: torch.Tensor
+    cls: torch.Tensor  # [C]
+    pos: torch.Tensor  # [P+1, C]
+    layers: List[VitLayerW]
+
+
+@dataclass
+class ProjW:
+    w0: torch.Tensor
+    b0: torch.Tensor
+    w2: torch.Tensor
+    b2: torch.Tensor
+
+
+@dataclass
+class LlmLayerW:
+    ln1: torch.Tensor
+    qkv_w: torch.Tensor
+    qkv_b: torch.Tensor
+    o_w: torch.Tensor
+    ln2: torch.Tensor
+    gate_up_w: torch.Tensor
+    down_w: torch.Tensor
+
+
+@dataclass
+class LlmW:
+    embed: torch.Tensor
+    layers: List[LlmLayerW]
+    norm: torch.Tensor
+    lm_head: torch.Tensor
+
+
+@dataclass
+class OmChatWeights:
+    vit: Optional[VitW]
+    proj: Optional[ProjW]
+    llm: LlmW
+
+
+def _dev(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+
+def from_state_dict(sd: Dict[str, torch.Tensor], cfg: OmChatQwen2Config, device="cuda") -> OmChatWeights:
+    if any(k.startswith("language_model.") for k in sd):
+        sd = from_hf_names(sd)
+    vc = cfg.vision_config
+    vit = proj = None
+    if (VT + "embeddings.class_embedding") in sd:
+        C = vc.hidden_size
+        pw = sd[VT + "embeddings.patch_embedding.weight"].reshape(C, -1)
+        patch_w = torch.zeros(C, PATCH_K, dtype=pw.dtype)
+        patch_w[:, : pw.shape[1]] = pw
+        layers = []
+        for li in range(vc.num_hidden_layers):
+            p = f"{VT}encoder.layers.{li}."
+            layers.append(VitLayerW(
+                norm1=_dev(sd[p + "norm1.weight"], device), qkv=_dev(sd[p + "attn.qkv.weight"], device),
+                q_norm=_dev(sd[p + "attn.q_norm.weight"], device), k_norm=_dev(sd[p + "attn.k_norm.weight"], device),
+                proj_w=_dev(sd[p + "attn.proj.weight"], device), proj_b=_dev(sd[p + "attn.proj.bias"], device),
+                ls1=_dev(sd[p + "ls1"], device), norm2=_dev(sd[p + "norm2.weight"], device),
+                fc1_w=_dev(sd[p + "mlp.fc1.weight"], device), fc1_b=_dev(sd[p + "mlp.fc1.bias"], device),
+                fc2_w=_dev(sd[p + "mlp.fc2.weight"], device), fc2_b=_dev(sd[p + "mlp.fc2.bias"], device),
+                ls2=_dev(sd[p + "ls2"], device)))
+        vit = VitW(patch_w=_dev(patch_w, device), patch_b=_dev(sd[VT + "embeddings.patch_embedding.bias"], device),
+                   cls=_dev(sd[VT + "embeddings.class_embedding"].reshape(-1), device),
+                   pos=_dev(sd[VT + "embeddings.position_embedding"].reshape(-1, C), device), layers=layers)
+        proj = ProjW(w0=_dev(sd["model.mm_projector.0.weight"], device), b0=_dev(sd["model.mm_projector.0.bias"], device),
+                     w2=_dev(sd["model.mm_projector.2.weight"], device), b2=_dev(sd["model.mm_projector.2.bias"], device))
+    layers = []
+    for li in range(cfg.num_hidden_layers):
+        p = f"model.layers.{li}."
+        qkv_w = torch.cat([sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"],
+                           sd[p + "self_attn.v_proj.weight"]], dim=0)
+        qkv_b = torch.cat([sd[p + "self_attn.q_proj.bias"], sd[p + "self_attn.k_proj.bias"],
+                           sd[p + "self_attn.v_proj.bias"]], dim=0)
+        layers.append(LlmLayerW(
+            ln1=_dev(sd[p + "input_layernorm.weight"], device), qkv_w=_dev(qkv_w, device), qkv_b=_dev(qkv_b, device),
+            o_w=_dev(sd[p + "self_attn.o_proj.weight"], device), ln2=_dev(sd[p + "post_attention_layernorm.weight"], device),
+            gate_up_w=_dev(interleave_gate_up(sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]), device),
+            down_w=_dev(sd[p + "mlp.down_proj.weight"], device)))
+    llm = LlmW(embed=_dev(sd["model.embed_tokens.weight"], device), layers=layers,
+               norm=_dev(sd["model.norm.weight"], device), lm_head=_dev(sd["lm_head.weight"], device))
+    return OmChatWeights(vit=vit, proj=proj, llm=llm)
+
+
+def random_init(cfg: OmChatQwen2Config, device="cuda", seed: int = 0, vision: bool = True, text: bool = True) -> OmChatWeights:
+    """Random weights of the configured architecture created directly on the device (no host copy of the 13B model).
+    Scales follow HF `_init_weights` (normal std 0.02 for Linear/Embedding; ViT cls/pos randn; layer-scale 0.1; norm
+    weights 1) with small perturbations so every parameter matters. Layout identical to from_state_dict()."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    vc = cfg.vision_config
+
+    def rn(*shape, std=0.02, mean=0.0):
+        return (torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * std + mean).to(torch.bfloat16)
+
+    vit = proj = None
+    if vision:
+        C, I = vc.hidden_size, vc.intermediate_size
+        patch_w = torch.zeros(C, PATCH_K, device=device, dtype=torch.bfloat16)
+        patch_w[:, :588] = rn(C, 588)
+        layers = [VitLayerW(norm1=rn(C, std=0.02, mean=1.0), qkv=rn(3 * C, C), q_norm=rn(C, std=0.02, mean=1.0),
+                            k_norm=rn(C, std=0.02, mean=1.0), proj_w=rn(C, C), proj_b=rn(C), ls1=rn(C, std=0.01, mean=0.1),
+                            norm2=rn(C, std=0.02, mean=1.0), fc1_w=rn(I, C), fc1_b=rn(I), fc2_w=rn(C, I), fc2_b=rn(C),
+                            ls2=rn(C, std=0.01, mean=0.1)) for _ in range(vc.num_hidden_layers)]
+        vit = VitW(patch_w=patch_w, patch_b=rn(C), cls=rn(C, std=1.0), pos=rn(vc.num_patches + 1, C, std=1.0), layers=layers)
+        H = cfg.hidden_size
+        Cin = C * cfg.pixel_shuffle_down ** 2
+        proj = ProjW(w0=rn(H, Cin), b0=rn(H), w2=rn(H, H), b2=rn(H))
+    H, I, D = cfg.hidden_size, cfg.intermediate_size, cfg.head_dim
+    nq, nkv = cfg.num_attention_heads, cfg.num_key_value_heads
+    layers = []
+    if text:
+        layers = [LlmLayerW(ln1=rn(H, std=0.02, mean=1.0), qkv_w=rn((nq + 2 * nkv) * D, H), qkv_b=rn((nq + 2 * nkv) * D),
+                            o_w=rn(H, nq * D), ln2=rn(H, std=0.02, mean=1.0), gate_up_w=rn(2 * I, H), down_w=rn(H, I))
+                  for _ in range(cfg.num_hidden_layers)]
+    llm = LlmW(embed=rn(cfg.vocab_size, H) if text else torch.zeros(1, H, device=device, dtype=torch.bfloat16),
+               layers=layers, norm=rn(H, std=0.02, mean=1.0),
+               lm_head=rn(cfg.vocab_size, H) if text else torch.zeros(8, H, device=device, dtype=torch.bfloat16))
+    return OmChatWeights(vit=vit, proj=proj, llm=llm)
+
+
+def to_reference_state_dict(w: OmChatWeights, cfg: OmChatQwen2Config) -> Dict[str, torch.Tensor]:
+    """Inverse of from_state_dict (bf16 tensors on their current device) — lets the parity tests hand the SAME weights
+    to the checker under the reference's parameter names."""
+    sd: Dict[str, torch.Tensor] = {}
+    vc = cfg.vision_config
+    if w.vit is not None:
+        C = vc.hidden_size
+        sd[VT + "embeddings.class_embedding"] = w.vit.cls.view(1, 1, C)
+        sd[VT + "embeddings.position_embedding"] = w.vit.pos.view(1, -1, C)
+        sd[VT + "embeddings.patch_embedding.weight"] = w.vit.patch_w[:, :588].reshape(C, 3, 14, 14)
+        sd[VT + "embeddings.patch_embedding.bias"] = w.vit.patch_b
+        for li, l in enumerate(w.vit.layers):
+            p = f"{VT}encoder.layers.{li}."
+            sd.update({p + "norm1.weight": l.norm1, p + "attn.qkv.weight": l.qkv, p + "attn.q_norm.weight": l.q_norm,
+                       p + "attn.k_norm.weight": l.k_norm, p + "attn.proj.weight": l.proj_w, p + "attn.proj.bias": l.proj_b,
+                       p + "ls1": l.ls1, p + "norm2.weight": l.norm2, p + "mlp.fc1.weight": l.fc1_w,
+                       p + "mlp.fc1.bias": l.fc1_b, p + "mlp.fc2.weight": l.fc2_w, p + "mlp.fc2.bias": l.fc2_b, p + "ls2": l.ls2})
+        sd.update({"model.mm_projector.0.weight": w.proj.w0, "model.mm_projector.0.bias": w.proj.b0,
+                   "model.mm_projector.2.weight": w.proj.w2, "model.mm_projector.2.bias": w.proj.b2})
+    D = cfg.head_dim
+    nq, nkv = cfg.num_attention_heads * D, cfg.num_key_value_heads * D
+    for li, l in enumerate(w.llm.layers):
+        p = f"model.layers.{li}."
+        I2, K = l.gate_up_w.shape
+        gu = l.gate_up_w.view(I2 // 256, 2, 128, K)
+        sd.update({p + "input_layernorm.weight": l.ln1, p + "post_attention_layernorm.weight": l.ln2,
+                   p + "self_attn.q_proj.weight": l.qkv_w[:nq], p + "self_attn.k_proj.weight": l.qkv_w[nq:nq + nkv],
+                   p + "self_attn.v_proj.weight": l.qkv_w[nq + nkv:], p + "self_attn.q_proj.bias": l.qkv_b[:nq],
+                   p + "self_attn.k_proj.bias": l.qkv_b[nq:nq + nkv], p + "self_attn.v_proj.bias": l.qkv_b[nq + nkv:],
+                   p + "self_attn.o_proj.weight": l.o_w, p + "mlp.gate_proj.weight": gu[:, 0].reshape(I2 // 2, K),
+                   p + "mlp.up_proj.weight": gu[:, 1].reshape(I2 // 2, K), p + "mlp.down_proj.weight": l.down_w})
+    sd["model.embed_tokens.weight"] = w.llm.embed
+    sd["model.norm.weight"] = w.llm.norm
+    sd["lm_head.weight"] = w.llm.lm_head
+    return sd
