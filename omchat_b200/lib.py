@@ -40,6 +40,16 @@ SIGNATURES = {
 }
 
 _lib = None
+_launches = 0  # kernels launched through this binding (bench.py's gpu_launches; graph replays are added by the caller)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def add_launches(n: int):
+    global _launches
+    _launches += n
 
 
 class OmcError(RuntimeError):
@@ -63,7 +73,12 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+_KERNELS_PER_CALL = {"omc_splice": 2, "omc_argmax": 2}
+
+
 def _check(rc: int, what: str):
+    global _launches
+    _launches += _KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         msg = load().omc_last_error().decode(errors="replace")
         raise OmcError(f"{what} failed ({rc}): {msg}")

@@ -105,7 +105,76 @@ class LlmW:
     embed: torch.Tensor
     layers: List[LlmLayerW]
     norm: torch.Tensor
-    lm_head: torch.Tensor
+    lm_head: torch.Tensor  # [V_local, C] (vocab-parallel under TP)
+    q_heads_local: int = 28
+    kv_heads_local: int = 4
+
+
+@dataclass
+class TPPlan:
+    """Which slices of the Qwen2 weights one tensor-parallel rank owns.
+    q_heads: global q-head indices (-1 = zero pad head), kv_heads: global kv-head indices, i_lo/i_hi: MLP rows,
+    i_pad: zero rows appended so the local intermediate size is a multiple of 128 (SwiGLU interleave block),
+    v_lo/v_hi: vocab rows of lm_head."""
+    q_heads: List[int]
+    kv_heads: List[int]
+    i_lo: int
+    i_hi: int
+    i_pad: int
+    v_lo: int
+    v_hi: int
+
+
+def tp_plan(cfg: OmChatQwen2Config, rank: int, size: int) -> TPPlan:
+    Hq, Hkv, I, V = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.intermediate_size, cfg.vocab_size
+    G = Hq // Hkv
+    if size <= Hkv:
+        if Hkv % size:
+            raise ValueError(f"tp_size {size} must divide the {Hkv} kv heads (or be a multiple of it)")
+        per = Hkv // size
+        kv = list(range(rank * per, (rank + 1) * per))
+        q = [g * G + j for g in kv for j in range(G)]
+    else:
+        if size % Hkv:
+            raise ValueError(f"tp_size {size} must be a multiple of the {Hkv} kv heads")
+        rep = size // Hkv  # ranks sharing one (replicated) kv head; its G q-heads are dealt to them, padded
+        g, part = rank // rep, rank % rep
+        chunk = (G + rep - 1) // rep
+        q = [g * G + j if j < G else -1 for j in range(part * chunk, (part + 1) * chunk)]
+        kv = [g]
+    if I % size or V % size:
+        raise ValueError("tp_size must divide intermediate_size and vocab_size")
+    il = I // size
+    return TPPlan(q_heads=q, kv_heads=kv, i_lo=rank * il, i_hi=(rank + 1) * il, i_pad=(-il) % 128,
+                  v_lo=rank * (V // size), v_hi=(rank + 1) * (V // size))
+
+
+def _take_heads(t: torch.Tensor, heads: List[int], D: int, dim: int) -> torch.Tensor:
+    """Select head blocks (D rows/cols each) along `dim`; -1 inserts a zero block."""
+    parts = []
+    for hd in heads:
+        if hd < 0:
+            shp = list(t.shape)
+            shp[dim] = D
+            parts.append(torch.zeros(shp, dtype=t.dtype, device=t.device))
+        else:
+            parts.append(t.narrow(dim, hd * D, D))
+    return torch.cat(parts, dim=dim)
+
+
+def shard_llm_layer(q_w, q_b, k_w, k_b, v_w, v_b, o_w, gate, up, down, plan: TPPlan, D: int):
+    """Column-parallel q/k/v + gate/up, row-parallel o/down for one rank; returns the fused kernel layouts."""
+    qkv_w = torch.cat([_take_heads(q_w, plan.q_heads, D, 0), _take_heads(k_w, plan.kv_heads, D, 0),
+                       _take_heads(v_w, plan.kv_heads, D, 0)], dim=0)
+    qkv_b = torch.cat([_take_heads(q_b, plan.q_heads, D, 0), _take_heads(k_b, plan.kv_heads, D, 0),
+                       _take_heads(v_b, plan.kv_heads, D, 0)], dim=0)
+    o = _take_heads(o_w, plan.q_heads, D, 1)
+    g, u, d = gate[plan.i_lo:plan.i_hi], up[plan.i_lo:plan.i_hi], down[:, plan.i_lo:plan.i_hi]
+    if plan.i_pad:
+        z = torch.zeros(plan.i_pad, g.shape[1], dtype=g.dtype, device=g.device)
+        g, u = torch.cat([g, z]), torch.cat([u, z])
+        d = torch.cat([d, torch.zeros(d.shape[0], plan.i_pad, dtype=d.dtype, device=d.device)], dim=1)
+    return qkv_w, qkv_b, o.contiguous(), interleave_gate_up(g, u), d.contiguous()
 
 
 @dataclass
@@ -119,7 +188,8 @@ def _dev(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
 
 
-def from_state_dict(sd: Dict[str, torch.Tensor], cfg: OmChatQwen2Config, device="cuda") -> OmChatWeights:
+def from_state_dict(sd: Dict[str, torch.Tensor], cfg: OmChatQwen2Config, device="cuda", tp_rank: int = 0,
+                    tp_size: int = 1) -> OmChatWeights:
     if any(k.startswith("language_model.") for k in sd):
         sd = from_hf_names(sd)
     vc = cfg.vision_config
@@ -145,27 +215,32 @@ def from_state_dict(sd: Dict[str, torch.Tensor], cfg: OmChatQwen2Config, device=
                    pos=_dev(sd[VT + "embeddings.position_embedding"].reshape(-1, C), device), layers=layers)
         proj = ProjW(w0=_dev(sd["model.mm_projector.0.weight"], device), b0=_dev(sd["model.mm_projector.0.bias"], device),
                      w2=_dev(sd["model.mm_projector.2.weight"], device), b2=_dev(sd["model.mm_projector.2.bias"], device))
+    plan = tp_plan(cfg, tp_rank, tp_size)
+    D = cfg.head_dim
     layers = []
     for li in range(cfg.num_hidden_layers):
         p = f"model.layers.{li}."
-        qkv_w = torch.cat([sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"],
-                           sd[p + "self_attn.v_proj.weight"]], dim=0)
-        qkv_b = torch.cat([sd[p + "self_attn.q_proj.bias"], sd[p + "self_attn.k_proj.bias"],
-                           sd[p + "self_attn.v_proj.bias"]], dim=0)
+        a = p + "self_attn."
+        qkv_w, qkv_b, o_w, gu, down = shard_llm_layer(
+            sd[a + "q_proj.weight"], sd[a + "q_proj.bias"], sd[a + "k_proj.weight"], sd[a + "k_proj.bias"],
+            sd[a + "v_proj.weight"], sd[a + "v_proj.bias"], sd[a + "o_proj.weight"], sd[p + "mlp.gate_proj.weight"],
+            sd[p + "mlp.up_proj.weight"], sd[p + "mlp.down_proj.weight"], plan, D)
         layers.append(LlmLayerW(
             ln1=_dev(sd[p + "input_layernorm.weight"], device), qkv_w=_dev(qkv_w, device), qkv_b=_dev(qkv_b, device),
-            o_w=_dev(sd[p + "self_attn.o_proj.weight"], device), ln2=_dev(sd[p + "post_attention_layernorm.weight"], device),
-            gate_up_w=_dev(interleave_gate_up(sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]), device),
-            down_w=_dev(sd[p + "mlp.down_proj.weight"], device)))
+            o_w=_dev(o_w, device), ln2=_dev(sd[p + "post_attention_layernorm.weight"], device),
+            gate_up_w=_dev(gu, device), down_w=_dev(down, device)))
     llm = LlmW(embed=_dev(sd["model.embed_tokens.weight"], device), layers=layers,
-               norm=_dev(sd["model.norm.weight"], device), lm_head=_dev(sd["lm_head.weight"], device))
+               norm=_dev(sd["model.norm.weight"], device), lm_head=_dev(sd["lm_head.weight"][plan.v_lo:plan.v_hi], device),
+               q_heads_local=len(plan.q_heads), kv_heads_local=len(plan.kv_heads))
     return OmChatWeights(vit=vit, proj=proj, llm=llm)
 
 
-def random_init(cfg: OmChatQwen2Config, device="cuda", seed: int = 0, vision: bool = True, text: bool = True) -> OmChatWeights:
+def random_init(cfg: OmChatQwen2Config, device="cuda", seed: int = 0, vision: bool = True, text: bool = True,
+                tp_rank: int = 0, tp_size: int = 1) -> OmChatWeights:
     """Random weights of the configured architecture created directly on the device (no host copy of the 13B model).
     Scales follow HF `_init_weights` (normal std 0.02 for Linear/Embedding; ViT cls/pos randn; layer-scale 0.1; norm
-    weights 1) with small perturbations so every parameter matters. Layout identical to from_state_dict()."""
+    weights 1) with small perturbations so every parameter matters. Layout identical to from_state_dict(). Under TP
+    every rank draws the same full matrices from the same seed and keeps its shard."""
     g = torch.Generator(device=device).manual_seed(seed)
     vc = cfg.vision_config
 
@@ -187,14 +262,21 @@ def random_init(cfg: OmChatQwen2Config, device="cuda", seed: int = 0, vision: bo
         proj = ProjW(w0=rn(H, Cin), b0=rn(H), w2=rn(H, H), b2=rn(H))
     H, I, D = cfg.hidden_size, cfg.intermediate_size, cfg.head_dim
     nq, nkv = cfg.num_attention_heads, cfg.num_key_value_heads
+    plan = tp_plan(cfg, tp_rank, tp_size)
     layers = []
     if text:
-        layers = [LlmLayerW(ln1=rn(H, std=0.02, mean=1.0), qkv_w=rn((nq + 2 * nkv) * D, H), qkv_b=rn((nq + 2 * nkv) * D),
-                            o_w=rn(H, nq * D), ln2=rn(H, std=0.02, mean=1.0), gate_up_w=rn(2 * I, H), down_w=rn(H, I))
-                  for _ in range(cfg.num_hidden_layers)]
+        for _ in range(cfg.num_hidden_layers):
+            ln1, ln2 = rn(H, std=0.02, mean=1.0), rn(H, std=0.02, mean=1.0)
+            qkv_w, qkv_b, o_w, gu, down = shard_llm_layer(
+                rn(nq * D, H), rn(nq * D), rn(nkv * D, H), rn(nkv * D), rn(nkv * D, H), rn(nkv * D), rn(H, nq * D),
+                rn(I, H), rn(I, H), rn(H, I), plan, D)
+            layers.append(LlmLayerW(ln1=ln1, qkv_w=qkv_w.contiguous(), qkv_b=qkv_b.contiguous(), o_w=o_w, ln2=ln2,
+                                    gate_up_w=gu.contiguous(), down_w=down))
     llm = LlmW(embed=rn(cfg.vocab_size, H) if text else torch.zeros(1, H, device=device, dtype=torch.bfloat16),
                layers=layers, norm=rn(H, std=0.02, mean=1.0),
-               lm_head=rn(cfg.vocab_size, H) if text else torch.zeros(8, H, device=device, dtype=torch.bfloat16))
+               lm_head=rn(cfg.vocab_size, H)[plan.v_lo:plan.v_hi].contiguous() if text
+               else torch.zeros(8, H, device=device, dtype=torch.bfloat16),
+               q_heads_local=len(plan.q_heads), kv_heads_local=len(plan.kv_heads))
     return OmChatWeights(vit=vit, proj=proj, llm=llm)
 
 
