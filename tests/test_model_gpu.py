@@ -57,7 +57,10 @@ def check(got, ref, what, rel=0.04, cos_min=0.999):
     assert torch.isfinite(got).all(), what
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item() + 1e-6
-    cos = torch.nn.functional.cosine_similarity(got.reshape(-1, got.shape[-1]), ref.reshape(-1, ref.shape[-1]), dim=-1)
+    g2, r2 = got.reshape(-1, got.shape[-1]), ref.reshape(-1, ref.shape[-1])
+    live = r2.abs().amax(dim=-1) > 0  # padded positions are all-zero rows in both: cosine is undefined there
+    assert torch.equal(g2[~live], r2[~live]), f"{what}: padding rows must be exactly zero"
+    cos = torch.nn.functional.cosine_similarity(g2[live], r2[live], dim=-1) if live.any() else torch.ones(1)
     print(f"{what}: max-abs err {err:.4g} (scale {scale:.4g}, rel {err / scale:.4g}), min cosine {cos.min().item():.6f}")
     assert err <= rel * scale, f"{what}: max abs err {err:.5g} vs scale {scale:.5g}"
     assert cos.min().item() >= cos_min, f"{what}: min cosine {cos.min().item():.6f}"
