@@ -29,7 +29,7 @@ extern "C" {
 #define OMC_EPI_NONE 0   /* Y = X W^T (+ bias) */
 #define OMC_EPI_GELU 1   /* Y = gelu_erf(X W^T + bias) */
 #define OMC_EPI_RES 2    /* Y = res + scale * (X W^T + bias)   (scale, bias optional) */
-#define OMC_EPI_SWIGLU 3 /* W rows interleaved [128 gate | 128 up] per 256: Y[:, N/2] = silu(gate) * up */
+#define OMC_EPI_SWIGLU 3 /* W rows alternate gate_i, up_i (row 2i, 2i+1): Y[:, i] = silu(gate_i) * up_i, Y is [M, N/2] */
 
 const char* omc_last_error(void);
 int omc_version(void);
@@ -125,6 +125,54 @@ int omc_splice(const int64_t* ids, const int32_t* seq_offsets, int n_seq, int S_
 /* greedy sampling (HF GenerationMixin argmax as driven by cli.py:60-70): next[b] = argmax_v logits[b, v]
  * (lowest index on ties), logits fp32 [B, V] with row stride ldl. workspace: 128*B floats. */
 int omc_argmax(const float* logits, long long ldl, int B, int V, int64_t* next, float* workspace, void* stream);
+
+/* ---- persistent decode step ("megakernel", omchat_b200/csrc/decode_mega.cu) ------------------------------------------
+ * One cooperative launch = one whole Qwen2 decode step for 1..4 sequences: embed_tokens (omchat_arch.py:139), every
+ * Qwen2DecoderLayer (modeling_qwen2.py:280-310: RMSNorm, q/k/v + bias, RoPE, paged KV append + GQA attention, o_proj,
+ * SwiGLU MLP, residuals), final norm + lm_head (:411,470-472) and the greedy argmax of GenerationMixin (cli.py:60-70).
+ * The caller describes the model once (omc_decode_desc: plain device pointers and sizes), builds a plan on the HOST
+ * (omc_decode_plan_build is pure CPU code), copies the plan bytes to the device and launches omc_decode_step per token.
+ * Per-layer pointer arrays are HOST arrays of device pointers. Weight matrices must be contiguous [N, K] bf16;
+ * gate_up_w is the [2*inter, hidden] matrix with rows alternating gate_i, up_i (OMC_EPI_SWIGLU layout).
+ * State: tokens[batch] (in: the tokens to feed, out: the greedy next tokens), ctx_lens[batch] (in: tokens already in
+ * the cache, incremented by the kernel), token_hist[hist_capacity, batch] / hist_pos[1] (optional history of the sampled
+ * tokens, appended at *hist_pos), h/qkv/attn/act/logits scratch of [batch, hidden | (q+2kv)*128 | q*128 | inter | vocab].
+ * workspace: omc_decode_workspace_bytes(grid) bytes, ZERO-INITIALISED once by the caller. grid = CTAs = omc_num_sms(). */
+typedef struct omc_decode_desc {
+  int32_t n_layers, batch, hidden, q_heads, kv_heads, inter, vocab, vocab_offset;
+  int32_t page_size, max_pages, grid, hist_capacity;
+  float eps, attn_scale;
+  const void* embed;
+  const void* final_norm;
+  const void* lm_head;
+  const float* inv_freq;
+  const void* const* ln1;
+  const void* const* qkv_w;
+  const void* const* qkv_b;
+  const void* const* o_w;
+  const void* const* ln2;
+  const void* const* gate_up_w;
+  const void* const* down_w;
+  void* kv_pool; /* layer 0 pool [num_pages, 2, kv_heads, page_size, 128]; layer l at + l * kv_layer_stride elements */
+  long long kv_layer_stride;
+  const int32_t* block_table;
+  int32_t* ctx_lens;
+  int64_t* tokens;
+  int64_t* token_hist;
+  int32_t* hist_pos;
+  void* h;
+  void* qkv;
+  void* attn;
+  void* act;
+  float* logits;
+  void* workspace;
+  int32_t* status; /* optional int32[4], zeroed by the caller, device-accessible (pinned host memory is fine): a watchdog
+                      inside the kernel writes {code, CTA, detail, thread} here before trapping; NULL = in workspace */
+} omc_decode_desc;
+long long omc_decode_plan_bytes(int n_layers);
+long long omc_decode_workspace_bytes(int grid);
+int omc_decode_plan_build(const omc_decode_desc* desc, void* plan_host);
+int omc_decode_step(const void* plan_host, const void* plan_dev, void* stream);
 
 #ifdef __cplusplus
 }

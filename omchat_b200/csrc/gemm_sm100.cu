@@ -183,20 +183,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t t_addr = tmem_base + acc * Cfg::kAccStride + ((uint32_t)(quarter * 32) << 16);
 
       if (p.epi == EPI_SWIGLU) {
-        constexpr int HALF = BN / 2;
+        // W rows alternate gate_i, up_i: accumulator columns (2j, 2j+1) -> output column j
         const int n_out = p.N >> 1;
 #pragma unroll 1
-        for (int c = 0; c < HALF; c += 16) {
-          uint32_t g[16], u[16];
-          tmem_ld16(t_addr + c, g);
-          tmem_ld16(t_addr + HALF + c, u);
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c, v);
           tmem_ld_wait();
-          const int col = nt * HALF + c;
+          const int col = (nt * BN + c) >> 1;
+          if (col >= n_out) break;
           uint32_t o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float a0 = silu(__uint_as_float(g[2 * j])) * __uint_as_float(u[2 * j]);
-            float a1 = silu(__uint_as_float(g[2 * j + 1])) * __uint_as_float(u[2 * j + 1]);
+            float a0 = silu(__uint_as_float(v[4 * j])) * __uint_as_float(v[4 * j + 1]);
+            float a1 = silu(__uint_as_float(v[4 * j + 2])) * __uint_as_float(v[4 * j + 3]);
             o[j] = pack_bf16(a0, a1);
           }
           if (row_ok) {
@@ -407,13 +407,11 @@ extern "C" int omc_gemm_bf16(const void* X, long long ldx, const void* W, long l
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int bn = tile_cfg & 0xFFFF, cg = (tile_cfg >> 16) & 0xF, max_ctas = (tile_cfg >> 20) & 0xFFF;
   if (bn == 0) {
-    // auto: 2-CTA pairs with the widest N tile that divides N (SwiGLU tiles pair gate/up halves: needs full tiles)
+    // auto: 2-CTA pairs with the widest N tile that divides N
     cg = 2;
     bn = (N % 256 == 0) ? 256 : (N % 160 == 0) ? 160 : (N % 192 == 0) ? 192 : (N % 128 == 0) ? 128 : 256;
   }
   if (cg == 0) cg = 2;
-  if (epi == EPI_SWIGLU && N % bn != 0)
-    return set_error(OMC_ERR_SHAPE, "omc_gemm_bf16: SwiGLU needs N to be a multiple of the N tile");
 #define OMC_GEMM_CASE(BN_, CG_) \
   if (bn == BN_ && cg == CG_) return launch_gemm<BN_, CG_>(X, ldx, W, ldw, p, max_ctas, st);
   OMC_GEMM_CASE(256, 1)

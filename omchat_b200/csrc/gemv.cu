@@ -40,14 +40,9 @@ __device__ __forceinline__ void fma8(float& acc, uint4 w, const float* xv) {
   acc = fmaf(d.x, xv[6], acc); acc = fmaf(d.y, xv[7], acc);
 }
 
-// weight row index of slot j (0..3) of row-group grp. SwiGLU: rows are interleaved [128 gate | 128 up] per 256, a
-// group holds gate rows (g, g+1) and their up rows (g+128, g+129).
-__device__ __forceinline__ int group_row(int grp, int j, int epi) {
-  if (epi != EPI_SWIGLU) return grp * kRows + j;
-  const int pair0 = grp * 2;                      // first output column of the group
-  const int blk = pair0 >> 7, within = pair0 & 127;
-  return blk * 256 + within + (j & 1) + ((j >> 1) << 7);
-}
+// weight row index of slot j (0..3) of row-group grp. SwiGLU: W rows alternate gate_i, up_i, so a group of 4 rows holds
+// two (gate, up) pairs = output columns 2*grp and 2*grp+1.
+__device__ __forceinline__ int group_row(int grp, int j, int) { return grp * kRows + j; }
 
 template <int NB>
 __global__ void __launch_bounds__(kGemvThreads) gemv_bf16_kernel(const GemvParams p) {
@@ -160,7 +155,7 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_bf16_kernel(const GemvParam
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             if (col0 + c < (p.N >> 1)) {
-              const float val = silu_f(acc[c][b]) * acc[2 + c][b];
+              const float val = silu_f(acc[2 * c][b]) * acc[2 * c + 1][b];
               static_cast<bf16*>(p.out)[(long long)b * p.ldo + col0 + c] = __float2bfloat16(val);
             }
           }
@@ -219,8 +214,8 @@ extern "C" int omc_gemv_bf16(const void* x, long long ldx, const void* W, long l
   if ((size_t)B * K * 2 > 200 * 1024) return set_error(OMC_ERR_SHAPE, "omc_gemv_bf16: B*K too large for shared memory");
   if (epi != EPI_NONE && epi != EPI_RES && epi != EPI_SWIGLU) return set_error(OMC_ERR_ARG, "omc_gemv_bf16: unknown epilogue");
   if (epi == EPI_RES && res == nullptr) return set_error(OMC_ERR_ARG, "omc_gemv_bf16: EPI_RES needs a residual");
-  if (epi == EPI_SWIGLU && (N % 256 != 0 || bias != nullptr || out_is_f32))
-    return set_error(OMC_ERR_ARG, "omc_gemv_bf16: SwiGLU needs N % 256 == 0, no bias, bf16 output");
+  if (epi == EPI_SWIGLU && (N % 4 != 0 || bias != nullptr || out_is_f32))
+    return set_error(OMC_ERR_ARG, "omc_gemv_bf16: SwiGLU needs N % 4 == 0, no bias, bf16 output");
   GemvParams p;
   p.x = (const bf16*)x; p.ldx = ldx; p.W = (const bf16*)W; p.ldw = ldw; p.out = out; p.ldo = ldo;
   p.N = N; p.K = K; p.norm_w = (const bf16*)norm_w; p.eps = eps; p.bias = (const bf16*)bias;

@@ -10,7 +10,7 @@ Data layout in HBM
   * tokens of all sequences of a prefill are PACKED: activations are [T_total, C] bf16, sequence s owns rows
     offsets[s]..offsets[s+1]; attention runs var-len over cu_seqlens, so padding never reaches a kernel
   * q|k|v of a layer share one [T, (Hq+2*Hkv)*128] buffer (one GEMM, fused bias); gate|up share one weight matrix with
-    rows interleaved [128 gate | 128 up] so SwiGLU is a GEMM/GEMV epilogue
+    rows alternating gate_i, up_i so SwiGLU is a GEMM/GEMV epilogue
   * KV cache: one pool per layer [num_pages, 2, Hkv, page_size, 128] bf16 + an int32 block table [n_seq, max_pages]
     (replaces DynamicCache / torch.cat per step, modeling_qwen2.py:227)
 Per layer, prefill = rmsnorm, qkv GEMM(+bias), RoPE+KV-append, causal flash attention, o GEMM(+residual), rmsnorm,
@@ -25,6 +25,7 @@ result is the new residual stream. lm_head is vocab-parallel; greedy sampling al
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -36,6 +37,8 @@ from .weights import LlmW
 
 GEMV_MAX_B = 8
 GEMV_MAX_SMEM = 200 * 1024
+MEGA_MAX_B = 4  # the persistent decode kernel (csrc/decode_mega.cu) handles 1..4 sequences
+MEGA_HIST = 4096  # token-history rows kept on the device between host reads
 
 
 def rope_inv_freq(cfg: OmChatQwen2Config, device) -> torch.Tensor:
@@ -110,6 +113,7 @@ class Qwen2Decoder:
         self.V_local = w.lm_head.shape[0]
         self.scale = cfg.head_dim ** -0.5
         self.eps = cfg.rms_norm_eps
+        self.mega_enabled = os.environ.get("OMCHAT_B200_NO_MEGA", "0") != "1"
         self._dec = {}  # decode state per batch size
         self._caches = {}  # reusable caches for generate(), keyed by (n_seq, capacity)
 
@@ -241,14 +245,41 @@ class Qwen2Decoder:
             st.all_val = torch.empty(self.tp.size, B, device=dev, dtype=torch.float32)
             st.all_idx = torch.empty(self.tp.size, B, device=dev, dtype=torch.int64)
         st.graphs = {}  # id(cache) -> (CUDAGraph, kernel launches per replay, cache)
+        st.hist = torch.zeros(MEGA_HIST, B, device=dev, dtype=torch.int64)
+        st.hist_pos = torch.zeros(1, device=dev, dtype=torch.int32)
+        st.plans = {}  # id(cache) -> (lib.DecodePlan, cache): the persistent decode kernel bakes the cache pointers in
         self._dec[key] = st
         return st
+
+    def use_mega(self, B: int) -> bool:
+        """Small-batch decode runs as ONE persistent cooperative kernel per token (csrc/decode_mega.cu)."""
+        return (self.mega_enabled and self.tp.size == 1 and B <= MEGA_MAX_B and self.C <= 4096
+                and len(self.w.layers) * 5 + 2 <= 192)
+
+    def _mega_plan(self, st, cache: PagedKVCache):
+        ent = st.plans.get(id(cache))
+        if ent is not None and ent[1] is cache:
+            return ent[0]
+        if len(st.plans) >= 4:
+            st.plans.pop(next(iter(st.plans)))
+        plan = lib.DecodePlan(
+            layers=self.w.layers, embed=self.w.embed, final_norm=self.w.norm, lm_head=self.w.lm_head,
+            inv_freq=self.inv_freq, cfg_dims=(self.C, self.Hq, self.Hkv, self.I_local, self.V_local),
+            kv_pool=cache.pool, block_table=cache.block_table, ctx_lens=cache.ctx_lens, tokens=st.tokens,
+            token_hist=st.hist, hist_pos=st.hist_pos, h=st.h, qkv=st.qkv, attn=st.attn, act=st.act, logits=st.logits,
+            page_size=cache.page_size, eps=self.eps, scale=self.scale)
+        st.plans[id(cache)] = (plan, cache)
+        return plan
 
     def _decode_body(self, st, cache: PagedKVCache, sample: bool = True):
         """One decode step for st.tokens (the tokens generated last step): embeds them, runs the 28 layers against the
         paged cache (appending their K/V), computes logits and, if `sample`, overwrites st.tokens with the greedy next
         tokens. Only device work, no host sync: capturable in a CUDA graph."""
         B = st.B
+        if self.use_mega(B):
+            # embed + all layers + lm_head + argmax + ctx_lens += 1 in one launch (always samples into st.tokens)
+            self._mega_plan(st, cache).step()
+            return
         cache.ctx_lens.add_(1)  # context length INCLUDING the token being processed
         lib.embed_lookup(st.tokens, self.w.embed, out=st.h)
         h = st.h
@@ -312,6 +343,21 @@ class Qwen2Decoder:
         st.tokens.copy_(first_tokens.view(-1))
         out = torch.empty(steps, B, device=self.device, dtype=torch.int64)
         if steps <= 0:
+            return out.t()
+        if self.use_mega(B):
+            # one persistent kernel per token; the kernel appends every sampled token to st.hist on the device
+            plan = self._mega_plan(st, cache)
+            done = 0
+            while done < steps:
+                n = min(MEGA_HIST, steps - done)
+                st.hist_pos.zero_()
+                for i in range(n):
+                    plan.step()
+                    if on_token is not None:
+                        on_token(done + i, st.tokens)
+                out[done:done + n].copy_(st.hist[:n])
+                done += n
+            cache.host_lens = [x + steps for x in cache.host_lens]
             return out.t()
         if use_graph and id(cache) not in st.graphs:
             # warm up once eagerly (sets kernel attributes, loads modules), then capture

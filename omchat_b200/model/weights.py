@@ -6,8 +6,9 @@ convert_omchat_to_hf.py:26-35 read backwards), or random-initialised directly on
 Layout decisions (all K-major = nn.Linear's own [out, in] layout, so no transposes):
   - patch-embed conv weight [C,3,14,14] -> [C, 640] (K = 588 zero-padded to a TMA-legal row pitch)
   - Qwen2 q/k/v -> one [Hq*128 + 2*Hkv*128, hidden] matrix + one bias vector
-  - Qwen2 gate/up -> one [2*I, hidden] matrix, rows interleaved [128 gate | 128 up] per 256 so a single N-tile of the
-    GEMM (or a warp of the GEMV) holds matching gate/up columns for the fused SwiGLU epilogue
+  - Qwen2 gate/up -> one [2*I, hidden] matrix with rows alternating gate_i, up_i, so adjacent accumulator columns of
+    the GEMM (or adjacent rows of a decode GEMV warp) are a matching gate/up pair for the fused SwiGLU epilogue, and any
+    even row split is a valid tensor-parallel shard
 """
 from __future__ import annotations
 
@@ -51,8 +52,7 @@ def from_hf_names(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
 
 def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     I, K = gate.shape
-    assert I % 128 == 0, "intermediate size must be a multiple of 128 for the fused SwiGLU layout"
-    return torch.stack([gate.view(I // 128, 128, K), up.view(I // 128, 128, K)], dim=1).reshape(2 * I, K)
+    return torch.stack([gate, up], dim=1).reshape(2 * I, K)
 
 
 @dataclass
@@ -114,7 +114,7 @@ class LlmW:
 class TPPlan:
     """Which slices of the Qwen2 weights one tensor-parallel rank owns.
     q_heads: global q-head indices (-1 = zero pad head), kv_heads: global kv-head indices, i_lo/i_hi: MLP rows,
-    i_pad: zero rows appended so the local intermediate size is a multiple of 128 (SwiGLU interleave block),
+    i_pad: zero rows appended so the local intermediate size is a multiple of 8 (GEMM N/K granularity),
     v_lo/v_hi: vocab rows of lm_head."""
     q_heads: List[int]
     kv_heads: List[int]
@@ -145,7 +145,7 @@ def tp_plan(cfg: OmChatQwen2Config, rank: int, size: int) -> TPPlan:
     if I % size or V % size:
         raise ValueError("tp_size must divide intermediate_size and vocab_size")
     il = I // size
-    return TPPlan(q_heads=q, kv_heads=kv, i_lo=rank * il, i_hi=(rank + 1) * il, i_pad=(-il) % 128,
+    return TPPlan(q_heads=q, kv_heads=kv, i_lo=rank * il, i_hi=(rank + 1) * il, i_pad=(-il) % 8,
                   v_lo=rank * (V // size), v_hi=(rank + 1) * (V // size))
 
 
@@ -304,7 +304,7 @@ def to_reference_state_dict(w: OmChatWeights, cfg: OmChatQwen2Config) -> Dict[st
     for li, l in enumerate(w.llm.layers):
         p = f"model.layers.{li}."
         I2, K = l.gate_up_w.shape
-        gu = l.gate_up_w.view(I2 // 256, 2, 128, K)
+        gu = l.gate_up_w.view(I2 // 2, 2, K)
         sd.update({p + "input_layernorm.weight": l.ln1, p + "post_attention_layernorm.weight": l.ln2,
                    p + "self_attn.q_proj.weight": l.qkv_w[:nq], p + "self_attn.k_proj.weight": l.qkv_w[nq:nq + nkv],
                    p + "self_attn.v_proj.weight": l.qkv_w[nq + nkv:], p + "self_attn.q_proj.bias": l.qkv_b[:nq],

@@ -60,3 +60,45 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+\S*oracle", src, flags=re.M), f"{f} imports the oracle"
+
+
+def _fake_desc(lib, n_layers=28, batch=1, hidden=3584, q=28, kv=4, inter=18944, vocab=152064, grid=148):
+    import ctypes
+    d = lib.DecodeDesc()
+    d.n_layers, d.batch, d.hidden, d.q_heads, d.kv_heads, d.inter, d.vocab = n_layers, batch, hidden, q, kv, inter, vocab
+    d.page_size, d.max_pages, d.grid, d.hist_capacity = 64, 32, grid, 16
+    d.eps, d.attn_scale = 1e-6, 128 ** -0.5
+    arr = (ctypes.c_void_p * n_layers)(*[0x1000 * (i + 1) for i in range(n_layers)])
+    for k in ("ln1", "qkv_w", "qkv_b", "o_w", "ln2", "gate_up_w", "down_w"):
+        setattr(d, k, ctypes.cast(arr, ctypes.c_void_p))
+    for k in ("embed", "final_norm", "lm_head", "inv_freq", "kv_pool", "block_table", "ctx_lens", "tokens", "h", "qkv",
+              "attn", "act", "logits", "workspace"):
+        setattr(d, k, 0x100000)
+    return d, arr
+
+
+def test_decode_plan_build_is_host_only(built):
+    """omc_decode_plan_build is pure CPU code: the op list of the persistent decode kernel can be checked without a GPU."""
+    import ctypes
+    import struct
+    from omchat_b200 import lib
+    l = lib.load()
+    d, _keep = _fake_desc(lib)
+    n = l.omc_decode_plan_bytes(28)
+    buf = ctypes.create_string_buffer(n)
+    assert l.omc_decode_plan_build(ctypes.byref(d), buf) == 0, l.omc_last_error()
+    hdr = struct.unpack_from("16i", buf.raw, 0)
+    n_ops, B, C, Hq, Hkv, G = hdr[:6]
+    nslots, region_a, smem = hdr[13], hdr[14], hdr[15]
+    assert (n_ops, B, C, Hq, Hkv, G) == (28 * 5 + 2, 1, 3584, 28, 4, 7)
+    assert hdr[9] == 148 // 4  # key splits per (sequence, kv head)
+    assert nslots >= 6 and region_a >= 18944 * 2 and smem <= 227 * 1024
+    assert l.omc_decode_workspace_bytes(148) > 148 * 8 * 130 * 4
+    # batch 4 still leaves a ring; batch 5 is refused; SwiGLU pair that cannot fit a ring stage is refused
+    d4, _k4 = _fake_desc(lib, batch=4)
+    assert l.omc_decode_plan_build(ctypes.byref(d4), buf) == 0
+    assert struct.unpack_from("16i", buf.raw, 0)[13] >= 2
+    d5, _k5 = _fake_desc(lib, batch=5)
+    assert l.omc_decode_plan_build(ctypes.byref(d5), buf) == -2
+    dbad, _kb = _fake_desc(lib, hidden=8192)
+    assert l.omc_decode_plan_build(ctypes.byref(dbad), buf) == -2

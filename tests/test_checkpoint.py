@@ -51,6 +51,6 @@ def test_tp_plan_covers_every_head_and_row_once():
         assert sorted(set(h for p in plans for h in p.kv_heads)) == list(range(cfg.num_key_value_heads))
         for p in plans:  # a rank's q heads all belong to kv heads it holds
             assert all(h < 0 or h // 7 in p.kv_heads for h in p.q_heads)
-            assert (p.i_hi - p.i_lo + p.i_pad) % 128 == 0
+            assert (p.i_hi - p.i_lo + p.i_pad) % 8 == 0
         assert [p.i_lo for p in plans] == [r * cfg.intermediate_size // size for r in range(size)]
         assert plans[-1].i_hi == cfg.intermediate_size and plans[-1].v_hi == cfg.vocab_size

@@ -1,0 +1,135 @@
+"""GPU parity of the persistent decode kernel (csrc/decode_mega.cu, one launch per token) against
+  (1) the per-op kernel path (GEMV + paged attention kernels, already pinned against the oracle in test_kernels_gpu.py) on
+      full-width Qwen2-7B layer shapes (hidden 3584, 28q/4kv heads, inter 18944, vocab 152064, 2 layers), and
+  (2) the CPU oracle (fp32 restatement of transformers' Qwen2 decoder) on the tiny configuration.
+Integer results (sampled token ids, context lengths, token history) must match exactly; logits within bf16 tolerance
+(cosine >= 0.999, max-abs <= 2 % of scale) since the two paths sum in different orders; appended K/V rows bit-exact.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import omchat_oracle as O  # noqa: E402  (checker only)
+
+
+def _decoder(layers, seed=0, **kw):
+    from omchat_b200.config import OmChatQwen2Config
+    from omchat_b200.model.decoder import Qwen2Decoder
+    from omchat_b200.model.weights import random_init
+    cfg = OmChatQwen2Config(num_hidden_layers=layers, **kw)
+    w = random_init(cfg, device="cuda", seed=seed, vision=False)
+    return cfg, w, Qwen2Decoder(cfg, w.llm)
+
+
+def _prefill(dec, cfg, lens, seed=1):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    T = sum(lens)
+    emb = (torch.randn(T, cfg.hidden_size, generator=g, device="cuda") * 0.02).to(torch.bfloat16)
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).cuda()
+    seq = torch.cat([torch.full((n,), i, dtype=torch.int32) for i, n in enumerate(lens)]).cuda()
+    offs = [0]
+    for n in lens:
+        offs.append(offs[-1] + n)
+    cache = dec.new_cache(len(lens), max(lens) + 40)
+    logits = dec.prefill(emb, pos, seq, offs, cache, logits="last")
+    return cache, logits.argmax(-1)
+
+
+@pytest.mark.parametrize("lens", [[200], [130, 77], [64, 300, 129], [1, 5, 257, 40]])
+def test_mega_matches_per_op_path_full_width(lens):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg, w, dec = _decoder(2)
+    B, steps = len(lens), 6
+    cache_a, first = _prefill(dec, cfg, lens)
+    cache_b, first_b = _prefill(dec, cfg, lens)
+    assert torch.equal(first, first_b)
+    assert dec.use_mega(B)
+    toks_a, logits_a = [], []
+    cur = first.clone()
+    for _ in range(steps):
+        lg = dec.decode_step(cur, cache_a).clone()
+        st = dec._decode_state(B, cache_a.capacity)
+        cur = st.tokens.clone()
+        assert torch.equal(cur, lg.argmax(-1)), "in-kernel argmax must agree with argmax of the logits it wrote"
+        toks_a.append(cur)
+        logits_a.append(lg)
+    dec.mega_enabled = False
+    try:
+        cur = first.clone()
+        for i in range(steps):
+            lg = dec.decode_step(cur, cache_b).clone()
+            ref_tok = lg.argmax(-1)
+            cos = torch.nn.functional.cosine_similarity(logits_a[i], lg, dim=-1).min().item()
+            err = (logits_a[i] - lg).abs().max().item() / lg.abs().max().item()
+            assert cos >= 0.999 and err <= 0.02, (i, cos, err)
+            # feed the mega path's token so both caches see the same sequence even if a near-tie flipped an argmax
+            top2 = torch.topk(lg, 2, dim=-1).values
+            for b in range(B):
+                if int(ref_tok[b]) != int(toks_a[i][b]):
+                    assert float(top2[b, 0] - top2[b, 1]) < 0.02 * float(lg[b].abs().max()), (i, b)
+            cur = toks_a[i]
+    finally:
+        dec.mega_enabled = True
+    assert cache_a.ctx_lens.tolist() == cache_b.ctx_lens.tolist() == [n + steps for n in lens]
+    # appended K/V rows: same bf16 inputs, same rounding -> compare closely (different reduction order upstream)
+    for li in range(2):
+        for s in range(B):
+            ka, va = cache_a.gather(li, s)
+            kb, vb = cache_b.gather(li, s)
+            assert torch.equal(ka[:, :lens[s]], kb[:, :lens[s]])  # prefill part untouched
+            assert (ka.float() - kb.float()).abs().max().item() <= 0.02 * kb.float().abs().max().item()
+            assert (va.float() - vb.float()).abs().max().item() <= 0.02 * vb.float().abs().max().item()
+
+
+def test_mega_generate_history_and_repeatability():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg, w, dec = _decoder(2)
+    lens = [90, 33]
+    cache, first = _prefill(dec, cfg, lens)
+    out1 = dec.generate_greedy(first, cache, 12)
+    assert out1.shape == (2, 12) and cache.host_lens == [102, 45] and cache.ctx_lens.tolist() == [102, 45]
+    cache2, first2 = _prefill(dec, cfg, lens)
+    out2 = dec.generate_greedy(first2, cache2, 5)
+    out3 = dec.generate_greedy(out2[:, -1].contiguous(), cache2, 7)  # resumed generation continues the same sequence
+    assert torch.equal(out1, torch.cat([out2, out3], dim=1))
+
+
+def test_mega_vs_oracle_tiny():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tiny import TINY, tiny_state_dict
+    from omchat_b200.config import OmChatQwen2Config
+    from omchat_b200.model.decoder import Qwen2Decoder
+    from omchat_b200.model.weights import from_state_dict
+    sd = {k: v.to(torch.bfloat16).float() for k, v in tiny_state_dict(0).items()}
+    cfg = OmChatQwen2Config(vocab_size=TINY["vocab"], hidden_size=TINY["hidden"], intermediate_size=TINY["inter"],
+                            num_hidden_layers=TINY["layers"], num_attention_heads=TINY["heads"],
+                            num_key_value_heads=TINY["kv_heads"], rope_theta=TINY["rope_theta"], kv_page_size=16,
+                            mm_vision_tower=None)
+    w = from_state_dict({k: v for k, v in sd.items() if not k.startswith("model.vision") and "mm_projector" not in k}, cfg)
+    dec = Qwen2Decoder(cfg, w.llm)
+    ocfg = O.OracleConfig(hidden=TINY["hidden"], heads=TINY["heads"], kv_heads=TINY["kv_heads"], inter=TINY["inter"],
+                          layers=TINY["layers"], vocab=TINY["vocab"], rope_theta=TINY["rope_theta"])
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(0, TINY["vocab"], (1, 37), generator=g)
+    emb = sd["model.embed_tokens.weight"][ids[0]]
+    logits, past = O.qwen2_forward(emb[None], torch.arange(37)[None], sd, ocfg)
+    cache = dec.new_cache(1, 64)
+    lg = dec.prefill(emb.to(torch.bfloat16).cuda(), torch.arange(37, dtype=torch.int32).cuda(),
+                     torch.zeros(37, dtype=torch.int32).cuda(), [0, 37], cache, logits="last")
+    tok = int(logits[0, -1].argmax())
+    assert int(lg.argmax(-1)) == tok
+    for step in range(5):
+        want, past = O.qwen2_forward(sd["model.embed_tokens.weight"][torch.tensor([[tok]])], torch.tensor([[37 + step]]),
+                                     sd, ocfg, past)
+        got = dec.decode_step(torch.tensor([tok]).cuda(), cache).float().cpu()[0]
+        cos = torch.nn.functional.cosine_similarity(got, want[0, -1], dim=0).item()
+        assert cos >= 0.999, (step, cos)
+        nxt = int(want[0, -1].argmax())
+        top2 = torch.topk(want[0, -1], 2).values
+        if int(got.argmax()) != nxt:
+            assert float(top2[0] - top2[1]) < 0.05 * float(want.abs().max())
+        tok = nxt

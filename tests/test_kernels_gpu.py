@@ -92,9 +92,9 @@ def test_gemm_epilogues(L, cfg):
 
 
 def interleave_gate_up(gate, up):
-    """[I,K],[I,K] -> [2I,K] in blocks [128 gate | 128 up] (the layout EPI_SWIGLU expects)."""
+    """[I,K],[I,K] -> [2I,K] with rows alternating gate_i, up_i (the layout EPI_SWIGLU expects)."""
     I, K = gate.shape
-    return torch.stack([gate.view(I // 128, 128, K), up.view(I // 128, 128, K)], dim=1).reshape(2 * I, K)
+    return torch.stack([gate, up], dim=1).reshape(2 * I, K)
 
 
 @pytest.mark.parametrize("cg", [1, 2])
