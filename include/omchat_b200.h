@@ -137,15 +137,17 @@ int omc_argmax(const float* logits, long long ldl, int B, int V, int64_t* next, 
  * State: tokens[batch] (in: the tokens to feed, out: the greedy next tokens), ctx_lens[batch] (in: tokens already in
  * the cache, incremented by the kernel), token_hist[hist_capacity, batch] / hist_pos[1] (optional history of the sampled
  * tokens, appended at *hist_pos), h/qkv/attn/act/logits scratch of [batch, hidden | (q+2kv)*128 | q*128 | inter | vocab].
- * workspace: omc_decode_workspace_bytes(grid) bytes, ZERO-INITIALISED once by the caller. grid = CTAs = omc_num_sms(). */
+ * workspace: omc_decode_workspace_bytes(desc) bytes, ZERO-INITIALISED once by the caller. grid = CTAs = omc_num_sms(). */
 typedef struct omc_decode_desc {
   int32_t n_layers, batch, hidden, q_heads, kv_heads, inter, vocab, vocab_offset;
   int32_t page_size, max_pages, grid, hist_capacity;
+  int32_t rope_positions, reserved0;
   float eps, attn_scale;
   const void* embed;
   const void* final_norm;
   const void* lm_head;
-  const float* inv_freq;
+  const float* rope_cs; /* fp32 [rope_positions][64][2]: (cos, sin)(pos * inv_freq[i]), computed by the host exactly as
+                           Qwen2RotaryEmbedding does (modeling_qwen2.py:102-113); rope_positions >= max_pages * page_size */
   const void* const* ln1;
   const void* const* qkv_w;
   const void* const* qkv_b;
@@ -168,11 +170,14 @@ typedef struct omc_decode_desc {
   void* workspace;
   int32_t* status; /* optional int32[4], zeroed by the caller, device-accessible (pinned host memory is fine): a watchdog
                       inside the kernel writes {code, CTA, detail, thread} here before trapping; NULL = in workspace */
+  void* prof;      /* optional uint64[grid][5*n_layers+2][4] device buffer: per-CTA, per-op %globaltimer stamps (op start,
+                      after grid barrier, after activation staging, end) for tools/prof_mega.py; NULL = off */
 } omc_decode_desc;
 long long omc_decode_plan_bytes(int n_layers);
-long long omc_decode_workspace_bytes(int grid);
+long long omc_decode_workspace_bytes(const omc_decode_desc* desc); /* uses batch, hidden, heads, inter, grid */
 int omc_decode_plan_build(const omc_decode_desc* desc, void* plan_host);
-int omc_decode_step(const void* plan_host, const void* plan_dev, void* stream);
+/* epoch: a counter the caller increments on every launch that uses the same workspace (it tags the in-flight activations) */
+int omc_decode_step(const void* plan_host, const void* plan_dev, unsigned int epoch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,14 +7,20 @@
 //                shared-memory ring with cp.async.bulk (TMA, mbarrier complete_tx, L2 evict-first). The ring refills
 //                itself: the warp that finishes reading a slot immediately issues the copy of the stage that will
 //                occupy it next (stage + nslots), whichever op that belongs to. Weights are immutable, so the stream runs
-//                ahead across phase boundaries: the ring (~170 KB/SM, 25 MB chip-wide) stays full while the CTA sits in a
-//                grid barrier, stages activations or runs the attention phase, which hides those behind HBM streaming.
-//   8 warps      per op: grid barrier -> stage the activation vector(s) in shared memory (RMSNorm fused) -> each warp
-//                owns whole "units" (R weight rows x full K) of the ring, dot products with fp32 accumulation,
-//                warp-shuffle reduction, fused epilogue (bias / residual / SwiGLU / fp32 logits + running argmax).
-// Attention runs inside the same kernel: (sequence, kv-head) items are split over CTAs by key range, the 7 query heads
-// of a group share each K/V row read, partial (m, l, O) are merged by the last CTA to finish (self-resetting counters).
-// Grid barriers are a monotonic global counter (release add / acquire spin), reset by the last CTA to leave the kernel.
+//                ahead across op boundaries while the CTA waits for activations or runs the attention phase.
+//   8 warps      per op: gather the activation vector(s) into shared memory (RMSNorm fused) -> each warp owns whole
+//                "units" (R weight rows x full K) of the ring, dot products with fp32 accumulation, warp-shuffle
+//                reduction, fused epilogue (bias / residual / SwiGLU / fp32 logits + running argmax).
+//   no barriers  there is no grid-wide barrier. Every activation that crosses CTAs travels in a flag-in-data buffer (the
+//                LL idea of NCCL): each 32-bit word is {16-bit sequence tag, bf16 value} (64-bit {tag, fp32} for the
+//                attention partials), written with one store and polled by the readers, so "data has arrived" is the
+//                synchronisation and a producer->consumer hand-off costs one L2 round trip. Buffers are double-buffered by
+//                layer parity; a writer can only reach a buffer again after every reader of its previous contents has
+//                moved two phases on (it needs their outputs first), so tags never alias. The residual stream stays in
+//                the shared memory of the CTA that owns those rows (o_proj and down_proj partition rows identically).
+// Attention runs inside the same kernel: (sequence, kv-head) items are split over all CTAs by key range, K/V loads are
+// issued before the CTA waits for q, the 7 query heads of a group share each K/V row read, and partial (m, l, O) are
+// merged head by head by designated CTAs that poll the partials (no counters).
 //
 // Reference call sites replaced: transformers models/qwen2/modeling_qwen2.py:280-310 (decoder layer), :206-246 (attention,
 // RoPE :124-146, cache update :227), :46-48 (MLP), :258-263 (RMSNorm), :411,470-472 (final norm + lm_head) and the HF
@@ -33,15 +39,17 @@ namespace omc {
 typedef __nv_bfloat16 bf16;
 
 constexpr int kMegaThreads = 256;
-constexpr int kConsumers = 256;
 constexpr int kCWarps = 8;
 constexpr int kRMax = 4;            // weight rows per ring stage (upper bound)
 constexpr int kSlotBytes = 19456;   // ring slot: 2 rows of K=3584 (14336 B) or half a row of K=18944 (18944 B)
 constexpr int kMaxSlots = 12;
 constexpr int kMaxOps = 192;
-constexpr int kAttnKeysPerCta = 128;
+constexpr int kAttnKeysPerCta = 32;
 constexpr int kPartStride = 130;    // O[128], m, l
 constexpr int kAttnScratchBytes = kCWarps * 8 * kPartStride * 4;
+constexpr int kHRows = 64;          // residual rows one CTA can own
+constexpr int kMaxBt = 1024;        // block-table entries cached in shared memory (batch * max_pages)
+constexpr int kMetaBytes = 2048 + 4 * kHRows * 2 + kMaxBt * 4;  // barriers/scratch | residual slab | block table
 constexpr int kSmemLimit = 227 * 1024;
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // a protocol bug must end in a trap, never in a hung GPU
 
@@ -52,13 +60,13 @@ struct MegaOp {  // 112 bytes
   int32_t type, N, K, epi;
   int32_t R, ksplit, gran, flags;
   const bf16* W;
-  const bf16* x;
   const bf16* norm_w;
   const bf16* bias;
-  const bf16* res;
-  void* out;
-  bf16* aux;  // GEMV + F_X_EMBED: residual stream to seed (h);  ATTN: this layer's KV pool
-  int32_t ldx, ldo, ldr, pad[3];
+  const uint32_t* x_ll;  // input vector(s) [B][ldx], flag-in-data words {tag16, bf16}; null with F_X_EMBED
+  uint32_t* out_ll;      // output vector(s) [B][ldo] in the same format (null for lm_head)
+  float* out_f32;        // lm_head: fp32 logits [B][ldo]
+  bf16* pool;            // ATTN: this layer's KV pool
+  int32_t ldx, ldo, in_op, parity, pad[2];  // in_op: index of the op whose tag the input carries
 };
 static_assert(sizeof(MegaOp) == 112, "MegaOp layout");
 
@@ -67,19 +75,17 @@ struct MegaPlan {  // header, followed by n_ops MegaOp
   int32_t grid, nsplit_max, vocab_offset, hist_capacity, kmax, nslots, region_a_bytes, smem_bytes;
   float eps, scale_log2, pad0, pad1;
   const bf16* embed;
-  const float* inv_freq;
+  const float* rope_cs;  // [positions][64][2] fp32 (cos, sin)
   const int32_t* block_table;
   int32_t* ctx_lens;
   int64_t* tokens;
   int64_t* token_hist;
   int32_t* hist_pos;
-  unsigned int* bar_ctr;
-  unsigned int* exit_ctr;
-  float* attn_part;
-  unsigned int* attn_ctr;
-  float* amax_val;
-  int32_t* amax_idx;
+  uint2* attn_part;   // [2][grid][8][130] {fp32 bits, tag32}
+  uint2* amax_part;   // [grid][4][2]      {value bits | index, tag32}
   int32_t* err_flag;
+  unsigned long long* prof;  // optional [grid][n_ops][4] globaltimer stamps: op start, inputs staged, op end, -
+  unsigned long long pad2;
 };
 static_assert(sizeof(MegaPlan) % 16 == 0, "MegaPlan must keep the op array 16-byte aligned");
 
@@ -91,16 +97,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(kEvictFirst)
       : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ uint4 ld_poll_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
 }
-__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void consumer_sync() { __syncthreads(); }
-
 // err_flag[0..3] = {code, CTA, detail, thread}; the flag may live in pinned host memory so it survives the trap
 __device__ __noinline__ void mega_fail(int32_t* err_flag, int code, int detail = 0) {
   if (err_flag && atomicCAS(reinterpret_cast<int*>(err_flag), 0, code) == 0) {
@@ -117,26 +118,50 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// bounded mbarrier wait (wall-clock bound, checked every 256 polls)
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, int32_t* err_flag, int code, int detail) {
-  if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = global_ns();
-  unsigned int spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0 && global_ns() - t0 > kWaitLimitNs) mega_fail(err_flag, code, detail);
+// wall-clock watchdog for the polling loops: call once per failed poll
+struct Watchdog {
+  unsigned long long t0;
+  unsigned int spins;
+  __device__ __forceinline__ Watchdog() : t0(0), spins(0) {}
+  __device__ __forceinline__ void tick(int32_t* err_flag, int code, int detail) {
+    if ((++spins & 255u) == 0) {
+      if (t0 == 0) t0 = global_ns();
+      else if (global_ns() - t0 > kWaitLimitNs) mega_fail(err_flag, code, detail);
+    }
   }
+};
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, int32_t* err_flag, int code, int detail) {
+  Watchdog wd;
+  while (!mbar_try_wait(bar, parity)) wd.tick(err_flag, code, detail);
 }
 
-__device__ __forceinline__ void slab_of(const MegaOp& op, int cta, int grid, int& row0, int& rows) {
-  const long long ng = op.N / op.gran;
+__device__ __forceinline__ uint32_t tag32_of(uint32_t epoch, int op_idx) { return epoch * 256u + (uint32_t)op_idx + 1u; }
+__device__ __forceinline__ uint32_t tag16_of(uint32_t t32) { return ((t32 % 65535u) + 1u) << 16; }  // pre-shifted, never 0
+__device__ __forceinline__ bool ll4_ok(uint4 v, uint32_t tag) {
+  return ((v.x ^ tag) < 65536u) & ((v.y ^ tag) < 65536u) & ((v.z ^ tag) < 65536u) & ((v.w ^ tag) < 65536u);
+}
+// 4 flag-in-data words -> 4 packed bf16
+__device__ __forceinline__ uint2 ll4_data(uint4 v) {
+  return make_uint2((v.x & 0xffffu) | (v.y << 16), (v.z & 0xffffu) | (v.w << 16));
+}
+__device__ __forceinline__ uint32_t ll4_word(float x, uint32_t tag) {
+  return tag | (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x));
+}
+
+__device__ __forceinline__ void slab_rows(int N, int gran, int cta, int grid, int& row0, int& rows) {
+  const long long ng = N / gran;
   const int g0 = (int)(ng * cta / grid), g1 = (int)(ng * (cta + 1) / grid);
-  row0 = g0 * op.gran;
-  rows = (g1 - g0) * op.gran;
+  row0 = g0 * gran;
+  rows = (g1 - g0) * gran;
 }
 
 __device__ __forceinline__ void unpack8(uint4 v, float* f) {
   float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void unpack4(uint2 v, float* f) {
+  const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
 }
 __device__ __forceinline__ float dot8(uint4 w, const float* x, float acc) {
   float f[8];
@@ -147,9 +172,6 @@ __device__ __forceinline__ float dot8(uint4 w, const float* x, float acc) {
 }
 __device__ __forceinline__ float silu_m(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
-__device__ __forceinline__ float ldcg_bf16(const bf16* p) {
-  return __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p))));
-}
 
 // Position of a stage index in the op list: the GEMV op that owns it and this CTA's slab of that op.
 struct StageCursor {
@@ -164,18 +186,22 @@ struct MegaCtx {
   uint64_t* full;
   volatile uint32_t* gen;  // gen[slot] = number of copies issued into the slot so far (monotonic: no parity aliasing)
   float* red;            // [16] floats of block-reduction scratch
-  int* flag;             // [4] ints
+  float* am_v;           // [8 warps][16]
+  int* am_i;
+  int* s_ctx;            // [4] context lengths at kernel start
+  bf16* s_h;             // [4][kHRows] residual rows owned by this CTA
+  int* s_bt;             // block table copy [B][max_pages]
   uint8_t* region_a;     // activation vectors / attention scratch
   uint8_t* ring;
   int nslots, cta, grid, n_ops;
-  unsigned int bar_target;
+  uint32_t epoch;
 };
 
 __device__ __forceinline__ void cursor_load(const MegaCtx& c, StageCursor& k) {
   while (k.op_i < c.n_ops && c.ops[k.op_i].type != OP_GEMV) ++k.op_i;
   if (k.op_i < c.n_ops) {
     const MegaOp& op = c.ops[k.op_i];
-    slab_of(op, c.cta, c.grid, k.row0, k.rows);
+    slab_rows(op.N, op.gran, c.cta, c.grid, k.row0, k.rows);
     k.cnt = (uint32_t)(((k.rows + op.R - 1) / op.R) * op.ksplit);
   } else {
     k.cnt = 0;
@@ -209,116 +235,119 @@ __device__ __forceinline__ void issue_stage(const MegaCtx& c, StageCursor& k, ui
 // copy of stage s has actually been issued, then for its bytes.
 __device__ __forceinline__ void wait_stage(const MegaCtx& c, uint32_t s, uint32_t slot) {
   const uint32_t g = s / (uint32_t)c.nslots;
-  if (c.gen[slot] < g + 1u) {
-    const unsigned long long t0 = global_ns();
-    unsigned int spins = 0;
-    while (c.gen[slot] < g + 1u) {
-      if ((++spins & 1023u) == 0 && global_ns() - t0 > kWaitLimitNs) mega_fail(c.P->err_flag, 4, (int)s);
-    }
-  }
+  Watchdog wd;
+  while (c.gen[slot] < g + 1u) wd.tick(c.P->err_flag, 4, (int)s);
   __threadfence_block();
   mbar_wait_bounded(&c.full[slot], g & 1u, c.P->err_flag, 3, (int)s);
 }
 
-// ------------------------------------------------------------------------------------------------ grid barrier
-__device__ __forceinline__ void grid_sync(MegaCtx& c, int ctid) {
-  consumer_sync();
-  c.bar_target += (unsigned int)c.grid;
-  if (ctid == 0) {
-    __threadfence();
-    red_release_gpu_add(c.P->bar_ctr, 1u);
-    unsigned int spins = 0;
-    unsigned long long t0 = 0;
-    while (ld_acquire_gpu(c.P->bar_ctr) < c.bar_target) {
-      if ((++spins & 1023u) == 0) {
-        if (t0 == 0) t0 = global_ns();
-        else if (global_ns() - t0 > kWaitLimitNs) mega_fail(c.P->err_flag, 2, (int)c.bar_target);
-      }
-    }
-    __threadfence();
-  }
-  consumer_sync();
-}
-
 // ------------------------------------------------------------------------------------------------ activation staging
-// x[b, :K] (bf16, produced earlier in this launch by other CTAs: read through L2) -> shared memory, optionally
-// RMS-normalised: out = w * bf16(x * rsqrt(mean(x^2) + eps))  [modeling_qwen2.py:258-263].
+// Gather x[b, :K] into shared memory as bf16, optionally RMS-normalised: out = w * bf16(x * rsqrt(mean(x^2) + eps))
+// [modeling_qwen2.py:258-263]. The source is either the embedding row of this step's token (first op) or a
+// flag-in-data vector another phase is producing right now: polling it IS the synchronisation with the producers.
 template <int NB>
 __device__ void stage_x(MegaCtx& c, const MegaOp& op, int ctid) {
   const MegaPlan& P = *c.P;
-  const int K = op.K, nvec = K >> 3;
-  uint4* xs = reinterpret_cast<uint4*>(c.region_a);
+  const int K = op.K;
+  bf16* xs = reinterpret_cast<bf16*>(c.region_a);
+  const uint32_t tag = (op.flags & F_X_EMBED) ? 0u : tag16_of(tag32_of(c.epoch, op.in_op));
+  // norm weights (K <= 4096: at most 4 chunks per thread) are fetched before the wait so they are not a second round trip
+  uint2 gw[4];
+  if (op.norm_w != nullptr) {
+    const uint2* wv = reinterpret_cast<const uint2*>(op.norm_w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = ctid + j * kMegaThreads;
+      if (i < (K >> 2)) gw[j] = __ldg(wv + i);
+    }
+  }
 #pragma unroll 1
   for (int b = 0; b < NB; ++b) {
     if (b >= P.B) break;
-    const uint4* src;
-    if (op.flags & F_X_EMBED) src = reinterpret_cast<const uint4*>(P.embed + (long long)P.tokens[b] * P.C);
-    else src = reinterpret_cast<const uint4*>(op.x + (long long)b * op.ldx);
-    uint4* dst = xs + (long long)b * nvec;
-    if (op.norm_w == nullptr) {
-      for (int i = ctid; i < nvec; i += kConsumers) dst[i] = __ldcg(src + i);
+    uint2* dst = reinterpret_cast<uint2*>(xs + (long long)b * K);  // 4 bf16 per element
+    const int n4 = K >> 2;
+    float ss = 0.f;
+    if (op.flags & F_X_EMBED) {
+      const uint2* src = reinterpret_cast<const uint2*>(P.embed + (long long)P.tokens[b] * P.C);
+      for (int i = ctid; i < n4; i += kMegaThreads) {
+        const uint2 v = __ldg(src + i);
+        dst[i] = v;
+        float f[4];
+        unpack4(v, f);
+        ss += f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3];
+      }
+      // seed the residual rows this CTA owns (the slab of the [C, *] row-parallel ops)
+      int h0, hr;
+      slab_rows(P.C, 1, c.cta, c.grid, h0, hr);
+      if (ctid < hr) c.s_h[b * kHRows + ctid] = P.embed[(long long)P.tokens[b] * P.C + h0 + ctid];
     } else {
-      uint4 v[2];
-      float ss = 0.f;
+      const uint4* src = reinterpret_cast<const uint4*>(op.x_ll + (long long)b * op.ldx);
+      constexpr int UN = 10;
+#pragma unroll 1
+      for (int base = ctid; base < n4; base += kMegaThreads * UN) {
+        uint4 v[UN];
+        Watchdog wd;
+        bool ok;
+        do {
+          ok = true;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int i = ctid + j * kConsumers;
-        if (i < nvec) {
-          v[j] = __ldcg(src + i);
-          float f[8];
-          unpack8(v[j], f);
+          for (int u = 0; u < UN; ++u) {
+            const int i = base + u * kMegaThreads;
+            if (i < n4) v[u] = ld_poll_v4(src + i);
+          }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+          for (int u = 0; u < UN; ++u) {
+            const int i = base + u * kMegaThreads;
+            if (i < n4 && !ll4_ok(v[u], tag)) ok = false;
+          }
+          if (!ok) wd.tick(P.err_flag, 5, op.in_op);
+        } while (!ok);
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int i = base + u * kMegaThreads;
+          if (i < n4) {
+            const uint2 d = ll4_data(v[u]);
+            dst[i] = d;
+            float f[4];
+            unpack4(d, f);
+            ss += f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3];
+          }
         }
       }
-      if (op.aux != nullptr && (op.flags & F_X_EMBED)) {
-        // seed the residual stream h with the raw embedding row: every CTA writes its own slice
-        const int lo = (int)((long long)nvec * c.cta / c.grid), hi = (int)((long long)nvec * (c.cta + 1) / c.grid);
-        uint4* hdst = reinterpret_cast<uint4*>(op.aux + (long long)b * op.ldr);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int i = ctid + j * kConsumers;
-          if (i >= lo && i < hi) __stcg(hdst + i, v[j]);
-        }
-      }
+    }
+    if (op.norm_w != nullptr) {
       ss = warp_sum(ss);
-      consumer_sync();  // c.red free (previous b / previous user done)
+      __syncthreads();  // c.red free, raw vector fully in shared memory
       if ((ctid & 31) == 0) c.red[ctid >> 5] = ss;
-      consumer_sync();
+      __syncthreads();
       float tot = 0.f;
 #pragma unroll
       for (int w = 0; w < kCWarps; ++w) tot += c.red[w];
       const float rstd = rsqrtf(tot / (float)K + P.eps);
-      const uint4* wv = reinterpret_cast<const uint4*>(op.norm_w);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int i = ctid + j * kConsumers;
-        if (i < nvec) {
-          const uint4 g = __ldg(wv + i);
-          uint32_t xi[4] = {v[j].x, v[j].y, v[j].z, v[j].w}, gi[4] = {g.x, g.y, g.z, g.w}, oo[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 a = unpack_bf16(xi[q]), w2 = unpack_bf16(gi[q]);
-            float2 n = unpack_bf16(pack_bf16(a.x * rstd, a.y * rstd));
-            oo[q] = pack_bf16(n.x * w2.x, n.y * w2.y);
-          }
-          dst[i] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int i = ctid + j * kMegaThreads;
+        if (i >= n4) break;
+        const uint2 g = gw[j], v = dst[i];
+        const float2 a0 = unpack_bf16(v.x), a1 = unpack_bf16(v.y), g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y);
+        const float2 n0 = unpack_bf16(pack_bf16(a0.x * rstd, a0.y * rstd)), n1 = unpack_bf16(pack_bf16(a1.x * rstd, a1.y * rstd));
+        dst[i] = make_uint2(pack_bf16(n0.x * g0.x, n0.y * g0.y), pack_bf16(n1.x * g1.x, n1.y * g1.y));
       }
     }
   }
-  consumer_sync();
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------ GEMV consumer
 template <int NB>
-__device__ void gemv_consume(MegaCtx& c, const MegaOp& op, uint32_t sc_base, int row0, int rows, int cw, int lane,
-                             StageCursor& refill, float& best_v, int& best_i) {
+__device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t sc_base, int row0, int rows, int cw,
+                             int lane, StageCursor& refill, float& best_v, int& best_i) {
   const MegaPlan& P = *c.P;
   const int R = op.R, ksplit = op.ksplit;
   const int Kc = op.K / ksplit, nv = Kc >> 3, nvK = op.K >> 3;
   const int units = (rows + R - 1) / R;
   const uint4* xs = reinterpret_cast<const uint4*>(c.region_a);
+  const uint32_t otag = tag16_of(tag32_of(c.epoch, op_idx));
 #pragma unroll 1
   for (int u = cw; u < units; u += kCWarps) {
     const int r = u * R;
@@ -348,8 +377,23 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, uint32_t sc_base, int
           }
         }
       } else if (rows_here == 1) {
-#pragma unroll 4
-        for (int j = lane; j < nv; j += 32) {
+        float a2[NB];  // second accumulator chain: two independent FMA streams per lane
+#pragma unroll
+        for (int b = 0; b < NB; ++b) a2[b] = 0.f;
+        int j = lane;
+#pragma unroll 2
+        for (; j + 32 < nv; j += 64) {
+          const uint4 w0 = wb[j], w1 = wb[j + 32];
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            float xf[8];
+            unpack8(xb[b * nvK + j], xf);
+            acc[0][b] = dot8(w0, xf, acc[0][b]);
+            unpack8(xb[b * nvK + j + 32], xf);
+            a2[b] = dot8(w1, xf, a2[b]);
+          }
+        }
+        for (; j < nv; j += 32) {
           const uint4 w0 = wb[j];
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
@@ -358,6 +402,8 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, uint32_t sc_base, int
             acc[0][b] = dot8(w0, xf, acc[0][b]);
           }
         }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[0][b] += a2[b];
       } else {
 #pragma unroll 1
         for (int j = lane; j < nv; j += 32) {
@@ -383,7 +429,8 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, uint32_t sc_base, int
       for (int b = 0; b < NB; ++b) acc[i][b] = warp_sum(acc[i][b]);
 
     // ---- epilogue: lane (i * NB + b) owns output (row r + i, sequence b)
-    const int grow = row0 + r;
+    const int lrow = r;            // row index inside this CTA's slab
+    const int grow = row0 + r;     // global row
     if (op.epi == EPI_SWIGLU) {
 #pragma unroll
       for (int pr = 0; pr < kRMax / 2; ++pr)
@@ -391,7 +438,7 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, uint32_t sc_base, int
         for (int b = 0; b < NB; ++b)
           if (2 * pr < rows_here && b < P.B && lane == pr * NB + b) {
             const float val = silu_m(acc[2 * pr][b]) * acc[2 * pr + 1][b];
-            static_cast<bf16*>(op.out)[(long long)b * op.ldo + (grow >> 1) + pr] = __float2bfloat16(val);
+            __stcg(op.out_ll + (long long)b * op.ldo + (grow >> 1) + pr, ll4_word(val, otag));
           }
     } else {
 #pragma unroll
@@ -402,12 +449,20 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, uint32_t sc_base, int
             const int row = grow + i;
             float val = acc[i][b];
             if (op.bias) val += __bfloat162float(op.bias[row]);
-            if (op.epi == EPI_RES) val += ldcg_bf16(op.res + (long long)b * op.ldr + row);
-            if (op.flags & F_OUT_F32) static_cast<float*>(op.out)[(long long)b * op.ldo + row] = val;
-            else static_cast<bf16*>(op.out)[(long long)b * op.ldo + row] = __float2bfloat16(val);
-            if ((op.flags & F_ARGMAX) && (val > best_v || (val == best_v && row < best_i))) {
-              best_v = val;
-              best_i = row;
+            if (op.epi == EPI_RES) {
+              // residual stream: bf16, resident in the shared memory of the CTA that owns the row
+              bf16* hp = c.s_h + b * kHRows + lrow + i;
+              val += __bfloat162float(*hp);
+              *hp = __float2bfloat16(val);
+            }
+            if (op.flags & F_OUT_F32) {
+              op.out_f32[(long long)b * op.ldo + row] = val;
+              if ((op.flags & F_ARGMAX) && (val > best_v || (val == best_v && row < best_i))) {
+                best_v = val;
+                best_i = row;
+              }
+            } else {
+              __stcg(op.out_ll + (long long)b * op.ldo + row, ll4_word(val, otag));
             }
           }
     }
@@ -420,18 +475,17 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, uint32_t sc_base, int
 // one coalesced 256-byte warp access); the G query heads of the group are all evaluated against each K/V row read.
 // RoPE (rotate-half, pairs (i, i+64) = lanes (l, l^16)) of the new q/k and the cache append are fused in; K is rounded
 // to bf16 before use exactly like the cached copy later steps will read.
-__device__ __forceinline__ void unpack4(uint2 v, float* f) {
-  const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
-}
-
-__device__ void attn_phase(MegaCtx& c, const MegaOp& op, int ctid) {
+// Every global access here costs a full L2 round trip under the weight stream, so the phase is organised as few
+// dependent round trips as possible: [K/V + rotary table] (issued before the wait) -> [q poll] -> compute -> [partials of
+// all splits polled in one batch by the merging CTA] -> output.
+template <int G>
+__device__ __noinline__ void attn_phase(MegaCtx& c, const MegaOp& op, int op_idx, int ctid) {
   const MegaPlan& P = *c.P;
   const int items = P.B * P.Hkv;
   const int item = c.cta % items, split = c.cta / items;
   if (split >= P.nsplit_max) return;
-  const int b = item / P.Hkv, kvh = item % P.Hkv, G = P.G;
-  const int n_cached = __ldcg(P.ctx_lens + b);  // keys already in the cache; the new token sits at position n_cached
+  const int b = item / P.Hkv, kvh = item % P.Hkv;
+  const int n_cached = c.s_ctx[b];  // keys already in the cache; the new token sits at position n_cached
   int nsplit = (n_cached + kAttnKeysPerCta - 1) / kAttnKeysPerCta;
   nsplit = max(1, min(nsplit, P.nsplit_max));
   if (split >= nsplit) return;
@@ -440,73 +494,115 @@ __device__ void attn_phase(MegaCtx& c, const MegaOp& op, int ctid) {
   const bool has_new = (split == nsplit - 1);
 
   const int cw = ctid >> 5, lane = ctid & 31;
-  const bf16* qrow = op.x + (long long)b * op.ldx;
-  bf16* pool = op.aux;
+  bf16* pool = op.pool;
+  const int* bt = c.s_bt + b * P.max_pages;
   const long long page_stride = 2LL * P.Hkv * P.page_size * 128;
   const long long v_off = (long long)P.Hkv * P.page_size * 128;
   const float sl2 = P.scale_log2;
+  const uint32_t itag = tag16_of(tag32_of(c.epoch, op.in_op));
+  const uint32_t otag16 = tag16_of(tag32_of(c.epoch, op_idx));
+  const uint32_t otag32 = tag32_of(c.epoch, op_idx);
 
-  // rotary factors of the new position for this lane's 4 dims
-  float cs[4], sn[4];
+  constexpr int U = 6;  // keys in flight per warp (one batch covers 48 keys per CTA)
+  uint2 kr[U], vr[U];
+  auto load_keys = [&](int kb) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) sincosf((float)n_cached * P.inv_freq[(lane & 15) * 4 + e], &sn[e], &cs[e]);
+    for (int u = 0; u < U; ++u) {
+      const int kk = kb + kCWarps * u;
+      if (kk < k1) {
+        const bf16* kp = pool + (long long)bt[kk / P.page_size] * page_stride +
+                         ((long long)kvh * P.page_size + kk % P.page_size) * 128 + lane * 4;
+        kr[u] = __ldcg(reinterpret_cast<const uint2*>(kp));
+        vr[u] = __ldcg(reinterpret_cast<const uint2*>(kp + v_off));
+      }
+    }
+  };
+  load_keys(k0 + cw);  // the cache does not depend on this step's qkv: fetch before waiting for q
+  // rotary factors of the new position for this lane's 4 dims: table of (cos, sin)(pos * inv_freq) computed in fp32 by
+  // the host exactly as Qwen2RotaryEmbedding does (modeling_qwen2.py:102-113)
+  float cs[4], sn[4];
+  {
+    const float4* t = reinterpret_cast<const float4*>(P.rope_cs + ((long long)n_cached * 64 + (lane & 15) * 4) * 2);
+    const float4 t0 = __ldg(t), t1 = __ldg(t + 1);
+    cs[0] = t0.x; sn[0] = t0.y; cs[1] = t0.z; sn[1] = t0.w;
+    cs[2] = t1.x; sn[2] = t1.y; cs[3] = t1.z; sn[3] = t1.w;
+  }
   const float sgn = (lane < 16) ? -1.f : 1.f;
-
-  auto load_rot = [&](const bf16* head, float* outv) {
+  auto rot = [&](uint4 own_ll, float* outv) {  // all 32 lanes must call (shuffle): the partner's dims sit in lane ^ 16
+    const uint2 d = ll4_data(own_ll);
+    const uint2 pd = make_uint2(__shfl_xor_sync(0xffffffffu, d.x, 16), __shfl_xor_sync(0xffffffffu, d.y, 16));
     float own[4], par[4];
-    unpack4(__ldcg(reinterpret_cast<const uint2*>(head + lane * 4)), own);
-    unpack4(__ldcg(reinterpret_cast<const uint2*>(head + (lane ^ 16) * 4)), par);
+    unpack4(d, own);
+    unpack4(pd, par);
 #pragma unroll
     for (int e = 0; e < 4; ++e) outv[e] = bf16_round(own[e] * cs[e] + sgn * par[e] * sn[e]);
   };
 
-  float q[8][4];
+  // ---- wait for q (G heads) [and k, v of the new token in the warp that owns it]: this lane's 4 dims
+  const uint32_t* qll = op.x_ll + (long long)b * op.ldx;
+  const bool new_here = has_new && cw == 0;
+  float q[G][4], knew[4], vnew[4];
+  uint2 vraw = make_uint2(0u, 0u);
+  {
+    uint4 qo[G], ko, vo;
+    Watchdog wd;
+    bool ok;
+    do {
+      ok = true;
 #pragma unroll
-  for (int h = 0; h < 8; ++h) {
-    if (h < G) load_rot(qrow + (kvh * G + h) * 128, q[h]);
-    else q[h][0] = q[h][1] = q[h][2] = q[h][3] = 0.f;
+      for (int h = 0; h < G; ++h) qo[h] = ld_poll_v4(qll + (kvh * G + h) * 128 + lane * 4);
+      if (new_here) {
+        ko = ld_poll_v4(qll + (P.Hq + kvh) * 128 + lane * 4);
+        vo = ld_poll_v4(qll + (P.Hq + P.Hkv + kvh) * 128 + lane * 4);
+        ok = ll4_ok(ko, itag) && ll4_ok(vo, itag);
+      }
+#pragma unroll
+      for (int h = 0; h < G; ++h)
+        if (!ll4_ok(qo[h], itag)) ok = false;
+      if (!ok) wd.tick(P.err_flag, 6, op.in_op);
+    } while (!ok);
+#pragma unroll
+    for (int h = 0; h < G; ++h) rot(qo[h], q[h]);
+    if (new_here) {
+      rot(ko, knew);
+      vraw = ll4_data(vo);
+      unpack4(vraw, vnew);
+    }
   }
-  float m[8], l[8], o[8][4];
+  float m[G], l[G], o[G][4];
 #pragma unroll
-  for (int h = 0; h < 8; ++h) {
+  for (int h = 0; h < G; ++h) {
     m[h] = -INFINITY;
     l[h] = 0.f;
     o[h][0] = o[h][1] = o[h][2] = o[h][3] = 0.f;
   }
   auto consume_key = [&](const float* kf, const float* vf) {
+    float s[G];
 #pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      if (h < G) {
-        float s = q[h][0] * kf[0];
-        s = fmaf(q[h][1], kf[1], s);
-        s = fmaf(q[h][2], kf[2], s);
-        s = fmaf(q[h][3], kf[3], s);
-        s = warp_sum(s);
-        const float m_new = fmaxf(m[h], s);
-        const float corr = exp2f((m[h] - m_new) * sl2);  // m = -inf -> 0
-        const float p = exp2f((s - m_new) * sl2);
-        m[h] = m_new;
-        l[h] = l[h] * corr + p;
+    for (int h = 0; h < G; ++h) {
+      s[h] = q[h][0] * kf[0];
+      s[h] = fmaf(q[h][1], kf[1], s[h]);
+      s[h] = fmaf(q[h][2], kf[2], s[h]);
+      s[h] = fmaf(q[h][3], kf[3], s[h]);
+    }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[h][e] = fmaf(o[h][e], corr, p * vf[e]);
-      }
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int h = 0; h < G; ++h) s[h] += __shfl_xor_sync(0xffffffffu, s[h], off);
+#pragma unroll
+    for (int h = 0; h < G; ++h) {
+      const float m_new = fmaxf(m[h], s[h]);
+      const float corr = exp2f((m[h] - m_new) * sl2);  // m = -inf -> 0
+      const float p = exp2f((s[h] - m_new) * sl2);
+      m[h] = m_new;
+      l[h] = l[h] * corr + p;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[h][e] = fmaf(o[h][e], corr, p * vf[e]);
     }
   };
-
-  constexpr int U = 4;  // keys in flight per warp
 #pragma unroll 1
   for (int kb = k0 + cw; kb < k1; kb += kCWarps * U) {
-    uint2 kr[U], vr[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int kk = kb + kCWarps * u;
-      if (kk < k1) {
-        const int page = __ldg(P.block_table + (long long)b * P.max_pages + kk / P.page_size);
-        const bf16* kp = pool + (long long)page * page_stride + ((long long)kvh * P.page_size + kk % P.page_size) * 128 + lane * 4;
-        kr[u] = __ldcg(reinterpret_cast<const uint2*>(kp));
-        vr[u] = __ldcg(reinterpret_cast<const uint2*>(kp + v_off));
-      }
-    }
+    if (kb != k0 + cw) load_keys(kb);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (kb + kCWarps * u < k1) {  // warp-uniform
@@ -517,32 +613,26 @@ __device__ void attn_phase(MegaCtx& c, const MegaOp& op, int ctid) {
       }
     }
   }
-  if (has_new && cw == 0) {
-    // the new token: rotate K, append K/V to the cache, attend to it
-    float kf[4], vf[4];
-    load_rot(qrow + (P.Hq + kvh) * 128, kf);
-    const uint2 vraw = __ldcg(reinterpret_cast<const uint2*>(qrow + (P.Hq + P.Hkv + kvh) * 128 + lane * 4));
-    unpack4(vraw, vf);
-    const int page = __ldg(P.block_table + (long long)b * P.max_pages + n_cached / P.page_size);
-    bf16* kp = pool + (long long)page * page_stride + ((long long)kvh * P.page_size + n_cached % P.page_size) * 128 + lane * 4;
-    *reinterpret_cast<uint2*>(kp) = make_uint2(pack_bf16(kf[0], kf[1]), pack_bf16(kf[2], kf[3]));
+  if (new_here) {
+    // the new token: append rotated K and V to the cache, attend to it
+    bf16* kp = pool + (long long)bt[n_cached / P.page_size] * page_stride +
+               ((long long)kvh * P.page_size + n_cached % P.page_size) * 128 + lane * 4;
+    *reinterpret_cast<uint2*>(kp) = make_uint2(pack_bf16(knew[0], knew[1]), pack_bf16(knew[2], knew[3]));
     *reinterpret_cast<uint2*>(kp + v_off) = vraw;
-    consume_key(kf, vf);
+    consume_key(knew, vnew);
   }
   float* part = reinterpret_cast<float*>(c.region_a);  // [8 warps][8 heads][130]
 #pragma unroll
-  for (int h = 0; h < 8; ++h) {
-    if (h < G) {
-      float* dst = part + (cw * 8 + h) * kPartStride;
-      *reinterpret_cast<float2*>(dst + lane * 4) = make_float2(o[h][0], o[h][1]);
-      *reinterpret_cast<float2*>(dst + lane * 4 + 2) = make_float2(o[h][2], o[h][3]);
-      if (lane == 0) {
-        dst[128] = m[h];
-        dst[129] = l[h];
-      }
+  for (int h = 0; h < G; ++h) {
+    float* dst = part + (cw * 8 + h) * kPartStride;
+    *reinterpret_cast<float2*>(dst + lane * 4) = make_float2(o[h][0], o[h][1]);
+    *reinterpret_cast<float2*>(dst + lane * 4 + 2) = make_float2(o[h][2], o[h][3]);
+    if (lane == 0) {
+      dst[128] = m[h];
+      dst[129] = l[h];
     }
   }
-  consumer_sync();
+  __syncthreads();
   // ---- merge the 8 warps: thread -> (head = ctid / 32, dims 4 * (ctid % 32) ..)
   const int h = ctid >> 5, d4 = (ctid & 31) * 4;
   float acc4[4] = {0.f, 0.f, 0.f, 0.f}, m_tot = -INFINITY, l_tot = 0.f;
@@ -556,79 +646,141 @@ __device__ void attn_phase(MegaCtx& c, const MegaOp& op, int ctid) {
       for (int e = 0; e < 4; ++e) acc4[e] += pw[d4 + e] * sc;
     }
   }
-  bf16* outp = static_cast<bf16*>(op.out) + (long long)b * op.ldo + (kvh * G + h) * 128 + d4;
+  uint32_t* outp = op.out_ll + (long long)b * op.ldo + kvh * G * 128;  // this kv group's heads
   if (nsplit == 1) {
     if (h < G) {
       const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-      *reinterpret_cast<uint2*>(outp) = make_uint2(pack_bf16(acc4[0] * inv, acc4[1] * inv), pack_bf16(acc4[2] * inv, acc4[3] * inv));
+      __stcg(reinterpret_cast<uint4*>(outp + h * 128 + d4),
+             make_uint4(ll4_word(acc4[0] * inv, otag16), ll4_word(acc4[1] * inv, otag16), ll4_word(acc4[2] * inv, otag16),
+                        ll4_word(acc4[3] * inv, otag16)));
     }
     return;
   }
-  float* wsb = P.attn_part + ((long long)item * P.nsplit_max) * 8 * kPartStride;
+  // ---- publish this CTA's partial {fp32, tag}
+  uint2* wsb = P.attn_part + (((long long)op.parity * P.grid + (long long)item * P.nsplit_max) * 8) * kPartStride;
   if (h < G) {
-    float* dst = wsb + ((long long)split * 8 + h) * kPartStride;
-    __stcg(reinterpret_cast<float2*>(dst + d4), make_float2(acc4[0], acc4[1]));
-    __stcg(reinterpret_cast<float2*>(dst + d4 + 2), make_float2(acc4[2], acc4[3]));
-    if ((ctid & 31) == 0) {
-      __stcg(dst + 128, m_tot);
-      __stcg(dst + 129, l_tot);
+    uint2* dst = wsb + ((long long)split * 8 + h) * kPartStride;
+    __stcg(reinterpret_cast<uint4*>(dst + d4), make_uint4(__float_as_uint(acc4[0]), otag32, __float_as_uint(acc4[1]), otag32));
+    __stcg(reinterpret_cast<uint4*>(dst + d4 + 2), make_uint4(__float_as_uint(acc4[2]), otag32, __float_as_uint(acc4[3]), otag32));
+    if ((ctid & 31) == 0)
+      __stcg(reinterpret_cast<uint4*>(dst + 128), make_uint4(__float_as_uint(m_tot), otag32, __float_as_uint(l_tot), otag32));
+  }
+  // ---- merge: head hh belongs to the CTA of split (hh % nsplit). The (head, split) partials this CTA must read are
+  // dealt round-robin to its 8 warps, each warp polls its share in ONE batch, warps combine through shared memory.
+  int n_mine = 0;
+  for (int hh = split; hh < G; hh += nsplit) ++n_mine;
+  if (n_mine == 0) return;          // CTA-uniform
+  __syncthreads();                  // everyone is done reading `part`: reuse it as [8 warps][4 heads][130] + m_tot[4]
+  constexpr int MS = 5;             // (head, split) pairs per warp: 8 * 5 = 40 >= nsplit_max (37) or 4 heads x 7 splits
+  float a4[MS][4], ml_m[MS], ml_l[MS];
+  int pair_h[MS];
+  {
+    uint4 va[MS], vb[MS], vm[MS];
+    Watchdog wd;
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int t = 0; t < MS; ++t) {
+        const int pidx = cw + kCWarps * t;  // pair index = wi * nsplit + sp
+        pair_h[t] = -1;
+        if (pidx < n_mine * nsplit) {
+          const int wi = pidx / nsplit, sp = pidx - wi * nsplit;
+          pair_h[t] = wi;
+          const uint2* src = wsb + ((long long)sp * 8 + (split + wi * nsplit)) * kPartStride;
+          va[t] = ld_poll_v4(src + lane * 4);
+          vb[t] = ld_poll_v4(src + lane * 4 + 2);
+          vm[t] = ld_poll_v4(src + 128);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < MS; ++t)
+        if (pair_h[t] >= 0 && !(va[t].y == otag32 && va[t].w == otag32 && vb[t].y == otag32 && vb[t].w == otag32 &&
+                                vm[t].y == otag32 && vm[t].w == otag32))
+          ok = false;
+      if (!ok) wd.tick(P.err_flag, 9, split);
+    } while (!ok);
+#pragma unroll
+    for (int t = 0; t < MS; ++t) {
+      a4[t][0] = __uint_as_float(va[t].x); a4[t][1] = __uint_as_float(va[t].z);
+      a4[t][2] = __uint_as_float(vb[t].x); a4[t][3] = __uint_as_float(vb[t].z);
+      ml_m[t] = __uint_as_float(vm[t].x);
+      ml_l[t] = __uint_as_float(vm[t].z);
     }
   }
-  __threadfence();
-  consumer_sync();
-  if (ctid == 0) {
-    const unsigned int prev = atomicAdd(P.attn_ctr + item, 1u);
-    const int last = (prev == (unsigned int)nsplit - 1) ? 1 : 0;
-    if (last) P.attn_ctr[item] = 0u;  // self-reset for the next layer / launch
-    c.flag[0] = last;
+  // per warp: combine its pairs head by head (at most 4 heads per CTA), then across warps through shared memory
+#pragma unroll 1
+  for (int wi = 0; wi < n_mine; ++wi) {
+    float mw = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < MS; ++t)
+      if (pair_h[t] == wi) mw = fmaxf(mw, ml_m[t]);
+    float lw = 0.f, ow[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < MS; ++t)
+      if (pair_h[t] == wi) {
+        const float sc = (ml_m[t] == -INFINITY) ? 0.f : exp2f((ml_m[t] - mw) * sl2);
+        lw += ml_l[t] * sc;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ow[e] += a4[t][e] * sc;
+      }
+    float* dst = part + (cw * 4 + wi) * kPartStride;
+    *reinterpret_cast<float2*>(dst + lane * 4) = make_float2(ow[0], ow[1]);
+    *reinterpret_cast<float2*>(dst + lane * 4 + 2) = make_float2(ow[2], ow[3]);
+    if (lane == 0) {
+      dst[128] = mw;
+      dst[129] = lw;
+    }
   }
-  consumer_sync();
-  const int is_last = c.flag[0];
-  consumer_sync();  // flag may be rewritten by a later phase
-  if (!is_last) return;
-  __threadfence();
-  if (h < G) {
-    float mt = -INFINITY, lt = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) mt = fmaxf(mt, __ldcg(wsb + ((long long)sp * 8 + h) * kPartStride + 128));
-    acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) {
-      const float* ps = wsb + ((long long)sp * 8 + h) * kPartStride;
-      const float ms = __ldcg(ps + 128);
-      const float sc = (ms == -INFINITY) ? 0.f : exp2f((ms - mt) * sl2);
-      lt += __ldcg(ps + 129) * sc;
-      const float2 o01 = __ldcg(reinterpret_cast<const float2*>(ps + d4));
-      const float2 o23 = __ldcg(reinterpret_cast<const float2*>(ps + d4 + 2));
-      acc4[0] += o01.x * sc; acc4[1] += o01.y * sc; acc4[2] += o23.x * sc; acc4[3] += o23.y * sc;
+  __syncthreads();
+  if (cw < n_mine) {  // warp wi finishes head split + wi * nsplit
+    const int wi = cw, hh = split + wi * nsplit;
+    float mt = -INFINITY;
+    for (int w = 0; w < kCWarps; ++w) mt = fmaxf(mt, part[(w * 4 + wi) * kPartStride + 128]);
+    float lt = 0.f, of[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int w = 0; w < kCWarps; ++w) {
+      const float* pw = part + (w * 4 + wi) * kPartStride;
+      const float sc = (pw[128] == -INFINITY) ? 0.f : exp2f((pw[128] - mt) * sl2);
+      lt += pw[129] * sc;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) of[e] += pw[lane * 4 + e] * sc;
     }
     const float inv = lt > 0.f ? 1.f / lt : 0.f;
-    *reinterpret_cast<uint2*>(outp) = make_uint2(pack_bf16(acc4[0] * inv, acc4[1] * inv), pack_bf16(acc4[2] * inv, acc4[3] * inv));
+    __stcg(reinterpret_cast<uint4*>(outp + hh * 128 + lane * 4),
+           make_uint4(ll4_word(of[0] * inv, otag16), ll4_word(of[1] * inv, otag16), ll4_word(of[2] * inv, otag16),
+                      ll4_word(of[3] * inv, otag16)));
   }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int NB>
-__global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const MegaPlan* __restrict__ plan) {
+template <int NB, int G>
+__global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const MegaPlan* __restrict__ plan, uint32_t epoch) {
   extern __shared__ __align__(128) uint8_t mega_smem[];
   const MegaPlan& P = *plan;
   const int n_ops = P.n_ops;
-  // layout: ops | barriers + scratch (2 KB) | region A | ring
+  // layout: ops | meta (barriers + scratch 2 KB, residual slab, block table) | region A | ring
   MegaOp* s_ops = reinterpret_cast<MegaOp*>(mega_smem);
   const int ops_bytes = (n_ops * (int)sizeof(MegaOp) + 127) & ~127;
-  uint64_t* full = reinterpret_cast<uint64_t*>(mega_smem + ops_bytes);
+  uint8_t* meta = mega_smem + ops_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(meta);
   volatile uint32_t* gen = reinterpret_cast<volatile uint32_t*>(full + kMaxSlots);  // kMaxSlots counters
   float* red = reinterpret_cast<float*>(const_cast<uint32_t*>(gen) + kMaxSlots + 4);  // 16 floats
-  int* flag = reinterpret_cast<int*>(red + 16);             // 4 ints
-  float* am_v = reinterpret_cast<float*>(flag + 4);         // [8 warps][16 lanes]
+  int* s_ctx = reinterpret_cast<int*>(red + 16);                                    // 4 ints
+  float* am_v = reinterpret_cast<float*>(s_ctx + 4);                                // [8 warps][16 lanes]
   int* am_i = reinterpret_cast<int*>(am_v + kCWarps * 16);
-  uint8_t* region_a = mega_smem + ops_bytes + 2048;
+  bf16* s_h = reinterpret_cast<bf16*>(meta + 2048);
+  int* s_bt = reinterpret_cast<int*>(meta + 2048 + 4 * kHRows * 2);
+  uint8_t* region_a = meta + kMetaBytes;
   uint8_t* ring = region_a + P.region_a_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  {  // copy the op list into shared memory (16-byte chunks), init the ring barriers
+  {  // copy the op list, context lengths and block table into shared memory, init the ring barriers
     const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(plan) + sizeof(MegaPlan));
     uint4* dst = reinterpret_cast<uint4*>(s_ops);
     const int n16 = n_ops * (int)sizeof(MegaOp) / 16;
     for (int i = tid; i < n16; i += kMegaThreads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < P.B * P.max_pages; i += kMegaThreads) s_bt[i] = P.block_table[i];
+    if (tid < P.B) s_ctx[tid] = P.ctx_lens[tid];
     if (tid == 0) {
       for (int s = 0; s < P.nslots; ++s) {
         mbar_init(&full[s], 1);
@@ -640,9 +792,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   __syncthreads();
 
   MegaCtx c;
-  c.P = plan; c.ops = s_ops; c.full = full; c.gen = gen; c.red = red; c.flag = flag;
-  c.region_a = region_a; c.ring = ring; c.nslots = P.nslots; c.cta = blockIdx.x; c.grid = gridDim.x; c.n_ops = n_ops;
-  c.bar_target = 0;
+  c.P = plan; c.ops = s_ops; c.full = full; c.gen = gen; c.red = red; c.am_v = am_v; c.am_i = am_i; c.s_ctx = s_ctx;
+  c.s_h = s_h; c.s_bt = s_bt; c.region_a = region_a; c.ring = ring; c.nslots = P.nslots; c.cta = blockIdx.x;
+  c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch;
 
   // every warp keeps its own cursor into the stage sequence for the refills it issues
   StageCursor refill;
@@ -657,15 +809,17 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   uint32_t sc_base = 0;
   float best_v = -INFINITY;
   int best_i = 0x7fffffff;
+  unsigned long long* prof = P.prof ? P.prof + ((size_t)c.cta * n_ops) * 4 : nullptr;
 #pragma unroll 1
   for (int i = 0; i < n_ops; ++i) {
     const MegaOp& op = s_ops[i];
-    if (i > 0) grid_sync(c, ctid);
+    if (prof && ctid == 0) prof[i * 4 + 0] = global_ns();
     if (op.type == OP_GEMV) {
       stage_x<NB>(c, op, ctid);
+      if (prof && ctid == 0) prof[i * 4 + 1] = global_ns();
       int row0, rows;
-      slab_of(op, c.cta, c.grid, row0, rows);
-      gemv_consume<NB>(c, op, sc_base, row0, rows, cw, lane, refill, best_v, best_i);
+      slab_rows(op.N, op.gran, c.cta, c.grid, row0, rows);
+      gemv_consume<NB>(c, op, i, sc_base, row0, rows, cw, lane, refill, best_v, best_i);
       sc_base += (uint32_t)(((rows + op.R - 1) / op.R) * op.ksplit);
       if (op.flags & F_ARGMAX) {
         // CTA-level partial argmax per sequence: lane (i * NB + b) tracked sequence b = lane % NB
@@ -673,7 +827,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
           am_v[cw * 16 + lane] = best_v;
           am_i[cw * 16 + lane] = best_i;
         }
-        consumer_sync();
+        __syncthreads();
         if (ctid < NB && ctid < P.B) {
           float bv = -INFINITY;
           int bi = 0x7fffffff;
@@ -683,25 +837,36 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
               const int ix = am_i[w * 16 + ln];
               if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
             }
-          __stcg(P.amax_val + c.cta * NB + ctid, bv);
-          __stcg(P.amax_idx + c.cta * NB + ctid, bi);
+          const uint32_t t = tag32_of(epoch, i);
+          __stcg(reinterpret_cast<uint4*>(P.amax_part + ((long long)c.cta * 4 + ctid) * 2),
+                 make_uint4(__float_as_uint(bv), t, (uint32_t)bi, t));
         }
         best_v = -INFINITY;
         best_i = 0x7fffffff;
       }
+      __syncthreads();  // region A (activations) and the residual slab are reused by the next op
     } else if (op.type == OP_ATTN) {
-      attn_phase(c, op, ctid);
+      attn_phase<G>(c, op, i, ctid);
+      __syncthreads();
     } else if (op.type == OP_FINAL) {
       // greedy sampling: lowest index among the maxima (HF argmax), token history, context lengths
       if (c.cta == 0 && cw == 0) {
-        const int pos = P.hist_pos ? __ldcg(P.hist_pos) : 0;
+        const uint32_t t = tag32_of(epoch, op.in_op);
+        const int pos = P.hist_pos ? *P.hist_pos : 0;
         for (int b = 0; b < P.B; ++b) {
           float bv = -INFINITY;
           int bi = 0x7fffffff;
           for (int k = lane; k < c.grid; k += 32) {
-            const float v = __ldcg(P.amax_val + k * NB + b);
-            const int ix = __ldcg(P.amax_idx + k * NB + b);
-            if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+            uint4 v;
+            Watchdog wd;
+            while (true) {
+              v = ld_poll_v4(P.amax_part + ((long long)k * 4 + b) * 2);
+              if (v.y == t && v.w == t) break;
+              wd.tick(P.err_flag, 10, k);
+            }
+            const float val = __uint_as_float(v.x);
+            const int ix = (int)v.z;
+            if (val > bv || (val == bv && ix < bi)) { bv = val; bi = ix; }
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
@@ -713,23 +878,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
             const long long tok = (long long)bi + P.vocab_offset;
             P.tokens[b] = tok;
             if (P.token_hist && pos < P.hist_capacity) P.token_hist[(long long)pos * P.B + b] = tok;
-            P.ctx_lens[b] = P.ctx_lens[b] + 1;
+            P.ctx_lens[b] = s_ctx[b] + 1;
           }
         }
         if (lane == 0 && P.hist_pos) *P.hist_pos = pos + 1;
       }
     }
-  }
-  // ===================== exit: the last CTA to leave resets the barrier counters for the next launch =====================
-  consumer_sync();
-  if (ctid == 0) {
-    __threadfence();
-    const unsigned int prev = atomicAdd(P.exit_ctr, 1u);
-    if (prev == (unsigned int)c.grid - 1) {
-      *P.bar_ctr = 0u;
-      *P.exit_ctr = 0u;
-      __threadfence();
-    }
+    if (prof && ctid == 0) prof[i * 4 + 2] = global_ns();
   }
 }
 
@@ -742,21 +897,25 @@ static int pick_ksplit(int K) {
 }
 
 struct WsLayout {
-  long long bar, exitc, err, attn_ctr, amax_val, amax_idx, attn_part, total;
+  long long err, h1, qkv, attn, h2, act, part, amax, total;
 };
-static WsLayout ws_layout(int grid) {
+static WsLayout ws_layout(int grid, int B, int C, int qw, int aw, int I) {
   WsLayout w;
   long long off = 0;
-  w.bar = off; off += 128;
-  w.exitc = off; off += 128;
-  w.err = off; off += 128;
-  w.attn_ctr = off; off += 4LL * grid;  // one counter per (sequence, kv head) item, items <= grid
-  off = (off + 127) & ~127LL;
-  w.amax_val = off; off += 4LL * grid * 4;
-  w.amax_idx = off; off += 4LL * grid * 4;
-  off = (off + 127) & ~127LL;
-  w.attn_part = off; off += 4LL * grid * 8 * kPartStride;
-  w.total = (off + 127) & ~127LL;
+  auto take = [&](long long bytes) {
+    const long long at = off;
+    off = (off + bytes + 127) & ~127LL;
+    return at;
+  };
+  w.err = take(128);
+  w.h1 = take(2LL * B * C * 4);
+  w.qkv = take(2LL * B * qw * 4);
+  w.attn = take(2LL * B * aw * 4);
+  w.h2 = take(2LL * B * C * 4);
+  w.act = take(2LL * B * I * 4);
+  w.part = take(2LL * grid * 8 * kPartStride * 8);
+  w.amax = take((long long)grid * 4 * 2 * 8);
+  w.total = off;
   return w;
 }
 
@@ -769,9 +928,9 @@ extern "C" long long omc_decode_plan_bytes(int n_layers) {
   return (long long)sizeof(MegaPlan) + (long long)(5 * n_layers + 2) * (long long)sizeof(MegaOp);
 }
 
-extern "C" long long omc_decode_workspace_bytes(int grid) {
-  if (grid <= 0) return -1;
-  return ws_layout(grid).total;
+extern "C" long long omc_decode_workspace_bytes(const omc_decode_desc* d) {
+  if (d == nullptr || d->grid < 1 || d->batch < 1) return -1;
+  return ws_layout(d->grid, d->batch, d->hidden, (d->q_heads + 2 * d->kv_heads) * 128, d->q_heads * 128, d->inter).total;
 }
 
 extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) {
@@ -779,23 +938,36 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   if (d->batch < 1 || d->batch > 4) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: batch must be 1..4");
   if (d->n_layers < 0 || 5 * d->n_layers + 2 > kMaxOps) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: too many layers");
   if (d->grid < 1) return set_error(OMC_ERR_ARG, "omc_decode_plan_build: grid must be the number of CTAs (SMs)");
-  if (d->kv_heads < 1 || d->q_heads % d->kv_heads != 0 || d->q_heads / d->kv_heads > 8)
-    return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: q heads per kv head must be 1..8");
+  {
+    const int g = d->kv_heads >= 1 && d->q_heads % d->kv_heads == 0 ? d->q_heads / d->kv_heads : 0;
+    if (!(g == 1 || g == 2 || g == 4 || g == 6 || g == 7 || g == 8))
+      return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: q heads per kv head must be one of 1, 2, 4, 6, 7, 8");
+  }
   if (d->batch * d->kv_heads > d->grid) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: batch * kv_heads exceeds the grid");
   if (d->hidden % 8 != 0 || d->hidden > 4096) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: hidden must be a multiple of 8, <= 4096");
+  if ((d->hidden + d->grid - 1) / d->grid + 1 > kHRows)
+    return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: hidden / grid exceeds the residual rows one CTA can own");
   if (d->inter % 8 != 0 || d->vocab < 1) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: inter % 8 != 0 or empty vocab");
-  if (d->page_size < 1 || d->max_pages < 1) return set_error(OMC_ERR_ARG, "omc_decode_plan_build: bad paging parameters");
+  if (d->page_size < 1 || d->max_pages < 1 || d->batch * d->max_pages > kMaxBt)
+    return set_error(OMC_ERR_ARG, "omc_decode_plan_build: bad paging parameters (batch * max_pages must be <= 1024)");
+  if (d->workspace == nullptr) return set_error(OMC_ERR_ARG, "omc_decode_plan_build: workspace is null");
+  if (d->rope_cs == nullptr || d->rope_positions < d->max_pages * d->page_size)
+    return set_error(OMC_ERR_ARG, "omc_decode_plan_build: rope_cs must cover max_pages * page_size positions");
   const int C = d->hidden, Hq = d->q_heads, Hkv = d->kv_heads, I = d->inter, B = d->batch;
   const int qw = (Hq + 2 * Hkv) * 128, aw = Hq * 128;
-  if (aw > 4096 * 8) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: too many heads");
+  const WsLayout w = ws_layout(d->grid, B, C, qw, aw, I);
+  uint8_t* ws = static_cast<uint8_t*>(d->workspace);
+  auto ll = [&](long long base, int parity, int width) {
+    return reinterpret_cast<uint32_t*>(ws + base) + (long long)parity * B * width;
+  };
   MegaPlan* P = static_cast<MegaPlan*>(plan_host);
   memset(P, 0, sizeof(MegaPlan));
   MegaOp* ops = reinterpret_cast<MegaOp*>(P + 1);
   int n = 0, kmax = 0;
   bool bad = false;
-  auto gemv = [&](const void* W, int N, int K, const void* x, int ldx, const void* norm_w, const void* bias, const void* res,
-                  int ldr, void* out, int ldo, int epi, int flags, void* aux) {
-    MegaOp& o = ops[n++];
+  auto gemv = [&](const void* W, int N, int K, const uint32_t* x_ll, int ldx, int in_op, const void* norm_w, const void* bias,
+                  uint32_t* out_ll, int ldo, int epi, int flags) -> int {
+    MegaOp& o = ops[n];
     memset(&o, 0, sizeof(o));
     o.type = OP_GEMV; o.N = N; o.K = K; o.epi = epi; o.flags = flags;
     o.gran = (epi == EPI_SWIGLU) ? 2 : 1;
@@ -810,26 +982,35 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
     } else if (o.gran == 2) bad = true;  // a (gate, up) pair must fit one ring stage
     o.R = R < 1 ? 1 : R;
     if (norm_w != nullptr && K > 4096) bad = true;
-    o.W = (const bf16*)W; o.x = (const bf16*)x; o.norm_w = (const bf16*)norm_w; o.bias = (const bf16*)bias;
-    o.res = (const bf16*)res; o.out = out; o.aux = (bf16*)aux; o.ldx = ldx; o.ldo = ldo; o.ldr = ldr;
+    o.W = (const bf16*)W; o.norm_w = (const bf16*)norm_w; o.bias = (const bf16*)bias;
+    o.x_ll = x_ll; o.out_ll = out_ll; o.ldx = ldx; o.ldo = ldo; o.in_op = in_op;
     if (K > kmax) kmax = K;
+    return n++;
   };
+  int prev = -1;  // op that produced the current residual-stream broadcast (h1)
   for (int li = 0; li < d->n_layers; ++li) {
-    gemv(d->qkv_w[li], qw, C, d->h, C, d->ln1[li], d->qkv_b[li], nullptr, C, d->qkv, qw, EPI_NONE,
-         li == 0 ? F_X_EMBED : 0, li == 0 ? d->h : nullptr);
-    MegaOp& a = ops[n++];
+    const int par = li & 1;
+    const int i_qkv = gemv(d->qkv_w[li], qw, C, li == 0 ? nullptr : ll(w.h1, par, C), C, prev, d->ln1[li], d->qkv_b[li],
+                           ll(w.qkv, par, qw), qw, EPI_NONE, li == 0 ? F_X_EMBED : 0);
+    MegaOp& a = ops[n];
     memset(&a, 0, sizeof(a));
-    a.type = OP_ATTN; a.x = (const bf16*)d->qkv; a.ldx = qw; a.out = d->attn; a.ldo = aw;
-    a.aux = static_cast<bf16*>(d->kv_pool) + (long long)li * d->kv_layer_stride;
-    gemv(d->o_w[li], C, aw, d->attn, aw, nullptr, nullptr, d->h, C, d->h, C, EPI_RES, 0, nullptr);
-    gemv(d->gate_up_w[li], 2 * I, C, d->h, C, d->ln2[li], nullptr, nullptr, C, d->act, I, EPI_SWIGLU, 0, nullptr);
-    gemv(d->down_w[li], C, I, d->act, I, nullptr, nullptr, d->h, C, d->h, C, EPI_RES, 0, nullptr);
+    a.type = OP_ATTN; a.x_ll = ll(w.qkv, par, qw); a.ldx = qw; a.in_op = i_qkv; a.out_ll = ll(w.attn, par, aw); a.ldo = aw;
+    a.parity = par;
+    a.pool = static_cast<bf16*>(d->kv_pool) + (long long)li * d->kv_layer_stride;
+    const int i_attn = n++;
+    const int i_o = gemv(d->o_w[li], C, aw, ll(w.attn, par, aw), aw, i_attn, nullptr, nullptr, ll(w.h2, par, C), C, EPI_RES, 0);
+    const int i_gu = gemv(d->gate_up_w[li], 2 * I, C, ll(w.h2, par, C), C, i_o, d->ln2[li], nullptr, ll(w.act, par, I), I,
+                          EPI_SWIGLU, 0);
+    prev = gemv(d->down_w[li], C, I, ll(w.act, par, I), I, i_gu, nullptr, nullptr, ll(w.h1, (li + 1) & 1, C), C, EPI_RES, 0);
   }
-  gemv(d->lm_head, d->vocab, C, d->h, C, d->final_norm, nullptr, nullptr, C, d->logits, d->vocab, EPI_NONE,
-       F_OUT_F32 | F_ARGMAX | (d->n_layers == 0 ? F_X_EMBED : 0), nullptr);
+  const int i_head = gemv(d->lm_head, d->vocab, C, d->n_layers == 0 ? nullptr : ll(w.h1, d->n_layers & 1, C), C, prev,
+                          d->final_norm, nullptr, nullptr, d->vocab, EPI_NONE,
+                          F_OUT_F32 | F_ARGMAX | (d->n_layers == 0 ? F_X_EMBED : 0));
+  ops[i_head].out_f32 = d->logits;
   MegaOp& f = ops[n++];
   memset(&f, 0, sizeof(f));
   f.type = OP_FINAL;
+  f.in_op = i_head;
   if (bad) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: a layer shape does not fit the ring (K % 8, SwiGLU pair > slot, norm K > 4096)");
   P->n_ops = n; P->B = B; P->C = C; P->Hq = Hq; P->Hkv = Hkv; P->G = Hq / Hkv;
   P->page_size = d->page_size; P->max_pages = d->max_pages; P->grid = d->grid;
@@ -839,31 +1020,26 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   if (region_a < kAttnScratchBytes) region_a = kAttnScratchBytes;
   region_a = (region_a + 127) & ~127;
   const int ops_bytes = (n * (int)sizeof(MegaOp) + 127) & ~127;
-  int nslots = (kSmemLimit - ops_bytes - 2048 - region_a) / kSlotBytes;
+  int nslots = (kSmemLimit - ops_bytes - kMetaBytes - region_a) / kSlotBytes;
   if (nslots > kMaxSlots) nslots = kMaxSlots;
   if (nslots < 2) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: activations leave no room for the weight ring");
   P->nslots = nslots; P->region_a_bytes = region_a;
-  P->smem_bytes = ops_bytes + 2048 + region_a + nslots * kSlotBytes;
+  P->smem_bytes = ops_bytes + kMetaBytes + region_a + nslots * kSlotBytes;
   P->eps = d->eps; P->scale_log2 = d->attn_scale * 1.4426950408889634f;
-  P->embed = (const bf16*)d->embed; P->inv_freq = d->inv_freq; P->block_table = d->block_table; P->ctx_lens = d->ctx_lens;
+  P->embed = (const bf16*)d->embed; P->rope_cs = d->rope_cs; P->block_table = d->block_table; P->ctx_lens = d->ctx_lens;
   P->tokens = d->tokens; P->token_hist = d->token_hist; P->hist_pos = d->hist_pos;
-  const WsLayout w = ws_layout(d->grid);
-  uint8_t* ws = static_cast<uint8_t*>(d->workspace);
-  P->bar_ctr = reinterpret_cast<unsigned int*>(ws + w.bar);
-  P->exit_ctr = reinterpret_cast<unsigned int*>(ws + w.exitc);
   P->err_flag = d->status ? d->status : reinterpret_cast<int32_t*>(ws + w.err);
-  P->attn_ctr = reinterpret_cast<unsigned int*>(ws + w.attn_ctr);
-  P->amax_val = reinterpret_cast<float*>(ws + w.amax_val);
-  P->amax_idx = reinterpret_cast<int32_t*>(ws + w.amax_idx);
-  P->attn_part = reinterpret_cast<float*>(ws + w.attn_part);
+  P->prof = static_cast<unsigned long long*>(d->prof);
+  P->attn_part = reinterpret_cast<uint2*>(ws + w.part);
+  P->amax_part = reinterpret_cast<uint2*>(ws + w.amax);
   return OMC_OK;
 }
 
-template <int NB>
-static int launch_mega(const MegaPlan* host, const void* plan_dev, cudaStream_t st) {
+template <int NB, int G>
+static int launch_mega(const MegaPlan* host, const void* plan_dev, uint32_t epoch, cudaStream_t st) {
   static int attr_smem = 0;
   if (host->smem_bytes > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, host->smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<NB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, host->smem_bytes);
     if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
     attr_smem = host->smem_bytes;
   }
@@ -873,26 +1049,27 @@ static int launch_mega(const MegaPlan* host, const void* plan_dev, cudaStream_t 
   cfg.dynamicSmemBytes = host->smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attrs[1];
-  attrs[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barriers depend on it
+  attrs[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait for each other's data
   attrs[0].val.cooperative = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
   const MegaPlan* arg = static_cast<const MegaPlan*>(plan_dev);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_mega_kernel<NB>, arg);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_mega_kernel<NB, G>, arg, epoch);
   if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
   return OMC_OK;
 }
 
-extern "C" int omc_decode_step(const void* plan_host, const void* plan_dev, void* stream) {
+extern "C" int omc_decode_step(const void* plan_host, const void* plan_dev, unsigned int epoch, void* stream) {
   if (plan_host == nullptr || plan_dev == nullptr) return set_error(OMC_ERR_ARG, "omc_decode_step: null plan");
   const MegaPlan* P = static_cast<const MegaPlan*>(plan_host);
   if (P->n_ops < 2 || P->n_ops > kMaxOps || P->grid < 1) return set_error(OMC_ERR_ARG, "omc_decode_step: plan not built");
   cudaStream_t st = (cudaStream_t)stream;
-  switch (P->B) {
-    case 1: return launch_mega<1>(P, plan_dev, st);
-    case 2: return launch_mega<2>(P, plan_dev, st);
-    case 3: return launch_mega<3>(P, plan_dev, st);
-    case 4: return launch_mega<4>(P, plan_dev, st);
-    default: return set_error(OMC_ERR_SHAPE, "omc_decode_step: batch must be 1..4");
-  }
+#define OMC_MEGA_CASE(NB_, G_) \
+  if (P->B == NB_ && P->G == G_) return launch_mega<NB_, G_>(P, plan_dev, epoch, st);
+#define OMC_MEGA_G(G_) OMC_MEGA_CASE(1, G_) OMC_MEGA_CASE(2, G_) OMC_MEGA_CASE(3, G_) OMC_MEGA_CASE(4, G_)
+  OMC_MEGA_G(1) OMC_MEGA_G(2) OMC_MEGA_G(4) OMC_MEGA_G(6) OMC_MEGA_G(7) OMC_MEGA_G(8)
+#undef OMC_MEGA_G
+#undef OMC_MEGA_CASE
+  return set_error(OMC_ERR_SHAPE, "omc_decode_step: batch must be 1..4 and q heads per kv head one of 1, 2, 4, 6, 7, 8");
 }
+

@@ -38,9 +38,9 @@ SIGNATURES = {
     "omc_splice": (_I, [_P, _P, _I, _I, _L, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P]),
     "omc_argmax": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "omc_decode_plan_bytes": (_L, [_I]),
-    "omc_decode_workspace_bytes": (_L, [_I]),
+    "omc_decode_workspace_bytes": (_L, [_P]),
     "omc_decode_plan_build": (_I, [_P, _P]),
-    "omc_decode_step": (_I, [_P, _P, _P]),
+    "omc_decode_step": (_I, [_P, _P, ctypes.c_uint, _P]),
 }
 
 _lib = None
@@ -267,13 +267,14 @@ def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None, workspace: 
 class DecodeDesc(ctypes.Structure):
     """Mirror of `omc_decode_desc` (include/omchat_b200.h)."""
     _fields_ = ([(n, ctypes.c_int32) for n in ("n_layers", "batch", "hidden", "q_heads", "kv_heads", "inter", "vocab",
-                                                 "vocab_offset", "page_size", "max_pages", "grid", "hist_capacity")]
+                                                 "vocab_offset", "page_size", "max_pages", "grid", "hist_capacity",
+                                                 "rope_positions", "reserved0")]
                 + [("eps", c_float), ("attn_scale", c_float)]
-                + [(n, c_void_p) for n in ("embed", "final_norm", "lm_head", "inv_freq", "ln1", "qkv_w", "qkv_b", "o_w",
+                + [(n, c_void_p) for n in ("embed", "final_norm", "lm_head", "rope_cs", "ln1", "qkv_w", "qkv_b", "o_w",
                                            "ln2", "gate_up_w", "down_w", "kv_pool")]
                 + [("kv_layer_stride", c_longlong)]
                 + [(n, c_void_p) for n in ("block_table", "ctx_lens", "tokens", "token_hist", "hist_pos", "h", "qkv",
-                                           "attn", "act", "logits", "workspace", "status")])
+                                           "attn", "act", "logits", "workspace", "status", "prof")])
 
 
 def num_sms() -> int:
@@ -287,15 +288,14 @@ class DecodePlan:
     """Host + device copies of one megakernel plan (omc_decode_plan_build) and the buffers it points at. The plan bakes in
     every pointer (weights, KV pool, block table, state), so it must be rebuilt when any of them is reallocated."""
 
-    def __init__(self, *, layers, embed, final_norm, lm_head, inv_freq, cfg_dims, kv_pool, block_table, ctx_lens, tokens,
+    def __init__(self, *, layers, embed, final_norm, lm_head, rope_cs, cfg_dims, kv_pool, block_table, ctx_lens, tokens,
                  token_hist, hist_pos, h, qkv, attn, act, logits, page_size, eps, scale, vocab_offset=0, grid=None):
         lib = load()
         n_layers = len(layers)
         B = tokens.numel()
         dev = tokens.device
         self.grid = grid or num_sms()
-        ws_bytes = lib.omc_decode_workspace_bytes(self.grid)
-        self.workspace = torch.zeros(ws_bytes, device=dev, dtype=torch.uint8)
+        self.epoch = 1
         arr = lambda ts: (c_void_p * max(n_layers, 1))(*[t.data_ptr() for t in ts])  # noqa: E731
         self._arrays = [arr([getattr(l, k) for l in layers]) for k in
                         ("ln1", "qkv_w", "qkv_b", "o_w", "ln2", "gate_up_w", "down_w")]
@@ -309,7 +309,9 @@ class DecodePlan:
         d.vocab_offset, d.page_size, d.max_pages = vocab_offset, page_size, block_table.shape[1]
         d.grid, d.hist_capacity = self.grid, (token_hist.shape[0] if token_hist is not None else 0)
         d.eps, d.attn_scale = eps, scale
-        d.embed, d.final_norm, d.lm_head, d.inv_freq = embed.data_ptr(), final_norm.data_ptr(), lm_head.data_ptr(), inv_freq.data_ptr()
+        d.embed, d.final_norm, d.lm_head, d.rope_cs = embed.data_ptr(), final_norm.data_ptr(), lm_head.data_ptr(), rope_cs.data_ptr()
+        assert rope_cs.dtype == torch.float32 and rope_cs.is_contiguous() and rope_cs.shape[1:] == (64, 2)
+        d.rope_positions = rope_cs.shape[0]
         (d.ln1, d.qkv_w, d.qkv_b, d.o_w, d.ln2, d.gate_up_w, d.down_w) = [ctypes.cast(a, c_void_p) for a in self._arrays]
         d.kv_pool = kv_pool.data_ptr()
         d.kv_layer_stride = kv_pool.stride(0) if n_layers > 0 else 0
@@ -317,9 +319,17 @@ class DecodePlan:
         d.token_hist = token_hist.data_ptr() if token_hist is not None else None
         d.hist_pos = hist_pos.data_ptr() if hist_pos is not None else None
         d.h, d.qkv, d.attn, d.act, d.logits = h.data_ptr(), qkv.data_ptr(), attn.data_ptr(), act.data_ptr(), logits.data_ptr()
+        ws_bytes = lib.omc_decode_workspace_bytes(ctypes.byref(d))
+        if ws_bytes <= 0:
+            raise OmcError("omc_decode_workspace_bytes failed")
+        self.workspace = torch.zeros(ws_bytes, device=dev, dtype=torch.uint8)
         d.workspace = self.workspace.data_ptr()
         self.status = torch.zeros(4, dtype=torch.int32).pin_memory()  # watchdog record, readable after a device trap
         d.status = self.status.data_ptr()
+        self.prof = None
+        if os.environ.get("OMCHAT_B200_MEGA_PROF", "0") == "1":
+            self.prof = torch.zeros(self.grid, 5 * n_layers + 2, 4, device=dev, dtype=torch.int64)
+            d.prof = self.prof.data_ptr()
         self.desc = d
         nbytes = lib.omc_decode_plan_bytes(n_layers)
         self.host = ctypes.create_string_buffer(nbytes)
@@ -327,9 +337,10 @@ class DecodePlan:
         if rc != 0:
             raise OmcError(f"omc_decode_plan_build failed ({rc}): {lib.omc_last_error().decode(errors='replace')}")
         self.dev = torch.frombuffer(bytearray(self.host.raw), dtype=torch.uint8).to(dev)
-        self._keep = (layers, embed, final_norm, lm_head, inv_freq, kv_pool, block_table, ctx_lens, tokens, token_hist,
+        self._keep = (layers, embed, final_norm, lm_head, rope_cs, kv_pool, block_table, ctx_lens, tokens, token_hist,
                       hist_pos, h, qkv, attn, act, logits)
 
     def step(self):
-        rc = load().omc_decode_step(self.host, self.dev.data_ptr(), _stream())
+        rc = load().omc_decode_step(self.host, self.dev.data_ptr(), self.epoch & 0xFFFFFF, _stream())
+        self.epoch += 1
         _check(rc, "omc_decode_step")

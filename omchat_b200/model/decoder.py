@@ -256,6 +256,17 @@ class Qwen2Decoder:
         return (self.mega_enabled and self.tp.size == 1 and B <= MEGA_MAX_B and self.C <= 4096
                 and len(self.w.layers) * 5 + 2 <= 192)
 
+    def _rope_table(self, positions: int) -> torch.Tensor:
+        """(cos, sin)(pos * inv_freq) in fp32 for pos < positions, [positions, 64, 2] — Qwen2RotaryEmbedding.forward
+        (modeling_qwen2.py:102-113) evaluated once on the device instead of per step inside the kernel."""
+        t = getattr(self, "_rope_cs", None)
+        if t is None or t.shape[0] < positions:
+            n = max(positions, 2048)
+            ang = torch.arange(n, device=self.device, dtype=torch.float32)[:, None] * self.inv_freq[None, :]
+            t = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+            self._rope_cs = t
+        return t
+
     def _mega_plan(self, st, cache: PagedKVCache):
         ent = st.plans.get(id(cache))
         if ent is not None and ent[1] is cache:
@@ -264,7 +275,7 @@ class Qwen2Decoder:
             st.plans.pop(next(iter(st.plans)))
         plan = lib.DecodePlan(
             layers=self.w.layers, embed=self.w.embed, final_norm=self.w.norm, lm_head=self.w.lm_head,
-            inv_freq=self.inv_freq, cfg_dims=(self.C, self.Hq, self.Hkv, self.I_local, self.V_local),
+            rope_cs=self._rope_table(cache.capacity), cfg_dims=(self.C, self.Hq, self.Hkv, self.I_local, self.V_local),
             kv_pool=cache.pool, block_table=cache.block_table, ctx_lens=cache.ctx_lens, tokens=st.tokens,
             token_hist=st.hist, hist_pos=st.hist_pos, h=st.h, qkv=st.qkv, attn=st.attn, act=st.act, logits=st.logits,
             page_size=cache.page_size, eps=self.eps, scale=self.scale)

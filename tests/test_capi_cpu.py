@@ -71,7 +71,8 @@ def _fake_desc(lib, n_layers=28, batch=1, hidden=3584, q=28, kv=4, inter=18944, 
     arr = (ctypes.c_void_p * n_layers)(*[0x1000 * (i + 1) for i in range(n_layers)])
     for k in ("ln1", "qkv_w", "qkv_b", "o_w", "ln2", "gate_up_w", "down_w"):
         setattr(d, k, ctypes.cast(arr, ctypes.c_void_p))
-    for k in ("embed", "final_norm", "lm_head", "inv_freq", "kv_pool", "block_table", "ctx_lens", "tokens", "h", "qkv",
+    d.rope_positions = 64 * 32
+    for k in ("embed", "final_norm", "lm_head", "rope_cs", "kv_pool", "block_table", "ctx_lens", "tokens", "h", "qkv",
               "attn", "act", "logits", "workspace"):
         setattr(d, k, 0x100000)
     return d, arr
@@ -93,7 +94,7 @@ def test_decode_plan_build_is_host_only(built):
     assert (n_ops, B, C, Hq, Hkv, G) == (28 * 5 + 2, 1, 3584, 28, 4, 7)
     assert hdr[9] == 148 // 4  # key splits per (sequence, kv head)
     assert nslots >= 6 and region_a >= 18944 * 2 and smem <= 227 * 1024
-    assert l.omc_decode_workspace_bytes(148) > 148 * 8 * 130 * 4
+    assert l.omc_decode_workspace_bytes(ctypes.byref(d)) > 2 * 148 * 8 * 130 * 8
     # batch 4 still leaves a ring; batch 5 is refused; SwiGLU pair that cannot fit a ring stage is refused
     d4, _k4 = _fake_desc(lib, batch=4)
     assert l.omc_decode_plan_build(ctypes.byref(d4), buf) == 0

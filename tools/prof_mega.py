@@ -1,0 +1,66 @@
+"""In-kernel timeline of the persistent decode kernel: per-op %globaltimer stamps of every CTA (OMCHAT_B200_MEGA_PROF=1).
+Prints, per op kind, the mean over layers of: barrier wait, activation staging, body, and the max-over-CTAs op duration."""
+import os, sys
+os.environ["OMCHAT_B200_MEGA_PROF"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from omchat_b200.config import OmChatQwen2Config
+from omchat_b200.model.decoder import Qwen2Decoder
+from omchat_b200.model.weights import random_init
+
+layers = int(sys.argv[1]) if len(sys.argv) > 1 else 28
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+ctx = int(sys.argv[3]) if len(sys.argv) > 3 else 1200
+cfg = OmChatQwen2Config(num_hidden_layers=layers)
+w = random_init(cfg, device="cuda", vision=False)
+dec = Qwen2Decoder(cfg, w.llm)
+cache = dec.new_cache(B, ctx + 64)
+cache.pool.normal_(0, 0.5)
+cache.host_lens = [ctx] * B
+cache.ctx_lens.fill_(ctx)
+toks = torch.randint(0, cfg.vocab_size, (B,), device="cuda")
+st = dec._decode_state(B, cache.capacity)
+plan = dec._mega_plan(st, cache)
+for _ in range(5):
+    dec.decode_step(toks, cache)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    plan.step()
+e1.record()
+torch.cuda.synchronize()
+print(f"step time {e0.elapsed_time(e1) / 10 * 1000:.1f} us (with profiling stamps on)")
+p = plan.prof.cpu().double()  # [grid, n_ops, 4]
+t0 = p[:, 0, 0].min()
+p = (p - t0) / 1000.0  # us
+n_ops = p.shape[1]
+names = ["qkv", "attn", "o", "gate_up", "down"]
+kinds = {}
+for i in range(n_ops):
+    k = names[i % 5] if i < 5 * layers else ("lm_head" if i == 5 * layers else "final")
+    kinds.setdefault(k, []).append(i)
+print(f"{'op':8s} {'n':>3s} {'wait+stage':>10s} {'body':>9s} {'op span':>9s} {'end skew':>9s}")
+for k, idx in kinds.items():
+    if k in ("attn", "final"):
+        stg = 0.0
+        body = (p[:, idx, 2] - p[:, idx, 0]).mean().item()
+    else:
+        stg = (p[:, idx, 1] - p[:, idx, 0]).mean().item()
+        body = (p[:, idx, 2] - p[:, idx, 1]).mean().item()
+    span = (p[:, idx, 2].max(dim=0).values - p[:, idx, 0].min(dim=0).values).mean().item()
+    skew = (p[:, idx, 2].max(dim=0).values - p[:, idx, 2].min(dim=0).values).mean().item()
+    print(f"{k:8s} {len(idx):3d} {stg:10.2f} {body:9.2f} {span:9.2f} {skew:9.2f}")
+print(f"whole step (first op start -> last op end): {(p[:, -1, 2].max() - p[:, 0, 0].min()).item():.1f} us")
+# critical path per layer: time between the slowest CTA finishing 'down' of consecutive layers
+if layers > 2:
+    ends = p[:, [5 * l + 4 for l in range(layers)], 2].max(dim=0).values
+    print(f"per-layer period (max-CTA end of down, mean over layers): {(ends[1:] - ends[:-1]).mean().item():.2f} us")
+# per-CTA detail of one mid-stack layer
+li = min(layers - 1, 3)
+for name, off in (("qkv", 0), ("attn", 1), ("o", 2), ("gate_up", 3), ("down", 4)):
+    i = 5 * li + off
+    total = p[:, i, 2] - p[:, i, 0]
+    wait = (p[:, i, 1] - p[:, i, 0]) if name != "attn" else total * 0
+    vals = ", ".join(f"{w:.1f}/{t:.1f}" for w, t in list(zip(wait.tolist(), total.tolist()))[:24])
+    print(f"layer {li} {name}: wait/total per CTA (first 24) [{vals}]")
