@@ -141,7 +141,8 @@ int omc_argmax(const float* logits, long long ldl, int B, int V, int64_t* next, 
 typedef struct omc_decode_desc {
   int32_t n_layers, batch, hidden, q_heads, kv_heads, inter, vocab, vocab_offset;
   int32_t page_size, max_pages, grid, hist_capacity;
-  int32_t rope_positions, reserved0;
+  int32_t rope_positions;
+  int32_t l2_prefetch_stages; /* how many ring stages (~14-19 KB each, per CTA) the L2 prefetch runs ahead; 0 = off */
   float eps, attn_scale;
   const void* embed;
   const void* final_norm;

@@ -48,6 +48,7 @@ constexpr int kAttnKeysPerCta = 32;
 constexpr int kPartStride = 130;    // O[128], m, l
 constexpr int kAttnScratchBytes = kCWarps * 8 * kPartStride * 4;
 constexpr int kHRows = 64;          // residual rows one CTA can own
+constexpr int kBiasRows = 128;      // slab rows whose bias is staged in shared memory (larger slabs read it from L2)
 constexpr int kMaxBt = 1024;        // block-table entries cached in shared memory (batch * max_pages)
 constexpr int kMetaBytes = 2048 + 4 * kHRows * 2 + kMaxBt * 4;  // barriers/scratch | residual slab | block table
 constexpr int kSmemLimit = 227 * 1024;
@@ -73,7 +74,8 @@ static_assert(sizeof(MegaOp) == 112, "MegaOp layout");
 struct MegaPlan {  // header, followed by n_ops MegaOp
   int32_t n_ops, B, C, Hq, Hkv, G, page_size, max_pages;
   int32_t grid, nsplit_max, vocab_offset, hist_capacity, kmax, nslots, region_a_bytes, smem_bytes;
-  float eps, scale_log2, pad0, pad1;
+  float eps, scale_log2;
+  int32_t pf_stages, pad1;
   const bf16* embed;
   const float* rope_cs;  // [positions][64][2] fp32 (cos, sin)
   const int32_t* block_table;
@@ -190,10 +192,11 @@ struct MegaCtx {
   int* am_i;
   int* s_ctx;            // [4] context lengths at kernel start
   bf16* s_h;             // [4][kHRows] residual rows owned by this CTA
+  float* s_bias;         // [kBiasRows] bias of this CTA's slab for the current op (fetched while waiting for x)
   int* s_bt;             // block table copy [B][max_pages]
   uint8_t* region_a;     // activation vectors / attention scratch
   uint8_t* ring;
-  int nslots, cta, grid, n_ops;
+  int nslots, cta, grid, n_ops, pf_stages;
   uint32_t epoch;
 };
 
@@ -207,26 +210,39 @@ __device__ __forceinline__ void cursor_load(const MegaCtx& c, StageCursor& k) {
     k.cnt = 0;
   }
 }
-// Issue the bulk copy of stage s (if it exists) into ring slot s % nslots. Called by ONE lane; `k` is the caller's cursor,
-// stage indices passed through one cursor are strictly increasing.
-__device__ __forceinline__ void issue_stage(const MegaCtx& c, StageCursor& k, uint32_t s) {
+// Locate stage s: advance cursor k (stage indices passed through one cursor are strictly increasing) and return the
+// global source address and byte count of the stage, or false when the op list is exhausted.
+__device__ __forceinline__ bool locate_stage(const MegaCtx& c, StageCursor& k, uint32_t s, const bf16*& src, uint32_t& bytes) {
   while (k.op_i < c.n_ops && s >= k.base + k.cnt) {
     k.base += k.cnt;
     ++k.op_i;
     cursor_load(c, k);
   }
-  if (k.op_i >= c.n_ops) return;
+  if (k.op_i >= c.n_ops) return false;
   const MegaOp& op = c.ops[k.op_i];
   const uint32_t rel = s - k.base;
   const int u = (int)(rel / (uint32_t)op.ksplit), ks = (int)(rel % (uint32_t)op.ksplit);
   const int r = u * op.R;
   const int rows_here = min(op.R, k.rows - r);
   const int Kc = op.K / op.ksplit;
-  const uint32_t bytes = (uint32_t)rows_here * (uint32_t)Kc * 2u;
+  bytes = (uint32_t)rows_here * (uint32_t)Kc * 2u;
+  src = op.W + (size_t)(k.row0 + r) * op.K + (size_t)ks * Kc;
+  return true;
+}
+// Issue the bulk copy of stage s (if it exists) into ring slot s % nslots, and ask L2 for the stage `pf_stages` further
+// down the stream: the shared-memory ring bounds how far the copies can run ahead (~150 KB/SM), the L2 prefetch lets HBM
+// keep streaming through the latency-bound phases (qkv -> attention -> o_proj) up to ~60 MB chip-wide ahead of use.
+// Called by ONE lane with that warp's cursors.
+__device__ __forceinline__ void issue_stage(const MegaCtx& c, StageCursor& k, StageCursor& kpf, uint32_t s) {
+  const bf16* src;
+  uint32_t bytes;
+  if (c.pf_stages > 0 && locate_stage(c, kpf, s + (uint32_t)c.pf_stages, src, bytes))
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+  if (!locate_stage(c, k, s, src, bytes)) return;
   const uint32_t slot = s % (uint32_t)c.nslots;
   fence_proxy_async();  // generic-proxy reads of this slot (previous stage) are ordered before the async-proxy refill
   mbar_arrive_expect_tx(&c.full[slot], bytes);
-  bulk_g2s(c.ring + (size_t)slot * kSlotBytes, op.W + (size_t)(k.row0 + r) * op.K + (size_t)ks * Kc, bytes, &c.full[slot]);
+  bulk_g2s(c.ring + (size_t)slot * kSlotBytes, src, bytes, &c.full[slot]);
   __threadfence_block();
   c.gen[slot] = s / (uint32_t)c.nslots + 1u;  // publish: the barrier is now in the phase that carries stage s
 }
@@ -251,7 +267,13 @@ __device__ void stage_x(MegaCtx& c, const MegaOp& op, int ctid) {
   const int K = op.K;
   bf16* xs = reinterpret_cast<bf16*>(c.region_a);
   const uint32_t tag = (op.flags & F_X_EMBED) ? 0u : tag16_of(tag32_of(c.epoch, op.in_op));
-  // norm weights (K <= 4096: at most 4 chunks per thread) are fetched before the wait so they are not a second round trip
+  // bias of this CTA's slab and the norm weights (K <= 4096: at most 4 chunks per thread) are fetched before the wait so
+  // that they do not cost a dependent round trip later
+  if (op.bias != nullptr) {
+    int r0, nr;
+    slab_rows(op.N, op.gran, c.cta, c.grid, r0, nr);
+    if (ctid < nr && ctid < kBiasRows) c.s_bias[ctid] = __bfloat162float(op.bias[r0 + ctid]);
+  }
   uint2 gw[4];
   if (op.norm_w != nullptr) {
     const uint2* wv = reinterpret_cast<const uint2*>(op.norm_w);
@@ -341,7 +363,7 @@ __device__ void stage_x(MegaCtx& c, const MegaOp& op, int ctid) {
 // ------------------------------------------------------------------------------------------------ GEMV consumer
 template <int NB>
 __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t sc_base, int row0, int rows, int cw,
-                             int lane, StageCursor& refill, float& best_v, int& best_i) {
+                             int lane, StageCursor& refill, StageCursor& refill_pf, float& best_v, int& best_i) {
   const MegaPlan& P = *c.P;
   const int R = op.R, ksplit = op.ksplit;
   const int Kc = op.K / ksplit, nv = Kc >> 3, nvK = op.K >> 3;
@@ -421,7 +443,7 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
         }
       }
       __syncwarp();
-      if (lane == 0) issue_stage(c, refill, s + (uint32_t)c.nslots);  // this slot is free again: refill it
+      if (lane == 0) issue_stage(c, refill, refill_pf, s + (uint32_t)c.nslots);  // this slot is free again: refill it
     }
 #pragma unroll
     for (int i = 0; i < kRMax; ++i)
@@ -448,7 +470,7 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
           if (i < rows_here && b < P.B && lane == i * NB + b) {
             const int row = grow + i;
             float val = acc[i][b];
-            if (op.bias) val += __bfloat162float(op.bias[row]);
+            if (op.bias) val += (lrow + i < kBiasRows) ? c.s_bias[lrow + i] : __bfloat162float(op.bias[row]);
             if (op.epi == EPI_RES) {
               // residual stream: bf16, resident in the shared memory of the CTA that owns the row
               bf16* hp = c.s_h + b * kHRows + lrow + i;
@@ -768,6 +790,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   int* s_ctx = reinterpret_cast<int*>(red + 16);                                    // 4 ints
   float* am_v = reinterpret_cast<float*>(s_ctx + 4);                                // [8 warps][16 lanes]
   int* am_i = reinterpret_cast<int*>(am_v + kCWarps * 16);
+  float* s_bias = reinterpret_cast<float*>(am_i + kCWarps * 16);  // kBiasRows floats (meta scratch: 1264 + 512 <= 2048)
   bf16* s_h = reinterpret_cast<bf16*>(meta + 2048);
   int* s_bt = reinterpret_cast<int*>(meta + 2048 + 4 * kHRows * 2);
   uint8_t* region_a = meta + kMetaBytes;
@@ -793,16 +816,23 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
 
   MegaCtx c;
   c.P = plan; c.ops = s_ops; c.full = full; c.gen = gen; c.red = red; c.am_v = am_v; c.am_i = am_i; c.s_ctx = s_ctx;
-  c.s_h = s_h; c.s_bt = s_bt; c.region_a = region_a; c.ring = ring; c.nslots = P.nslots; c.cta = blockIdx.x;
-  c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch;
+  c.s_h = s_h; c.s_bias = s_bias; c.s_bt = s_bt; c.region_a = region_a; c.ring = ring; c.nslots = P.nslots; c.cta = blockIdx.x;
+  c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch; c.pf_stages = P.pf_stages;
 
   // every warp keeps its own cursor into the stage sequence for the refills it issues
   StageCursor refill;
   refill.op_i = 0; refill.base = 0; refill.cnt = 0; refill.row0 = 0; refill.rows = 0;
   cursor_load(c, refill);
-  if (tid == 0) {  // prime the ring: stages 0 .. nslots-1
-    StageCursor k = refill;
-    for (int s = 0; s < P.nslots; ++s) issue_stage(c, k, (uint32_t)s);
+  StageCursor refill_pf = refill;
+  if (tid == 0) {  // prime the ring (stages 0 .. nslots-1) and the L2 prefetch window behind it
+    StageCursor k = refill, kpf = refill;
+    const bf16* src;
+    uint32_t bytes;
+    for (int s = P.nslots; s < P.nslots + P.pf_stages; ++s)
+      if (locate_stage(c, kpf, (uint32_t)s, src, bytes))
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+    StageCursor kpf2 = refill;
+    for (int s = 0; s < P.nslots; ++s) issue_stage(c, k, kpf2, (uint32_t)s);
   }
 
   const int ctid = tid, cw = warp;
@@ -819,7 +849,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
       if (prof && ctid == 0) prof[i * 4 + 1] = global_ns();
       int row0, rows;
       slab_rows(op.N, op.gran, c.cta, c.grid, row0, rows);
-      gemv_consume<NB>(c, op, i, sc_base, row0, rows, cw, lane, refill, best_v, best_i);
+      gemv_consume<NB>(c, op, i, sc_base, row0, rows, cw, lane, refill, refill_pf, best_v, best_i);
       sc_base += (uint32_t)(((rows + op.R - 1) / op.R) * op.ksplit);
       if (op.flags & F_ARGMAX) {
         // CTA-level partial argmax per sequence: lane (i * NB + b) tracked sequence b = lane % NB
@@ -1024,6 +1054,7 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   if (nslots > kMaxSlots) nslots = kMaxSlots;
   if (nslots < 2) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: activations leave no room for the weight ring");
   P->nslots = nslots; P->region_a_bytes = region_a;
+  P->pf_stages = d->l2_prefetch_stages < 0 ? 0 : d->l2_prefetch_stages;
   P->smem_bytes = ops_bytes + kMetaBytes + region_a + nslots * kSlotBytes;
   P->eps = d->eps; P->scale_log2 = d->attn_scale * 1.4426950408889634f;
   P->embed = (const bf16*)d->embed; P->rope_cs = d->rope_cs; P->block_table = d->block_table; P->ctx_lens = d->ctx_lens;

@@ -268,7 +268,7 @@ class DecodeDesc(ctypes.Structure):
     """Mirror of `omc_decode_desc` (include/omchat_b200.h)."""
     _fields_ = ([(n, ctypes.c_int32) for n in ("n_layers", "batch", "hidden", "q_heads", "kv_heads", "inter", "vocab",
                                                  "vocab_offset", "page_size", "max_pages", "grid", "hist_capacity",
-                                                 "rope_positions", "reserved0")]
+                                                 "rope_positions", "l2_prefetch_stages")]
                 + [("eps", c_float), ("attn_scale", c_float)]
                 + [(n, c_void_p) for n in ("embed", "final_norm", "lm_head", "rope_cs", "ln1", "qkv_w", "qkv_b", "o_w",
                                            "ln2", "gate_up_w", "down_w", "kv_pool")]
@@ -309,6 +309,7 @@ class DecodePlan:
         d.vocab_offset, d.page_size, d.max_pages = vocab_offset, page_size, block_table.shape[1]
         d.grid, d.hist_capacity = self.grid, (token_hist.shape[0] if token_hist is not None else 0)
         d.eps, d.attn_scale = eps, scale
+        d.l2_prefetch_stages = int(os.environ.get("OMCHAT_B200_MEGA_PF", "0"))
         d.embed, d.final_norm, d.lm_head, d.rope_cs = embed.data_ptr(), final_norm.data_ptr(), lm_head.data_ptr(), rope_cs.data_ptr()
         assert rope_cs.dtype == torch.float32 and rope_cs.is_contiguous() and rope_cs.shape[1:] == (64, 2)
         d.rope_positions = rope_cs.shape[0]
