@@ -46,6 +46,16 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one decode_mega_kernel launch from the committed ncu --set full
+    capture (profiles/r01_mega_traffic.json); None if the capture is absent."""
+    p = os.path.join(ROOT, "profiles", "r01_mega_traffic.json")
+    try:
+        return json.load(open(p))["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     """Samples SM clock + throttle reasons through NVML every 100 ms while the timed region runs."""
@@ -367,7 +377,7 @@ def main():
         gbs = bytes_per_launch / (us * 1e-6) / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": "decode_mega_kernel<1> (one persistent launch per token)",
                             "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                            "traffic": None, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                            "traffic": load_traffic(), "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                             "launches_per_step": new_tokens - 1, "bytes_per_launch": bytes_per_launch,
                             "avg_launch_us": us, "share_of_step": dec_ms / ms_per_step,
                             "algorithmic_bytes": "bf16 weights of 28 layers + final norm + lm_head (14.14 GB) + KV cache "
