@@ -111,6 +111,16 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def _finish(torch, dist):
+    """End of a multi-rank run: all ranks are done (barrier + device idle), then leave without tearing NCCL down —
+    destroy_process_group() after CUDA-graph-captured collectives was seen to hang at exit on the 2-GPU box."""
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 # --------------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's own CPU fp32 implementation of the path, timed on the host cores (oracle port; see
@@ -412,8 +422,7 @@ def main():
                                     "images_per_sec_vit_prefill": r["images_per_sec_vit_prefill"]}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        _finish(torch, dist)
 
 
 if __name__ == "__main__":

@@ -173,12 +173,34 @@ typedef struct omc_decode_desc {
                       inside the kernel writes {code, CTA, detail, thread} here before trapping; NULL = in workspace */
   void* prof;      /* optional uint64[grid][5*n_layers+2][4] device buffer: per-CTA, per-op %globaltimer stamps (op start,
                       after grid barrier, after activation staging, end) for tools/prof_mega.py; NULL = off */
+  /* Tensor parallelism INSIDE the persistent kernel (tp_size 2..8, one process per GPU; 0/1 = single GPU). The weight
+   * pointers above are this rank's Megatron shards (q/k/v and gate/up column-parallel: q_heads/kv_heads/inter are the LOCAL
+   * counts; o_proj/down_proj row-parallel; lm_head vocab-parallel with vocab = local rows and vocab_offset = first row).
+   * The all-reduce after o_proj and down_proj (the per-layer NCCL all-reduce of a Megatron decoder) is done by the kernel
+   * itself: every CTA pushes the fp32 partial sums of the rows it owns into the peers' exchange buffers with 8-byte
+   * {value, tag} stores over NVLink and polls its own buffer for theirs; greedy sampling exchanges (max, index) the same
+   * way. xchg[p] = rank p's exchange buffer (omc_decode_xchg_bytes bytes, zero-initialised, allocated with
+   * omc_peer_alloc and mapped into this process with omc_peer_open; xchg[tp_rank] = the local one). All ranks must
+   * launch omc_decode_step with the same epoch sequence. */
+  int32_t tp_rank, tp_size;
+  void* xchg[8];
 } omc_decode_desc;
 long long omc_decode_plan_bytes(int n_layers);
 long long omc_decode_workspace_bytes(const omc_decode_desc* desc); /* uses batch, hidden, heads, inter, grid */
 int omc_decode_plan_build(const omc_decode_desc* desc, void* plan_host);
 /* epoch: a counter the caller increments on every launch that uses the same workspace (it tags the in-flight activations) */
 int omc_decode_step(const void* plan_host, const void* plan_dev, unsigned int epoch, void* stream);
+long long omc_decode_xchg_bytes(const omc_decode_desc* desc); /* uses batch, hidden, tp_size */
+
+/* ---- peer (NVLink) memory for the tensor-parallel decode step ------------------------------------------------------
+ * Replaces the NCCL communicator a Megatron-style decoder would hand to its all-reduce: one exchange buffer per rank,
+ * visible to every rank of the node. omc_peer_alloc: cudaMalloc + zero-fill on the current device and export a 64-byte
+ * CUDA IPC handle; omc_peer_open: map another process's buffer (enables peer access); omc_peer_close / omc_peer_free undo
+ * them. The handles travel between the processes through the caller's own channel (torch.distributed here). */
+int omc_peer_alloc(long long bytes, void** ptr, void* handle64);
+int omc_peer_open(const void* handle64, void** ptr);
+int omc_peer_close(void* ptr);
+int omc_peer_free(void* ptr);
 
 #ifdef __cplusplus
 }

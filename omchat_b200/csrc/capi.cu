@@ -26,3 +26,54 @@ extern "C" int omc_num_sms(void) {
   }
   return n;
 }
+
+// ---- peer memory (CUDA IPC) for the tensor-parallel persistent decode kernel
+extern "C" int omc_peer_alloc(long long bytes, void** ptr, void* handle64) {
+  if (bytes <= 0 || ptr == nullptr || handle64 == nullptr) return omc::set_error(OMC_ERR_ARG, "omc_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    if (p) cudaFree(p);
+    cudaGetLastError();
+    return omc::set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return OMC_OK;
+}
+extern "C" int omc_peer_open(const void* handle64, void** ptr) {
+  if (handle64 == nullptr || ptr == nullptr) return omc::set_error(OMC_ERR_ARG, "omc_peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return omc::set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
+  }
+  *ptr = p;
+  return OMC_OK;
+}
+extern "C" int omc_peer_close(void* ptr) {
+  if (ptr == nullptr) return OMC_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return omc::set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
+  }
+  return OMC_OK;
+}
+extern "C" int omc_peer_free(void* ptr) {
+  if (ptr == nullptr) return OMC_OK;
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return omc::set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
+  }
+  return OMC_OK;
+}

@@ -50,7 +50,9 @@ constexpr int kAttnScratchBytes = kCWarps * 8 * kPartStride * 4;
 constexpr int kHRows = 64;          // residual rows one CTA can own
 constexpr int kBiasRows = 128;      // slab rows whose bias is staged in shared memory (larger slabs read it from L2)
 constexpr int kMaxBt = 1024;        // block-table entries cached in shared memory (batch * max_pages)
-constexpr int kMetaBytes = 2048 + 4 * kHRows * 2 + kMaxBt * 4;  // barriers/scratch | residual slab | block table
+constexpr int kMaxTp = 8;           // tensor-parallel ranks one step can span (peer exchange buffers over NVLink)
+constexpr int kXpBytes = kHRows * 4 * 4;  // this CTA's own row-parallel partial sums [kHRows][4 sequences] fp32
+constexpr int kMetaBytes = 2048 + 4 * kHRows * 2 + kMaxBt * 4 + kXpBytes;  // barriers/scratch | residual slab | block table | partials
 constexpr int kSmemLimit = 227 * 1024;
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // a protocol bug must end in a trap, never in a hung GPU
 
@@ -67,7 +69,8 @@ struct MegaOp {  // 112 bytes
   uint32_t* out_ll;      // output vector(s) [B][ldo] in the same format (null for lm_head)
   float* out_f32;        // lm_head: fp32 logits [B][ldo]
   bf16* pool;            // ATTN: this layer's KV pool
-  int32_t ldx, ldo, in_op, parity, pad[2];  // in_op: index of the op whose tag the input carries
+  int32_t ldx, ldo, in_op, parity, xslot, pad;  // in_op: index of the op whose tag the input carries; xslot: 1 + peer
+                                                // exchange slot of a row-parallel op under tensor parallelism (0 = none)
 };
 static_assert(sizeof(MegaOp) == 112, "MegaOp layout");
 
@@ -87,7 +90,9 @@ struct MegaPlan {  // header, followed by n_ops MegaOp
   uint2* amax_part;   // [grid][4][2]      {value bits | index, tag32}
   int32_t* err_flag;
   unsigned long long* prof;  // optional [grid][n_ops][4] globaltimer stamps: op start, inputs staged, op end, -
-  unsigned long long pad2;
+  int32_t tp_rank, tp_size;
+  uint2* xchg[kMaxTp];  // tensor parallelism: rank p's exchange buffer as mapped into THIS process (xchg[tp_rank] = own).
+                        // layout (uint2 {fp32 bits | index, tag32}): partials [4 slots][tp][B][C], then argmax [tp][B][2]
 };
 static_assert(sizeof(MegaPlan) % 16 == 0, "MegaPlan must keep the op array 16-byte aligned");
 
@@ -102,6 +107,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ uint4 ld_poll_v4(const void* p) {
   uint4 r;
   asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+// 8-byte flag-in-data word to / from a peer GPU's memory over NVLink (single-copy atomic: value and tag travel together)
+__device__ __forceinline__ void st_sys_v2(uint2* p, uint2 v) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint2 ld_sys_v2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
   return r;
 }
 // err_flag[0..3] = {code, CTA, detail, thread}; the flag may live in pinned host memory so it survives the trap
@@ -194,6 +208,7 @@ struct MegaCtx {
   bf16* s_h;             // [4][kHRows] residual rows owned by this CTA
   float* s_bias;         // [kBiasRows] bias of this CTA's slab for the current op (fetched while waiting for x)
   int* s_bt;             // block table copy [B][max_pages]
+  float* s_xp;           // [kHRows][4] own partial sums of a row-parallel op (tensor parallelism)
   uint8_t* region_a;     // activation vectors / attention scratch
   uint8_t* ring;
   int nslots, cta, grid, n_ops, pf_stages;
@@ -370,6 +385,11 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
   const int units = (rows + R - 1) / R;
   const uint4* xs = reinterpret_cast<const uint4*>(c.region_a);
   const uint32_t otag = tag16_of(tag32_of(c.epoch, op_idx));
+  // row-parallel op under tensor parallelism (o_proj / down_proj): partial sums are exchanged between the GPUs
+  const bool xon = P.tp_size > 1 && op.xslot > 0 && op.epi == EPI_RES;
+  const uint32_t xtag = tag32_of(c.epoch, op_idx);
+  const long long xslot_base = (long long)(op.xslot - 1) * P.tp_size;              // [slot][src rank][B][C]
+  const long long xoff_w = (xslot_base + P.tp_rank) * (long long)P.B * P.C;         // where peers find OUR partials
 #pragma unroll 1
   for (int u = cw; u < units; u += kCWarps) {
     const int r = u * R;
@@ -471,6 +491,17 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
             const int row = grow + i;
             float val = acc[i][b];
             if (op.bias) val += (lrow + i < kBiasRows) ? c.s_bias[lrow + i] : __bfloat162float(op.bias[row]);
+            if (xon) {
+              // tensor parallelism: this is rank tp_rank's PARTIAL sum over its K shard. Push it into every peer's
+              // exchange buffer over NVLink ({fp32, tag} in one 8-byte store) and keep the own copy; the all-reduce is
+              // finished below, after the warp has consumed all its units (the weight ring keeps streaming meanwhile).
+              const uint2 wv = make_uint2(__float_as_uint(val), xtag);
+              const long long off = xoff_w + (long long)b * P.C + row;
+              for (int p = 0; p < P.tp_size; ++p)
+                if (p != P.tp_rank) st_sys_v2(P.xchg[p] + off, wv);
+              c.s_xp[(lrow + i) * 4 + b] = val;
+              continue;
+            }
             if (op.epi == EPI_RES) {
               // residual stream: bf16, resident in the shared memory of the CTA that owns the row
               bf16* hp = c.s_h + b * kHRows + lrow + i;
@@ -487,6 +518,44 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
               __stcg(op.out_ll + (long long)b * op.ldo + row, ll4_word(val, otag));
             }
           }
+    }
+  }
+  if (xon) {
+    // ---- finish the all-reduce: h[row] += sum over ranks (fixed rank order -> bit-identical replicas on every GPU) of
+    // the partial sums; the peers' values are polled out of OUR exchange buffer (they pushed them), one lane per
+    // (row, sequence). Then the new residual row is broadcast to this GPU's CTAs like in the single-GPU path.
+    __syncwarp();
+    const uint2* xin = P.xchg[P.tp_rank];
+#pragma unroll 1
+    for (int u = cw; u < units; u += kCWarps) {
+      const int r = u * R;
+      const int rows_here = min(R, rows - r);
+      const int i = lane / NB, b = lane - i * NB;
+      if (i < rows_here && b < P.B) {
+        const int row = row0 + r + i;
+        float tot = 0.f;
+        for (int p = 0; p < P.tp_size; ++p) {
+          float v;
+          if (p == P.tp_rank) {
+            v = c.s_xp[(r + i) * 4 + b];
+          } else {
+            const uint2* src = xin + ((xslot_base + p) * (long long)P.B + b) * P.C + row;
+            uint2 w;
+            Watchdog wd;
+            while (true) {
+              w = ld_sys_v2(src);
+              if (w.y == xtag) break;
+              wd.tick(P.err_flag, 11, p);
+            }
+            v = __uint_as_float(w.x);
+          }
+          tot += v;
+        }
+        bf16* hp = c.s_h + b * kHRows + r + i;
+        tot += __bfloat162float(*hp);
+        *hp = __float2bfloat16(tot);
+        __stcg(op.out_ll + (long long)b * op.ldo + row, ll4_word(tot, otag));
+      }
     }
   }
 }
@@ -793,6 +862,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   float* s_bias = reinterpret_cast<float*>(am_i + kCWarps * 16);  // kBiasRows floats (meta scratch: 1264 + 512 <= 2048)
   bf16* s_h = reinterpret_cast<bf16*>(meta + 2048);
   int* s_bt = reinterpret_cast<int*>(meta + 2048 + 4 * kHRows * 2);
+  float* s_xp = reinterpret_cast<float*>(meta + 2048 + 4 * kHRows * 2 + kMaxBt * 4);
   uint8_t* region_a = meta + kMetaBytes;
   uint8_t* ring = region_a + P.region_a_bytes;
 
@@ -816,7 +886,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
 
   MegaCtx c;
   c.P = plan; c.ops = s_ops; c.full = full; c.gen = gen; c.red = red; c.am_v = am_v; c.am_i = am_i; c.s_ctx = s_ctx;
-  c.s_h = s_h; c.s_bias = s_bias; c.s_bt = s_bt; c.region_a = region_a; c.ring = ring; c.nslots = P.nslots; c.cta = blockIdx.x;
+  c.s_h = s_h; c.s_bias = s_bias; c.s_bt = s_bt; c.s_xp = s_xp; c.region_a = region_a; c.ring = ring; c.nslots = P.nslots; c.cta = blockIdx.x;
   c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch; c.pf_stages = P.pf_stages;
 
   // every warp keeps its own cursor into the stage sequence for the refills it issues
@@ -904,6 +974,39 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
           }
+          if (P.tp_size > 1) {
+            // vocab-parallel lm_head: every rank pushes its (max, global index) to all ranks (itself included), then
+            // picks the best of the tp_size candidates — lowest index among equal maxima, like a single argmax would
+            const uint32_t xt = tag32_of(epoch, i);
+            const long long abase = 4LL * P.tp_size * P.B * P.C;
+            if (lane < P.tp_size) {
+              uint2* dst = P.xchg[lane] + abase + ((long long)P.tp_rank * P.B + b) * 2;
+              st_sys_v2(dst, make_uint2(__float_as_uint(bv), xt));
+              st_sys_v2(dst + 1, make_uint2((uint32_t)(bi + P.vocab_offset), xt));
+            }
+            bv = -INFINITY;
+            bi = 0x7fffffff;
+            if (lane < P.tp_size) {
+              const uint2* src = P.xchg[P.tp_rank] + abase + ((long long)lane * P.B + b) * 2;
+              uint2 v0, v1;
+              Watchdog wd;
+              while (true) {
+                v0 = ld_sys_v2(src);
+                v1 = ld_sys_v2(src + 1);
+                if (v0.y == xt && v1.y == xt) break;
+                wd.tick(P.err_flag, 12, lane);
+              }
+              bv = __uint_as_float(v0.x);
+              bi = (int)v1.x;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            bi -= P.vocab_offset;  // the shared tail below adds it back
+          }
           if (lane == 0) {
             const long long tok = (long long)bi + P.vocab_offset;
             P.tokens[b] = tok;
@@ -963,6 +1066,12 @@ extern "C" long long omc_decode_workspace_bytes(const omc_decode_desc* d) {
   return ws_layout(d->grid, d->batch, d->hidden, (d->q_heads + 2 * d->kv_heads) * 128, d->q_heads * 128, d->inter).total;
 }
 
+extern "C" long long omc_decode_xchg_bytes(const omc_decode_desc* d) {
+  if (d == nullptr || d->batch < 1 || d->hidden < 1 || d->tp_size < 1 || d->tp_size > kMaxTp) return -1;
+  // partial sums [4 slots][tp][B][C] + argmax candidates [tp][B][2], 8-byte {value, tag} words
+  return (4LL * d->tp_size * d->batch * d->hidden + 2LL * d->tp_size * d->batch) * 8;
+}
+
 extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) {
   if (d == nullptr || plan_host == nullptr) return set_error(OMC_ERR_ARG, "omc_decode_plan_build: null argument");
   if (d->batch < 1 || d->batch > 4) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: batch must be 1..4");
@@ -981,6 +1090,12 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   if (d->page_size < 1 || d->max_pages < 1 || d->batch * d->max_pages > kMaxBt)
     return set_error(OMC_ERR_ARG, "omc_decode_plan_build: bad paging parameters (batch * max_pages must be <= 1024)");
   if (d->workspace == nullptr) return set_error(OMC_ERR_ARG, "omc_decode_plan_build: workspace is null");
+  const int tp = d->tp_size > 1 ? d->tp_size : 1;
+  if (tp > kMaxTp || (tp > 1 && (d->tp_rank < 0 || d->tp_rank >= tp)))
+    return set_error(OMC_ERR_ARG, "omc_decode_plan_build: tp_size must be <= 8 and 0 <= tp_rank < tp_size");
+  for (int p = 0; p < tp && tp > 1; ++p)
+    if (d->xchg[p] == nullptr)
+      return set_error(OMC_ERR_ARG, "omc_decode_plan_build: xchg[p] (peer exchange buffers, omc_decode_xchg_bytes each) is null");
   if (d->rope_cs == nullptr || d->rope_positions < d->max_pages * d->page_size)
     return set_error(OMC_ERR_ARG, "omc_decode_plan_build: rope_cs must cover max_pages * page_size positions");
   const int C = d->hidden, Hq = d->q_heads, Hkv = d->kv_heads, I = d->inter, B = d->batch;
@@ -1029,9 +1144,11 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
     a.pool = static_cast<bf16*>(d->kv_pool) + (long long)li * d->kv_layer_stride;
     const int i_attn = n++;
     const int i_o = gemv(d->o_w[li], C, aw, ll(w.attn, par, aw), aw, i_attn, nullptr, nullptr, ll(w.h2, par, C), C, EPI_RES, 0);
+    ops[i_o].xslot = 1 + par;  // row-parallel under TP: partial sums cross the GPUs through exchange slot par
     const int i_gu = gemv(d->gate_up_w[li], 2 * I, C, ll(w.h2, par, C), C, i_o, d->ln2[li], nullptr, ll(w.act, par, I), I,
                           EPI_SWIGLU, 0);
     prev = gemv(d->down_w[li], C, I, ll(w.act, par, I), I, i_gu, nullptr, nullptr, ll(w.h1, (li + 1) & 1, C), C, EPI_RES, 0);
+    ops[prev].xslot = 3 + par;
   }
   const int i_head = gemv(d->lm_head, d->vocab, C, d->n_layers == 0 ? nullptr : ll(w.h1, d->n_layers & 1, C), C, prev,
                           d->final_norm, nullptr, nullptr, d->vocab, EPI_NONE,
@@ -1061,6 +1178,9 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   P->tokens = d->tokens; P->token_hist = d->token_hist; P->hist_pos = d->hist_pos;
   P->err_flag = d->status ? d->status : reinterpret_cast<int32_t*>(ws + w.err);
   P->prof = static_cast<unsigned long long*>(d->prof);
+  P->tp_rank = tp > 1 ? d->tp_rank : 0;
+  P->tp_size = tp;
+  for (int p = 0; p < tp && tp > 1; ++p) P->xchg[p] = static_cast<uint2*>(d->xchg[p]);
   P->attn_part = reinterpret_cast<uint2*>(ws + w.part);
   P->amax_part = reinterpret_cast<uint2*>(ws + w.amax);
   return OMC_OK;

@@ -41,6 +41,11 @@ SIGNATURES = {
     "omc_decode_workspace_bytes": (_L, [_P]),
     "omc_decode_plan_build": (_I, [_P, _P]),
     "omc_decode_step": (_I, [_P, _P, ctypes.c_uint, _P]),
+    "omc_decode_xchg_bytes": (_L, [_P]),
+    "omc_peer_alloc": (_I, [_L, ctypes.POINTER(c_void_p), _P]),
+    "omc_peer_open": (_I, [_P, ctypes.POINTER(c_void_p)]),
+    "omc_peer_close": (_I, [_P]),
+    "omc_peer_free": (_I, [_P]),
 }
 
 _lib = None
@@ -274,7 +279,8 @@ class DecodeDesc(ctypes.Structure):
                                            "ln2", "gate_up_w", "down_w", "kv_pool")]
                 + [("kv_layer_stride", c_longlong)]
                 + [(n, c_void_p) for n in ("block_table", "ctx_lens", "tokens", "token_hist", "hist_pos", "h", "qkv",
-                                           "attn", "act", "logits", "workspace", "status", "prof")])
+                                           "attn", "act", "logits", "workspace", "status", "prof")]
+                + [("tp_rank", ctypes.c_int32), ("tp_size", ctypes.c_int32), ("xchg", c_void_p * 8)])
 
 
 def num_sms() -> int:
@@ -284,12 +290,61 @@ def num_sms() -> int:
     return n
 
 
+class PeerExchange:
+    """One exchange buffer per tensor-parallel rank, each mapped into every rank's address space (CUDA IPC over NVLink):
+    the persistent decode kernel's replacement for the NCCL communicator (include/omchat_b200.h, omc_peer_*).
+    `group` is the torch.distributed group whose ranks share the node; the 64-byte handles travel through it."""
+
+    def __init__(self, nbytes: int, rank: int, size: int, group=None):
+        import torch.distributed as dist
+        lib = load()
+        self.rank, self.size, self.nbytes = rank, size, nbytes
+        own = c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        rc = lib.omc_peer_alloc(nbytes, ctypes.byref(own), handle)
+        if rc != 0:
+            raise OmcError(f"omc_peer_alloc failed ({rc}): {lib.omc_last_error().decode(errors='replace')}")
+        self.own = own.value
+        handles = [None] * size
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ptrs = []
+        for p in range(size):
+            if p == rank:
+                self.ptrs.append(self.own)
+                continue
+            ptr = c_void_p()
+            rc = lib.omc_peer_open(handles[p], ctypes.byref(ptr))
+            if rc != 0:
+                raise OmcError(f"omc_peer_open(rank {p}) failed ({rc}): {lib.omc_last_error().decode(errors='replace')}")
+            self.ptrs.append(ptr.value)
+        dist.barrier(group=group)
+
+    def close(self):
+        lib = load()
+        for p, ptr in enumerate(self.ptrs):
+            if p != self.rank and ptr:
+                lib.omc_peer_close(ptr)
+        if self.own:
+            lib.omc_peer_free(self.own)
+        self.ptrs, self.own = [], None
+
+
+def decode_xchg_bytes(batch: int, hidden: int, tp_size: int) -> int:
+    d = DecodeDesc()
+    d.batch, d.hidden, d.tp_size = batch, hidden, tp_size
+    n = load().omc_decode_xchg_bytes(ctypes.byref(d))
+    if n <= 0:
+        raise OmcError("omc_decode_xchg_bytes failed")
+    return n
+
+
 class DecodePlan:
     """Host + device copies of one megakernel plan (omc_decode_plan_build) and the buffers it points at. The plan bakes in
     every pointer (weights, KV pool, block table, state), so it must be rebuilt when any of them is reallocated."""
 
     def __init__(self, *, layers, embed, final_norm, lm_head, rope_cs, cfg_dims, kv_pool, block_table, ctx_lens, tokens,
-                 token_hist, hist_pos, h, qkv, attn, act, logits, page_size, eps, scale, vocab_offset=0, grid=None):
+                 token_hist, hist_pos, h, qkv, attn, act, logits, page_size, eps, scale, vocab_offset=0, grid=None,
+                 tp_rank=0, tp_size=1, xchg_ptrs=None):
         lib = load()
         n_layers = len(layers)
         B = tokens.numel()
@@ -320,6 +375,11 @@ class DecodePlan:
         d.token_hist = token_hist.data_ptr() if token_hist is not None else None
         d.hist_pos = hist_pos.data_ptr() if hist_pos is not None else None
         d.h, d.qkv, d.attn, d.act, d.logits = h.data_ptr(), qkv.data_ptr(), attn.data_ptr(), act.data_ptr(), logits.data_ptr()
+        d.tp_rank, d.tp_size = tp_rank, tp_size
+        if tp_size > 1:
+            assert xchg_ptrs is not None and len(xchg_ptrs) == tp_size
+            for p, ptr in enumerate(xchg_ptrs):
+                d.xchg[p] = ptr
         ws_bytes = lib.omc_decode_workspace_bytes(ctypes.byref(d))
         if ws_bytes <= 0:
             raise OmcError("omc_decode_workspace_bytes failed")
@@ -341,7 +401,11 @@ class DecodePlan:
         self._keep = (layers, embed, final_norm, lm_head, rope_cs, kv_pool, block_table, ctx_lens, tokens, token_hist,
                       hist_pos, h, qkv, attn, act, logits)
 
-    def step(self):
-        rc = load().omc_decode_step(self.host, self.dev.data_ptr(), self.epoch & 0xFFFFFF, _stream())
-        self.epoch += 1
+    def step(self, epoch: Optional[int] = None):
+        """One decode step. `epoch` tags the in-flight activations: by default a per-plan counter; under tensor parallelism
+        the caller passes a counter shared by every plan that uses the same peer exchange buffers."""
+        if epoch is None:
+            epoch = self.epoch
+            self.epoch += 1
+        rc = load().omc_decode_step(self.host, self.dev.data_ptr(), epoch & 0xFFFFFF, _stream())
         _check(rc, "omc_decode_step")

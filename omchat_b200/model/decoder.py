@@ -114,6 +114,10 @@ class Qwen2Decoder:
         self.scale = cfg.head_dim ** -0.5
         self.eps = cfg.rms_norm_eps
         self.mega_enabled = os.environ.get("OMCHAT_B200_NO_MEGA", "0") != "1"
+        # tp > 1: all-reduce inside the persistent kernel over NVLink peer memory (0 = per-op kernels + NCCL all-reduce)
+        self.tp_mega_enabled = os.environ.get("OMCHAT_B200_TP_MEGA", "1") != "0"
+        self._xchg = {}  # batch -> lib.PeerExchange (tensor-parallel persistent decode kernel)
+        self._mega_epoch = 1  # shared by every plan that uses the peer exchange buffers: identical on all ranks
         self._dec = {}  # decode state per batch size
         self._caches = {}  # reusable caches for generate(), keyed by (n_seq, capacity)
 
@@ -253,8 +257,17 @@ class Qwen2Decoder:
 
     def use_mega(self, B: int) -> bool:
         """Small-batch decode runs as ONE persistent cooperative kernel per token (csrc/decode_mega.cu)."""
-        return (self.mega_enabled and self.tp.size == 1 and B <= MEGA_MAX_B and self.C <= 4096
-                and len(self.w.layers) * 5 + 2 <= 192)
+        return (self.mega_enabled and B <= MEGA_MAX_B and self.C <= 4096 and len(self.w.layers) * 5 + 2 <= 192
+                and (self.tp.size == 1 or (self.tp.size <= 8 and self.tp_mega_enabled)))
+
+    def _peer_exchange(self, B: int):
+        """The per-rank exchange buffers of the tensor-parallel decode kernel (collective: every rank must call this at
+        the same point — it does, the first decode step of a batch size)."""
+        px = self._xchg.get(B)
+        if px is None:
+            px = lib.PeerExchange(lib.decode_xchg_bytes(B, self.C, self.tp.size), self.tp.rank, self.tp.size, self.tp.group)
+            self._xchg[B] = px
+        return px
 
     def _rope_table(self, positions: int) -> torch.Tensor:
         """(cos, sin)(pos * inv_freq) in fp32 for pos < positions, [positions, 64, 2] — Qwen2RotaryEmbedding.forward
@@ -267,7 +280,9 @@ class Qwen2Decoder:
             self._rope_cs = t
         return t
 
-    def _mega_plan(self, st, cache: PagedKVCache):
+    def _mega_plan(self, st, cache: PagedKVCache, xchg_ptrs=None, grid=None):
+        """xchg_ptrs / grid: overrides for tests that emulate several ranks inside one process (default: the peer
+        exchange buffers of the process group, one CTA per SM)."""
         ent = st.plans.get(id(cache))
         if ent is not None and ent[1] is cache:
             return ent[0]
@@ -278,9 +293,18 @@ class Qwen2Decoder:
             rope_cs=self._rope_table(cache.capacity), cfg_dims=(self.C, self.Hq, self.Hkv, self.I_local, self.V_local),
             kv_pool=cache.pool, block_table=cache.block_table, ctx_lens=cache.ctx_lens, tokens=st.tokens,
             token_hist=st.hist, hist_pos=st.hist_pos, h=st.h, qkv=st.qkv, attn=st.attn, act=st.act, logits=st.logits,
-            page_size=cache.page_size, eps=self.eps, scale=self.scale)
+            page_size=cache.page_size, eps=self.eps, scale=self.scale,
+            vocab_offset=self.tp.rank * self.V_local if self.tp.size > 1 else 0, tp_rank=self.tp.rank, tp_size=self.tp.size,
+            xchg_ptrs=(xchg_ptrs or self._peer_exchange(st.B).ptrs) if self.tp.size > 1 else None, grid=grid)
         st.plans[id(cache)] = (plan, cache)
         return plan
+
+    def _mega_step(self, plan):
+        if self.tp.size == 1:
+            plan.step()
+        else:
+            plan.step(self._mega_epoch)
+            self._mega_epoch += 1
 
     def _decode_body(self, st, cache: PagedKVCache, sample: bool = True):
         """One decode step for st.tokens (the tokens generated last step): embeds them, runs the 28 layers against the
@@ -289,7 +313,7 @@ class Qwen2Decoder:
         B = st.B
         if self.use_mega(B):
             # embed + all layers + lm_head + argmax + ctx_lens += 1 in one launch (always samples into st.tokens)
-            self._mega_plan(st, cache).step()
+            self._mega_step(self._mega_plan(st, cache))
             return
         cache.ctx_lens.add_(1)  # context length INCLUDING the token being processed
         lib.embed_lookup(st.tokens, self.w.embed, out=st.h)
@@ -363,7 +387,7 @@ class Qwen2Decoder:
                 n = min(MEGA_HIST, steps - done)
                 st.hist_pos.zero_()
                 for i in range(n):
-                    plan.step()
+                    self._mega_step(plan)
                     if on_token is not None:
                         on_token(done + i, st.tokens)
                 out[done:done + n].copy_(st.hist[:n])

@@ -133,3 +133,18 @@ def test_mega_vs_oracle_tiny():
         if int(got.argmax()) != nxt:
             assert float(top2[0] - top2[1]) < 0.05 * float(want.abs().max())
         tok = nxt
+
+
+@pytest.mark.parametrize("tp,lens", [(2, "130,77"), (4, "200"), (2, "64,300,129,5")])
+def test_mega_tensor_parallel_emulated_on_one_gpu(tp, lens):
+    """The in-kernel all-reduce / argmax exchange of the tensor-parallel decode step, with the ranks emulated as
+    co-resident cooperative kernels on one GPU (tests/tp_mega_emulation.py; a subprocess so a trap stays contained)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import os
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tp_mega_emulation.py")
+    r = subprocess.run([sys.executable, script, str(tp), lens], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert f"tp{tp} emulation ok" in r.stdout

@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Multi-GPU check of the tensor-parallel persistent decode kernel (run under torchrun, one rank per GPU):
+
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/tp_mega_check.py [--layers 28] [--batch 1]
+
+Runs the same greedy generation twice on the same sharded weights — (a) per-op kernels + NCCL all-reduce in a CUDA graph,
+(b) ONE persistent kernel per token with the all-reduce done over NVLink peer memory inside the kernel — and checks that
+both give the same tokens (ties within bf16 noise excepted, reported) and that every rank agrees; prints ms/token of each.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, default=28)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--ctx", type=int, default=1088)
+    ap.add_argument("--steps", type=int, default=64)
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from omchat_b200 import lib
+    from omchat_b200.config import OmChatQwen2Config
+    from omchat_b200.model.decoder import Qwen2Decoder, TPInfo
+    from omchat_b200.model.weights import random_init
+    lib.load()
+    dev = torch.device("cuda", local)
+    cfg = OmChatQwen2Config(num_hidden_layers=a.layers, eos_token_id=-1)
+    w = random_init(cfg, device=dev, seed=0, vision=False, tp_rank=rank, tp_size=world)
+    dec = Qwen2Decoder(cfg, w.llm, TPInfo(rank=rank, size=world, group=dist.group.WORLD))
+    B, T = a.batch, a.ctx
+    g = torch.Generator(device=dev).manual_seed(1)
+    emb = (torch.randn(B * T, cfg.hidden_size, generator=g, device=dev) * 0.02).to(torch.bfloat16)
+    pos = torch.arange(T, dtype=torch.int32, device=dev).repeat(B)
+    seq = torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(T)
+    offs = [i * T for i in range(B + 1)]
+
+    def run(mega: bool):
+        dec.tp_mega_enabled = mega
+        cache = dec.new_cache(B, T + a.steps + 8)
+        logits = dec.prefill(emb.clone(), pos, seq, offs, cache, logits="last")
+        st = dec._decode_state(B, cache.capacity)
+        st.logits.copy_(logits)
+        dec._greedy(st)
+        first = st.tokens.clone()
+        dec.generate_greedy(first, cache, 4)  # warm-up (graph capture / plan build / peer buffers)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        toks = dec.generate_greedy(st.tokens.clone(), cache, a.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        return first, toks, e0.elapsed_time(e1) / a.steps
+
+    f0, t0, ms0 = run(False)
+    f1, t1, ms1 = run(True)
+    assert dec.use_mega(B), "the persistent kernel was not selected"
+    same = bool(torch.equal(t0, t1)) and bool(torch.equal(f0, f1))
+    first_diff = -1
+    if not same:
+        nz = (t0 != t1).any(dim=0).nonzero()
+        first_diff = int(nz[0]) if nz.numel() else -1
+    # every rank must hold the same tokens
+    gathered = [torch.empty_like(t1) for _ in range(world)]
+    dist.all_gather(gathered, t1.contiguous())
+    agree = all(torch.equal(gathered[0], x) for x in gathered)
+    t = torch.tensor([ms0, ms1], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"tp": world, "batch": B, "layers": a.layers, "ctx": T, "steps": a.steps,
+                          "ms_per_token_nccl_graph": t[0].item(), "ms_per_token_tp_megakernel": t[1].item(),
+                          "tokens_identical": same, "first_diff_step": first_diff, "ranks_agree": agree,
+                          "tokens_head": t1[0, :8].tolist()}), flush=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ok = agree and (same or first_diff > 8)
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
