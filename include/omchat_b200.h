@@ -81,10 +81,14 @@ int omc_select_pixel_shuffle(const void* hidden, void* out, int B, int G, int C,
  * q rows [total, Hq, 128] with row stride ldq (elements), k/v rows [total, Hkv, 128] with strides ldk/ldv, out row
  * stride ldo. Sequence s covers rows cu_seqlens[s]..cu_seqlens[s+1] (int32, device). causal=0: ViT attention
  * (modeling_intern_vit.py:148-152 / flash_attention.py:43-55); causal=1 with Hq = 7*Hkv: Qwen2 GQA prefill
- * (modeling_qwen2.py:161-184,229-243). */
+ * (modeling_qwen2.py:161-184,229-243). total_rows = rows of the packed q/k/v/out buffers (= cu_seqlens[num_seqs]; the
+ * bound of the TMA tensor maps). Every full 128-row query tile runs on the tcgen05/TMEM kernel (S and O accumulators and
+ * the P operand in tensor memory, K/V tiles by TMA); the ragged tail rows run on the mma.sync kernel.
+ * omc_attention_set_impl(1) forces the mma.sync kernel for everything (A/B comparison; env OMCHAT_B200_ATTN_LEGACY=1). */
 int omc_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
-                      void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen, int Hq,
-                      int Hkv, int causal, float scale, void* stream);
+                      void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
+                      long long total_rows, int Hq, int Hkv, int causal, float scale, void* stream);
+int omc_attention_set_impl(int impl);
 
 /* ---- Qwen2 decoder glue ----------------------------------------------------------------------------------------
  * RoPE (rotate-half, pairs (i, i+64), theta, fp32 angles: modeling_qwen2.py:102-113,124-146) applied in place to the

@@ -10,6 +10,7 @@
 // transformers models/qwen2/modeling_qwen2.py:124-146,161-184,227-243.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <math.h>
 #include <stdint.h>
 
@@ -73,6 +74,7 @@ struct AttnParams {
   const int32_t* cu;
   int Hq, Hkv, causal;
   float scale_log2;
+  int tail_mode;  // 1: only the ragged tail (rows >= 128 * (len / 128)) — the full tiles run on the tcgen05 kernel
 };
 
 // cooperative cp.async of `rows` rows (256 B each) from global (row stride ld elements) into a swizzled tile;
@@ -96,7 +98,8 @@ __global__ void __launch_bounds__(kAttThreads) attention_fwd_kernel(const AttnPa
   const int seq = blockIdx.z, head = blockIdx.y;
   const int row0 = p.cu[seq], len = p.cu[seq + 1] - row0;
   // heavy (late) causal tiles first
-  const int mt = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int mt = p.tail_mode ? (len / 128) * (128 / kAttM) + (int)blockIdx.x
+                             : (p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x);
   const int m0 = mt * kAttM;
   if (m0 >= len) return;
   const int kvh = head / (p.Hq / p.Hkv);
@@ -477,9 +480,22 @@ __global__ void __launch_bounds__(kDecThreads) paged_decode_attn_kernel(const De
 
 using namespace omc;
 
+namespace omc {
+int launch_fa_sm100(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
+                    long long ldo, const int32_t* cu, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv,
+                    int causal, float scale_log2, cudaStream_t stream);
+}
+
+static int g_attn_impl = -1;  // 0 = tcgen05 kernel for full tiles + mma.sync tail, 1 = mma.sync kernel for everything
+extern "C" int omc_attention_set_impl(int impl) {
+  if (impl != 0 && impl != 1) return set_error(OMC_ERR_ARG, "omc_attention_set_impl: 0 (tcgen05) or 1 (mma.sync)");
+  g_attn_impl = impl;
+  return OMC_OK;
+}
+
 extern "C" int omc_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                                  void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
-                                 int Hq, int Hkv, int causal, float scale, void* stream) {
+                                 long long total_rows, int Hq, int Hkv, int causal, float scale, void* stream) {
   if (num_seqs <= 0 || max_seqlen <= 0) return OMC_OK;
   if (Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0) return set_error(OMC_ERR_SHAPE, "omc_attention_fwd: Hq must be a multiple of Hkv");
   if ((ldq | ldk | ldv | ldo) % 8 != 0) return set_error(OMC_ERR_ALIGN, "omc_attention_fwd: row strides must be multiples of 8");
@@ -494,6 +510,22 @@ extern "C" int omc_attention_fwd(const void* q, long long ldq, const void* k, lo
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
   p.cu = cu_seqlens; p.Hq = Hq; p.Hkv = Hkv; p.causal = causal;
   p.scale_log2 = scale * kLog2e;
+  p.tail_mode = 0;
+  if (g_attn_impl < 0) {
+    const char* e = getenv("OMCHAT_B200_ATTN_LEGACY");
+    g_attn_impl = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  if (g_attn_impl == 0 && max_seqlen >= 128 && total_rows > 0) {
+    // full 128-row query tiles: tcgen05 / TMEM kernel (attention_sm100.cu); ragged tails: this file's kernel
+    int rc = launch_fa_sm100(q, ldq, k, ldk, v, ldv, out, ldo, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
+                             causal, p.scale_log2, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (num_seqs == 1 && max_seqlen % 128 == 0) return OMC_OK;  // a single sequence of whole tiles has no tail
+    p.tail_mode = 1;
+    dim3 tgrid(128 / kAttM, Hq, num_seqs);
+    attention_fwd_kernel<<<tgrid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(p);
+    return check_launch("attention_fwd(tail)");
+  }
   dim3 grid((max_seqlen + kAttM - 1) / kAttM, Hq, num_seqs);
   attention_fwd_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(p);
   return check_launch("attention_fwd");

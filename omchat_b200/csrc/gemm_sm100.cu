@@ -313,7 +313,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] (leading dim ld elements), box = [box_rows, 64 cols], 128-byte swizzle.
-static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(OMC_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15))

@@ -29,7 +29,8 @@ SIGNATURES = {
     "omc_vit_im2col": (_I, [_P, _I, _P, _L, _I, _I, _I, _P]),
     "omc_vit_assemble": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "omc_select_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _P]),
-    "omc_attention_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "omc_attention_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _L, _I, _I, _I, _F, _P]),
+    "omc_attention_set_impl": (_I, [_I]),
     "omc_rope_kv_store": (_I, [_P, _L, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
     "omc_decode_attn_splits": (_I, [_I, _I, _I]),
     "omc_decode_attn_workspace_bytes": (_L, [_I, _I, _I, _I]),
@@ -82,7 +83,7 @@ def load() -> ctypes.CDLL:
     return lib
 
 
-_KERNELS_PER_CALL = {"omc_splice": 2, "omc_argmax": 2}
+_KERNELS_PER_CALL = {"omc_splice": 2, "omc_argmax": 2, "omc_attention_fwd": 2}
 
 
 def _check(rc: int, what: str):
@@ -188,10 +189,18 @@ def attention(q, k, v, out, cu_seqlens: torch.Tensor, max_seqlen: int, Hq: int, 
     _need_cuda(q, k, v, out, cu_seqlens)
     assert cu_seqlens.dtype == torch.int32
     rc = load().omc_attention_fwd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
-                                  out.stride(0), _ptr(cu_seqlens), cu_seqlens.numel() - 1, max_seqlen, Hq, Hkv,
+                                  out.stride(0), _ptr(cu_seqlens), cu_seqlens.numel() - 1, max_seqlen,
+                                  min(q.shape[0], k.shape[0], v.shape[0], out.shape[0]), Hq, Hkv,
                                   1 if causal else 0, scale, _stream())
     _check(rc, "omc_attention_fwd")
     return out
+
+
+def attention_set_impl(legacy: bool):
+    """True: mma.sync kernel for everything; False (default): tcgen05 kernel for full tiles + mma.sync tail."""
+    rc = load().omc_attention_set_impl(1 if legacy else 0)
+    if rc != 0:
+        raise OmcError("omc_attention_set_impl failed")
 
 
 def rope_kv_store(qkv, pos, seq_ids, Hq, Hkv, inv_freq, kv_pool, block_table, page_size):

@@ -229,9 +229,14 @@ def _ref_attention(q, k, v, causal, scale):
     return torch.einsum("hst,thd->shd", w.softmax(-1), v)
 
 
+@pytest.mark.parametrize("legacy", [False, True])
 @pytest.mark.parametrize("causal,Hq,Hkv,lens", [(False, 2, 2, [257, 257]), (False, 5, 5, [1025]), (True, 14, 2, [300, 1, 64, 129]),
-                                                (True, 7, 1, [1088])])
-def test_attention_fwd(L, causal, Hq, Hkv, lens):
+                                                (True, 7, 1, [1088]), (False, 1, 1, [128]), (True, 2, 1, [256, 128]),
+                                                (False, 3, 3, [144, 16, 640]), (True, 4, 2, [513, 127, 384])])
+def test_attention_fwd(L, causal, Hq, Hkv, lens, legacy):
+    """legacy=False: tcgen05/TMEM kernel on every full 128-row query tile + mma.sync kernel on the ragged tails (the
+    product path); legacy=True: mma.sync kernel on everything. Same fp32 reference, same tolerance."""
+    L.attention_set_impl(legacy)
     g = torch.Generator().manual_seed(sum(lens))
     total = sum(lens)
     q = bf(torch.randn(total, Hq, 128, generator=g))
@@ -249,6 +254,7 @@ def test_attention_fwd(L, causal, Hq, Hkv, lens):
         want = _ref_attention(q[o:o + n].float(), k[o:o + n].float(), v[o:o + n].float(), causal, scale)
         assert_close(out[o:o + n].view(n * Hq, 128), want.reshape(n * Hq, 128), rel=2 ** -6, what=f"attention len {n}")
         o += n
+    L.attention_set_impl(False)
 
 
 def _make_paged(B, Hkv, ctx_max, page, g):

@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""tcgen05 attention kernel vs the mma.sync kernel vs an fp32 torch reference; prints errors per query tile and timings.
+  python tools/attn_check.py [quick]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from omchat_b200 import lib  # noqa: E402
+
+
+def ref(q, k, v, causal, scale):
+    S, Hq, D = q.shape
+    Hkv = k.shape[1]
+    k = k.repeat_interleave(Hq // Hkv, dim=1)
+    v = v.repeat_interleave(Hq // Hkv, dim=1)
+    w = torch.einsum("shd,thd->hst", q, k) * scale
+    if causal:
+        w = w.masked_fill(torch.triu(torch.ones(S, S, dtype=torch.bool, device=q.device), 1), float("-inf"))
+    return torch.einsum("hst,thd->shd", w.softmax(-1), v)
+
+
+def run(lens, Hq, Hkv, causal, legacy, reps=0):
+    g = torch.Generator(device="cuda").manual_seed(sum(lens))
+    total = sum(lens)
+    W = (Hq + 2 * Hkv) * 128
+    qkv = torch.randn(total, W, generator=g, device="cuda").to(torch.bfloat16)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    out = torch.zeros(total, Hq * 128, device="cuda", dtype=torch.bfloat16)
+    scale = 128 ** -0.5
+    lib.attention_set_impl(legacy)
+    a = (qkv[:, :Hq * 128], qkv[:, Hq * 128:(Hq + Hkv) * 128], qkv[:, (Hq + Hkv) * 128:], out, cu, max(lens), Hq, Hkv, causal, scale)
+    lib.attention(*a)
+    torch.cuda.synchronize()
+    ms = None
+    if reps:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            lib.attention(*a)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+    return qkv, out, ms
+
+
+def check(lens, Hq, Hkv, causal):
+    qkv, out, _ = run(lens, Hq, Hkv, causal, legacy=False)
+    o = 0
+    worst = 0.0
+    for n in lens:
+        q = qkv[o:o + n, :Hq * 128].float().view(n, Hq, 128)
+        k = qkv[o:o + n, Hq * 128:(Hq + Hkv) * 128].float().view(n, Hkv, 128)
+        v = qkv[o:o + n, (Hq + Hkv) * 128:].float().view(n, Hkv, 128)
+        want = ref(q, k, v, causal, 128 ** -0.5)
+        got = out[o:o + n].float().view(n, Hq, 128)
+        err = (got - want).abs().amax(dim=(1, 2)) / want.abs().max()
+        tiles = [f"{err[i:i + 128].max().item():.4f}" for i in range(0, n, 128)]
+        worst = max(worst, err.max().item())
+        print(f"  len {n} causal {causal} Hq {Hq} Hkv {Hkv}: rel err per 128-row tile {tiles} nan {bool(torch.isnan(got).any())}")
+        o += n
+    return worst
+
+
+if __name__ == "__main__":
+    lib.load()
+    cases = [([128], 1, 1, False), ([256], 2, 1, False), ([144], 1, 1, False), ([1025], 2, 2, False), ([128], 1, 1, True),
+             ([384], 2, 1, True), ([1088], 7, 1, True), ([300, 1, 64, 129, 513], 4, 2, True), ([257, 640], 2, 2, False)]
+    worst = 0.0
+    for c in cases:
+        worst = max(worst, check(*c))
+    print("worst rel err", worst)
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        sys.exit(0 if worst < 0.02 else 1)
+    for name, lens, Hq, Hkv, causal in [("vit 8 crops", [1025] * 8, 25, 25, False), ("vit 64 crops", [1025] * 64, 25, 25, False),
+                                        ("prefill 1088", [1088], 28, 4, True), ("prefill 32x1024", [1024] * 32, 28, 4, True)]:
+        fl = sum(4.0 * n * n * 128 * Hq * (0.5 if causal else 1.0) for n in lens)
+        for legacy in (True, False):
+            _, _, ms = run(lens, Hq, Hkv, causal, legacy, reps=10)
+            print(f"{name:18s} {'mma.sync' if legacy else 'tcgen05 '} {ms * 1000:9.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s")
+    sys.exit(0 if worst < 0.02 else 1)
