@@ -376,7 +376,7 @@ __device__ void stage_x(MegaCtx& c, const MegaOp& op, int ctid) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMV consumer
-template <int NB>
+template <int NB, bool TP>
 __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t sc_base, int row0, int rows, int cw,
                              int lane, StageCursor& refill, StageCursor& refill_pf, float& best_v, int& best_i) {
   const MegaPlan& P = *c.P;
@@ -386,10 +386,11 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
   const uint4* xs = reinterpret_cast<const uint4*>(c.region_a);
   const uint32_t otag = tag16_of(tag32_of(c.epoch, op_idx));
   // row-parallel op under tensor parallelism (o_proj / down_proj): partial sums are exchanged between the GPUs
-  const bool xon = P.tp_size > 1 && op.xslot > 0 && op.epi == EPI_RES;
-  const uint32_t xtag = tag32_of(c.epoch, op_idx);
-  const long long xslot_base = (long long)(op.xslot - 1) * P.tp_size;              // [slot][src rank][B][C]
-  const long long xoff_w = (xslot_base + P.tp_rank) * (long long)P.B * P.C;         // where peers find OUR partials
+  // (compiled out of the single-GPU instantiation: the weight-streaming loop below is register-bound)
+  const bool xon = TP && op.xslot > 0 && op.epi == EPI_RES;
+  const uint32_t xtag = TP ? tag32_of(c.epoch, op_idx) : 0u;
+  const long long xslot_base = TP ? (long long)(op.xslot - 1) * P.tp_size : 0;                 // [slot][src rank][B][C]
+  const long long xoff_w = TP ? (xslot_base + P.tp_rank) * (long long)P.B * P.C : 0;            // where peers find OUR partials
 #pragma unroll 1
   for (int u = cw; u < units; u += kCWarps) {
     const int r = u * R;
@@ -491,7 +492,7 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
             const int row = grow + i;
             float val = acc[i][b];
             if (op.bias) val += (lrow + i < kBiasRows) ? c.s_bias[lrow + i] : __bfloat162float(op.bias[row]);
-            if (xon) {
+            if (TP && xon) {
               // tensor parallelism: this is rank tp_rank's PARTIAL sum over its K shard. Push it into every peer's
               // exchange buffer over NVLink ({fp32, tag} in one 8-byte store) and keep the own copy; the all-reduce is
               // finished below, after the warp has consumed all its units (the weight ring keeps streaming meanwhile).
@@ -520,7 +521,7 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
           }
     }
   }
-  if (xon) {
+  if (TP && xon) {
     // ---- finish the all-reduce: h[row] += sum over ranks (fixed rank order -> bit-identical replicas on every GPU) of
     // the partial sums; the peers' values are polled out of OUR exchange buffer (they pushed them), one lane per
     // (row, sequence). Then the new residual row is broadcast to this GPU's CTAs like in the single-GPU path.
@@ -844,7 +845,7 @@ __device__ __noinline__ void attn_phase(MegaCtx& c, const MegaOp& op, int op_idx
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int NB, int G>
+template <int NB, int G, bool TP>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const MegaPlan* __restrict__ plan, uint32_t epoch) {
   extern __shared__ __align__(128) uint8_t mega_smem[];
   const MegaPlan& P = *plan;
@@ -919,7 +920,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
       if (prof && ctid == 0) prof[i * 4 + 1] = global_ns();
       int row0, rows;
       slab_rows(op.N, op.gran, c.cta, c.grid, row0, rows);
-      gemv_consume<NB>(c, op, i, sc_base, row0, rows, cw, lane, refill, refill_pf, best_v, best_i);
+      gemv_consume<NB, TP>(c, op, i, sc_base, row0, rows, cw, lane, refill, refill_pf, best_v, best_i);
       sc_base += (uint32_t)(((rows + op.R - 1) / op.R) * op.ksplit);
       if (op.flags & F_ARGMAX) {
         // CTA-level partial argmax per sequence: lane (i * NB + b) tracked sequence b = lane % NB
@@ -974,7 +975,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
           }
-          if (P.tp_size > 1) {
+          if (TP) {
             // vocab-parallel lm_head: every rank pushes its (max, global index) to all ranks (itself included), then
             // picks the best of the tp_size candidates — lowest index among equal maxima, like a single argmax would
             const uint32_t xt = tag32_of(epoch, i);
@@ -1186,11 +1187,11 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   return OMC_OK;
 }
 
-template <int NB, int G>
+template <int NB, int G, bool TP>
 static int launch_mega(const MegaPlan* host, const void* plan_dev, uint32_t epoch, cudaStream_t st) {
   static int attr_smem = 0;
   if (host->smem_bytes > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<NB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, host->smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<NB, G, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, host->smem_bytes);
     if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
     attr_smem = host->smem_bytes;
   }
@@ -1205,7 +1206,7 @@ static int launch_mega(const MegaPlan* host, const void* plan_dev, uint32_t epoc
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
   const MegaPlan* arg = static_cast<const MegaPlan*>(plan_dev);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_mega_kernel<NB, G>, arg, epoch);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_mega_kernel<NB, G, TP>, arg, epoch);
   if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
   return OMC_OK;
 }
@@ -1215,10 +1216,15 @@ extern "C" int omc_decode_step(const void* plan_host, const void* plan_dev, unsi
   const MegaPlan* P = static_cast<const MegaPlan*>(plan_host);
   if (P->n_ops < 2 || P->n_ops > kMaxOps || P->grid < 1) return set_error(OMC_ERR_ARG, "omc_decode_step: plan not built");
   cudaStream_t st = (cudaStream_t)stream;
-#define OMC_MEGA_CASE(NB_, G_) \
-  if (P->B == NB_ && P->G == G_) return launch_mega<NB_, G_>(P, plan_dev, epoch, st);
-#define OMC_MEGA_G(G_) OMC_MEGA_CASE(1, G_) OMC_MEGA_CASE(2, G_) OMC_MEGA_CASE(3, G_) OMC_MEGA_CASE(4, G_)
-  OMC_MEGA_G(1) OMC_MEGA_G(2) OMC_MEGA_G(4) OMC_MEGA_G(6) OMC_MEGA_G(7) OMC_MEGA_G(8)
+#define OMC_MEGA_CASE(NB_, G_, TP_) \
+  if (P->B == NB_ && P->G == G_) return launch_mega<NB_, G_, TP_>(P, plan_dev, epoch, st);
+#define OMC_MEGA_G(G_, TP_) OMC_MEGA_CASE(1, G_, TP_) OMC_MEGA_CASE(2, G_, TP_) OMC_MEGA_CASE(3, G_, TP_) OMC_MEGA_CASE(4, G_, TP_)
+  if (P->tp_size > 1) {
+    // tensor-parallel instantiations (in-kernel NVLink all-reduce): Qwen2-7B at TP 2/4 (G = 7) and TP 8 (G = 4), G = 2 tests
+    OMC_MEGA_G(2, true) OMC_MEGA_G(4, true) OMC_MEGA_G(7, true)
+    return set_error(OMC_ERR_SHAPE, "omc_decode_step: tensor parallelism needs batch 1..4 and 2, 4 or 7 q heads per kv head");
+  }
+  OMC_MEGA_G(1, false) OMC_MEGA_G(2, false) OMC_MEGA_G(4, false) OMC_MEGA_G(6, false) OMC_MEGA_G(7, false) OMC_MEGA_G(8, false)
 #undef OMC_MEGA_G
 #undef OMC_MEGA_CASE
   return set_error(OMC_ERR_SHAPE, "omc_decode_step: batch must be 1..4 and q heads per kv head one of 1, 2, 4, 6, 7, 8");

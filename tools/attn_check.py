@@ -65,6 +65,11 @@ def check(lens, Hq, Hkv, causal):
 
 if __name__ == "__main__":
     lib.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "prof":  # a few launches of the ViT shape for ncu
+        crops = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+        run([1025] * crops, 25, 25, False, legacy=False, reps=3)
+        run([1024] * 8, 28, 4, True, legacy=False, reps=2)
+        sys.exit(0)
     cases = [([128], 1, 1, False), ([256], 2, 1, False), ([144], 1, 1, False), ([1025], 2, 2, False), ([128], 1, 1, True),
              ([384], 2, 1, True), ([1088], 7, 1, True), ([300, 1, 64, 129, 513], 4, 2, True), ([257, 640], 2, 2, False)]
     worst = 0.0
