@@ -515,17 +515,9 @@ extern "C" int omc_attention_fwd(const void* q, long long ldq, const void* k, lo
     const char* e = getenv("OMCHAT_B200_ATTN_LEGACY");
     g_attn_impl = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  if (g_attn_impl == 0 && max_seqlen >= 128 && total_rows > 0) {
-    // full 128-row query tiles: tcgen05 / TMEM kernel (attention_sm100.cu); ragged tails: this file's kernel
-    int rc = launch_fa_sm100(q, ldq, k, ldk, v, ldv, out, ldo, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
-                             causal, p.scale_log2, (cudaStream_t)stream);
-    if (rc) return rc;
-    if (num_seqs == 1 && max_seqlen % 128 == 0) return OMC_OK;  // a single sequence of whole tiles has no tail
-    p.tail_mode = 1;
-    dim3 tgrid(128 / kAttM, Hq, num_seqs);
-    attention_fwd_kernel<<<tgrid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(p);
-    return check_launch("attention_fwd(tail)");
-  }
+  if (g_attn_impl == 0 && total_rows > 0)  // tcgen05 / TMEM kernel (attention_sm100.cu)
+    return launch_fa_sm100(q, ldq, k, ldk, v, ldv, out, ldo, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
+                           causal, p.scale_log2, (cudaStream_t)stream);
   dim3 grid((max_seqlen + kAttM - 1) / kAttM, Hq, num_seqs);
   attention_fwd_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(p);
   return check_launch("attention_fwd");

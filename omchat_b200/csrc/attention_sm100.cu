@@ -3,7 +3,9 @@
 // Serves the same call sites as the mma.sync kernel of attention.cu (InternAttention._flash_attn
 // intern_vit_6b/modeling_intern_vit.py:157-172 — non-causal, 1025 tokens, 25 heads — and the causal GQA attention of the
 // Qwen2 prefill, transformers modeling_qwen2.py:161-184,206-246) for every FULL 128-row query tile of a packed var-len
-// batch; the ragged tail (len % 128 rows) stays on the mma.sync kernel (attention.cu, tail mode).
+// batch. A ragged last query tile is computed like a full one (its extra rows read whatever rows follow in the packed
+// buffer, or TMA zero fill) and only the rows inside the sequence are stored; attention.cu keeps the mma.sync kernel as the
+// A/B baseline.
 //
 // One CTA = one (sequence, head, 256-query block) = two 128-row query tiles that ping-pong on the tensor pipe:
 //   warp 0        TMA producer: Q tiles once, then K_j / V_j tiles (128 keys x 128 dims, two 64-column 128B-swizzled boxes
@@ -49,6 +51,27 @@ struct FaParams {
   float scale_log2;
 };
 
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2): halves the issue slots of the softmax scale and row-sum
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -60,11 +83,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV, const FaParams p) {
   const int seq = blockIdx.z, head = blockIdx.y;
   const int row0 = p.cu[seq], len = p.cu[seq + 1] - row0;
-  const int n_full = len / kFaTile;
-  const int nblk = (n_full + 1) >> 1;
+  const int n_tiles = (len + kFaTile - 1) / kFaTile;  // the last tile may be ragged: its rows >= len are computed on
+  const int nblk = (n_tiles + 1) >> 1;                // whatever the TMA box brings in and never stored
   const int blk = p.causal ? ((int)gridDim.x - 1 - (int)blockIdx.x) : (int)blockIdx.x;  // heavy causal blocks first
   if (blk >= nblk) return;  // uniform for the CTA, before any barrier / allocation
-  const int ntile = min(2, n_full - blk * 2);
+  const int ntile = min(2, n_tiles - blk * 2);
   const int q0 = blk * 2 * kFaTile;
   const int kvh = head / (p.Hq / p.Hkv);
   int kv_len[2], nkv[2];
@@ -226,6 +249,70 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         int lim = nvalid - 1;                       // columns 0..lim of this tile are visible to this row
         if (p.causal) lim = min(lim, qi - kbase);
         const bool masked = !__all_sync(0xffffffffu, lim >= ncols - 1);
+        if (!masked && ncols == kFaTile) {
+          // ===== fast path (full, unmasked tile): ONE pass, the whole S row in registers =====
+          uint32_t v[128];
+          tmem_ld32(tS, v);
+          tmem_ld32(tS + 32u, v + 32);
+          tmem_ld32(tS + 64u, v + 64);
+          tmem_ld32(tS + 96u, v + 96);
+          tmem_ld_wait();
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              mx4[c] = max3(mx4[c], __uint_as_float(v[i + 2 * c]), __uint_as_float(v[i + 2 * c + 1]));
+          }
+          const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+          if (j == 0) {
+            m_ref = mx;
+          } else {
+            const bool grow = (mx - m_ref) * sl2 > kFaRescaleLog2;
+            if (__any_sync(0xffffffffu, grow)) {
+              const float m_use = grow ? mx : m_ref;
+              const float alpha = ex2((m_ref - m_use) * sl2);
+              l_sum *= alpha;
+              m_ref = m_use;
+#pragma unroll 1
+              for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t o[32];
+                tmem_ld32(tO + (uint32_t)c0, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st32(tO + (uint32_t)c0, o);
+              }
+            }
+          }
+          const float neg_m = -m_ref * sl2;
+          const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
+          uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
+          uint32_t pk[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const uint64_t x = f2_fma(f2_pack(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2_2, negm_2);
+            float x0, x1;
+            f2_unpack(x, x0, x1);
+            const float e0 = ex2(x0), e1 = ex2(x1);
+            acc2[i & 3] = f2_add(acc2[i & 3], f2_pack(e0, e1));
+            pk[i] = pack_bf16(e0, e1);
+          }
+          tmem_st32(tS, pk);
+          tmem_st32(tS + 32u, pk + 32);
+          {
+            float a0, a1, b0, b1;
+            f2_unpack(f2_add(f2_add(acc2[0], acc2[1]), f2_add(acc2[2], acc2[3])), a0, a1);
+            (void)b0; (void)b1;
+            l_sum += a0 + a1;
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[t]);
+          continue;
+        }
+        // ===== general path (ragged last K/V tile, causal diagonal): two chunked passes with masking =====
         // ---- pass 1: row maximum
         float mx = -INFINITY;
         for (int c0 = 0; c0 < ncols; c0 += 32) {
@@ -313,11 +400,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_after();
       const float inv = 1.0f / l_sum;
       bf16* orow = p.out + (long long)(row0 + qi) * p.ldo + head * 128;
+      const bool row_ok = qi < len;  // rows of a ragged last tile beyond the sequence are not stored
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tO + (uint32_t)c0, v);
         tmem_ld_wait();
+        if (!row_ok) continue;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
@@ -343,7 +432,6 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 int launch_fa_sm100(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                     long long ldo, const int32_t* cu, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv,
                     int causal, float scale_log2, cudaStream_t stream) {
-  if (max_seqlen < kFaTile) return OMC_OK;  // nothing but tails
   if ((reinterpret_cast<uintptr_t>(out) & 15) || (ldo % 8) != 0)
     return set_error(OMC_ERR_ALIGN, "omc_attention_fwd: output must be 16-byte aligned with a row stride multiple of 8");
   CUtensorMap tmQ, tmK, tmV;
@@ -362,7 +450,7 @@ int launch_fa_sm100(const void* q, long long ldq, const void* k, long long ldk, 
   FaParams p;
   p.cu = cu; p.out = static_cast<bf16*>(out); p.ldo = ldo; p.Hq = Hq; p.Hkv = Hkv; p.causal = causal;
   p.scale_log2 = scale_log2;
-  dim3 grid((max_seqlen / kFaTile + 1) / 2, Hq, num_seqs);
+  dim3 grid(((max_seqlen + kFaTile - 1) / kFaTile + 1) / 2, Hq, num_seqs);
   fa_fwd_sm100_kernel<<<grid, kFaThreads, kFaSmem, stream>>>(tmQ, tmK, tmV, p);
   return check_launch("fa_fwd_sm100");
 }

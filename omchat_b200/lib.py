@@ -83,7 +83,7 @@ def load() -> ctypes.CDLL:
     return lib
 
 
-_KERNELS_PER_CALL = {"omc_splice": 2, "omc_argmax": 2, "omc_attention_fwd": 2}
+_KERNELS_PER_CALL = {"omc_splice": 2, "omc_argmax": 2}
 
 
 def _check(rc: int, what: str):
