@@ -255,6 +255,9 @@ def main():
         raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL_DEBUG=VERSION/INFO writes to stdout: keep the ONE JSON line clean
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and os.environ.get("OMCHAT_B200_KEEP_NCCL_DEBUG") != "1":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from omchat_b200 import lib
     from omchat_b200.config import OmChatQwen2Config

@@ -89,6 +89,9 @@ int omc_attention_fwd(const void* q, long long ldq, const void* k, long long ldk
                       void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
                       long long total_rows, int Hq, int Hkv, int causal, float scale, void* stream);
 int omc_attention_set_impl(int impl);
+/* diagnostic: device buffer of 12 x 8 uint64 filled by CTA (0,0,0) of the tcgen05 kernel with per-warp clock accumulators
+ * (tools/attn_check.py prof-clocks); NULL = off */
+int omc_attention_set_prof(void* dev_buf);
 
 /* ---- Qwen2 decoder glue ----------------------------------------------------------------------------------------
  * RoPE (rotate-half, pairs (i, i+64), theta, fp32 angles: modeling_qwen2.py:102-113,124-146) applied in place to the

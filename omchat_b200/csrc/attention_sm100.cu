@@ -49,7 +49,9 @@ struct FaParams {
   long long ldo;
   int Hq, Hkv, causal;
   float scale_log2;
+  unsigned long long* prof;  // optional [12 warps][8] clock accumulators of CTA (0,0,0) (omc_attention_set_prof)
 };
+#define FA_CLK(var) const long long var = prof_on ? clock64() : 0
 
 // packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2): halves the issue slots of the softmax scale and row-sum
 __device__ __forceinline__ uint64_t f2_pack(float a, float b) {
@@ -116,6 +118,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  long long pa[6] = {0, 0, 0, 0, 0, 0};
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -206,7 +210,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         bool v_waited = false, k_waited = false;
         for (int t = 0; t < ntile; ++t) {
           if (j < nkv[t]) {
+            FA_CLK(c0);
             mbar_wait(&p_ready[t], (uint32_t)j & 1u);
+            FA_CLK(c1);
+            pa[0] += c1 - c0;
             if (!v_waited) {
               mbar_wait(&v_full[j & 1], (uint32_t)(j >> 1) & 1u);
               v_waited = true;
@@ -227,6 +234,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         umma_commit(&v_empty[j & 1]);
         if (j + 1 < nkv_max) umma_commit(&k_empty[(j + 1) & 1]);
       }
+      if (prof_on) p.prof[1 * 8 + 0] = (unsigned long long)pa[0];
     }
   } else if (warp >= 4) {
     // ============================================ softmax / epilogue ============================================
@@ -241,8 +249,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float sl2 = p.scale_log2;
       float m_ref = -INFINITY, l_sum = 0.f;
       for (int j = 0; j < nkv[t]; ++j) {
+        FA_CLK(c0);
         mbar_wait(&s_full[t], (uint32_t)j & 1u);
         tc_fence_after();
+        FA_CLK(c1);
+        pa[0] += c1 - c0;
         const int kbase = j * kFaTile;
         const int nvalid = min(kFaTile, kv_len[t] - kbase);
         const int ncols = (nvalid + 15) & ~15;
@@ -257,6 +268,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_ld32(tS + 64u, v + 64);
           tmem_ld32(tS + 96u, v + 96);
           tmem_ld_wait();
+          FA_CLK(c2);
+          pa[1] += c2 - c1;
           float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
           for (int i = 0; i < 128; i += 8) {
@@ -286,6 +299,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
           }
           const float neg_m = -m_ref * sl2;
+          FA_CLK(c3);
+          pa[2] += c3 - c2;
           const uint64_t sl2_2 = f2_pack(sl2, sl2), negm_2 = f2_pack(neg_m, neg_m);
           uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
           uint32_t pk[64];
@@ -298,6 +313,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             acc2[i & 3] = f2_add(acc2[i & 3], f2_pack(e0, e1));
             pk[i] = pack_bf16(e0, e1);
           }
+          FA_CLK(c4);
+          pa[3] += c4 - c3;
           tmem_st32(tS, pk);
           tmem_st32(tS + 32u, pk + 32);
           {
@@ -310,6 +327,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_ready[t]);
+          FA_CLK(c5);
+          pa[4] += c5 - c4;
           continue;
         }
         // ===== general path (ragged last K/V tile, causal diagonal): two chunked passes with masking =====
@@ -396,6 +415,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) mbar_arrive(&p_ready[t]);
       }
       // ---- epilogue: O / l -> bf16 -> global (each thread owns one output row: 256 contiguous bytes)
+      if (prof_on && lane == 0)
+        for (int i = 0; i < 5; ++i) p.prof[warp * 8 + i] = (unsigned long long)pa[i];
       mbar_wait(&o_final[t], 0);
       tc_fence_after();
       const float inv = 1.0f / l_sum;
@@ -428,6 +449,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+static unsigned long long* g_fa_prof = nullptr;
+void set_fa_prof(void* ptr) { g_fa_prof = static_cast<unsigned long long*>(ptr); }
+
 // host launcher (called by omc_attention_fwd in attention.cu): full 128-row query tiles of every sequence
 int launch_fa_sm100(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                     long long ldo, const int32_t* cu, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv,
@@ -450,6 +474,7 @@ int launch_fa_sm100(const void* q, long long ldq, const void* k, long long ldk, 
   FaParams p;
   p.cu = cu; p.out = static_cast<bf16*>(out); p.ldo = ldo; p.Hq = Hq; p.Hkv = Hkv; p.causal = causal;
   p.scale_log2 = scale_log2;
+  p.prof = g_fa_prof;
   dim3 grid(((max_seqlen + kFaTile - 1) / kFaTile + 1) / 2, Hq, num_seqs);
   fa_fwd_sm100_kernel<<<grid, kFaThreads, kFaSmem, stream>>>(tmQ, tmK, tmV, p);
   return check_launch("fa_fwd_sm100");

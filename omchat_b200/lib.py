@@ -31,6 +31,7 @@ SIGNATURES = {
     "omc_select_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "omc_attention_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _L, _I, _I, _I, _F, _P]),
     "omc_attention_set_impl": (_I, [_I]),
+    "omc_attention_set_prof": (_I, [_P]),
     "omc_rope_kv_store": (_I, [_P, _L, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
     "omc_decode_attn_splits": (_I, [_I, _I, _I]),
     "omc_decode_attn_workspace_bytes": (_L, [_I, _I, _I, _I]),

@@ -65,6 +65,18 @@ def check(lens, Hq, Hkv, causal):
 
 if __name__ == "__main__":
     lib.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "clocks":  # in-kernel clock accumulators of CTA (0,0,0)
+        buf = torch.zeros(12, 8, dtype=torch.int64, device="cuda")
+        lib.load().omc_attention_set_prof(buf.data_ptr())
+        run([1025] * 8, 25, 25, False, legacy=False, reps=2)
+        torch.cuda.synchronize()
+        b = buf.cpu()
+        print("MMA warp: cycles waiting for P:", int(b[1, 0]))
+        print("softmax warps (9 K/V steps, 8 on the fast path): wait S | tmem ld | max+rescale | exp | st+signal")
+        for w in range(4, 12):
+            print(f"  warp {w}:", [int(x) for x in b[w, :5]])
+        lib.load().omc_attention_set_prof(None)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "prof":  # a few launches of the ViT shape for ncu
         crops = int(sys.argv[2]) if len(sys.argv) > 2 else 8
         run([1025] * crops, 25, 25, False, legacy=False, reps=3)
