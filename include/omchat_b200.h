@@ -46,6 +46,15 @@ int omc_gemm_bf16(const void* X, long long ldx, const void* W, long long ldw, vo
                   int K, const void* bias, const void* scale, const void* res, long long ldr, int epi, int out_is_f32,
                   int tile_cfg, void* stream);
 
+/* Skinny variant for M <= 64 (batched decode steps too large for the GEMV kernels; HBM-bound): operands swapped so the
+ * 128-row tcgen05 tile runs along N (all TMA bytes are weight bytes), small N split along K over CTAs with an fp32
+ * red.global.add reduction in `workspace` (omc_gemm_skinny_workspace_bytes(max N) bytes, ZERO-INITIALISED once by the caller;
+ * the kernel leaves it zeroed). Same epilogues and argument meaning as omc_gemm_bf16. workspace may be NULL (no split-K). */
+long long omc_gemm_skinny_workspace_bytes(int max_n);
+int omc_gemm_skinny_bf16(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M, int N,
+                         int K, const void* bias, const void* scale, const void* res, long long ldr, int epi,
+                         int out_is_f32, void* workspace, long long workspace_bytes, void* stream);
+
 /* ---- decode-time linear layers: split-K GEMV, 128-bit loads, warp-shuffle reductions ---------------------------
  * out[B,N] = epi( norm(x)[B,K] W[N,K]^T ), B <= 8. If norm_w != NULL the input is RMS-normalised first
  * (Qwen2RMSNorm modeling_qwen2.py:258-263 fused in). epi: NONE (+bias), RES (+res), SWIGLU (interleaved W).

@@ -24,6 +24,8 @@ SIGNATURES = {
     "omc_version": (_I, []),
     "omc_num_sms": (_I, []),
     "omc_gemm_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _L, _I, _I, _I, _P]),
+    "omc_gemm_skinny_workspace_bytes": (_L, [_I]),
+    "omc_gemm_skinny_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _L, _I, _I, _P, _L, _P]),
     "omc_gemv_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _L, _I, _I, _P]),
     "omc_rmsnorm": (_I, [_P, _L, _P, _P, _L, _I, _I, _F, _P]),
     "omc_vit_im2col": (_I, [_P, _I, _P, _L, _I, _I, _I, _P]),
@@ -109,6 +111,22 @@ def _need_cuda(*ts):
             raise OmcError("omchat_b200 kernels need CUDA tensors (no CPU fallback)")
 
 
+SKINNY_MAX_M = 64  # rows up to which gemm() streams the weights through the swapped-operand skinny kernel
+SKINNY_ENABLED = os.environ.get("OMCHAT_B200_NO_SKINNY", "0") != "1"
+_skinny_ws = {}
+
+
+def _skinny_workspace(device, n: int) -> torch.Tensor:
+    """Zeroed split-K workspace of the skinny GEMM, one per device, grown on demand (the kernel leaves it zeroed)."""
+    key = str(device)
+    ws = _skinny_ws.get(key)
+    need = load().omc_gemm_skinny_workspace_bytes(max(n, 160 * 1024))
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, device=device, dtype=torch.uint8)
+        _skinny_ws[key] = ws
+    return ws
+
+
 # ----------------------------------------------------------------------------------------------- wrappers
 def gemm(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, scale=None, res=None,
          epi: int = EPI_NONE, out_f32: bool = False, tile_cfg: int = 0) -> torch.Tensor:
@@ -121,6 +139,13 @@ def gemm(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *
     if out is None:
         out = torch.empty(M, n_out, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     assert out.shape == (M, n_out) and out.stride(1) == 1
+    if M <= SKINNY_MAX_M and tile_cfg == 0 and SKINNY_ENABLED:
+        ws = _skinny_workspace(x.device, N)
+        rc = load().omc_gemm_skinny_bf16(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
+                                         _ptr(bias), _ptr(scale), _ptr(res), res.stride(0) if res is not None else 0, epi,
+                                         1 if out_f32 else 0, ws.data_ptr(), ws.numel(), _stream())
+        _check(rc, "omc_gemm_skinny_bf16")
+        return out
     rc = load().omc_gemm_bf16(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
                               _ptr(bias), _ptr(scale), _ptr(res), res.stride(0) if res is not None else 0, epi,
                               1 if out_f32 else 0, tile_cfg, _stream())

@@ -110,6 +110,36 @@ def test_gemm_swiglu(L, cg):
     assert_close(out, want, what="swiglu")
 
 
+@pytest.mark.parametrize("M", [1, 9, 16, 17, 32, 33, 64])
+@pytest.mark.parametrize("N,K", [(256, 64), (3584, 1792), (1000, 4104), (37888 // 8, 512)])
+def test_gemm_skinny(L, M, N, K):
+    """Swapped-operand tcgen05 GEMM for M <= 64 (csrc/gemm_skinny.cu): split-K with the red.add reduction for small N,
+    ragged N / K tails, every epilogue; the workspace must come back zeroed (second call = same result)."""
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    x = bf(torch.randn(M, K, generator=g)).cuda()
+    w = bf(torch.randn(N, K, generator=g) * 0.1).cuda()
+    bias = bf(torch.randn(N, generator=g)).cuda()
+    scale = bf(torch.randn(N, generator=g) * 0.1 + 0.1).cuda()
+    res = bf(torch.randn(M, N, generator=g)).cuda()
+    lin = ref_linear(x, w, bias)
+    assert L.SKINNY_ENABLED and M <= L.SKINNY_MAX_M
+    for rep in range(2):
+        assert_close(L.gemm(x, w), ref_linear(x, w), what=f"skinny plain rep {rep}")
+    assert_close(L.gemm(x, w, bias=bias, epi=L.EPI_GELU), torch.nn.functional.gelu(lin), what="skinny gelu")
+    want = res.float().cpu() + scale.float().cpu() * lin
+    assert_close(L.gemm(x, w, bias=bias, scale=scale, res=res, epi=L.EPI_RES), want, what="skinny res")
+    h = res.clone()
+    L.gemm(x, w, out=h, res=h, epi=L.EPI_RES)
+    assert_close(h, res.float().cpu() + ref_linear(x, w), what="skinny res in place")
+    assert_close(L.gemm(x, w, out_f32=True), ref_linear(x, w), what="skinny f32 out")
+    if N % 16 == 0:
+        gate, up = w[0::2].cpu(), w[1::2].cpu()
+        wantg = torch.nn.functional.silu(ref_linear(x, gate)) * ref_linear(x, up)
+        assert_close(L.gemm(x, w, epi=L.EPI_SWIGLU), wantg, what="skinny swiglu")
+    for ws in L._skinny_ws.values():
+        assert int(ws.count_nonzero()) == 0, "split-K workspace must be left zeroed"
+
+
 def test_gemm_strided_views_and_errors(L):
     g = torch.Generator().manual_seed(11)
     big = bf(torch.randn(200, 1024, generator=g)).cuda()
