@@ -6,8 +6,9 @@
   python bench.py --gpus N --steps K --warmup W            # this repository's sm_100a path
   python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU fp32 path (oracle port)
 
-N > 1 (torchrun, one rank per GPU): the SAME request served by N GPUs — Qwen2 decoder tensor-parallel over NCCL
-(column/row parallel + 2 all-reduces per layer), the single crop's vision tower replicated ("scaling": "strong").
+N > 1 (torchrun, one rank per GPU): the SAME request served by N GPUs — Qwen2 decoder tensor-parallel (column/row
+parallel, 2 all-reduces per layer: NCCL at prefill, inside the persistent decode kernel over NVLink peer memory at decode),
+the single crop's vision tower replicated ("scaling": "strong").
 Other workloads: --workload c3 (vision tower + projector, 64 crops data-parallel) and --workload c4 (decoder TP, 1024-token
 prefill + batch-32 decode).
 
@@ -366,7 +367,8 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD_C2, "prefill_tokens": T, "image_tokens": L, "new_tokens": new_tokens,
-                   "parallelism": "single GPU" if world == 1 else f"decoder tp{world} (NCCL all-reduce x56/forward), vision replicated",
+                   "parallelism": "single GPU" if world == 1 else
+                   f"decoder tp{world} (all-reduce x56/forward: NCCL at prefill, in-kernel NVLink exchange at decode), vision replicated",
                    "kv_cache": f"paged, page {cfg.kv_page_size}, shuffled block table",
                    "decode": "persistent megakernel, 1 launch/token" if dec.use_mega(1) else ("cuda graph" if not args.no_graph else "eager"),
                    "l2": "no flush needed: every step streams 26 GB of weights (>> 126 MB L2)"},
