@@ -93,7 +93,8 @@ int omc_select_pixel_shuffle(const void* hidden, void* out, int B, int G, int C,
  * (modeling_qwen2.py:161-184,229-243). total_rows = rows of the packed q/k/v/out buffers (= cu_seqlens[num_seqs]; the
  * bound of the TMA tensor maps). Every full 128-row query tile runs on the tcgen05/TMEM kernel (S and O accumulators and
  * the P operand in tensor memory, K/V tiles by TMA); the ragged tail rows run on the mma.sync kernel.
- * omc_attention_set_impl(1) forces the mma.sync kernel for everything (A/B comparison; env OMCHAT_B200_ATTN_LEGACY=1). */
+ * omc_attention_set_impl: 0 = tcgen05 kernel (default), 1 = mma.sync kernel for everything (A/B baseline; env
+ * OMCHAT_B200_ATTN_LEGACY=1), 2 = the first tcgen05 kernel (128-key tiles, single-buffered S). */
 int omc_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                       void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
                       long long total_rows, int Hq, int Hkv, int causal, float scale, void* stream);

@@ -486,7 +486,7 @@ int launch_fa_sm100(const void* q, long long ldq, const void* k, long long ldk, 
                     int causal, float scale_log2, cudaStream_t stream);
 }
 
-namespace omc { void set_fa_prof(void* ptr); }
+namespace omc { void set_fa_prof(void* ptr); void set_fa_version(int v); }
 /* diagnostic: device buffer of 12 x 8 uint64 that CTA (0,0,0) of the tcgen05 attention kernel fills with per-warp clock
  * accumulators (softmax warps: wait S, TMEM load, max/rescale, exp, store+signal; MMA warp: wait P); NULL = off */
 extern "C" int omc_attention_set_prof(void* dev_buf) {
@@ -495,8 +495,10 @@ extern "C" int omc_attention_set_prof(void* dev_buf) {
 }
 static int g_attn_impl = -1;  // 0 = tcgen05 kernel for full tiles + mma.sync tail, 1 = mma.sync kernel for everything
 extern "C" int omc_attention_set_impl(int impl) {
-  if (impl != 0 && impl != 1) return set_error(OMC_ERR_ARG, "omc_attention_set_impl: 0 (tcgen05) or 1 (mma.sync)");
-  g_attn_impl = impl;
+  if (impl < 0 || impl > 2)
+    return set_error(OMC_ERR_ARG, "omc_attention_set_impl: 0 (tcgen05, default), 1 (mma.sync) or 2 (tcgen05 with 128-key tiles)");
+  g_attn_impl = impl == 1 ? 1 : 0;
+  omc::set_fa_version(impl == 2 ? 1 : 2);
   return OMC_OK;
 }
 

@@ -222,9 +222,10 @@ def attention(q, k, v, out, cu_seqlens: torch.Tensor, max_seqlen: int, Hq: int, 
     return out
 
 
-def attention_set_impl(legacy: bool):
-    """True: mma.sync kernel for everything; False (default): tcgen05 kernel for full tiles + mma.sync tail."""
-    rc = load().omc_attention_set_impl(1 if legacy else 0)
+def attention_set_impl(legacy):
+    """False / 0 (default): tcgen05 kernel (64-key tiles, double-buffered S); True / 1: mma.sync kernel; 2: the first
+    tcgen05 kernel (128-key tiles) — kept for A/B measurements."""
+    rc = load().omc_attention_set_impl(int(legacy))
     if rc != 0:
         raise OmcError("omc_attention_set_impl failed")
 

@@ -68,7 +68,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "clocks":  # in-kernel clock accumulators of CTA (0,0,0)
         buf = torch.zeros(12, 8, dtype=torch.int64, device="cuda")
         lib.load().omc_attention_set_prof(buf.data_ptr())
-        run([1025] * 8, 25, 25, False, legacy=False, reps=2)
+        run([1025] * 8, 25, 25, False, legacy=int(sys.argv[2]) if len(sys.argv) > 2 else 0, reps=2)
         torch.cuda.synchronize()
         b = buf.cpu()
         print("MMA warp: cycles waiting for P:", int(b[1, 0]))
@@ -93,7 +93,7 @@ if __name__ == "__main__":
     for name, lens, Hq, Hkv, causal in [("vit 8 crops", [1025] * 8, 25, 25, False), ("vit 64 crops", [1025] * 64, 25, 25, False),
                                         ("prefill 1088", [1088], 28, 4, True), ("prefill 32x1024", [1024] * 32, 28, 4, True)]:
         fl = sum(4.0 * n * n * 128 * Hq * (0.5 if causal else 1.0) for n in lens)
-        for legacy in (True, False):
+        for legacy, label in ((1, "mma.sync   "), (2, "tcgen05 v1 "), (0, "tcgen05 v2 ")):
             _, _, ms = run(lens, Hq, Hkv, causal, legacy, reps=10)
-            print(f"{name:18s} {'mma.sync' if legacy else 'tcgen05 '} {ms * 1000:9.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s")
+            print(f"{name:18s} {label} {ms * 1000:9.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s")
     sys.exit(0 if worst < 0.02 else 1)
