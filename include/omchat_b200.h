@@ -85,6 +85,18 @@ int omc_vit_assemble(const void* patch, const void* cls, const void* pos, void* 
  * Pure gather: bit-exact. */
 int omc_select_pixel_shuffle(const void* hidden, void* out, int B, int G, int C, int down, void* stream);
 
+/* ---- any-resolution image preprocessing (the step in front of the path) -------------------------------
+ * process_anyres_image (omchat/mm_utils.py:119-158): PIL bicubic resize (Pillow Resample.c, 8 bpc fixed point) of an RGB
+ * uint8 HWC image, black-canvas padding, 448x448 patches + the whole image at 448x448, CLIPImageProcessor rescale/normalise
+ * (internVIT_encoder.py:26-29). omc_resample_u8 = one separable pass (vertical = 0: width changes, 1: height changes) with
+ * HOST-computed Pillow weights: coefs int32 [out, ksize] (22-bit fixed point), bounds int32 [out, 2] = (first tap, taps).
+ * Bit-exact against Pillow. omc_anyres_pack gathers the crops [1 + patches, 3, crop, crop] (fp32 or bf16) through a
+ * [3][256] fp32 look-up table (value -> normalised float, built by the host with the reference formulas). */
+int omc_resample_u8(const void* src, int src_h, int src_w, void* dst, int dst_h, int dst_w, const int32_t* coefs,
+                    const int32_t* bounds, int ksize, int vertical, void* stream);
+int omc_anyres_pack(const void* thumb, const void* resized, int new_w, int new_h, int target_w, int target_h, int paste_x,
+                    int paste_y, int crop, const float* lut, void* out, int out_is_bf16, void* stream);
+
 /* ---- attention ---------------------------------------------------------------------------------------------------
  * Flash-style softmax(Q K^T * scale) V with head_dim 128, fp32 softmax, over packed variable-length sequences.
  * q rows [total, Hq, 128] with row stride ldq (elements), k/v rows [total, Hkv, 128] with strides ldk/ldv, out row

@@ -31,6 +31,8 @@ SIGNATURES = {
     "omc_vit_im2col": (_I, [_P, _I, _P, _L, _I, _I, _I, _P]),
     "omc_vit_assemble": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "omc_select_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "omc_resample_u8": (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _I, _I, _P]),
+    "omc_anyres_pack": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "omc_attention_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _L, _I, _I, _I, _F, _P]),
     "omc_attention_set_impl": (_I, [_I]),
     "omc_attention_set_prof": (_I, [_P]),
@@ -207,6 +209,29 @@ def select_pixel_shuffle(hidden: torch.Tensor, B: int, G: int, down: int) -> tor
     out = torch.empty(B * (G // down) ** 2, C * down * down, device=hidden.device, dtype=torch.bfloat16)
     rc = load().omc_select_pixel_shuffle(_ptr(hidden), _ptr(out), B, G, C, down, _stream())
     _check(rc, "omc_select_pixel_shuffle")
+    return out
+
+
+def resample_u8(src: torch.Tensor, dst_h: int, dst_w: int, coefs: torch.Tensor, bounds: torch.Tensor, vertical: bool):
+    """One separable Pillow-bicubic pass over an RGB uint8 image [H, W, 3] (omc_resample_u8)."""
+    _need_cuda(src, coefs, bounds)
+    assert src.dtype == torch.uint8 and src.dim() == 3 and src.shape[2] == 3 and src.is_contiguous()
+    assert coefs.dtype == torch.int32 and bounds.dtype == torch.int32 and coefs.is_contiguous() and bounds.is_contiguous()
+    dst = torch.empty(dst_h, dst_w, 3, device=src.device, dtype=torch.uint8)
+    rc = load().omc_resample_u8(_ptr(src), src.shape[0], src.shape[1], _ptr(dst), dst_h, dst_w, _ptr(coefs), _ptr(bounds),
+                                coefs.shape[1], 1 if vertical else 0, _stream())
+    _check(rc, "omc_resample_u8")
+    return dst
+
+
+def anyres_pack(thumb, resized, target_w, target_h, paste_x, paste_y, crop, lut, dtype=torch.float32):
+    _need_cuda(thumb, resized, lut)
+    assert lut.dtype == torch.float32 and lut.shape == (3, 256) and lut.is_contiguous()
+    n = 1 + (target_w // crop) * (target_h // crop)
+    out = torch.empty(n, 3, crop, crop, device=thumb.device, dtype=dtype)
+    rc = load().omc_anyres_pack(_ptr(thumb), _ptr(resized), resized.shape[1], resized.shape[0], target_w, target_h, paste_x,
+                                paste_y, crop, _ptr(lut), _ptr(out), 1 if dtype == torch.bfloat16 else 0, _stream())
+    _check(rc, "omc_anyres_pack")
     return out
 
 

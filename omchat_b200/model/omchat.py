@@ -123,6 +123,19 @@ class OmChatQwen2ForCausalLM:
         feats = self.get_vision_tower()(images, self.config.pixel_shuffle_down)
         return self.get_model().mm_projector(feats)
 
+    def process_images(self, images):
+        """GPU replacement of omchat.mm_utils.process_images / process_anyres_image (mm_utils.py:119-182) for
+        image_aspect_ratio == 'anyres': PIL images / uint8 [H,W,3] arrays -> crops [n, 3, 448, 448] on the model's device
+        (Pillow-exact bicubic, csrc/preprocess.cu), ready to be passed as `images=` together with
+        omchat_b200.prompt.image_prompt(n_crops, text)."""
+        from ..preprocess import AnyResPreprocessor
+        pre = getattr(self, "_anyres", None)
+        if pre is None:
+            pre = AnyResPreprocessor(self.config.image_grid_pinpoints, crop=self.config.vision_config.image_size,
+                                     device=self.device, dtype=torch.bfloat16)
+            self._anyres = pre
+        return pre.process_images(images if isinstance(images, (list, tuple)) else [images])
+
     def _to_dev(self, t):
         if isinstance(t, (list, tuple)):
             t = torch.stack([x for x in t])
