@@ -66,3 +66,29 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def processor_golden():
+    """The reference OmChatProcessor.__call__ (omchat/hf/processing_omchat.py:169-246) on a stub `self` whose image
+    processor only reports crop counts — what is pinned is the id sequence it builds."""
+    import numpy as np
+    pr = load("ref_processing_omchat", "/root/reference/omchat/hf/processing_omchat.py")
+    from types import SimpleNamespace
+    cases = []
+    for text, nums in [("What's the content of the image?", [5]), ("<image> describe <image> both", [3, 4]),
+                       ("A <image> B <image> C <image> D", [2, 10, 3]), ("question<image>", [10])]:
+        mx = max(nums)
+        fake = SimpleNamespace(
+            image_processor=lambda images, return_tensors=None, n=nums, mx=mx: {
+                "pixel_values": torch.zeros(len(n), mx, 3, 2, 2), "num_patches": torch.tensor(n)},
+            tokenizer=ToyTokenizer())
+        out = pr.OmChatProcessor.__call__(fake, text, images=[object()] * len(nums))
+        cases.append({"text": text, "num_patches": nums, "ids": out["input_ids"][0].tolist(), "n_images": int(out["images"].shape[0])})
+    return cases
+
+
+if __name__ == "__main__":
+    g = json.load(open(os.path.join(HERE, "golden_prompt.json")))
+    g["processor"] = processor_golden()
+    json.dump(g, open(os.path.join(HERE, "golden_prompt.json"), "w"), indent=0)
+    print("processor cases", len(g["processor"]))

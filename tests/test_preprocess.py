@@ -93,3 +93,22 @@ def test_gpu_resize_is_pillow_bit_exact():
     assert isinstance(out, list) and out[1].shape[0] == 4
     with pytest.raises(ValueError):
         pre(np.zeros((4, 4), dtype=np.uint8))
+
+
+@pytest.mark.gpu
+def test_gpu_hf_image_processor_surface():
+    """OmChatImageProcessor (HF twin, image_processing_omchat.py:569-733): pixel_values zero-padded along the patch axis +
+    num_patches; OmChatProcessor wires crops and placeholders together."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from omchat_b200.processing import OmChatImageProcessor, OmChatProcessor
+    from toy_tokenizer import ToyTokenizer
+    ip = OmChatImageProcessor(image_grid_pinpoints=PINPOINTS)
+    a, b = synthetic_image(0, 640, 480), synthetic_image(1, 300, 900)
+    out = ip([a, b])
+    assert tuple(out.pixel_values.shape) == (2, 5, 3, 448, 448) and out.num_patches.tolist() == [5, 4]
+    assert torch.equal(out.pixel_values[0].cpu(), torch.from_numpy(PO.process_anyres(a, PINPOINTS)))
+    assert torch.equal(out.pixel_values[1, :4].cpu(), torch.from_numpy(PO.process_anyres(b, PINPOINTS)))
+    assert float(out.pixel_values[1, 4].abs().max()) == 0.0
+    feats = OmChatProcessor(ip, ToyTokenizer())("What is <image> this?", images=[a])
+    assert tuple(feats.images.shape) == (5, 3, 448, 448) and feats.input_ids[0].tolist().count(-200) == 5

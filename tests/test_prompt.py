@@ -46,3 +46,23 @@ def test_keywords_stopping_matches_reference():
         crit = P.KeywordsStoppingCriteria(["<|im_end|>", "STOP"], tok, prompt)
         ids = torch.tensor([tok.encode("hello ") + tok.encode_nobos(case["tail"])])
         assert bool(crit(ids, None)) == case["stop"], case
+
+
+def test_processor_context_matches_reference():
+    """OmChatProcessor.__call__ (omchat_b200/processing.py) builds the same ids as the reference's HF processor for one and
+    several images (crop counts from a stub image processor: no GPU needed)."""
+    from types import SimpleNamespace
+    from omchat_b200.processing import BatchFeature, OmChatProcessor
+    assert len(GOLD["processor"]) == 4
+    for case in GOLD["processor"]:
+        nums = case["num_patches"]
+        mx = max(nums)
+        ip = lambda images, return_tensors=None, n=nums, mx=mx: BatchFeature(  # noqa: E731
+            pixel_values=torch.zeros(len(n), mx, 3, 2, 2), num_patches=torch.tensor(n))
+        proc = OmChatProcessor(image_processor=ip, tokenizer=ToyTokenizer())
+        out = proc(case["text"], images=[object()] * len(nums))
+        assert out.input_ids[0].tolist() == case["ids"], case["text"]
+        assert out["images"].shape[0] == case["n_images"] == sum(nums)
+        assert out.input_ids[0].tolist().count(-200) == sum(nums)
+    out = OmChatProcessor(tokenizer=ToyTokenizer())("just <image> text")
+    assert "images" not in out and out.input_ids.shape[0] == 1
