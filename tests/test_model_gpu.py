@@ -194,3 +194,35 @@ def test_paged_cache_contents_match_oracle_kv(model, golden, sd_bf16):
         k, v = res.past_key_values.gather(li, 0)
         check(k, past[li][0][0], f"cached K layer {li}")
         check(v, past[li][1][0], f"cached V layer {li}")
+
+
+def test_end_to_end_image_bytes_to_tokens(sd_bf16):
+    """The widened path in one piece: uint8 image -> GPU any-res preprocessing (model.process_images) -> ChatML prompt with
+    one placeholder per crop (prompt.image_prompt / make_context) -> splice -> prefill -> greedy decode, against the CPU
+    oracles fed the same bytes (preprocess_oracle + omchat_oracle)."""
+    from oracle import preprocess_oracle as PO
+    from omchat_b200 import prompt as P
+    from omchat_b200.model.omchat import OmChatQwen2ForCausalLM
+    from preprocess_images import synthetic_image
+    from toy_tokenizer import ToyTokenizer
+    S = TINY["image_size"]
+    pins = [[S, 2 * S], [2 * S, S], [2 * S, 2 * S]]
+    m = OmChatQwen2ForCausalLM.from_state_dict(sd_bf16, tiny_cfgs(image_grid_pinpoints=pins), device="cuda")
+    img = synthetic_image(2, 500, 230)
+    crops = m.process_images([img])  # [1, n, 3, S, S] bf16
+    want_crops = torch.from_numpy(PO.process_anyres(img, pins, crop=S))
+    assert crops.shape[0] == 1 and torch.equal(crops[0].cpu(), want_crops.to(torch.bfloat16))
+    n = crops.shape[1]
+    _, ids = P.make_context(ToyTokenizer(), P.image_prompt(n, "What is this?"), None, "You are a helpful assistant.")
+    ids = [t if t == -200 else (t % 997) + 1 for t in ids]  # the toy tokenizer's ids folded into the tiny vocabulary
+    assert ids.count(-200) == n
+    ids = torch.tensor([ids])
+    new = 6
+    out = m.generate(ids, images=crops[0], max_new_tokens=new, do_sample=False, eos_token_id=-1)
+    got = out[0, ids.shape[1]:].tolist()
+    want, step_logits = O.greedy_generate(ids, want_crops.to(torch.bfloat16).float(), sd_bf16, oracle_cfg(), max_new_tokens=new)
+    for i in range(new):
+        if got[i] != want[i]:
+            top2 = torch.topk(step_logits[i], 2).values
+            assert float(top2[0] - top2[1]) < 0.05 * float(step_logits[i].abs().max()), (i, got, want)
+            break
