@@ -171,7 +171,10 @@ typedef struct omc_decode_desc {
   int32_t n_layers, batch, hidden, q_heads, kv_heads, inter, vocab, vocab_offset;
   int32_t page_size, max_pages, grid, hist_capacity;
   int32_t rope_positions;
-  int32_t l2_prefetch_stages; /* how many ring stages (~14-19 KB each, per CTA) the L2 prefetch runs ahead; 0 = off */
+  int32_t l2_prefetch_stages; /* how many ring stages (one slot each, per CTA) the L2 prefetch runs ahead; 0 = off */
+  int32_t ring_slot_bytes;    /* bytes of one shared-memory ring slot (multiple of 128); 0 = default (14336 = 2 rows of
+                                 K = 3584; longer rows travel as equal K chunks of at most one slot) */
+  int32_t scalar_gemv;        /* A/B switch: 1 = compute the dot products with FFMA instead of mma.sync (default 0) */
   float eps, attn_scale;
   const void* embed;
   const void* final_norm;
@@ -200,8 +203,9 @@ typedef struct omc_decode_desc {
   void* workspace;
   int32_t* status; /* optional int32[4], zeroed by the caller, device-accessible (pinned host memory is fine): a watchdog
                       inside the kernel writes {code, CTA, detail, thread} here before trapping; NULL = in workspace */
-  void* prof;      /* optional uint64[grid][5*n_layers+2][4] device buffer: per-CTA, per-op %globaltimer stamps (op start,
-                      after grid barrier, after activation staging, end) for tools/prof_mega.py; NULL = off */
+  void* prof;      /* optional uint64[grid][5*n_layers+2][8] device buffer for tools/prof_mega.py: per-CTA, per-op
+                      %globaltimer stamps (op start, activations staged, op end), SM id, and warp 0's clock64 cycles in
+                      stage wait / dot products / refill issue / reduce + epilogue; NULL = off */
   /* Tensor parallelism INSIDE the persistent kernel (tp_size 2..8, one process per GPU; 0/1 = single GPU). The weight
    * pointers above are this rank's Megatron shards (q/k/v and gate/up column-parallel: q_heads/kv_heads/inter are the LOCAL
    * counts; o_proj/down_proj row-parallel; lm_head vocab-parallel with vocab = local rows and vocab_offset = first row).

@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v",
 ]
+NVCC_FLAGS += os.environ.get("OMCHAT_B200_NVCC_EXTRA", "").split()  # e.g. -DOMC_MEGA_DETAIL=1 for tools/prof_mega.py
 
 
 def _nvcc() -> str:

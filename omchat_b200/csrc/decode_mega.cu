@@ -38,11 +38,15 @@ namespace omc {
 
 typedef __nv_bfloat16 bf16;
 
+#ifndef OMC_MEGA_DETAIL
+#define OMC_MEGA_DETAIL 0  // 1: warp 0 also records a clock64 breakdown of the GEMV loop (tools/prof_mega.py)
+#endif
 constexpr int kMegaThreads = 256;
 constexpr int kCWarps = 8;
 constexpr int kRMax = 4;            // weight rows per ring stage (upper bound)
-constexpr int kSlotBytes = 19456;   // ring slot: 2 rows of K=3584 (14336 B) or half a row of K=18944 (18944 B)
-constexpr int kMaxSlots = 12;
+constexpr int kSlotBytesDefault = 14336;  // ring slot: 2 rows of K=3584; a K=18944 row travels as 3 chunks (6400|6400|6144)
+constexpr int kSlotBytesMax = 32768;
+constexpr int kMaxSlots = 16;
 constexpr int kMaxOps = 192;
 constexpr int kAttnKeysPerCta = 32;
 constexpr int kPartStride = 130;    // O[128], m, l
@@ -50,18 +54,21 @@ constexpr int kAttnScratchBytes = kCWarps * 8 * kPartStride * 4;
 constexpr int kHRows = 64;          // residual rows one CTA can own
 constexpr int kBiasRows = 128;      // slab rows whose bias is staged in shared memory (larger slabs read it from L2)
 constexpr int kMaxBt = 1024;        // block-table entries cached in shared memory (batch * max_pages)
+constexpr int kProfStride = 8;       // uint64 per (CTA, op) in the optional profile buffer
 constexpr int kMaxTp = 8;           // tensor-parallel ranks one step can span (peer exchange buffers over NVLink)
 constexpr int kXpBytes = kHRows * 4 * 4;  // this CTA's own row-parallel partial sums [kHRows][4 sequences] fp32
-constexpr int kMetaBytes = 2048 + 4 * kHRows * 2 + kMaxBt * 4 + kXpBytes;  // barriers/scratch | residual slab | block table | partials
+constexpr int kHdrBytes = 512;  // shared copy of the MegaPlan header (256 B) + the kernel's MegaCtx (256 B)
+__host__ __device__ __forceinline__ int ops_bytes_of(int n_ops) { return (n_ops * 88 + 127) & ~127; }
+__host__ __device__ __forceinline__ int front_bytes_of(int n_ops) { return kHdrBytes + ops_bytes_of(n_ops) + ((n_ops * 24 + 127) & ~127); }
+constexpr int kMetaFixed = 2048 + 4 * kHRows * 2 + kXpBytes;  // barriers/scratch | residual slab | partials | block table (sized per plan)
+__host__ __device__ __forceinline__ int bt_bytes_of(int B, int max_pages) { return (B * max_pages * 4 + 127) & ~127; }
 constexpr int kSmemLimit = 227 * 1024;
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // a protocol bug must end in a trap, never in a hung GPU
 
 enum { OP_GEMV = 1, OP_ATTN = 2, OP_FINAL = 3 };
 enum { F_OUT_F32 = 1, F_X_EMBED = 2, F_ARGMAX = 4 };
 
-struct MegaOp {  // 112 bytes
-  int32_t type, N, K, epi;
-  int32_t R, ksplit, gran, flags;
+struct MegaOp {  // 88 bytes (the op list lives in shared memory: every byte here is a byte less of weight ring)
   const bf16* W;
   const bf16* norm_w;
   const bf16* bias;
@@ -69,16 +76,27 @@ struct MegaOp {  // 112 bytes
   uint32_t* out_ll;      // output vector(s) [B][ldo] in the same format (null for lm_head)
   float* out_f32;        // lm_head: fp32 logits [B][ldo]
   bf16* pool;            // ATTN: this layer's KV pool
-  int32_t ldx, ldo, in_op, parity, xslot, pad;  // in_op: index of the op whose tag the input carries; xslot: 1 + peer
-                                                // exchange slot of a row-parallel op under tensor parallelism (0 = none)
+  int32_t N, K, ldx, ldo;
+  int32_t kc0;           // elements per K chunk (chunk ks = [ks*kc0, min(K, (ks+1)*kc0)))
+  int16_t in_op;         // index of the op whose tag the input carries
+  uint8_t type, epi, R, ksplit, gran, flags, parity;
+  uint8_t xslot;         // 1 + peer exchange slot of a row-parallel op under tensor parallelism (0 = none)
 };
-static_assert(sizeof(MegaOp) == 112, "MegaOp layout");
+static_assert(sizeof(MegaOp) == 88, "MegaOp layout");
+// Per-CTA view of a GEMV op, built once per launch in shared memory: this CTA's row slab and where its stages sit in the
+// CTA's stage sequence (locating a stage must not cost 64-bit divisions on the refill path)
+struct SlabEnt {  // 24 bytes
+  const bf16* w0;      // first weight row of the slab
+  uint32_t base, cnt;  // stages [base, base + cnt) of this CTA's stream belong to the op (cnt = 0: not a GEMV)
+  int32_t row0, rows;
+};
 
 struct MegaPlan {  // header, followed by n_ops MegaOp
   int32_t n_ops, B, C, Hq, Hkv, G, page_size, max_pages;
   int32_t grid, nsplit_max, vocab_offset, hist_capacity, kmax, nslots, region_a_bytes, smem_bytes;
   float eps, scale_log2;
-  int32_t pf_stages, pad1;
+  int32_t pf_stages, slot_bytes;
+  int32_t scalar_gemv, prof_mode, poll_ns, pad2;  // prof_mode: which breakdown warp 0 records (0 phases, 1 refill issue, 2 epilogue)  // scalar_gemv: A/B switch, 1 = FFMA dot products instead of the mma.sync path
   const bf16* embed;
   const float* rope_cs;  // [positions][64][2] fp32 (cos, sin)
   const int32_t* block_table;
@@ -89,12 +107,14 @@ struct MegaPlan {  // header, followed by n_ops MegaOp
   uint2* attn_part;   // [2][grid][8][130] {fp32 bits, tag32}
   uint2* amax_part;   // [grid][4][2]      {value bits | index, tag32}
   int32_t* err_flag;
-  unsigned long long* prof;  // optional [grid][n_ops][4] globaltimer stamps: op start, inputs staged, op end, -
+  unsigned long long* prof;  // optional [grid][n_ops][8]: globaltimer stamps op start, inputs staged, op end, SM id, then
+                             // warp 0's clock64 cycles spent in: stage wait, dot products, refill issue, reduce + epilogue
   int32_t tp_rank, tp_size;
   uint2* xchg[kMaxTp];  // tensor parallelism: rank p's exchange buffer as mapped into THIS process (xchg[tp_rank] = own).
                         // layout (uint2 {fp32 bits | index, tag32}): partials [4 slots][tp][B][C], then argmax [tp][B][2]
 };
 static_assert(sizeof(MegaPlan) % 16 == 0, "MegaPlan must keep the op array 16-byte aligned");
+static_assert(sizeof(MegaPlan) <= 256 && sizeof(MegaOp) == 88 && sizeof(SlabEnt) == 24, "shared-memory front layout");
 
 // ------------------------------------------------------------------------------------------------ device helpers
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -189,16 +209,15 @@ __device__ __forceinline__ float dot8(uint4 w, const float* x, float acc) {
 __device__ __forceinline__ float silu_m(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
-// Position of a stage index in the op list: the GEMV op that owns it and this CTA's slab of that op.
+// Position of a stage index in the op list: the op that owns it (a hint that only moves forward; n_ops = exhausted)
 struct StageCursor {
-  int op_i;            // index of the current GEMV op (n_ops = exhausted)
-  uint32_t base, cnt;  // stages [base, base + cnt) belong to op_i
-  int row0, rows;
+  int op_i;
 };
 
 struct MegaCtx {
-  const MegaPlan* P;     // global
+  const MegaPlan* P;     // shared copy of the plan header
   const MegaOp* ops;     // shared copy
+  const SlabEnt* tab;    // shared: this CTA's slab of every op
   uint64_t* full;
   volatile uint32_t* gen;  // gen[slot] = number of copies issued into the slot so far (monotonic: no parity aliasing)
   float* red;            // [16] floats of block-reduction scratch
@@ -211,37 +230,42 @@ struct MegaCtx {
   float* s_xp;           // [kHRows][4] own partial sums of a row-parallel op (tensor parallelism)
   uint8_t* region_a;     // activation vectors / attention scratch
   uint8_t* ring;
-  int nslots, cta, grid, n_ops, pf_stages;
+  int nslots, cta, grid, n_ops, pf_stages, slot_bytes, scalar_gemv;
+  int prof_mode;
+  unsigned int poll_ns;  // back-off between failed polls of a flag-in-data vector (0 = spin)
+  unsigned long long* prof_op;  // this CTA's profile record of the current op (null = profiling off)
   uint32_t epoch;
 };
 
-__device__ __forceinline__ void cursor_load(const MegaCtx& c, StageCursor& k) {
-  while (k.op_i < c.n_ops && c.ops[k.op_i].type != OP_GEMV) ++k.op_i;
-  if (k.op_i < c.n_ops) {
-    const MegaOp& op = c.ops[k.op_i];
-    slab_rows(op.N, op.gran, c.cta, c.grid, k.row0, k.rows);
-    k.cnt = (uint32_t)(((k.rows + op.R - 1) / op.R) * op.ksplit);
-  } else {
-    k.cnt = 0;
-  }
-}
 // Locate stage s: advance cursor k (stage indices passed through one cursor are strictly increasing) and return the
 // global source address and byte count of the stage, or false when the op list is exhausted.
+static_assert(sizeof(MegaCtx) <= 256, "MegaCtx must fit its 256-byte shared-memory slot");
+
 __device__ __forceinline__ bool locate_stage(const MegaCtx& c, StageCursor& k, uint32_t s, const bf16*& src, uint32_t& bytes) {
-  while (k.op_i < c.n_ops && s >= k.base + k.cnt) {
-    k.base += k.cnt;
-    ++k.op_i;
-    cursor_load(c, k);
+  int oi = k.op_i;
+  uint32_t base = 0, cnt = 0;
+  while (oi < c.n_ops) {
+    const uint2 bc = *reinterpret_cast<const uint2*>(&c.tab[oi].base);
+    base = bc.x; cnt = bc.y;
+    if (s < base + cnt) break;
+    ++oi;
   }
-  if (k.op_i >= c.n_ops) return false;
-  const MegaOp& op = c.ops[k.op_i];
-  const uint32_t rel = s - k.base;
-  const int u = (int)(rel / (uint32_t)op.ksplit), ks = (int)(rel % (uint32_t)op.ksplit);
-  const int r = u * op.R;
-  const int rows_here = min(op.R, k.rows - r);
-  const int Kc = op.K / op.ksplit;
-  bytes = (uint32_t)rows_here * (uint32_t)Kc * 2u;
-  src = op.W + (size_t)(k.row0 + r) * op.K + (size_t)ks * Kc;
+  k.op_i = oi;
+  if (oi >= c.n_ops) return false;
+  const MegaOp& op = c.ops[oi];
+  const SlabEnt& e = c.tab[oi];
+  const uint32_t rel = s - base;
+  const int ksplit = op.ksplit, R = op.R, K = op.K;
+  int u = (int)rel, ks = 0;
+  if (ksplit > 1) {
+    u = (int)(rel / (uint32_t)ksplit);
+    ks = (int)rel - u * ksplit;
+  }
+  const int r = u * R;
+  const int rows_here = min(R, e.rows - r);
+  const int kbeg = ks * op.kc0, Kc = min(op.kc0, K - kbeg);
+  bytes = (uint32_t)(rows_here * Kc) * 2u;
+  src = e.w0 + ((size_t)(uint32_t)r * (uint32_t)K + (uint32_t)kbeg);
   return true;
 }
 // Issue the bulk copy of stage s (if it exists) into ring slot s % nslots, and ask L2 for the stage `pf_stages` further
@@ -257,7 +281,7 @@ __device__ __forceinline__ void issue_stage(const MegaCtx& c, StageCursor& k, St
   const uint32_t slot = s % (uint32_t)c.nslots;
   fence_proxy_async();  // generic-proxy reads of this slot (previous stage) are ordered before the async-proxy refill
   mbar_arrive_expect_tx(&c.full[slot], bytes);
-  bulk_g2s(c.ring + (size_t)slot * kSlotBytes, src, bytes, &c.full[slot]);
+  bulk_g2s(c.ring + (size_t)slot * c.slot_bytes, src, bytes, &c.full[slot]);
   __threadfence_block();
   c.gen[slot] = s / (uint32_t)c.nslots + 1u;  // publish: the barrier is now in the phase that carries stage s
 }
@@ -277,7 +301,7 @@ __device__ __forceinline__ void wait_stage(const MegaCtx& c, uint32_t s, uint32_
 // [modeling_qwen2.py:258-263]. The source is either the embedding row of this step's token (first op) or a
 // flag-in-data vector another phase is producing right now: polling it IS the synchronisation with the producers.
 template <int NB>
-__device__ void stage_x(MegaCtx& c, const MegaOp& op, int ctid) {
+__device__ void stage_x(MegaCtx& c, const MegaOp& op, int op_idx, int ctid) {
   const MegaPlan& P = *c.P;
   const int K = op.K;
   bf16* xs = reinterpret_cast<bf16*>(c.region_a);
@@ -285,18 +309,15 @@ __device__ void stage_x(MegaCtx& c, const MegaOp& op, int ctid) {
   // bias of this CTA's slab and the norm weights (K <= 4096: at most 4 chunks per thread) are fetched before the wait so
   // that they do not cost a dependent round trip later
   if (op.bias != nullptr) {
-    int r0, nr;
-    slab_rows(op.N, op.gran, c.cta, c.grid, r0, nr);
+    const int r0 = c.tab[op_idx].row0, nr = c.tab[op_idx].rows;
     if (ctid < nr && ctid < kBiasRows) c.s_bias[ctid] = __bfloat162float(op.bias[r0 + ctid]);
   }
-  uint2 gw[4];
+  // (the norm weights go to shared memory behind the activation vectors with cp.async: no registers held across the wait)
+  const uint2* gs = reinterpret_cast<const uint2*>(xs + (long long)NB * K);
   if (op.norm_w != nullptr) {
-    const uint2* wv = reinterpret_cast<const uint2*>(op.norm_w);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = ctid + j * kMegaThreads;
-      if (i < (K >> 2)) gw[j] = __ldg(wv + i);
-    }
+    for (int i = ctid; i < (K >> 3); i += kMegaThreads)
+      cp_async16(const_cast<uint2*>(gs) + 2 * i, op.norm_w + 8 * i, true);
+    cp_async_commit();
   }
 #pragma unroll 1
   for (int b = 0; b < NB; ++b) {
@@ -337,7 +358,10 @@ __device__ void stage_x(MegaCtx& c, const MegaOp& op, int ctid) {
             const int i = base + u * kMegaThreads;
             if (i < n4 && !ll4_ok(v[u], tag)) ok = false;
           }
-          if (!ok) wd.tick(P.err_flag, 5, op.in_op);
+          if (!ok) {
+            wd.tick(P.err_flag, 5, op.in_op);
+            if (c.poll_ns) __nanosleep(c.poll_ns);
+          }
         } while (!ok);
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
@@ -354,7 +378,8 @@ __device__ void stage_x(MegaCtx& c, const MegaOp& op, int ctid) {
     }
     if (op.norm_w != nullptr) {
       ss = warp_sum(ss);
-      __syncthreads();  // c.red free, raw vector fully in shared memory
+      cp_async_wait<0>();
+      __syncthreads();  // c.red free, raw vector and norm weights fully in shared memory
       if ((ctid & 31) == 0) c.red[ctid >> 5] = ss;
       __syncthreads();
       float tot = 0.f;
@@ -364,11 +389,12 @@ __device__ void stage_x(MegaCtx& c, const MegaOp& op, int ctid) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int i = ctid + j * kMegaThreads;
-        if (i >= n4) break;
-        const uint2 g = gw[j], v = dst[i];
-        const float2 a0 = unpack_bf16(v.x), a1 = unpack_bf16(v.y), g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y);
-        const float2 n0 = unpack_bf16(pack_bf16(a0.x * rstd, a0.y * rstd)), n1 = unpack_bf16(pack_bf16(a1.x * rstd, a1.y * rstd));
-        dst[i] = make_uint2(pack_bf16(n0.x * g0.x, n0.y * g0.y), pack_bf16(n1.x * g1.x, n1.y * g1.y));
+        if (i < n4) {
+          const uint2 g = gs[i], v = dst[i];
+          const float2 a0 = unpack_bf16(v.x), a1 = unpack_bf16(v.y), g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y);
+          const float2 n0 = unpack_bf16(pack_bf16(a0.x * rstd, a0.y * rstd)), n1 = unpack_bf16(pack_bf16(a1.x * rstd, a1.y * rstd));
+          dst[i] = make_uint2(pack_bf16(n0.x * g0.x, n0.y * g0.y), pack_bf16(n1.x * g1.x, n1.y * g1.y));
+        }
       }
     }
   }
@@ -376,12 +402,72 @@ __device__ void stage_x(MegaCtx& c, const MegaOp& op, int ctid) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMV consumer
+// Dot products of one or two weight rows (a K chunk of `nsteps` x 128 elements each, in the ring) with the staged
+// activation vector(s) on the tensor pipe. The scalar form (LDS.128 + 8 bf16->fp32 unpacks + 8 FFMA per 16 weight bytes)
+// costs ~45 issue slots per 512 B of weights and made the short ops (qkv, o_proj: data already in the ring when their
+// input arrives) instruction-bound; here 512 B of weights cost one ldmatrix + one mma.sync:
+//   A (16 x 16, row-major) = rows 0-7: the eight 16-byte pieces [0,8) of a 128-element group of weight row r0 (k 0-7) and
+//                            pieces [8,16) (k 8-15); rows 8-15: the same pieces of row r1
+//   B (16 x 8, "col")      = column n: pieces n and 8 + n of the same 128-element group of x
+// so D[m][m] (m < 8) is the partial dot product of row r0 over pieces m and 8 + m, D[8 + m][m] that of row r1; the other
+// 112 entries of D are discarded - the tensor pipe is idle anyway and the point is the issue slots. Each 8x8 ldmatrix
+// tile is 128 contiguous bytes of shared memory: conflict-free. fp32 accumulation inside the MMA (as in the GEMMs).
+// acc0[b] / acc1[b] receive this lane's share (sum over lanes = the dot product, reduced later with warp_sum).
+template <int NB>
+__device__ __forceinline__ void mma_rows(uint32_t w_addr, uint32_t row_pitch, bool two, uint32_t x_addr, uint32_t x_pitch,
+                                         int nsteps, int lane, float* acc0, float* acc1) {
+  const int mat = lane >> 3, ri = lane & 7;
+  const uint32_t a_addr = w_addr + (((mat & 1) && two) ? row_pitch : 0u) + (uint32_t)((mat >> 1) * 128 + ri * 16);
+  const uint32_t b_addr = x_addr + (uint32_t)lane * 16u;  // tiles: step s pieces 0-7, 8-15, step s+1 pieces 0-7, 8-15
+  float d[2][NB][4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int b = 0; b < NB; ++b) d[h][b][0] = d[h][b][1] = d[h][b][2] = d[h][b][3] = 0.f;
+  int s = 0;
+#pragma unroll 2
+  for (; s + 1 < nsteps; s += 2) {
+    uint32_t a0[4], a1[4];
+    ldmatrix_x4(a_addr + (uint32_t)s * 256u, a0[0], a0[1], a0[2], a0[3]);
+    ldmatrix_x4(a_addr + (uint32_t)s * 256u + 256u, a1[0], a1[1], a1[2], a1[3]);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      uint32_t x0, x1, x2, x3;
+      ldmatrix_x4(b_addr + (uint32_t)b * x_pitch + (uint32_t)s * 256u, x0, x1, x2, x3);
+      mma_bf16_16816(d[0][b], a0, x0, x1);
+      mma_bf16_16816(d[1][b], a1, x2, x3);
+    }
+  }
+  if (s < nsteps) {  // odd tail (the second half of the x tiles read past the chunk: still inside shared memory, unused)
+    uint32_t a0[4];
+    ldmatrix_x4(a_addr + (uint32_t)s * 256u, a0[0], a0[1], a0[2], a0[3]);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      uint32_t x0, x1, x2, x3;
+      ldmatrix_x4(b_addr + (uint32_t)b * x_pitch + (uint32_t)s * 256u, x0, x1, x2, x3);
+      mma_bf16_16816(d[0][b], a0, x0, x1);
+    }
+  }
+  // this lane holds D[g][2t], D[g][2t+1], D[g+8][2t], D[g+8][2t+1] (g = lane / 4, t = lane % 4): keep the diagonal
+  const int g = lane >> 2, t = lane & 3;
+  const bool on = (g >> 1) == t, odd = g & 1;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const float v0 = odd ? d[0][b][1] + d[1][b][1] : d[0][b][0] + d[1][b][0];
+    const float v1 = odd ? d[0][b][3] + d[1][b][3] : d[0][b][2] + d[1][b][2];
+    if (on) {
+      acc0[b] += v0;
+      if (two) acc1[b] += v1;
+    }
+  }
+}
+
 template <int NB, bool TP>
 __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t sc_base, int row0, int rows, int cw,
                              int lane, StageCursor& refill, StageCursor& refill_pf, float& best_v, int& best_i) {
   const MegaPlan& P = *c.P;
   const int R = op.R, ksplit = op.ksplit;
-  const int Kc = op.K / ksplit, nv = Kc >> 3, nvK = op.K >> 3;
+  const int nv0 = op.kc0 >> 3, nvK = op.K >> 3;
   const int units = (rows + R - 1) / R;
   const uint4* xs = reinterpret_cast<const uint4*>(c.region_a);
   const uint32_t otag = tag16_of(tag32_of(c.epoch, op_idx));
@@ -391,6 +477,12 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
   const uint32_t xtag = TP ? tag32_of(c.epoch, op_idx) : 0u;
   const long long xslot_base = TP ? (long long)(op.xslot - 1) * P.tp_size : 0;                 // [slot][src rank][B][C]
   const long long xoff_w = TP ? (xslot_base + P.tp_rank) * (long long)P.B * P.C : 0;            // where peers find OUR partials
+#if OMC_MEGA_DETAIL
+  const bool pw = c.prof_op != nullptr && cw == 0 && lane == 0;
+#else
+  constexpr bool pw = false;  // the cycle breakdown costs registers this kernel does not have: compile-time switch
+#endif
+  long long pc_wait = 0, pc_dot = 0, pc_issue = 0, pc_epi = 0;
 #pragma unroll 1
   for (int u = cw; u < units; u += kCWarps) {
     const int r = u * R;
@@ -404,10 +496,22 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
     for (int ks = 0; ks < ksplit; ++ks) {
       const uint32_t s = sc_base + (uint32_t)(u * ksplit + ks);
       const uint32_t slot = s % (uint32_t)c.nslots;
+      long long tk0 = 0;
+      if (pw) tk0 = clock64();
       wait_stage(c, s, slot);
-      const uint4* wb = reinterpret_cast<const uint4*>(c.ring + (size_t)slot * kSlotBytes);
-      const uint4* xb = xs + ks * nv;
-      if (rows_here == 2) {
+      if (pw) { const long long t = clock64(); pc_wait += t - tk0; tk0 = t; }
+      const uint4* wb = reinterpret_cast<const uint4*>(c.ring + (size_t)slot * c.slot_bytes);
+      const uint4* xb = xs + ks * nv0;
+      const int nv = min(nv0, nvK - ks * nv0);  // this chunk's length in 16-byte vectors (the last chunk may be shorter)
+      if ((nv & 15) == 0 && !c.scalar_gemv) {
+        // tensor-pipe path: the chunk is a whole number of 128-element groups
+        const uint32_t w_addr = smem_u32(wb), x_addr = smem_u32(xb);
+#pragma unroll
+        for (int i = 0; i < kRMax; i += 2)
+          if (i < rows_here)
+            mma_rows<NB>(w_addr + (uint32_t)(i * nv) * 16u, (uint32_t)nv * 16u, i + 1 < rows_here, x_addr, (uint32_t)nvK * 16u,
+                         nv >> 4, lane, acc[i], acc[i + 1]);
+      } else if (rows_here == 2) {
 #pragma unroll 2
         for (int j = lane; j < nv; j += 32) {
           const uint4 w0 = wb[j], w1 = wb[nv + j];
@@ -464,8 +568,12 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
         }
       }
       __syncwarp();
+      if (pw) { const long long t = clock64(); pc_dot += t - tk0; tk0 = t; }
       if (lane == 0) issue_stage(c, refill, refill_pf, s + (uint32_t)c.nslots);  // this slot is free again: refill it
+      if (pw) pc_issue += clock64() - tk0;
     }
+    long long te0 = 0;
+    if (pw) te0 = clock64();
 #pragma unroll
     for (int i = 0; i < kRMax; ++i)
 #pragma unroll
@@ -520,6 +628,13 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
             }
           }
     }
+    if (pw) pc_epi += clock64() - te0;
+  }
+  if (pw) {
+    c.prof_op[4] = (unsigned long long)pc_wait;
+    c.prof_op[5] = (unsigned long long)pc_dot;
+    c.prof_op[6] = (unsigned long long)pc_issue;
+    c.prof_op[7] = (unsigned long long)pc_epi;
   }
   if (TP && xon) {
     // ---- finish the all-reduce: h[row] += sum over ranks (fixed rank order -> bit-identical replicas on every GPU) of
@@ -848,31 +963,36 @@ __device__ __noinline__ void attn_phase(MegaCtx& c, const MegaOp& op, int op_idx
 template <int NB, int G, bool TP>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const MegaPlan* __restrict__ plan, uint32_t epoch) {
   extern __shared__ __align__(128) uint8_t mega_smem[];
-  const MegaPlan& P = *plan;
+  // layout: plan header | ops | slab table | meta (barriers + scratch 2 KB, residual slab, partials, block table) | region A | ring
+  // (the header is copied too: a plan field read from global memory costs an L2 round trip under the weight stream)
+  MegaPlan* s_plan = reinterpret_cast<MegaPlan*>(mega_smem);
+  for (int i = threadIdx.x; i < (int)(sizeof(MegaPlan) / 8); i += kMegaThreads)
+    reinterpret_cast<uint2*>(s_plan)[i] = __ldg(reinterpret_cast<const uint2*>(plan) + i);
+  __syncthreads();
+  const MegaPlan& P = *s_plan;
   const int n_ops = P.n_ops;
-  // layout: ops | meta (barriers + scratch 2 KB, residual slab, block table) | region A | ring
-  MegaOp* s_ops = reinterpret_cast<MegaOp*>(mega_smem);
-  const int ops_bytes = (n_ops * (int)sizeof(MegaOp) + 127) & ~127;
-  uint8_t* meta = mega_smem + ops_bytes;
+  MegaOp* s_ops = reinterpret_cast<MegaOp*>(mega_smem + kHdrBytes);
+  SlabEnt* s_tab = reinterpret_cast<SlabEnt*>(mega_smem + kHdrBytes + ops_bytes_of(n_ops));
+  uint8_t* meta = mega_smem + front_bytes_of(n_ops);
   uint64_t* full = reinterpret_cast<uint64_t*>(meta);
   volatile uint32_t* gen = reinterpret_cast<volatile uint32_t*>(full + kMaxSlots);  // kMaxSlots counters
   float* red = reinterpret_cast<float*>(const_cast<uint32_t*>(gen) + kMaxSlots + 4);  // 16 floats
   int* s_ctx = reinterpret_cast<int*>(red + 16);                                    // 4 ints
   float* am_v = reinterpret_cast<float*>(s_ctx + 4);                                // [8 warps][16 lanes]
   int* am_i = reinterpret_cast<int*>(am_v + kCWarps * 16);
-  float* s_bias = reinterpret_cast<float*>(am_i + kCWarps * 16);  // kBiasRows floats (meta scratch: 1264 + 512 <= 2048)
+  float* s_bias = reinterpret_cast<float*>(am_i + kCWarps * 16);  // kBiasRows floats (meta scratch: 1312 + 512 <= 2048)
   bf16* s_h = reinterpret_cast<bf16*>(meta + 2048);
-  int* s_bt = reinterpret_cast<int*>(meta + 2048 + 4 * kHRows * 2);
-  float* s_xp = reinterpret_cast<float*>(meta + 2048 + 4 * kHRows * 2 + kMaxBt * 4);
-  uint8_t* region_a = meta + kMetaBytes;
+  float* s_xp = reinterpret_cast<float*>(meta + 2048 + 4 * kHRows * 2);
+  int* s_bt = reinterpret_cast<int*>(meta + kMetaFixed);
+  uint8_t* region_a = meta + kMetaFixed + bt_bytes_of(P.B, P.max_pages);
   uint8_t* ring = region_a + P.region_a_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {  // copy the op list, context lengths and block table into shared memory, init the ring barriers
-    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(plan) + sizeof(MegaPlan));
-    uint4* dst = reinterpret_cast<uint4*>(s_ops);
-    const int n16 = n_ops * (int)sizeof(MegaOp) / 16;
-    for (int i = tid; i < n16; i += kMegaThreads) dst[i] = __ldg(src + i);
+    const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(plan) + sizeof(MegaPlan));
+    uint2* dst = reinterpret_cast<uint2*>(s_ops);
+    const int n8 = n_ops * (int)sizeof(MegaOp) / 8;
+    for (int i = tid; i < n8; i += kMegaThreads) dst[i] = __ldg(src + i);
     for (int i = tid; i < P.B * P.max_pages; i += kMegaThreads) s_bt[i] = P.block_table[i];
     if (tid < P.B) s_ctx[tid] = P.ctx_lens[tid];
     if (tid == 0) {
@@ -884,16 +1004,43 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     }
   }
   __syncthreads();
+  // this CTA's slab of every GEMV op, then (one thread) the running stage index where each op starts
+  for (int i = tid; i < n_ops; i += kMegaThreads) {
+    const MegaOp& op = s_ops[i];
+    SlabEnt e;
+    e.w0 = nullptr; e.base = 0; e.cnt = 0; e.row0 = 0; e.rows = 0;
+    if (op.type == OP_GEMV) {
+      slab_rows(op.N, op.gran, (int)blockIdx.x, (int)gridDim.x, e.row0, e.rows);
+      e.cnt = (uint32_t)(((e.rows + op.R - 1) / op.R) * op.ksplit);
+      e.w0 = op.W + (size_t)e.row0 * op.K;
+    }
+    s_tab[i] = e;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < n_ops; ++i) {
+      s_tab[i].base = run;
+      run += s_tab[i].cnt;
+    }
+  }
+  __syncthreads();
 
-  MegaCtx c;
-  c.P = plan; c.ops = s_ops; c.full = full; c.gen = gen; c.red = red; c.am_v = am_v; c.am_i = am_i; c.s_ctx = s_ctx;
+  // The context lives in shared memory, not in registers or on the stack: it is passed by reference into the phase
+  // functions, and a local-memory copy means LDL round trips to L2 (the L1 left beside 227 KB of shared memory does not
+  // hold it under the weight stream) on the refill path of every ring stage.
+  MegaCtx& c = *reinterpret_cast<MegaCtx*>(mega_smem + 256);
+  if (tid == 0) {
+  c.P = s_plan; c.ops = s_ops; c.tab = s_tab; c.full = full; c.gen = gen; c.red = red; c.am_v = am_v; c.am_i = am_i; c.s_ctx = s_ctx;
   c.s_h = s_h; c.s_bias = s_bias; c.s_bt = s_bt; c.s_xp = s_xp; c.region_a = region_a; c.ring = ring; c.nslots = P.nslots; c.cta = blockIdx.x;
-  c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch; c.pf_stages = P.pf_stages;
+  c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch; c.pf_stages = P.pf_stages; c.slot_bytes = P.slot_bytes; c.scalar_gemv = P.scalar_gemv; c.prof_mode = P.prof_mode; c.poll_ns = (unsigned int)P.poll_ns;
+  c.prof_op = nullptr;
+  }
+  __syncthreads();
 
   // every warp keeps its own cursor into the stage sequence for the refills it issues
   StageCursor refill;
-  refill.op_i = 0; refill.base = 0; refill.cnt = 0; refill.row0 = 0; refill.rows = 0;
-  cursor_load(c, refill);
+  refill.op_i = 0;
   StageCursor refill_pf = refill;
   if (tid == 0) {  // prime the ring (stages 0 .. nslots-1) and the L2 prefetch window behind it
     StageCursor k = refill, kpf = refill;
@@ -910,16 +1057,21 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   uint32_t sc_base = 0;
   float best_v = -INFINITY;
   int best_i = 0x7fffffff;
-  unsigned long long* prof = P.prof ? P.prof + ((size_t)c.cta * n_ops) * 4 : nullptr;
+  unsigned long long* prof = P.prof ? P.prof + ((size_t)c.cta * n_ops) * kProfStride : nullptr;
 #pragma unroll 1
   for (int i = 0; i < n_ops; ++i) {
     const MegaOp& op = s_ops[i];
-    if (prof && ctid == 0) prof[i * 4 + 0] = global_ns();
+    if (prof && ctid == 0) {
+      c.prof_op = prof + i * kProfStride;
+      prof[i * kProfStride + 0] = global_ns();
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      prof[i * kProfStride + 3] = smid;
+    }
     if (op.type == OP_GEMV) {
-      stage_x<NB>(c, op, ctid);
-      if (prof && ctid == 0) prof[i * 4 + 1] = global_ns();
-      int row0, rows;
-      slab_rows(op.N, op.gran, c.cta, c.grid, row0, rows);
+      stage_x<NB>(c, op, i, ctid);
+      if (prof && ctid == 0) prof[i * kProfStride + 1] = global_ns();
+      const int row0 = s_tab[i].row0, rows = s_tab[i].rows;
       gemv_consume<NB, TP>(c, op, i, sc_base, row0, rows, cw, lane, refill, refill_pf, best_v, best_i);
       sc_base += (uint32_t)(((rows + op.R - 1) / op.R) * op.ksplit);
       if (op.flags & F_ARGMAX) {
@@ -1018,16 +1170,23 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
         if (lane == 0 && P.hist_pos) *P.hist_pos = pos + 1;
       }
     }
-    if (prof && ctid == 0) prof[i * 4 + 2] = global_ns();
+    if (prof && ctid == 0) prof[i * kProfStride + 2] = global_ns();
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static int pick_ksplit(int K) {
-  const int nvec = K / 8;
-  for (int d = 1; d <= nvec; ++d)
-    if (nvec % d == 0 && (long long)(K / d) * 2 <= kSlotBytes) return d;
-  return -1;
+// Split a K-element row into the fewest chunks that fit a ring slot; chunks are kc0 elements (a multiple of 256 = one
+// 16-byte vector per lane per 8 rounds when possible, else of 8), the last one takes what is left.
+static int pick_ksplit(int K, int slot_bytes, int* kc0) {
+  const int cap = slot_bytes / 2;  // elements per slot
+  if (K < 8 || K % 8 != 0 || cap < 8) return -1;
+  const int d = (K + cap - 1) / cap;
+  int per = (K + d - 1) / d;
+  int c = (per + 255) & ~255;
+  if (c > cap) c = (per + 7) & ~7;
+  if (c > cap) return -1;
+  *kc0 = c;
+  return (K + c - 1) / c;
 }
 
 struct WsLayout {
@@ -1106,31 +1265,37 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   auto ll = [&](long long base, int parity, int width) {
     return reinterpret_cast<uint32_t*>(ws + base) + (long long)parity * B * width;
   };
+  int slot_bytes = d->ring_slot_bytes > 0 ? d->ring_slot_bytes : kSlotBytesDefault;
+  if (slot_bytes % 128 != 0 || slot_bytes < 1024 || slot_bytes > kSlotBytesMax)
+    return set_error(OMC_ERR_ARG, "omc_decode_plan_build: ring_slot_bytes must be a multiple of 128 in [1024, 32768]");
   MegaPlan* P = static_cast<MegaPlan*>(plan_host);
   memset(P, 0, sizeof(MegaPlan));
   MegaOp* ops = reinterpret_cast<MegaOp*>(P + 1);
-  int n = 0, kmax = 0;
+  int n = 0, kmax = 0, knorm = 0;
   bool bad = false;
   auto gemv = [&](const void* W, int N, int K, const uint32_t* x_ll, int ldx, int in_op, const void* norm_w, const void* bias,
                   uint32_t* out_ll, int ldo, int epi, int flags) -> int {
     MegaOp& o = ops[n];
     memset(&o, 0, sizeof(o));
-    o.type = OP_GEMV; o.N = N; o.K = K; o.epi = epi; o.flags = flags;
+    o.type = OP_GEMV; o.N = N; o.K = K; o.epi = (uint8_t)epi; o.flags = (uint8_t)flags;
     o.gran = (epi == EPI_SWIGLU) ? 2 : 1;
-    o.ksplit = pick_ksplit(K);
-    if (o.ksplit < 1 || K % 8 != 0 || N % o.gran != 0) { bad = true; o.ksplit = 1; }
+    o.kc0 = K;
+    const int ksp = pick_ksplit(K, slot_bytes, &o.kc0);
+    o.ksplit = (uint8_t)ksp;
+    if (ksp < 1 || ksp > 255 || K % 8 != 0 || N % o.gran != 0) { bad = true; o.ksplit = 1; o.kc0 = K; }
     int R = 1;
     if (o.ksplit == 1) {
-      R = kSlotBytes / (K * 2);
+      R = slot_bytes / (K * 2);
       if (R > kRMax) R = kRMax;
       if (o.gran == 2) R &= ~1;
       if (R < o.gran) bad = true;
     } else if (o.gran == 2) bad = true;  // a (gate, up) pair must fit one ring stage
-    o.R = R < 1 ? 1 : R;
+    o.R = (uint8_t)(R < 1 ? 1 : R);
     if (norm_w != nullptr && K > 4096) bad = true;
     o.W = (const bf16*)W; o.norm_w = (const bf16*)norm_w; o.bias = (const bf16*)bias;
-    o.x_ll = x_ll; o.out_ll = out_ll; o.ldx = ldx; o.ldo = ldo; o.in_op = in_op;
+    o.x_ll = x_ll; o.out_ll = out_ll; o.ldx = ldx; o.ldo = ldo; o.in_op = (int16_t)in_op;
     if (K > kmax) kmax = K;
+    if (norm_w != nullptr && K > knorm) knorm = K;
     return n++;
   };
   int prev = -1;  // op that produced the current residual-stream broadcast (h1)
@@ -1140,16 +1305,16 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
                            ll(w.qkv, par, qw), qw, EPI_NONE, li == 0 ? F_X_EMBED : 0);
     MegaOp& a = ops[n];
     memset(&a, 0, sizeof(a));
-    a.type = OP_ATTN; a.x_ll = ll(w.qkv, par, qw); a.ldx = qw; a.in_op = i_qkv; a.out_ll = ll(w.attn, par, aw); a.ldo = aw;
-    a.parity = par;
+    a.type = OP_ATTN; a.x_ll = ll(w.qkv, par, qw); a.ldx = qw; a.in_op = (int16_t)i_qkv; a.out_ll = ll(w.attn, par, aw); a.ldo = aw;
+    a.parity = (uint8_t)par;
     a.pool = static_cast<bf16*>(d->kv_pool) + (long long)li * d->kv_layer_stride;
     const int i_attn = n++;
     const int i_o = gemv(d->o_w[li], C, aw, ll(w.attn, par, aw), aw, i_attn, nullptr, nullptr, ll(w.h2, par, C), C, EPI_RES, 0);
-    ops[i_o].xslot = 1 + par;  // row-parallel under TP: partial sums cross the GPUs through exchange slot par
+    ops[i_o].xslot = (uint8_t)(1 + par);  // row-parallel under TP: partial sums cross the GPUs through exchange slot par
     const int i_gu = gemv(d->gate_up_w[li], 2 * I, C, ll(w.h2, par, C), C, i_o, d->ln2[li], nullptr, ll(w.act, par, I), I,
                           EPI_SWIGLU, 0);
     prev = gemv(d->down_w[li], C, I, ll(w.act, par, I), I, i_gu, nullptr, nullptr, ll(w.h1, (li + 1) & 1, C), C, EPI_RES, 0);
-    ops[prev].xslot = 3 + par;
+    ops[prev].xslot = (uint8_t)(3 + par);
   }
   const int i_head = gemv(d->lm_head, d->vocab, C, d->n_layers == 0 ? nullptr : ll(w.h1, d->n_layers & 1, C), C, prev,
                           d->final_norm, nullptr, nullptr, d->vocab, EPI_NONE,
@@ -1158,22 +1323,28 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   MegaOp& f = ops[n++];
   memset(&f, 0, sizeof(f));
   f.type = OP_FINAL;
-  f.in_op = i_head;
+  f.in_op = (int16_t)i_head;
   if (bad) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: a layer shape does not fit the ring (K % 8, SwiGLU pair > slot, norm K > 4096)");
   P->n_ops = n; P->B = B; P->C = C; P->Hq = Hq; P->Hkv = Hkv; P->G = Hq / Hkv;
   P->page_size = d->page_size; P->max_pages = d->max_pages; P->grid = d->grid;
   P->nsplit_max = d->grid / (B * Hkv);
   P->vocab_offset = d->vocab_offset; P->hist_capacity = d->hist_capacity; P->kmax = kmax;
   int region_a = B * kmax * 2;
+  if (region_a < (B + 1) * knorm * 2) region_a = (B + 1) * knorm * 2;  // normed ops stage the norm weights behind x
   if (region_a < kAttnScratchBytes) region_a = kAttnScratchBytes;
   region_a = (region_a + 127) & ~127;
-  const int ops_bytes = (n * (int)sizeof(MegaOp) + 127) & ~127;
-  int nslots = (kSmemLimit - ops_bytes - kMetaBytes - region_a) / kSlotBytes;
+  const int ops_bytes = front_bytes_of(n);  // plan header + op list + slab table
+  const int meta_bytes = kMetaFixed + bt_bytes_of(B, d->max_pages);
+  int nslots = (kSmemLimit - ops_bytes - meta_bytes - region_a) / slot_bytes;
   if (nslots > kMaxSlots) nslots = kMaxSlots;
   if (nslots < 2) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: activations leave no room for the weight ring");
   P->nslots = nslots; P->region_a_bytes = region_a;
   P->pf_stages = d->l2_prefetch_stages < 0 ? 0 : d->l2_prefetch_stages;
-  P->smem_bytes = ops_bytes + kMetaBytes + region_a + nslots * kSlotBytes;
+  P->slot_bytes = slot_bytes;
+  P->scalar_gemv = d->scalar_gemv & 1;
+  P->prof_mode = (d->scalar_gemv >> 8) & 0xff;  // tools/prof_mega.py: which breakdown warp 0 records
+  P->poll_ns = (d->scalar_gemv >> 16) & 0x7fff; // experiment: back-off between failed polls
+  P->smem_bytes = ops_bytes + meta_bytes + region_a + nslots * slot_bytes;
   P->eps = d->eps; P->scale_log2 = d->attn_scale * 1.4426950408889634f;
   P->embed = (const bf16*)d->embed; P->rope_cs = d->rope_cs; P->block_table = d->block_table; P->ctx_lens = d->ctx_lens;
   P->tokens = d->tokens; P->token_hist = d->token_hist; P->hist_pos = d->hist_pos;

@@ -1,7 +1,7 @@
 """In-kernel timeline of the persistent decode kernel: per-op %globaltimer stamps of every CTA (OMCHAT_B200_MEGA_PROF=1).
 Prints, per op kind, the mean over layers of: barrier wait, activation staging, body, and the max-over-CTAs op duration."""
 import os, sys
-os.environ["OMCHAT_B200_MEGA_PROF"] = "1"
+os.environ.setdefault("OMCHAT_B200_MEGA_PROF", "1")  # OMCHAT_B200_MEGA_PROF=0: only time the step (no stamps)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from omchat_b200.config import OmChatQwen2Config
@@ -30,8 +30,12 @@ for _ in range(10):
     plan.step()
 e1.record()
 torch.cuda.synchronize()
-print(f"step time {e0.elapsed_time(e1) / 10 * 1000:.1f} us (with profiling stamps on)")
-p = plan.prof.cpu().double()  # [grid, n_ops, 4]
+print(f"step time {e0.elapsed_time(e1) / 10 * 1000:.1f} us (profiling stamps {'on' if plan.prof is not None else 'off'})")
+if plan.prof is None:
+    sys.exit(0)
+p = plan.prof.cpu().double()  # [grid, n_ops, 8]
+smid = p[:, 0, 3].long().tolist()
+cyc = p[:, :, 4:8].clone()    # warp 0: cycles in stage wait, dot products, refill issue, reduce + epilogue
 t0 = p[:, 0, 0].min()
 p = (p - t0) / 1000.0  # us
 n_ops = p.shape[1]
@@ -51,6 +55,12 @@ for k, idx in kinds.items():
     span = (p[:, idx, 2].max(dim=0).values - p[:, idx, 0].min(dim=0).values).mean().item()
     skew = (p[:, idx, 2].max(dim=0).values - p[:, idx, 2].min(dim=0).values).mean().item()
     print(f"{k:8s} {len(idx):3d} {stg:10.2f} {body:9.2f} {span:9.2f} {skew:9.2f}")
+print("warp 0 cycle breakdown per op (mean over CTAs and layers, us at 1.965 GHz): stage wait / dots / issue / reduce+epilogue")
+for k, idx in kinds.items():
+    if k in ("attn", "final"):
+        continue
+    m = cyc[:, idx, :].mean(dim=(0, 1)) / 1965.0
+    print(f"  {k:8s} {m[0].item():7.2f} {m[1].item():7.2f} {m[2].item():7.2f} {m[3].item():7.2f}")
 print(f"whole step (first op start -> last op end): {(p[:, -1, 2].max() - p[:, 0, 0].min()).item():.1f} us")
 # critical path per layer: time between the slowest CTA finishing 'down' of consecutive layers
 if layers > 2:
@@ -64,3 +74,18 @@ for name, off in (("qkv", 0), ("attn", 1), ("o", 2), ("gate_up", 3), ("down", 4)
     wait = (p[:, i, 1] - p[:, i, 0]) if name != "attn" else total * 0
     vals = ", ".join(f"{w:.1f}/{t:.1f}" for w, t in list(zip(wait.tolist(), total.tolist()))[:24])
     print(f"layer {li} {name}: wait/total per CTA (first 24) [{vals}]")
+
+# per-CTA body time (mean over layers) against the SM the CTA ran on: is the end skew a property of the SM's position?
+if layers > 2:
+    import json
+    rec = {"smid": smid, "slot_bytes": int(os.environ.get("OMCHAT_B200_MEGA_SLOT", "0"))}
+    for name, off in (("qkv", 0), ("o", 2), ("gate_up", 3), ("down", 4)):
+        idx = [5 * l + off for l in range(layers)]
+        body = (p[:, idx, 2] - p[:, idx, 1])  # [grid, layers]
+        mean, std = body.mean(dim=1), body.std(dim=1)
+        rec[name] = {"mean": [round(v, 2) for v in mean.tolist()], "std_over_layers": [round(v, 2) for v in std.tolist()]}
+        print(f"{name}: per-CTA mean body {mean.min().item():.2f}..{mean.max().item():.2f} us (mean {mean.mean().item():.2f}), "
+              f"per-CTA std over layers mean {std.mean().item():.2f} us; spread of per-CTA means {mean.std().item():.2f} us")
+    out = os.environ.get("OMCHAT_B200_PROF_OUT")
+    if out:
+        json.dump(rec, open(out, "w"))
