@@ -57,7 +57,9 @@ constexpr int kMaxBt = 1024;        // block-table entries cached in shared memo
 constexpr int kProfStride = 8;       // uint64 per (CTA, op) in the optional profile buffer
 constexpr int kMaxTp = 8;           // tensor-parallel ranks one step can span (peer exchange buffers over NVLink)
 constexpr int kXpBytes = kHRows * 4 * 4;  // this CTA's own row-parallel partial sums [kHRows][4 sequences] fp32
-constexpr int kHdrBytes = 512;  // shared copy of the MegaPlan header (256 B) + the kernel's MegaCtx (256 B)
+constexpr int kHdrBytes = 768;  // shared: MegaPlan header (256 B) | the kernel's MegaCtx (256 B) | ring barriers + generations
+constexpr int kFullOff = 512;   // uint64 full[kMaxSlots]: mbarriers of the ring slots
+constexpr int kGenOff = 640;    // uint32 gen[kMaxSlots]: copies issued into each slot so far (monotonic: no parity aliasing)
 __host__ __device__ __forceinline__ int ops_bytes_of(int n_ops) { return (n_ops * 88 + 127) & ~127; }
 __host__ __device__ __forceinline__ int front_bytes_of(int n_ops) { return kHdrBytes + ops_bytes_of(n_ops) + ((n_ops * 24 + 127) & ~127); }
 constexpr int kMetaFixed = 2048 + 4 * kHRows * 2 + kXpBytes;  // barriers/scratch | residual slab | partials | block table (sized per plan)
@@ -209,6 +211,21 @@ __device__ __forceinline__ float dot8(uint4 w, const float* x, float acc) {
 __device__ __forceinline__ float silu_m(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
+// The dynamic shared memory of the kernel. Everything the refill path touches sits at an offset known at compile time or
+// kept in a register (RingHot): after every mbarrier / bulk-copy asm (memory clobber) the compiler must reload whatever it
+// reads through a pointer, and a pointer that itself lives in shared memory makes that a chain of dependent LDS behind
+// the ldmatrix traffic of the other warps - measured ~0.5 us per refill before this layout.
+extern __shared__ __align__(128) uint8_t mega_smem[];
+struct RingHot {  // by value, in registers
+  int tab_off, ring_off;  // byte offsets of the slab table and of ring slot 0
+  int slot_bytes, nslots, n_ops;
+};
+__device__ __forceinline__ uint64_t* ring_full(uint32_t slot) { return reinterpret_cast<uint64_t*>(mega_smem + kFullOff) + slot; }
+__device__ __forceinline__ volatile uint32_t* ring_gen(uint32_t slot) {
+  return reinterpret_cast<volatile uint32_t*>(mega_smem + kGenOff) + slot;
+}
+__device__ __forceinline__ const struct MegaOp* smem_ops() { return reinterpret_cast<const struct MegaOp*>(mega_smem + kHdrBytes); }
+
 // Position of a stage index in the op list: the op that owns it (a hint that only moves forward; n_ops = exhausted)
 struct StageCursor {
   int op_i;
@@ -216,10 +233,7 @@ struct StageCursor {
 
 struct MegaCtx {
   const MegaPlan* P;     // shared copy of the plan header
-  const MegaOp* ops;     // shared copy
   const SlabEnt* tab;    // shared: this CTA's slab of every op
-  uint64_t* full;
-  volatile uint32_t* gen;  // gen[slot] = number of copies issued into the slot so far (monotonic: no parity aliasing)
   float* red;            // [16] floats of block-reduction scratch
   float* am_v;           // [8 warps][16]
   int* am_i;
@@ -229,8 +243,7 @@ struct MegaCtx {
   int* s_bt;             // block table copy [B][max_pages]
   float* s_xp;           // [kHRows][4] own partial sums of a row-parallel op (tensor parallelism)
   uint8_t* region_a;     // activation vectors / attention scratch
-  uint8_t* ring;
-  int nslots, cta, grid, n_ops, pf_stages, slot_bytes, scalar_gemv;
+  int cta, grid, n_ops, pf_stages, scalar_gemv;
   int prof_mode;
   unsigned int poll_ns;  // back-off between failed polls of a flag-in-data vector (0 = spin)
   unsigned long long* prof_op;  // this CTA's profile record of the current op (null = profiling off)
@@ -241,19 +254,20 @@ struct MegaCtx {
 // global source address and byte count of the stage, or false when the op list is exhausted.
 static_assert(sizeof(MegaCtx) <= 256, "MegaCtx must fit its 256-byte shared-memory slot");
 
-__device__ __forceinline__ bool locate_stage(const MegaCtx& c, StageCursor& k, uint32_t s, const bf16*& src, uint32_t& bytes) {
+__device__ __forceinline__ bool locate_stage(const RingHot& h, StageCursor& k, uint32_t s, const bf16*& src, uint32_t& bytes) {
   int oi = k.op_i;
   uint32_t base = 0, cnt = 0;
-  while (oi < c.n_ops) {
-    const uint2 bc = *reinterpret_cast<const uint2*>(&c.tab[oi].base);
+  const SlabEnt* tab = reinterpret_cast<const SlabEnt*>(mega_smem + h.tab_off);
+  while (oi < h.n_ops) {
+    const uint2 bc = *reinterpret_cast<const uint2*>(&tab[oi].base);
     base = bc.x; cnt = bc.y;
     if (s < base + cnt) break;
     ++oi;
   }
   k.op_i = oi;
-  if (oi >= c.n_ops) return false;
-  const MegaOp& op = c.ops[oi];
-  const SlabEnt& e = c.tab[oi];
+  if (oi >= h.n_ops) return false;
+  const MegaOp& op = smem_ops()[oi];
+  const SlabEnt& e = tab[oi];
   const uint32_t rel = s - base;
   const int ksplit = op.ksplit, R = op.R, K = op.K;
   int u = (int)rel, ks = 0;
@@ -272,28 +286,27 @@ __device__ __forceinline__ bool locate_stage(const MegaCtx& c, StageCursor& k, u
 // down the stream: the shared-memory ring bounds how far the copies can run ahead (~150 KB/SM), the L2 prefetch lets HBM
 // keep streaming through the latency-bound phases (qkv -> attention -> o_proj) up to ~60 MB chip-wide ahead of use.
 // Called by ONE lane with that warp's cursors.
-__device__ __forceinline__ void issue_stage(const MegaCtx& c, StageCursor& k, StageCursor& kpf, uint32_t s) {
+__device__ __forceinline__ void issue_stage(const RingHot& h, int pf_stages, StageCursor& k, StageCursor& kpf, uint32_t s) {
   const bf16* src;
   uint32_t bytes;
-  if (c.pf_stages > 0 && locate_stage(c, kpf, s + (uint32_t)c.pf_stages, src, bytes))
+  if (pf_stages > 0 && locate_stage(h, kpf, s + (uint32_t)pf_stages, src, bytes))
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-  if (!locate_stage(c, k, s, src, bytes)) return;
-  const uint32_t slot = s % (uint32_t)c.nslots;
+  if (!locate_stage(h, k, s, src, bytes)) return;
+  const uint32_t g = s / (uint32_t)h.nslots, slot = s - g * (uint32_t)h.nslots;
   fence_proxy_async();  // generic-proxy reads of this slot (previous stage) are ordered before the async-proxy refill
-  mbar_arrive_expect_tx(&c.full[slot], bytes);
-  bulk_g2s(c.ring + (size_t)slot * c.slot_bytes, src, bytes, &c.full[slot]);
+  mbar_arrive_expect_tx(ring_full(slot), bytes);
+  bulk_g2s(mega_smem + h.ring_off + slot * (uint32_t)h.slot_bytes, src, bytes, ring_full(slot));
   __threadfence_block();
-  c.gen[slot] = s / (uint32_t)c.nslots + 1u;  // publish: the barrier is now in the phase that carries stage s
+  *ring_gen(slot) = g + 1u;  // publish: the barrier is now in the phase that carries stage s
 }
 // Wait until stage s has landed in its slot. A slot is shared by stages s, s + nslots, ... that different warps consume,
 // and an mbarrier parity wait is only meaningful for the phase in flight, so first wait (monotonic counter) until the
 // copy of stage s has actually been issued, then for its bytes.
-__device__ __forceinline__ void wait_stage(const MegaCtx& c, uint32_t s, uint32_t slot) {
-  const uint32_t g = s / (uint32_t)c.nslots;
+__device__ __forceinline__ void wait_stage(const MegaCtx& c, uint32_t s, uint32_t g, uint32_t slot) {
   Watchdog wd;
-  while (c.gen[slot] < g + 1u) wd.tick(c.P->err_flag, 4, (int)s);
+  while (*ring_gen(slot) < g + 1u) wd.tick(c.P->err_flag, 4, (int)s);
   __threadfence_block();
-  mbar_wait_bounded(&c.full[slot], g & 1u, c.P->err_flag, 3, (int)s);
+  mbar_wait_bounded(ring_full(slot), g & 1u, c.P->err_flag, 3, (int)s);
 }
 
 // ------------------------------------------------------------------------------------------------ activation staging
@@ -463,17 +476,25 @@ __device__ __forceinline__ void mma_rows(uint32_t w_addr, uint32_t row_pitch, bo
 }
 
 template <int NB, bool TP>
-__device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t sc_base, int row0, int rows, int cw,
-                             int lane, StageCursor& refill, StageCursor& refill_pf, float& best_v, int& best_i) {
+__device__ void gemv_consume(MegaCtx& c, const RingHot& h, const MegaOp& op, int op_idx, uint32_t sc_base, int row0, int rows,
+                             int cw, int lane, StageCursor& refill, StageCursor& refill_pf, float& best_v, int& best_i) {
   const MegaPlan& P = *c.P;
   const int R = op.R, ksplit = op.ksplit;
+  // loop invariants the epilogue and the refill need: read them from shared memory once, not once per unit
+  const int epi = op.epi, oflags = op.flags, ldo = op.ldo, PB = P.B, pf_stages = c.pf_stages;
+  const bool scalar = c.scalar_gemv != 0;
+  const bf16* const bias = op.bias;
+  uint32_t* const out_ll = op.out_ll;
+  float* const out_f32 = op.out_f32;
+  bf16* const s_h = c.s_h;
+  const float* const s_bias = c.s_bias;
   const int nv0 = op.kc0 >> 3, nvK = op.K >> 3;
   const int units = (rows + R - 1) / R;
   const uint4* xs = reinterpret_cast<const uint4*>(c.region_a);
   const uint32_t otag = tag16_of(tag32_of(c.epoch, op_idx));
   // row-parallel op under tensor parallelism (o_proj / down_proj): partial sums are exchanged between the GPUs
   // (compiled out of the single-GPU instantiation: the weight-streaming loop below is register-bound)
-  const bool xon = TP && op.xslot > 0 && op.epi == EPI_RES;
+  const bool xon = TP && op.xslot > 0 && epi == EPI_RES;
   const uint32_t xtag = TP ? tag32_of(c.epoch, op_idx) : 0u;
   const long long xslot_base = TP ? (long long)(op.xslot - 1) * P.tp_size : 0;                 // [slot][src rank][B][C]
   const long long xoff_w = TP ? (xslot_base + P.tp_rank) * (long long)P.B * P.C : 0;            // where peers find OUR partials
@@ -495,15 +516,15 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
 #pragma unroll 1
     for (int ks = 0; ks < ksplit; ++ks) {
       const uint32_t s = sc_base + (uint32_t)(u * ksplit + ks);
-      const uint32_t slot = s % (uint32_t)c.nslots;
+      const uint32_t sg = s / (uint32_t)h.nslots, slot = s - sg * (uint32_t)h.nslots;
       long long tk0 = 0;
       if (pw) tk0 = clock64();
-      wait_stage(c, s, slot);
+      wait_stage(c, s, sg, slot);
       if (pw) { const long long t = clock64(); pc_wait += t - tk0; tk0 = t; }
-      const uint4* wb = reinterpret_cast<const uint4*>(c.ring + (size_t)slot * c.slot_bytes);
+      const uint4* wb = reinterpret_cast<const uint4*>(mega_smem + h.ring_off + slot * (uint32_t)h.slot_bytes);
       const uint4* xb = xs + ks * nv0;
       const int nv = min(nv0, nvK - ks * nv0);  // this chunk's length in 16-byte vectors (the last chunk may be shorter)
-      if ((nv & 15) == 0 && !c.scalar_gemv) {
+      if ((nv & 15) == 0 && !scalar) {
         // tensor-pipe path: the chunk is a whole number of 128-element groups
         const uint32_t w_addr = smem_u32(wb), x_addr = smem_u32(xb);
 #pragma unroll
@@ -569,7 +590,7 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
       }
       __syncwarp();
       if (pw) { const long long t = clock64(); pc_dot += t - tk0; tk0 = t; }
-      if (lane == 0) issue_stage(c, refill, refill_pf, s + (uint32_t)c.nslots);  // this slot is free again: refill it
+      if (lane == 0) issue_stage(h, pf_stages, refill, refill_pf, s + (uint32_t)h.nslots);  // slot free again: refill it
       if (pw) pc_issue += clock64() - tk0;
     }
     long long te0 = 0;
@@ -582,24 +603,24 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
     // ---- epilogue: lane (i * NB + b) owns output (row r + i, sequence b)
     const int lrow = r;            // row index inside this CTA's slab
     const int grow = row0 + r;     // global row
-    if (op.epi == EPI_SWIGLU) {
+    if (epi == EPI_SWIGLU) {
 #pragma unroll
       for (int pr = 0; pr < kRMax / 2; ++pr)
 #pragma unroll
         for (int b = 0; b < NB; ++b)
-          if (2 * pr < rows_here && b < P.B && lane == pr * NB + b) {
+          if (2 * pr < rows_here && b < PB && lane == pr * NB + b) {
             const float val = silu_m(acc[2 * pr][b]) * acc[2 * pr + 1][b];
-            __stcg(op.out_ll + (long long)b * op.ldo + (grow >> 1) + pr, ll4_word(val, otag));
+            __stcg(out_ll + (long long)b * ldo + (grow >> 1) + pr, ll4_word(val, otag));
           }
     } else {
 #pragma unroll
       for (int i = 0; i < kRMax; ++i)
 #pragma unroll
         for (int b = 0; b < NB; ++b)
-          if (i < rows_here && b < P.B && lane == i * NB + b) {
+          if (i < rows_here && b < PB && lane == i * NB + b) {
             const int row = grow + i;
             float val = acc[i][b];
-            if (op.bias) val += (lrow + i < kBiasRows) ? c.s_bias[lrow + i] : __bfloat162float(op.bias[row]);
+            if (bias) val += (lrow + i < kBiasRows) ? s_bias[lrow + i] : __bfloat162float(bias[row]);
             if (TP && xon) {
               // tensor parallelism: this is rank tp_rank's PARTIAL sum over its K shard. Push it into every peer's
               // exchange buffer over NVLink ({fp32, tag} in one 8-byte store) and keep the own copy; the all-reduce is
@@ -611,20 +632,20 @@ __device__ void gemv_consume(MegaCtx& c, const MegaOp& op, int op_idx, uint32_t 
               c.s_xp[(lrow + i) * 4 + b] = val;
               continue;
             }
-            if (op.epi == EPI_RES) {
+            if (epi == EPI_RES) {
               // residual stream: bf16, resident in the shared memory of the CTA that owns the row
-              bf16* hp = c.s_h + b * kHRows + lrow + i;
+              bf16* hp = s_h + b * kHRows + lrow + i;
               val += __bfloat162float(*hp);
               *hp = __float2bfloat16(val);
             }
-            if (op.flags & F_OUT_F32) {
-              op.out_f32[(long long)b * op.ldo + row] = val;
-              if ((op.flags & F_ARGMAX) && (val > best_v || (val == best_v && row < best_i))) {
+            if (oflags & F_OUT_F32) {
+              out_f32[(long long)b * ldo + row] = val;
+              if ((oflags & F_ARGMAX) && (val > best_v || (val == best_v && row < best_i))) {
                 best_v = val;
                 best_i = row;
               }
             } else {
-              __stcg(op.out_ll + (long long)b * op.ldo + row, ll4_word(val, otag));
+              __stcg(out_ll + (long long)b * ldo + row, ll4_word(val, otag));
             }
           }
     }
@@ -974,13 +995,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   MegaOp* s_ops = reinterpret_cast<MegaOp*>(mega_smem + kHdrBytes);
   SlabEnt* s_tab = reinterpret_cast<SlabEnt*>(mega_smem + kHdrBytes + ops_bytes_of(n_ops));
   uint8_t* meta = mega_smem + front_bytes_of(n_ops);
-  uint64_t* full = reinterpret_cast<uint64_t*>(meta);
-  volatile uint32_t* gen = reinterpret_cast<volatile uint32_t*>(full + kMaxSlots);  // kMaxSlots counters
-  float* red = reinterpret_cast<float*>(const_cast<uint32_t*>(gen) + kMaxSlots + 4);  // 16 floats
+  float* red = reinterpret_cast<float*>(meta);  // 16 floats
   int* s_ctx = reinterpret_cast<int*>(red + 16);                                    // 4 ints
   float* am_v = reinterpret_cast<float*>(s_ctx + 4);                                // [8 warps][16 lanes]
   int* am_i = reinterpret_cast<int*>(am_v + kCWarps * 16);
-  float* s_bias = reinterpret_cast<float*>(am_i + kCWarps * 16);  // kBiasRows floats (meta scratch: 1312 + 512 <= 2048)
+  float* s_bias = reinterpret_cast<float*>(am_i + kCWarps * 16);  // kBiasRows floats (meta scratch: 1104 + 512 <= 2048)
   bf16* s_h = reinterpret_cast<bf16*>(meta + 2048);
   float* s_xp = reinterpret_cast<float*>(meta + 2048 + 4 * kHRows * 2);
   int* s_bt = reinterpret_cast<int*>(meta + kMetaFixed);
@@ -997,8 +1016,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     if (tid < P.B) s_ctx[tid] = P.ctx_lens[tid];
     if (tid == 0) {
       for (int s = 0; s < P.nslots; ++s) {
-        mbar_init(&full[s], 1);
-        gen[s] = 0u;
+        mbar_init(ring_full(s), 1);
+        *ring_gen(s) = 0u;
       }
       fence_barrier_init();
     }
@@ -1031,13 +1050,17 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   // hold it under the weight stream) on the refill path of every ring stage.
   MegaCtx& c = *reinterpret_cast<MegaCtx*>(mega_smem + 256);
   if (tid == 0) {
-  c.P = s_plan; c.ops = s_ops; c.tab = s_tab; c.full = full; c.gen = gen; c.red = red; c.am_v = am_v; c.am_i = am_i; c.s_ctx = s_ctx;
-  c.s_h = s_h; c.s_bias = s_bias; c.s_bt = s_bt; c.s_xp = s_xp; c.region_a = region_a; c.ring = ring; c.nslots = P.nslots; c.cta = blockIdx.x;
-  c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch; c.pf_stages = P.pf_stages; c.slot_bytes = P.slot_bytes; c.scalar_gemv = P.scalar_gemv; c.prof_mode = P.prof_mode; c.poll_ns = (unsigned int)P.poll_ns;
+  c.P = s_plan; c.tab = s_tab; c.red = red; c.am_v = am_v; c.am_i = am_i; c.s_ctx = s_ctx;
+  c.s_h = s_h; c.s_bias = s_bias; c.s_bt = s_bt; c.s_xp = s_xp; c.region_a = region_a; c.cta = blockIdx.x;
+  c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch; c.pf_stages = P.pf_stages; c.scalar_gemv = P.scalar_gemv; c.prof_mode = P.prof_mode; c.poll_ns = (unsigned int)P.poll_ns;
   c.prof_op = nullptr;
   }
   __syncthreads();
 
+  RingHot hot;
+  hot.tab_off = kHdrBytes + ops_bytes_of(n_ops);
+  hot.ring_off = (int)(ring - mega_smem);
+  hot.slot_bytes = P.slot_bytes; hot.nslots = P.nslots; hot.n_ops = n_ops;
   // every warp keeps its own cursor into the stage sequence for the refills it issues
   StageCursor refill;
   refill.op_i = 0;
@@ -1047,10 +1070,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     const bf16* src;
     uint32_t bytes;
     for (int s = P.nslots; s < P.nslots + P.pf_stages; ++s)
-      if (locate_stage(c, kpf, (uint32_t)s, src, bytes))
+      if (locate_stage(hot, kpf, (uint32_t)s, src, bytes))
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
     StageCursor kpf2 = refill;
-    for (int s = 0; s < P.nslots; ++s) issue_stage(c, k, kpf2, (uint32_t)s);
+    for (int s = 0; s < P.nslots; ++s) issue_stage(hot, P.pf_stages, k, kpf2, (uint32_t)s);
   }
 
   const int ctid = tid, cw = warp;
@@ -1072,7 +1095,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
       stage_x<NB>(c, op, i, ctid);
       if (prof && ctid == 0) prof[i * kProfStride + 1] = global_ns();
       const int row0 = s_tab[i].row0, rows = s_tab[i].rows;
-      gemv_consume<NB, TP>(c, op, i, sc_base, row0, rows, cw, lane, refill, refill_pf, best_v, best_i);
+      gemv_consume<NB, TP>(c, hot, op, i, sc_base, row0, rows, cw, lane, refill, refill_pf, best_v, best_i);
       sc_base += (uint32_t)(((rows + op.R - 1) / op.R) * op.ksplit);
       if (op.flags & F_ARGMAX) {
         // CTA-level partial argmax per sequence: lane (i * NB + b) tracked sequence b = lane % NB
