@@ -50,7 +50,7 @@ constexpr int kMaxSlots = 16;
 constexpr int kMaxOps = 192;
 constexpr int kAttnKeysPerCta = 32;
 constexpr int kPartStride = 130;    // O[128], m, l
-constexpr int kAttnScratchBytes = kCWarps * 8 * kPartStride * 4;
+constexpr int kAttnScratchBytes = (8 + 2 * 64) * 256;  // attention phase: Q tile [8][128] + K and V tiles [64][128] bf16 (34 KB)
 constexpr int kHRows = 64;          // residual rows one CTA can own
 constexpr int kBiasRows = 128;      // slab rows whose bias is staged in shared memory (larger slabs read it from L2)
 constexpr int kMaxBt = 1024;        // block-table entries cached in shared memory (batch * max_pages)
@@ -706,8 +706,17 @@ __device__ void gemv_consume(MegaCtx& c, const RingHot& h, const MegaOp& op, int
 // Every global access here costs a full L2 round trip under the weight stream, so the phase is organised as few
 // dependent round trips as possible: [K/V + rotary table] (issued before the wait) -> [q poll] -> compute -> [partials of
 // all splits polled in one batch by the merging CTA] -> output.
+// byte offset of 16-byte chunk `chunk` (0..15) of row `row` in a [rows][128] bf16 tile, XOR-swizzled (ldmatrix conflict-free)
+__device__ __forceinline__ uint32_t swz128(int row, int chunk) { return (uint32_t)(row * 256 + ((chunk ^ (row & 7)) << 4)); }
+
+constexpr int kAttnTile = 64;  // keys per shared-memory tile
+
 template <int G>
 __device__ __noinline__ void attn_phase(MegaCtx& c, const MegaOp& op, int op_idx, int ctid) {
+  // Tensor-pipe formulation (the scalar one - warp per key, 35 shuffles + 14 exp2 per key and warp - was issue-bound at
+  // ~0.8 us per key): the G query heads of the kv group are the M rows of mma.sync.m16n8k16 (rows G..15 are padding), the
+  // CTA's keys the N columns of S = Q K^T and the K rows of O = P V. Every warp computes the whole S (<= 64 keys, the tensor
+  // pipe is idle anyway) and owns 16 of the 128 output dims, so there is no merge between the warps.
   const MegaPlan& P = *c.P;
   const int items = P.B * P.Hkv;
   const int item = c.cta % items, split = c.cta / items;
@@ -720,32 +729,44 @@ __device__ __noinline__ void attn_phase(MegaCtx& c, const MegaOp& op, int op_idx
   const int per = (n_cached + nsplit - 1) / nsplit;
   const int k0 = split * per, k1 = min(n_cached, k0 + per);
   const bool has_new = (split == nsplit - 1);
+  const int nk_all = max(k1 - k0, 0) + (has_new ? 1 : 0);  // keys this CTA attends to (>= 1 when has_new)
 
-  const int cw = ctid >> 5, lane = ctid & 31;
+  const int cw = ctid >> 5, lane = ctid & 31, g = lane >> 2, tq = lane & 3;
   bf16* pool = op.pool;
   const int* bt = c.s_bt + b * P.max_pages;
-  const long long page_stride = 2LL * P.Hkv * P.page_size * 128;
-  const long long v_off = (long long)P.Hkv * P.page_size * 128;
+  const int page_size = P.page_size, Hkv = P.Hkv;
+  const long long page_stride = 2LL * Hkv * page_size * 128;
+  const long long v_off = (long long)Hkv * page_size * 128;
   const float sl2 = P.scale_log2;
   const uint32_t itag = tag16_of(tag32_of(c.epoch, op.in_op));
   const uint32_t otag16 = tag16_of(tag32_of(c.epoch, op_idx));
   const uint32_t otag32 = tag32_of(c.epoch, op_idx);
 
-  constexpr int U = 6;  // keys in flight per warp (one batch covers 48 keys per CTA)
-  uint2 kr[U], vr[U];
-  auto load_keys = [&](int kb) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int kk = kb + kCWarps * u;
-      if (kk < k1) {
-        const bf16* kp = pool + (long long)bt[kk / P.page_size] * page_stride +
-                         ((long long)kvh * P.page_size + kk % P.page_size) * 128 + lane * 4;
-        kr[u] = __ldcg(reinterpret_cast<const uint2*>(kp));
-        vr[u] = __ldcg(reinterpret_cast<const uint2*>(kp + v_off));
-      }
+  uint8_t* sQ = c.region_a;                    // [8][128] bf16, swizzled (2 KB)
+  uint8_t* sK = sQ + 8 * 256;                  // [64][128]
+  uint8_t* sV = sK + kAttnTile * 256;          // [64][128]
+  // cached keys [kt0, kt0 + cnt) of this CTA's range -> tile rows 0..cnt-1 (cp.async, 16 bytes per request); rows up to the
+  // next multiple of 16 are zero-filled (P = 0 there, but 0 * garbage must stay 0). `skip_row`: the row the new token's
+  // K/V will be written to by hand.
+  auto load_tile = [&](int kt0, int cnt, int skip_row) {
+    const int rows16 = (max(cnt, skip_row + 1) + 15) & ~15;
+    for (int i = ctid; i < rows16 * 32; i += kMegaThreads) {
+      const int row = i >> 5, part = i & 31, chunk = part & 15;
+      if (row == skip_row) continue;
+      const bool ok = row < cnt;
+      const int kk = kt0 + (ok ? row : 0);
+      const bf16* src = pool + (long long)bt[kk / page_size] * page_stride + ((long long)kvh * page_size + kk % page_size) * 128 +
+                        chunk * 8 + ((part & 16) ? v_off : 0);
+      cp_async16(((part & 16) ? sV : sK) + swz128(row, chunk), ok ? src : pool, ok);
     }
+    cp_async_commit();
   };
-  load_keys(k0 + cw);  // the cache does not depend on this step's qkv: fetch before waiting for q
+  const int ntiles = (nk_all + kAttnTile - 1) / kAttnTile;
+  {
+    // first tile: the cache does not depend on this step's qkv, fetch before waiting for q
+    const int cnt = min(k1 - k0, kAttnTile);
+    load_tile(k0, max(cnt, 0), (has_new && ntiles == 1) ? nk_all - 1 : -1);
+  }
   // rotary factors of the new position for this lane's 4 dims: table of (cos, sin)(pos * inv_freq) computed in fp32 by
   // the host exactly as Qwen2RotaryEmbedding does (modeling_qwen2.py:102-113)
   float cs[4], sn[4];
@@ -756,149 +777,190 @@ __device__ __noinline__ void attn_phase(MegaCtx& c, const MegaOp& op, int op_idx
     cs[2] = t1.x; sn[2] = t1.y; cs[3] = t1.z; sn[3] = t1.w;
   }
   const float sgn = (lane < 16) ? -1.f : 1.f;
-  auto rot = [&](uint4 own_ll, float* outv) {  // all 32 lanes must call (shuffle): the partner's dims sit in lane ^ 16
+  // RoPE (rotate-half: dims (i, i + 64) = lanes (l, l ^ 16)) of 4 dims per lane; result rounded to bf16 like the reference
+  auto rot = [&](uint4 own_ll) -> uint2 {  // all 32 lanes must call (shuffle)
     const uint2 d = ll4_data(own_ll);
     const uint2 pd = make_uint2(__shfl_xor_sync(0xffffffffu, d.x, 16), __shfl_xor_sync(0xffffffffu, d.y, 16));
-    float own[4], par[4];
+    float own[4], par[4], r[4];
     unpack4(d, own);
     unpack4(pd, par);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) outv[e] = bf16_round(own[e] * cs[e] + sgn * par[e] * sn[e]);
+    for (int e = 0; e < 4; ++e) r[e] = own[e] * cs[e] + sgn * par[e] * sn[e];
+    return make_uint2(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]));
   };
 
-  // ---- wait for q (G heads) [and k, v of the new token in the warp that owns it]: this lane's 4 dims
+  // ---- wait for q: warp h < G polls head h (this lane's 4 dims), rotates it and parks it in the Q tile; warp 7 of the CTA
+  // that owns the new token does the same for k (rotated) and v and appends both to the cache
   const uint32_t* qll = op.x_ll + (long long)b * op.ldx;
-  const bool new_here = has_new && cw == 0;
-  float q[G][4], knew[4], vnew[4];
-  uint2 vraw = make_uint2(0u, 0u);
-  {
-    uint4 qo[G], ko, vo;
+  const int r_new = (nk_all - 1) % kAttnTile;  // tile row of the new token (in the last tile)
+  if (cw < G) {
+    uint4 qo;
     Watchdog wd;
-    bool ok;
-    do {
-      ok = true;
-#pragma unroll
-      for (int h = 0; h < G; ++h) qo[h] = ld_poll_v4(qll + (kvh * G + h) * 128 + lane * 4);
-      if (new_here) {
-        ko = ld_poll_v4(qll + (P.Hq + kvh) * 128 + lane * 4);
-        vo = ld_poll_v4(qll + (P.Hq + P.Hkv + kvh) * 128 + lane * 4);
-        ok = ll4_ok(ko, itag) && ll4_ok(vo, itag);
-      }
-#pragma unroll
-      for (int h = 0; h < G; ++h)
-        if (!ll4_ok(qo[h], itag)) ok = false;
-      if (!ok) wd.tick(P.err_flag, 6, op.in_op);
-    } while (!ok);
-#pragma unroll
-    for (int h = 0; h < G; ++h) rot(qo[h], q[h]);
-    if (new_here) {
-      rot(ko, knew);
-      vraw = ll4_data(vo);
-      unpack4(vraw, vnew);
+    while (true) {
+      qo = ld_poll_v4(qll + (kvh * G + cw) * 128 + lane * 4);
+      if (ll4_ok(qo, itag)) break;
+      wd.tick(P.err_flag, 6, op.in_op);
+    }
+    const uint2 qr = rot(qo);
+    *reinterpret_cast<uint2*>(sQ + swz128(cw, lane >> 1) + (lane & 1) * 8) = qr;
+  }
+  uint2 knew_r = make_uint2(0u, 0u), vnew_r = make_uint2(0u, 0u);
+  if (has_new && cw == kCWarps - 1) {
+    uint4 ko, vo;
+    Watchdog wd;
+    while (true) {
+      ko = ld_poll_v4(qll + (P.Hq + kvh) * 128 + lane * 4);
+      vo = ld_poll_v4(qll + (P.Hq + Hkv + kvh) * 128 + lane * 4);
+      if (ll4_ok(ko, itag) && ll4_ok(vo, itag)) break;
+      wd.tick(P.err_flag, 6, op.in_op);
+    }
+    knew_r = rot(ko);
+    vnew_r = ll4_data(vo);
+    bf16* kp = pool + (long long)bt[n_cached / page_size] * page_stride + ((long long)kvh * page_size + n_cached % page_size) * 128 +
+               lane * 4;
+    *reinterpret_cast<uint2*>(kp) = knew_r;
+    *reinterpret_cast<uint2*>(kp + v_off) = vnew_r;
+    if (ntiles == 1) {
+      *reinterpret_cast<uint2*>(sK + swz128(r_new, lane >> 1) + (lane & 1) * 8) = knew_r;
+      *reinterpret_cast<uint2*>(sV + swz128(r_new, lane >> 1) + (lane & 1) * 8) = vnew_r;
     }
   }
-  float m[G], l[G], o[G][4];
-#pragma unroll
-  for (int h = 0; h < G; ++h) {
-    m[h] = -INFINITY;
-    l[h] = 0.f;
-    o[h][0] = o[h][1] = o[h][2] = o[h][3] = 0.f;
-  }
-  auto consume_key = [&](const float* kf, const float* vf) {
-    float s[G];
-#pragma unroll
-    for (int h = 0; h < G; ++h) {
-      s[h] = q[h][0] * kf[0];
-      s[h] = fmaf(q[h][1], kf[1], s[h]);
-      s[h] = fmaf(q[h][2], kf[2], s[h]);
-      s[h] = fmaf(q[h][3], kf[3], s[h]);
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-      for (int h = 0; h < G; ++h) s[h] += __shfl_xor_sync(0xffffffffu, s[h], off);
-#pragma unroll
-    for (int h = 0; h < G; ++h) {
-      const float m_new = fmaxf(m[h], s[h]);
-      const float corr = exp2f((m[h] - m_new) * sl2);  // m = -inf -> 0
-      const float p = exp2f((s[h] - m_new) * sl2);
-      m[h] = m_new;
-      l[h] = l[h] * corr + p;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[h][e] = fmaf(o[h][e], corr, p * vf[e]);
-    }
-  };
-#pragma unroll 1
-  for (int kb = k0 + cw; kb < k1; kb += kCWarps * U) {
-    if (kb != k0 + cw) load_keys(kb);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (kb + kCWarps * u < k1) {  // warp-uniform
-        float kf[4], vf[4];
-        unpack4(kr[u], kf);
-        unpack4(vr[u], vf);
-        consume_key(kf, vf);
-      }
-    }
-  }
-  if (new_here) {
-    // the new token: append rotated K and V to the cache, attend to it
-    bf16* kp = pool + (long long)bt[n_cached / P.page_size] * page_stride +
-               ((long long)kvh * P.page_size + n_cached % P.page_size) * 128 + lane * 4;
-    *reinterpret_cast<uint2*>(kp) = make_uint2(pack_bf16(knew[0], knew[1]), pack_bf16(knew[2], knew[3]));
-    *reinterpret_cast<uint2*>(kp + v_off) = vraw;
-    consume_key(knew, vnew);
-  }
-  float* part = reinterpret_cast<float*>(c.region_a);  // [8 warps][8 heads][130]
-#pragma unroll
-  for (int h = 0; h < G; ++h) {
-    float* dst = part + (cw * 8 + h) * kPartStride;
-    *reinterpret_cast<float2*>(dst + lane * 4) = make_float2(o[h][0], o[h][1]);
-    *reinterpret_cast<float2*>(dst + lane * 4 + 2) = make_float2(o[h][2], o[h][3]);
-    if (lane == 0) {
-      dst[128] = m[h];
-      dst[129] = l[h];
-    }
-  }
+#if OMC_MEGA_DETAIL
+  if (c.prof_op && ctid == 0) c.prof_op[4] = global_ns();  // q arrived
+#endif
+  cp_async_wait<0>();
   __syncthreads();
-  // ---- merge the 8 warps: thread -> (head = ctid / 32, dims 4 * (ctid % 32) ..)
-  const int h = ctid >> 5, d4 = (ctid & 31) * 4;
-  float acc4[4] = {0.f, 0.f, 0.f, 0.f}, m_tot = -INFINITY, l_tot = 0.f;
-  if (h < G) {
-    for (int w = 0; w < kCWarps; ++w) m_tot = fmaxf(m_tot, part[(w * 8 + h) * kPartStride + 128]);
-    for (int w = 0; w < kCWarps; ++w) {
-      const float* pw = part + (w * 8 + h) * kPartStride;
-      const float sc = (pw[128] == -INFINITY) ? 0.f : exp2f((pw[128] - m_tot) * sl2);
-      l_tot += pw[129] * sc;
+
+  uint32_t qf[8][4];
+  {
+    const uint32_t q_sa = smem_u32(sQ);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc4[e] += pw[d4 + e] * sc;
+    for (int ks = 0; ks < 8; ++ks)  // rows 8..15 of the A tile alias rows 0..7: their results are never read
+      ldmatrix_x4(q_sa + swz128(lane & 7, ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+  }
+  const uint32_t k_sa = smem_u32(sK), v_sa = smem_u32(sV);
+  float m_run = -INFINITY, l_run = 0.f;  // of head g (row g of the fragments)
+  float o[2][4];
+#pragma unroll
+  for (int n = 0; n < 2; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll 1
+  for (int t = 0; t < ntiles; ++t) {
+    const int nk = min(nk_all - t * kAttnTile, kAttnTile);  // keys in this tile (the new token included)
+    if (t > 0) {
+      // further tiles of a long context: single-buffered (load, wait, compute)
+      __syncthreads();
+      const bool last = (t == ntiles - 1);
+      const int cnt = nk - ((has_new && last) ? 1 : 0);
+      load_tile(k0 + t * kAttnTile, cnt, (has_new && last) ? r_new : -1);
+      if (has_new && last && cw == kCWarps - 1) {
+        *reinterpret_cast<uint2*>(sK + swz128(r_new, lane >> 1) + (lane & 1) * 8) = knew_r;
+        *reinterpret_cast<uint2*>(sV + swz128(r_new, lane >> 1) + (lane & 1) * 8) = vnew_r;
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    // S = Q K^T: 8-key n-tiles in pairs
+    float sc[kAttnTile / 8][4];
+#pragma unroll
+    for (int np = 0; np < kAttnTile / 16; ++np) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[2 * np][e] = sc[2 * np + 1][e] = 0.f;
+      if (np * 16 < nk) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          uint32_t b0, b1, b2, b3;
+          const int key = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+          const int chunk = ks * 2 + ((lane >> 3) & 1);
+          ldmatrix_x4(k_sa + swz128(key, chunk), b0, b1, b2, b3);
+          mma_bf16_16816(sc[2 * np], qf[ks], b0, b1);
+          mma_bf16_16816(sc[2 * np + 1], qf[ks], b2, b3);
+        }
+      }
+    }
+    // mask, row max of head g over the tile (this lane: keys nt*8 + 2*tq, +1), online softmax
+    float mx = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < kAttnTile / 8; ++nt) {
+      const int kl = nt * 8 + tq * 2;
+      sc[nt][0] = (kl < nk) ? sc[nt][0] : -INFINITY;
+      sc[nt][1] = (kl + 1 < nk) ? sc[nt][1] : -INFINITY;
+      mx = fmaxf(mx, fmaxf(sc[nt][0], sc[nt][1]));
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m_run, mx);  // finite: every tile holds at least one valid key
+    const float corr = exp2f((m_run - m_new) * sl2);  // m_run = -inf -> 0
+    m_run = m_new;
+    const float msc = m_new * sl2;
+    uint32_t pf[kAttnTile / 16][4];
+    float lsum = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < kAttnTile / 16; ++kk) {
+      const float p0 = exp2f(sc[2 * kk][0] * sl2 - msc), p1 = exp2f(sc[2 * kk][1] * sl2 - msc);
+      const float p2 = exp2f(sc[2 * kk + 1][0] * sl2 - msc), p3 = exp2f(sc[2 * kk + 1][1] * sl2 - msc);
+      lsum += (p0 + p1) + (p2 + p3);
+      pf[kk][0] = pack_bf16(p0, p1);
+      pf[kk][1] = 0u;  // padding rows g + 8
+      pf[kk][2] = pack_bf16(p2, p3);
+      pf[kk][3] = 0u;
+    }
+    l_run = l_run * corr + lsum;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      o[n][0] *= corr;
+      o[n][1] *= corr;
+    }
+    // O[:, 16*cw .. 16*cw+16) += P V
+#pragma unroll
+    for (int kk = 0; kk < kAttnTile / 16; ++kk) {
+      if (kk * 16 < nk) {
+        uint32_t b0, b1, b2, b3;
+        const int key = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        const int chunk = cw * 2 + (lane >> 4);
+        ldmatrix_x4_trans(v_sa + swz128(key, chunk), b0, b1, b2, b3);
+        mma_bf16_16816(o[0], pf[kk], b0, b1);
+        mma_bf16_16816(o[1], pf[kk], b2, b3);
+      }
     }
   }
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+#if OMC_MEGA_DETAIL
+  if (c.prof_op && ctid == 0) c.prof_op[7] = global_ns();  // P V done
+#endif
+  // this lane: head g, dims 16*cw + 8*n + 2*tq, +1
   uint32_t* outp = op.out_ll + (long long)b * op.ldo + kvh * G * 128;  // this kv group's heads
   if (nsplit == 1) {
-    if (h < G) {
-      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-      __stcg(reinterpret_cast<uint4*>(outp + h * 128 + d4),
-             make_uint4(ll4_word(acc4[0] * inv, otag16), ll4_word(acc4[1] * inv, otag16), ll4_word(acc4[2] * inv, otag16),
-                        ll4_word(acc4[3] * inv, otag16)));
+    if (g < G) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+        __stcg(reinterpret_cast<uint2*>(outp + g * 128 + cw * 16 + n * 8 + tq * 2),
+               make_uint2(ll4_word(o[n][0] * inv, otag16), ll4_word(o[n][1] * inv, otag16)));
     }
     return;
   }
-  // ---- publish this CTA's partial {fp32, tag}
+  // ---- publish this CTA's partial {fp32, tag}: unnormalised O relative to the raw score maximum m, then (m, l)
   uint2* wsb = P.attn_part + (((long long)op.parity * P.grid + (long long)item * P.nsplit_max) * 8) * kPartStride;
-  if (h < G) {
-    uint2* dst = wsb + ((long long)split * 8 + h) * kPartStride;
-    __stcg(reinterpret_cast<uint4*>(dst + d4), make_uint4(__float_as_uint(acc4[0]), otag32, __float_as_uint(acc4[1]), otag32));
-    __stcg(reinterpret_cast<uint4*>(dst + d4 + 2), make_uint4(__float_as_uint(acc4[2]), otag32, __float_as_uint(acc4[3]), otag32));
-    if ((ctid & 31) == 0)
-      __stcg(reinterpret_cast<uint4*>(dst + 128), make_uint4(__float_as_uint(m_tot), otag32, __float_as_uint(l_tot), otag32));
+  if (g < G) {
+    uint2* dst = wsb + ((long long)split * 8 + g) * kPartStride;
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+      __stcg(reinterpret_cast<uint4*>(dst + cw * 16 + n * 8 + tq * 2),
+             make_uint4(__float_as_uint(o[n][0]), otag32, __float_as_uint(o[n][1]), otag32));
+    if (cw == 0 && tq == 0)
+      __stcg(reinterpret_cast<uint4*>(dst + 128), make_uint4(__float_as_uint(m_run), otag32, __float_as_uint(l_run), otag32));
   }
+#if OMC_MEGA_DETAIL
+  if (c.prof_op && ctid == 0) c.prof_op[5] = global_ns();  // own partial published
+#endif
+  float* part = reinterpret_cast<float*>(c.region_a);  // merge scratch [8 warps][4 heads][130] (aliases the Q/K/V tiles)
   // ---- merge: head hh belongs to the CTA of split (hh % nsplit). The (head, split) partials this CTA must read are
   // dealt round-robin to its 8 warps, each warp polls its share in ONE batch, warps combine through shared memory.
   int n_mine = 0;
   for (int hh = split; hh < G; hh += nsplit) ++n_mine;
   if (n_mine == 0) return;          // CTA-uniform
-  __syncthreads();                  // everyone is done reading `part`: reuse it as [8 warps][4 heads][130] + m_tot[4]
+  __syncthreads();                  // everyone is done with the Q/K/V tiles: reuse them as [8 warps][4 heads][130]
   constexpr int MS = 5;             // (head, split) pairs per warp: 8 * 5 = 40 >= nsplit_max (37) or 4 heads x 7 splits
   float a4[MS][4], ml_m[MS], ml_l[MS];
   int pair_h[MS];

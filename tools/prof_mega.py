@@ -61,6 +61,14 @@ for k, idx in kinds.items():
         continue
     m = cyc[:, idx, :].mean(dim=(0, 1)) / 1965.0
     print(f"  {k:8s} {m[0].item():7.2f} {m[1].item():7.2f} {m[2].item():7.2f} {m[3].item():7.2f}")
+ai = kinds["attn"]
+raw = plan.prof.cpu().double()
+if raw[:, ai, 4].sum() > 0:  # detail build: stamps inside the attention phase (relative to the CTA's phase start)
+    st = (raw[:, ai, 4:8] - raw[:, ai, 0:1]) / 1000.0
+    for j, nm in enumerate(("q arrived", "own partial published", "warp 0: first K/V row in registers", "warp 0 done with its keys")):
+        v = st[:, :, j]
+        v = v[v > 0]
+        print(f"  attn: {nm:34s} +{v.mean().item():6.2f} us after phase start (max {v.max().item():6.2f}, n={v.numel()})")
 print(f"whole step (first op start -> last op end): {(p[:, -1, 2].max() - p[:, 0, 0].min()).item():.1f} us")
 # critical path per layer: time between the slowest CTA finishing 'down' of consecutive layers
 if layers > 2:
