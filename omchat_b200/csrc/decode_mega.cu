@@ -254,7 +254,8 @@ struct MegaCtx {
 // global source address and byte count of the stage, or false when the op list is exhausted.
 static_assert(sizeof(MegaCtx) <= 256, "MegaCtx must fit its 256-byte shared-memory slot");
 
-__device__ __forceinline__ bool locate_stage(const RingHot& h, StageCursor& k, uint32_t s, const bf16*& src, uint32_t& bytes) {
+__device__ __forceinline__ bool locate_stage(const RingHot& h, StageCursor& k, uint32_t s, const bf16*& src, uint32_t& bytes,
+                                             int& ncopies, uint32_t& pitch_bytes) {
   int oi = k.op_i;
   uint32_t base = 0, cnt = 0;
   const SlabEnt* tab = reinterpret_cast<const SlabEnt*>(mega_smem + h.tab_off);
@@ -272,13 +273,20 @@ __device__ __forceinline__ bool locate_stage(const RingHot& h, StageCursor& k, u
   const int ksplit = op.ksplit, R = op.R, K = op.K;
   int u = (int)rel, ks = 0;
   if (ksplit > 1) {
+    // split-K stage order: unit-major (the chunks of one row are consecutive stages, consumed back to back by one warp).
+    // Tried: chunk-major inside groups of 8 units so that consecutive stages go to different warps - 2.5 % slower (the
+    // op's end skew grew from 4.3 to 7 us); and the ring depth matters in whole units: 12 slots = 4 rows of 3 chunks, 10
+    // slots cost 48 % of down_proj's time.
     u = (int)(rel / (uint32_t)ksplit);
     ks = (int)rel - u * ksplit;
   }
   const int r = u * R;
   const int rows_here = min(R, e.rows - r);
   const int kbeg = ks * op.kc0, Kc = min(op.kc0, K - kbeg);
-  bytes = (uint32_t)(rows_here * Kc) * 2u;
+  // whole rows are one contiguous copy; a K chunk of several rows is one copy per row (row pitch K)
+  ncopies = ksplit > 1 ? rows_here : 1;
+  bytes = (uint32_t)((ksplit > 1 ? 1 : rows_here) * Kc) * 2u;
+  pitch_bytes = (uint32_t)K * 2u;
   src = e.w0 + ((size_t)(uint32_t)r * (uint32_t)K + (uint32_t)kbeg);
   return true;
 }
@@ -288,14 +296,20 @@ __device__ __forceinline__ bool locate_stage(const RingHot& h, StageCursor& k, u
 // Called by ONE lane with that warp's cursors.
 __device__ __forceinline__ void issue_stage(const RingHot& h, int pf_stages, StageCursor& k, StageCursor& kpf, uint32_t s) {
   const bf16* src;
-  uint32_t bytes;
-  if (pf_stages > 0 && locate_stage(h, kpf, s + (uint32_t)pf_stages, src, bytes))
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-  if (!locate_stage(h, k, s, src, bytes)) return;
+  uint32_t bytes, pitch;
+  int ncopies;
+  if (pf_stages > 0 && locate_stage(h, kpf, s + (uint32_t)pf_stages, src, bytes, ncopies, pitch))
+    for (int i = 0; i < ncopies; ++i)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(src) + (size_t)i * pitch),
+                   "r"(bytes)
+                   : "memory");
+  if (!locate_stage(h, k, s, src, bytes, ncopies, pitch)) return;
   const uint32_t g = s / (uint32_t)h.nslots, slot = s - g * (uint32_t)h.nslots;
   fence_proxy_async();  // generic-proxy reads of this slot (previous stage) are ordered before the async-proxy refill
-  mbar_arrive_expect_tx(ring_full(slot), bytes);
-  bulk_g2s(mega_smem + h.ring_off + slot * (uint32_t)h.slot_bytes, src, bytes, ring_full(slot));
+  mbar_arrive_expect_tx(ring_full(slot), bytes * (uint32_t)ncopies);
+  uint8_t* dst = mega_smem + h.ring_off + slot * (uint32_t)h.slot_bytes;
+  for (int i = 0; i < ncopies; ++i)
+    bulk_g2s(dst + (size_t)i * bytes, reinterpret_cast<const uint8_t*>(src) + (size_t)i * pitch, bytes, ring_full(slot));
   __threadfence_block();
   *ring_gen(slot) = g + 1u;  // publish: the barrier is now in the phase that carries stage s
 }
@@ -1130,10 +1144,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   if (tid == 0) {  // prime the ring (stages 0 .. nslots-1) and the L2 prefetch window behind it
     StageCursor k = refill, kpf = refill;
     const bf16* src;
-    uint32_t bytes;
+    uint32_t bytes, pitch;
+    int ncopies;
     for (int s = P.nslots; s < P.nslots + P.pf_stages; ++s)
-      if (locate_stage(hot, kpf, (uint32_t)s, src, bytes))
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+      if (locate_stage(hot, kpf, (uint32_t)s, src, bytes, ncopies, pitch))
+        for (int i = 0; i < ncopies; ++i)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(src) + (size_t)i * pitch),
+                       "r"(bytes)
+                       : "memory");
     StageCursor kpf2 = refill;
     for (int s = 0; s < P.nslots; ++s) issue_stage(hot, P.pf_stages, k, kpf2, (uint32_t)s);
   }
@@ -1262,8 +1280,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
 // ------------------------------------------------------------------------------------------------ host side
 // Split a K-element row into the fewest chunks that fit a ring slot; chunks are kc0 elements (a multiple of 256 = one
 // 16-byte vector per lane per 8 rounds when possible, else of 8), the last one takes what is left.
-static int pick_ksplit(int K, int slot_bytes, int* kc0) {
-  const int cap = slot_bytes / 2;  // elements per slot
+static int pick_ksplit(int K, int slot_bytes, int rows, int* kc0) {
+  const int cap = slot_bytes / (2 * rows);  // elements of one row per slot
   if (K < 8 || K % 8 != 0 || cap < 8) return -1;
   const int d = (K + cap - 1) / cap;
   int per = (K + d - 1) / d;
@@ -1365,16 +1383,25 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
     o.type = OP_GEMV; o.N = N; o.K = K; o.epi = (uint8_t)epi; o.flags = (uint8_t)flags;
     o.gran = (epi == EPI_SWIGLU) ? 2 : 1;
     o.kc0 = K;
-    const int ksp = pick_ksplit(K, slot_bytes, &o.kc0);
+    // stage geometry: R whole rows when two of them fit a slot, else the same K chunk of TWO rows (one bulk copy per
+    // row): the tensor-pipe dot product shares every activation fragment between the two rows, and a one-row stage costs
+    // twice the ldmatrix traffic per weight byte (down_proj was shared-memory-bandwidth bound that way)
+    int R = slot_bytes / (K * 2);
+    if (R > kRMax) R = kRMax;
+    if (o.gran == 2) R &= ~1;
+    int ksp = 1;
+    if (R < 2) {
+      // split-K stages: one row per stage by default. (Two-row stages - the same K chunk of two rows, one bulk copy per row,
+      // activation fragments shared by both rows - measured 0.5 % slower: the ring is latency-bound, not LDS-bound.)
+      R = 1;
+      ksp = pick_ksplit(K, slot_bytes, 1, &o.kc0);
+      if (d->scalar_gemv & 2) {
+        R = 2;
+        ksp = pick_ksplit(K, slot_bytes, 2, &o.kc0);
+      }
+    }
     o.ksplit = (uint8_t)ksp;
-    if (ksp < 1 || ksp > 255 || K % 8 != 0 || N % o.gran != 0) { bad = true; o.ksplit = 1; o.kc0 = K; }
-    int R = 1;
-    if (o.ksplit == 1) {
-      R = slot_bytes / (K * 2);
-      if (R > kRMax) R = kRMax;
-      if (o.gran == 2) R &= ~1;
-      if (R < o.gran) bad = true;
-    } else if (o.gran == 2) bad = true;  // a (gate, up) pair must fit one ring stage
+    if (ksp < 1 || ksp > 255 || K % 8 != 0 || N % o.gran != 0 || R < o.gran) { bad = true; o.ksplit = 1; o.kc0 = K; }
     o.R = (uint8_t)(R < 1 ? 1 : R);
     if (norm_w != nullptr && K > 4096) bad = true;
     o.W = (const bf16*)W; o.norm_w = (const bf16*)norm_w; o.bias = (const bf16*)bias;
@@ -1422,11 +1449,12 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   const int meta_bytes = kMetaFixed + bt_bytes_of(B, d->max_pages);
   int nslots = (kSmemLimit - ops_bytes - meta_bytes - region_a) / slot_bytes;
   if (nslots > kMaxSlots) nslots = kMaxSlots;
+  if (((d->scalar_gemv >> 4) & 15) >= 2 && nslots > ((d->scalar_gemv >> 4) & 15)) nslots = (d->scalar_gemv >> 4) & 15;  // experiment
   if (nslots < 2) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: activations leave no room for the weight ring");
   P->nslots = nslots; P->region_a_bytes = region_a;
   P->pf_stages = d->l2_prefetch_stages < 0 ? 0 : d->l2_prefetch_stages;
   P->slot_bytes = slot_bytes;
-  P->scalar_gemv = d->scalar_gemv & 1;
+  P->scalar_gemv = d->scalar_gemv & 1;  // (bit 1: one-row stages for split-K ops, an A/B switch of the plan builder)
   P->prof_mode = (d->scalar_gemv >> 8) & 0xff;  // tools/prof_mega.py: which breakdown warp 0 records
   P->poll_ns = (d->scalar_gemv >> 16) & 0x7fff; // experiment: back-off between failed polls
   P->smem_bytes = ops_bytes + meta_bytes + region_a + nslots * slot_bytes;

@@ -427,7 +427,7 @@ class DecodePlan:
         d.eps, d.attn_scale = eps, scale
         d.l2_prefetch_stages = int(os.environ.get("OMCHAT_B200_MEGA_PF", "0"))
         d.ring_slot_bytes = int(os.environ.get("OMCHAT_B200_MEGA_SLOT", "0"))  # 0 = the library's default
-        d.scalar_gemv = (int(os.environ.get("OMCHAT_B200_MEGA_SCALAR", "0"))  # A/B: FFMA dot products instead of mma.sync
+        d.scalar_gemv = (int(os.environ.get("OMCHAT_B200_MEGA_SCALAR", "0"))  # A/B: 1 = FFMA dots, 2 = one-row split-K stages
                          | int(os.environ.get("OMCHAT_B200_MEGA_PROFMODE", "0")) << 8  # profiling detail (tools/prof_mega.py)
                          | int(os.environ.get("OMCHAT_B200_MEGA_POLLNS", "0")) << 16)  # experiment: poll back-off (ns)
         d.embed, d.final_norm, d.lm_head, d.rope_cs = embed.data_ptr(), final_norm.data_ptr(), lm_head.data_ptr(), rope_cs.data_ptr()
