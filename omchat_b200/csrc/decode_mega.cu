@@ -47,28 +47,38 @@ constexpr int kRMax = 4;            // weight rows per ring stage (upper bound)
 constexpr int kSlotBytesDefault = 14336;  // ring slot: 2 rows of K=3584; a K=18944 row travels as 3 chunks (6400|6400|6144)
 constexpr int kSlotBytesMax = 32768;
 constexpr int kMaxSlots = 16;
-constexpr int kMaxOps = 192;
+constexpr int kMaxSub = 8;                      // K-chunk sub-ops a wide MLP may be cut into
+constexpr int kOpsPerLayerMax = 3 + 2 * kMaxSub;
+constexpr int kMaxOps = 640;
 constexpr int kAttnKeysPerCta = 32;
 constexpr int kPartStride = 130;    // O[128], m, l
-constexpr int kAttnScratchBytes = (8 + 2 * 64) * 256;  // attention phase: Q tile [8][128] + K and V tiles [64][128] bf16 (34 KB)
+constexpr int kAttnScratchBytes = (8 + 2 * 48) * 256;  // attention phase: Q tile [8][128] + K and V tiles [48][128] bf16 (26 KB)
 constexpr int kHRows = 64;          // residual rows one CTA can own
 constexpr int kBiasRows = 128;      // slab rows whose bias is staged in shared memory (larger slabs read it from L2)
 constexpr int kMaxBt = 1024;        // block-table entries cached in shared memory (batch * max_pages)
 constexpr int kProfStride = 8;       // uint64 per (CTA, op) in the optional profile buffer
 constexpr int kMaxTp = 8;           // tensor-parallel ranks one step can span (peer exchange buffers over NVLink)
 constexpr int kXpBytes = kHRows * 4 * 4;  // this CTA's own row-parallel partial sums [kHRows][4 sequences] fp32
-constexpr int kHdrBytes = 768;  // shared: MegaPlan header (256 B) | the kernel's MegaCtx (256 B) | ring barriers + generations
+// shared-memory front: MegaPlan header (256 B) | the kernel's MegaCtx (256 B) | ring barriers + generations | a WINDOW of
+// the op list and of the per-CTA slab table (the whole list, 16 KB for 28 layers, would cost the ring a slot: the ops
+// live in global memory and a sliding window of kWin entries - op i at index i % kWin - is refreshed one op per iteration)
+constexpr int kWin = 32;        // ops [cur, cur + kWin - 3] are valid while op `cur` runs; refills look < 24 ops ahead
+constexpr int kOpsOff = 704;
+constexpr int kTabOff = kOpsOff + kWin * 96;
+constexpr int kHdrBytes = (kTabOff + kWin * 24 + 127) & ~127;
 constexpr int kFullOff = 512;   // uint64 full[kMaxSlots]: mbarriers of the ring slots
 constexpr int kGenOff = 640;    // uint32 gen[kMaxSlots]: copies issued into each slot so far (monotonic: no parity aliasing)
-__host__ __device__ __forceinline__ int ops_bytes_of(int n_ops) { return (n_ops * 88 + 127) & ~127; }
-__host__ __device__ __forceinline__ int front_bytes_of(int n_ops) { return kHdrBytes + ops_bytes_of(n_ops) + ((n_ops * 24 + 127) & ~127); }
 constexpr int kMetaFixed = 2048 + 4 * kHRows * 2 + kXpBytes;  // barriers/scratch | residual slab | partials | block table (sized per plan)
 __host__ __device__ __forceinline__ int bt_bytes_of(int B, int max_pages) { return (B * max_pages * 4 + 127) & ~127; }
 constexpr int kSmemLimit = 227 * 1024;
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;  // a protocol bug must end in a trap, never in a hung GPU
 
 enum { OP_GEMV = 1, OP_ATTN = 2, OP_FINAL = 3 };
-enum { F_OUT_F32 = 1, F_X_EMBED = 2, F_ARGMAX = 4 };
+enum { F_OUT_F32 = 1, F_X_EMBED = 2, F_ARGMAX = 4, F_X_KEEP = 8, F_ADD_PART = 16 };
+// epilogues of the K-chunk sub-ops of a row-parallel GEMV (private to this kernel; the public OMC_EPI_* stop at 3):
+// the first chunk stores the row's partial sum in shared memory, middle chunks add to it, the last chunk (EPI_RES +
+// F_ADD_PART) adds it to its own sum before the usual epilogue
+enum { EPI_PART_SET = 8, EPI_PART_ADD = 9 };
 
 struct MegaOp {  // 88 bytes (the op list lives in shared memory: every byte here is a byte less of weight ring)
   const bf16* W;
@@ -80,11 +90,13 @@ struct MegaOp {  // 88 bytes (the op list lives in shared memory: every byte her
   bf16* pool;            // ATTN: this layer's KV pool
   int32_t N, K, ldx, ldo;
   int32_t kc0;           // elements per K chunk (chunk ks = [ks*kc0, min(K, (ks+1)*kc0)))
+  int32_t ldw;           // row pitch of W in elements (= K unless the op is a K-chunk sub-op of a wider matrix)
   int16_t in_op;         // index of the op whose tag the input carries
   uint8_t type, epi, R, ksplit, gran, flags, parity;
   uint8_t xslot;         // 1 + peer exchange slot of a row-parallel op under tensor parallelism (0 = none)
+  int32_t pad;
 };
-static_assert(sizeof(MegaOp) == 88, "MegaOp layout");
+static_assert(sizeof(MegaOp) == 96, "MegaOp layout");
 // Per-CTA view of a GEMV op, built once per launch in shared memory: this CTA's row slab and where its stages sit in the
 // CTA's stage sequence (locating a stage must not cost 64-bit divisions on the refill path)
 struct SlabEnt {  // 24 bytes
@@ -92,6 +104,7 @@ struct SlabEnt {  // 24 bytes
   uint32_t base, cnt;  // stages [base, base + cnt) of this CTA's stream belong to the op (cnt = 0: not a GEMV)
   int32_t row0, rows;
 };
+static_assert(sizeof(SlabEnt) == 24 && (kWin & (kWin - 1)) == 0, "window layout");
 
 struct MegaPlan {  // header, followed by n_ops MegaOp
   int32_t n_ops, B, C, Hq, Hkv, G, page_size, max_pages;
@@ -116,7 +129,7 @@ struct MegaPlan {  // header, followed by n_ops MegaOp
                         // layout (uint2 {fp32 bits | index, tag32}): partials [4 slots][tp][B][C], then argmax [tp][B][2]
 };
 static_assert(sizeof(MegaPlan) % 16 == 0, "MegaPlan must keep the op array 16-byte aligned");
-static_assert(sizeof(MegaPlan) <= 256 && sizeof(MegaOp) == 88 && sizeof(SlabEnt) == 24, "shared-memory front layout");
+static_assert(sizeof(MegaPlan) == 256 && sizeof(MegaOp) == 96, "shared-memory front layout (and lib.py's op parser)");
 
 // ------------------------------------------------------------------------------------------------ device helpers
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -173,7 +186,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
   while (!mbar_try_wait(bar, parity)) wd.tick(err_flag, code, detail);
 }
 
-__device__ __forceinline__ uint32_t tag32_of(uint32_t epoch, int op_idx) { return epoch * 256u + (uint32_t)op_idx + 1u; }
+__device__ __forceinline__ uint32_t tag32_of(uint32_t epoch, int op_idx) { return epoch * 1024u + (uint32_t)op_idx + 1u; }
 __device__ __forceinline__ uint32_t tag16_of(uint32_t t32) { return ((t32 % 65535u) + 1u) << 16; }  // pre-shifted, never 0
 __device__ __forceinline__ bool ll4_ok(uint4 v, uint32_t tag) {
   return ((v.x ^ tag) < 65536u) & ((v.y ^ tag) < 65536u) & ((v.z ^ tag) < 65536u) & ((v.w ^ tag) < 65536u);
@@ -191,6 +204,21 @@ __device__ __forceinline__ void slab_rows(int N, int gran, int cta, int grid, in
   const int g0 = (int)(ng * cta / grid), g1 = (int)(ng * (cta + 1) / grid);
   row0 = g0 * gran;
   rows = (g1 - g0) * gran;
+}
+
+// this CTA's slab of a GEMV op and its stage count; `base` = stage index where the op starts in the CTA's stream
+__device__ __forceinline__ SlabEnt make_slab(const MegaOp& op, uint32_t base) {
+  SlabEnt e;
+  e.w0 = nullptr; e.base = base; e.cnt = 0; e.row0 = 0; e.rows = 0;
+  if (op.type == OP_GEMV) {
+    slab_rows(op.N, op.gran, (int)blockIdx.x, (int)gridDim.x, e.row0, e.rows);
+    e.cnt = (uint32_t)(((e.rows + op.R - 1) / op.R) * op.ksplit);
+    e.w0 = op.W + (size_t)e.row0 * op.ldw;
+  }
+  return e;
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 
 __device__ __forceinline__ void unpack8(uint4 v, float* f) {
@@ -217,14 +245,15 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // the ldmatrix traffic of the other warps - measured ~0.5 us per refill before this layout.
 extern __shared__ __align__(128) uint8_t mega_smem[];
 struct RingHot {  // by value, in registers
-  int tab_off, ring_off;  // byte offsets of the slab table and of ring slot 0
+  int ring_off;  // byte offset of ring slot 0
   int slot_bytes, nslots, n_ops;
 };
 __device__ __forceinline__ uint64_t* ring_full(uint32_t slot) { return reinterpret_cast<uint64_t*>(mega_smem + kFullOff) + slot; }
 __device__ __forceinline__ volatile uint32_t* ring_gen(uint32_t slot) {
   return reinterpret_cast<volatile uint32_t*>(mega_smem + kGenOff) + slot;
 }
-__device__ __forceinline__ const struct MegaOp* smem_ops() { return reinterpret_cast<const struct MegaOp*>(mega_smem + kHdrBytes); }
+__device__ __forceinline__ MegaOp* win_ops() { return reinterpret_cast<MegaOp*>(mega_smem + kOpsOff); }    // [kWin]
+__device__ __forceinline__ SlabEnt* win_tab() { return reinterpret_cast<SlabEnt*>(mega_smem + kTabOff); }  // [kWin]
 
 // Position of a stage index in the op list: the op that owns it (a hint that only moves forward; n_ops = exhausted)
 struct StageCursor {
@@ -233,7 +262,7 @@ struct StageCursor {
 
 struct MegaCtx {
   const MegaPlan* P;     // shared copy of the plan header
-  const SlabEnt* tab;    // shared: this CTA's slab of every op
+  const MegaOp* gops;    // the whole op list in global memory (the window is refreshed from it)
   float* red;            // [16] floats of block-reduction scratch
   float* am_v;           // [8 warps][16]
   int* am_i;
@@ -254,23 +283,25 @@ struct MegaCtx {
 // global source address and byte count of the stage, or false when the op list is exhausted.
 static_assert(sizeof(MegaCtx) <= 256, "MegaCtx must fit its 256-byte shared-memory slot");
 
-__device__ __forceinline__ bool locate_stage(const RingHot& h, StageCursor& k, uint32_t s, const bf16*& src, uint32_t& bytes,
-                                             int& ncopies, uint32_t& pitch_bytes) {
-  int oi = k.op_i;
+__device__ __forceinline__ bool locate_stage(const RingHot& h, int cur_op, StageCursor& k, uint32_t s, const bf16*& src,
+                                             uint32_t& bytes, int& ncopies, uint32_t& pitch_bytes) {
+  int oi = max(k.op_i, cur_op);  // entries of finished ops have been recycled: never look behind the running op
   uint32_t base = 0, cnt = 0;
-  const SlabEnt* tab = reinterpret_cast<const SlabEnt*>(mega_smem + h.tab_off);
-  while (oi < h.n_ops) {
-    const uint2 bc = *reinterpret_cast<const uint2*>(&tab[oi].base);
+  const SlabEnt* tab = win_tab();
+  const int hi = min(h.n_ops, cur_op + kWin - 2);
+  while (oi < hi) {
+    const uint2 bc = *reinterpret_cast<const uint2*>(&tab[oi & (kWin - 1)].base);
     base = bc.x; cnt = bc.y;
     if (s < base + cnt) break;
     ++oi;
   }
   k.op_i = oi;
   if (oi >= h.n_ops) return false;
-  const MegaOp& op = smem_ops()[oi];
-  const SlabEnt& e = tab[oi];
+  if (oi >= hi) __trap();  // the stage lies beyond the op window (host-side checks make this unreachable)
+  const MegaOp& op = win_ops()[oi & (kWin - 1)];
+  const SlabEnt& e = tab[oi & (kWin - 1)];
   const uint32_t rel = s - base;
-  const int ksplit = op.ksplit, R = op.R, K = op.K;
+  const int ksplit = op.ksplit, R = op.R, K = op.K, ldw = op.ldw;
   int u = (int)rel, ks = 0;
   if (ksplit > 1) {
     // split-K stage order: unit-major (the chunks of one row are consecutive stages, consumed back to back by one warp).
@@ -283,27 +314,29 @@ __device__ __forceinline__ bool locate_stage(const RingHot& h, StageCursor& k, u
   const int r = u * R;
   const int rows_here = min(R, e.rows - r);
   const int kbeg = ks * op.kc0, Kc = min(op.kc0, K - kbeg);
-  // whole rows are one contiguous copy; a K chunk of several rows is one copy per row (row pitch K)
-  ncopies = ksplit > 1 ? rows_here : 1;
-  bytes = (uint32_t)((ksplit > 1 ? 1 : rows_here) * Kc) * 2u;
-  pitch_bytes = (uint32_t)K * 2u;
-  src = e.w0 + ((size_t)(uint32_t)r * (uint32_t)K + (uint32_t)kbeg);
+  // whole rows of a dense matrix are one contiguous copy; a K chunk of several rows is one copy per row (row pitch ldw)
+  const bool dense = (ksplit == 1) & (ldw == K);
+  ncopies = dense ? 1 : rows_here;
+  bytes = (uint32_t)((dense ? rows_here : 1) * Kc) * 2u;
+  pitch_bytes = (uint32_t)ldw * 2u;
+  src = e.w0 + ((size_t)(uint32_t)r * (uint32_t)ldw + (uint32_t)kbeg);
   return true;
 }
 // Issue the bulk copy of stage s (if it exists) into ring slot s % nslots, and ask L2 for the stage `pf_stages` further
 // down the stream: the shared-memory ring bounds how far the copies can run ahead (~150 KB/SM), the L2 prefetch lets HBM
 // keep streaming through the latency-bound phases (qkv -> attention -> o_proj) up to ~60 MB chip-wide ahead of use.
 // Called by ONE lane with that warp's cursors.
-__device__ __forceinline__ void issue_stage(const RingHot& h, int pf_stages, StageCursor& k, StageCursor& kpf, uint32_t s) {
+__device__ __forceinline__ void issue_stage(const RingHot& h, int cur_op, int pf_stages, StageCursor& k, StageCursor& kpf,
+                                            uint32_t s) {
   const bf16* src;
   uint32_t bytes, pitch;
   int ncopies;
-  if (pf_stages > 0 && locate_stage(h, kpf, s + (uint32_t)pf_stages, src, bytes, ncopies, pitch))
+  if (pf_stages > 0 && locate_stage(h, cur_op, kpf, s + (uint32_t)pf_stages, src, bytes, ncopies, pitch))
     for (int i = 0; i < ncopies; ++i)
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(src) + (size_t)i * pitch),
                    "r"(bytes)
                    : "memory");
-  if (!locate_stage(h, k, s, src, bytes, ncopies, pitch)) return;
+  if (!locate_stage(h, cur_op, k, s, src, bytes, ncopies, pitch)) return;
   const uint32_t g = s / (uint32_t)h.nslots, slot = s - g * (uint32_t)h.nslots;
   fence_proxy_async();  // generic-proxy reads of this slot (previous stage) are ordered before the async-proxy refill
   mbar_arrive_expect_tx(ring_full(slot), bytes * (uint32_t)ncopies);
@@ -336,7 +369,7 @@ __device__ void stage_x(MegaCtx& c, const MegaOp& op, int op_idx, int ctid) {
   // bias of this CTA's slab and the norm weights (K <= 4096: at most 4 chunks per thread) are fetched before the wait so
   // that they do not cost a dependent round trip later
   if (op.bias != nullptr) {
-    const int r0 = c.tab[op_idx].row0, nr = c.tab[op_idx].rows;
+    const int r0 = win_tab()[op_idx & (kWin - 1)].row0, nr = win_tab()[op_idx & (kWin - 1)].rows;
     if (ctid < nr && ctid < kBiasRows) c.s_bias[ctid] = __bfloat162float(op.bias[r0 + ctid]);
   }
   // (the norm weights go to shared memory behind the activation vectors with cp.async: no registers held across the wait)
@@ -604,7 +637,7 @@ __device__ void gemv_consume(MegaCtx& c, const RingHot& h, const MegaOp& op, int
       }
       __syncwarp();
       if (pw) { const long long t = clock64(); pc_dot += t - tk0; tk0 = t; }
-      if (lane == 0) issue_stage(h, pf_stages, refill, refill_pf, s + (uint32_t)h.nslots);  // slot free again: refill it
+      if (lane == 0) issue_stage(h, op_idx, pf_stages, refill, refill_pf, s + (uint32_t)h.nslots);  // slot free: refill it
       if (pw) pc_issue += clock64() - tk0;
     }
     long long te0 = 0;
@@ -635,6 +668,12 @@ __device__ void gemv_consume(MegaCtx& c, const RingHot& h, const MegaOp& op, int
             const int row = grow + i;
             float val = acc[i][b];
             if (bias) val += (lrow + i < kBiasRows) ? s_bias[lrow + i] : __bfloat162float(bias[row]);
+            if (epi >= EPI_PART_SET) {  // K-chunk sub-op: keep the row's running sum in shared memory
+              float* pp = c.s_xp + (lrow + i) * 4 + b;
+              *pp = (epi == EPI_PART_SET) ? val : *pp + val;
+              continue;
+            }
+            if (oflags & F_ADD_PART) val += c.s_xp[(lrow + i) * 4 + b];
             if (TP && xon) {
               // tensor parallelism: this is rank tp_rank's PARTIAL sum over its K shard. Push it into every peer's
               // exchange buffer over NVLink ({fp32, tag} in one 8-byte store) and keep the own copy; the all-reduce is
@@ -723,7 +762,7 @@ __device__ void gemv_consume(MegaCtx& c, const RingHot& h, const MegaOp& op, int
 // byte offset of 16-byte chunk `chunk` (0..15) of row `row` in a [rows][128] bf16 tile, XOR-swizzled (ldmatrix conflict-free)
 __device__ __forceinline__ uint32_t swz128(int row, int chunk) { return (uint32_t)(row * 256 + ((chunk ^ (row & 7)) << 4)); }
 
-constexpr int kAttnTile = 64;  // keys per shared-memory tile
+constexpr int kAttnTile = 48;  // keys per shared-memory tile (one tile covers contexts up to ~1700 on 148 CTAs)
 
 template <int G>
 __device__ __noinline__ void attn_phase(MegaCtx& c, const MegaOp& op, int op_idx, int ctid) {
@@ -1060,7 +1099,7 @@ __device__ __noinline__ void attn_phase(MegaCtx& c, const MegaOp& op, int op_idx
 template <int NB, int G, bool TP>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const MegaPlan* __restrict__ plan, uint32_t epoch) {
   extern __shared__ __align__(128) uint8_t mega_smem[];
-  // layout: plan header | ops | slab table | meta (barriers + scratch 2 KB, residual slab, partials, block table) | region A | ring
+  // layout: plan header | ctx | ring barriers | op window | slab window | meta (scratch 2 KB, residual slab, partials, block table) | region A | ring
   // (the header is copied too: a plan field read from global memory costs an L2 round trip under the weight stream)
   MegaPlan* s_plan = reinterpret_cast<MegaPlan*>(mega_smem);
   for (int i = threadIdx.x; i < (int)(sizeof(MegaPlan) / 8); i += kMegaThreads)
@@ -1068,9 +1107,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   __syncthreads();
   const MegaPlan& P = *s_plan;
   const int n_ops = P.n_ops;
-  MegaOp* s_ops = reinterpret_cast<MegaOp*>(mega_smem + kHdrBytes);
-  SlabEnt* s_tab = reinterpret_cast<SlabEnt*>(mega_smem + kHdrBytes + ops_bytes_of(n_ops));
-  uint8_t* meta = mega_smem + front_bytes_of(n_ops);
+  MegaOp* s_ops = win_ops();
+  SlabEnt* s_tab = win_tab();
+  const MegaOp* gops = reinterpret_cast<const MegaOp*>(reinterpret_cast<const uint8_t*>(plan) + sizeof(MegaPlan));
+  const int n_win = min(n_ops, kWin);
+  uint8_t* meta = mega_smem + kHdrBytes;
   float* red = reinterpret_cast<float*>(meta);  // 16 floats
   int* s_ctx = reinterpret_cast<int*>(red + 16);                                    // 4 ints
   float* am_v = reinterpret_cast<float*>(s_ctx + 4);                                // [8 warps][16 lanes]
@@ -1084,9 +1125,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {  // copy the op list, context lengths and block table into shared memory, init the ring barriers
-    const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(plan) + sizeof(MegaPlan));
+    const uint2* src = reinterpret_cast<const uint2*>(gops);
     uint2* dst = reinterpret_cast<uint2*>(s_ops);
-    const int n8 = n_ops * (int)sizeof(MegaOp) / 8;
+    const int n8 = n_win * (int)sizeof(MegaOp) / 8;
     for (int i = tid; i < n8; i += kMegaThreads) dst[i] = __ldg(src + i);
     for (int i = tid; i < P.B * P.max_pages; i += kMegaThreads) s_bt[i] = P.block_table[i];
     if (tid < P.B) s_ctx[tid] = P.ctx_lens[tid];
@@ -1099,22 +1140,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     }
   }
   __syncthreads();
-  // this CTA's slab of every GEMV op, then (one thread) the running stage index where each op starts
-  for (int i = tid; i < n_ops; i += kMegaThreads) {
-    const MegaOp& op = s_ops[i];
-    SlabEnt e;
-    e.w0 = nullptr; e.base = 0; e.cnt = 0; e.row0 = 0; e.rows = 0;
-    if (op.type == OP_GEMV) {
-      slab_rows(op.N, op.gran, (int)blockIdx.x, (int)gridDim.x, e.row0, e.rows);
-      e.cnt = (uint32_t)(((e.rows + op.R - 1) / op.R) * op.ksplit);
-      e.w0 = op.W + (size_t)e.row0 * op.K;
-    }
-    s_tab[i] = e;
-  }
+  // this CTA's slab of the first kWin ops, then (one thread) the running stage index where each op starts
+  for (int i = tid; i < n_win; i += kMegaThreads) s_tab[i] = make_slab(s_ops[i], 0u);
   __syncthreads();
   if (tid == 0) {
     uint32_t run = 0;
-    for (int i = 0; i < n_ops; ++i) {
+    for (int i = 0; i < n_win; ++i) {
       s_tab[i].base = run;
       run += s_tab[i].cnt;
     }
@@ -1126,7 +1157,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   // hold it under the weight stream) on the refill path of every ring stage.
   MegaCtx& c = *reinterpret_cast<MegaCtx*>(mega_smem + 256);
   if (tid == 0) {
-  c.P = s_plan; c.tab = s_tab; c.red = red; c.am_v = am_v; c.am_i = am_i; c.s_ctx = s_ctx;
+  c.P = s_plan; c.gops = gops; c.red = red; c.am_v = am_v; c.am_i = am_i; c.s_ctx = s_ctx;
   c.s_h = s_h; c.s_bias = s_bias; c.s_bt = s_bt; c.s_xp = s_xp; c.region_a = region_a; c.cta = blockIdx.x;
   c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch; c.pf_stages = P.pf_stages; c.scalar_gemv = P.scalar_gemv; c.prof_mode = P.prof_mode; c.poll_ns = (unsigned int)P.poll_ns;
   c.prof_op = nullptr;
@@ -1134,7 +1165,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   __syncthreads();
 
   RingHot hot;
-  hot.tab_off = kHdrBytes + ops_bytes_of(n_ops);
   hot.ring_off = (int)(ring - mega_smem);
   hot.slot_bytes = P.slot_bytes; hot.nslots = P.nslots; hot.n_ops = n_ops;
   // every warp keeps its own cursor into the stage sequence for the refills it issues
@@ -1147,13 +1177,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     uint32_t bytes, pitch;
     int ncopies;
     for (int s = P.nslots; s < P.nslots + P.pf_stages; ++s)
-      if (locate_stage(hot, kpf, (uint32_t)s, src, bytes, ncopies, pitch))
+      if (locate_stage(hot, 0, kpf, (uint32_t)s, src, bytes, ncopies, pitch))
         for (int i = 0; i < ncopies; ++i)
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t*>(src) + (size_t)i * pitch),
                        "r"(bytes)
                        : "memory");
     StageCursor kpf2 = refill;
-    for (int s = 0; s < P.nslots; ++s) issue_stage(hot, P.pf_stages, k, kpf2, (uint32_t)s);
+    for (int s = 0; s < P.nslots; ++s) issue_stage(hot, 0, P.pf_stages, k, kpf2, (uint32_t)s);
   }
 
   const int ctid = tid, cw = warp;
@@ -1163,7 +1193,22 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   unsigned long long* prof = P.prof ? P.prof + ((size_t)c.cta * n_ops) * kProfStride : nullptr;
 #pragma unroll 1
   for (int i = 0; i < n_ops; ++i) {
-    const MegaOp& op = s_ops[i];
+    const MegaOp& op = s_ops[i & (kWin - 1)];
+    if (cw == kCWarps - 1 && i >= 1) {
+      // slide the op window (warp 7, off the critical path: cp.async, no register staging): op i-1 is finished, its
+      // entry takes op j1 = i-1+kWin; the slab entry of j1-1, copied one iteration ago, is built now. An entry is
+      // first read (by a refill that runs ahead, or by the op loop) many block-wide barriers after it was written.
+      const int j1 = i - 1 + kWin, j2 = j1 - 1;
+      cp_async_wait<0>();
+      __syncwarp();
+      if (lane == 0 && j2 >= kWin && j2 < n_ops) {
+        const SlabEnt& prev = s_tab[(j2 - 1) & (kWin - 1)];
+        s_tab[j2 & (kWin - 1)] = make_slab(s_ops[j2 & (kWin - 1)], prev.base + prev.cnt);
+      }
+      if (j1 < n_ops && lane < (int)sizeof(MegaOp) / 8)
+        cp_async8(reinterpret_cast<uint2*>(&s_ops[j1 & (kWin - 1)]) + lane, reinterpret_cast<const uint2*>(gops + j1) + lane);
+      cp_async_commit();
+    }
     if (prof && ctid == 0) {
       c.prof_op = prof + i * kProfStride;
       prof[i * kProfStride + 0] = global_ns();
@@ -1172,9 +1217,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
       prof[i * kProfStride + 3] = smid;
     }
     if (op.type == OP_GEMV) {
-      stage_x<NB>(c, op, i, ctid);
+      if (!(op.flags & F_X_KEEP)) stage_x<NB>(c, op, i, ctid);  // F_X_KEEP: the previous op staged the same vector
       if (prof && ctid == 0) prof[i * kProfStride + 1] = global_ns();
-      const int row0 = s_tab[i].row0, rows = s_tab[i].rows;
+      const int row0 = s_tab[i & (kWin - 1)].row0, rows = s_tab[i & (kWin - 1)].rows;
       gemv_consume<NB, TP>(c, hot, op, i, sc_base, row0, rows, cw, lane, refill, refill_pf, best_v, best_i);
       sc_base += (uint32_t)(((rows + op.R - 1) / op.R) * op.ksplit);
       if (op.flags & F_ARGMAX) {
@@ -1321,7 +1366,7 @@ using namespace omc;
 
 extern "C" long long omc_decode_plan_bytes(int n_layers) {
   if (n_layers < 0) return -1;
-  return (long long)sizeof(MegaPlan) + (long long)(5 * n_layers + 2) * (long long)sizeof(MegaOp);
+  return (long long)sizeof(MegaPlan) + (long long)(kOpsPerLayerMax * n_layers + 2) * (long long)sizeof(MegaOp);
 }
 
 extern "C" long long omc_decode_workspace_bytes(const omc_decode_desc* d) {
@@ -1338,7 +1383,7 @@ extern "C" long long omc_decode_xchg_bytes(const omc_decode_desc* d) {
 extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) {
   if (d == nullptr || plan_host == nullptr) return set_error(OMC_ERR_ARG, "omc_decode_plan_build: null argument");
   if (d->batch < 1 || d->batch > 4) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: batch must be 1..4");
-  if (d->n_layers < 0 || 5 * d->n_layers + 2 > kMaxOps) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: too many layers");
+  if (d->n_layers < 0 || kOpsPerLayerMax * d->n_layers + 2 > kMaxOps) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: too many layers");
   if (d->grid < 1) return set_error(OMC_ERR_ARG, "omc_decode_plan_build: grid must be the number of CTAs (SMs)");
   {
     const int g = d->kv_heads >= 1 && d->q_heads % d->kv_heads == 0 ? d->q_heads / d->kv_heads : 0;
@@ -1377,15 +1422,14 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   int n = 0, kmax = 0, knorm = 0;
   bool bad = false;
   auto gemv = [&](const void* W, int N, int K, const uint32_t* x_ll, int ldx, int in_op, const void* norm_w, const void* bias,
-                  uint32_t* out_ll, int ldo, int epi, int flags) -> int {
+                  uint32_t* out_ll, int ldo, int epi, int flags, int ldw = 0) -> int {
     MegaOp& o = ops[n];
     memset(&o, 0, sizeof(o));
     o.type = OP_GEMV; o.N = N; o.K = K; o.epi = (uint8_t)epi; o.flags = (uint8_t)flags;
+    o.ldw = ldw > 0 ? ldw : K;
     o.gran = (epi == EPI_SWIGLU) ? 2 : 1;
     o.kc0 = K;
-    // stage geometry: R whole rows when two of them fit a slot, else the same K chunk of TWO rows (one bulk copy per
-    // row): the tensor-pipe dot product shares every activation fragment between the two rows, and a one-row stage costs
-    // twice the ldmatrix traffic per weight byte (down_proj was shared-memory-bandwidth bound that way)
+    // stage geometry: R whole rows when two of them fit a slot, else K chunks of one row
     int R = slot_bytes / (K * 2);
     if (R > kRMax) R = kRMax;
     if (o.gran == 2) R &= ~1;
@@ -1423,9 +1467,38 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
     const int i_attn = n++;
     const int i_o = gemv(d->o_w[li], C, aw, ll(w.attn, par, aw), aw, i_attn, nullptr, nullptr, ll(w.h2, par, C), C, EPI_RES, 0);
     ops[i_o].xslot = (uint8_t)(1 + par);  // row-parallel under TP: partial sums cross the GPUs through exchange slot par
-    const int i_gu = gemv(d->gate_up_w[li], 2 * I, C, ll(w.h2, par, C), C, i_o, d->ln2[li], nullptr, ll(w.act, par, I), I,
-                          EPI_SWIGLU, 0);
-    prev = gemv(d->down_w[li], C, I, ll(w.act, par, I), I, i_gu, nullptr, nullptr, ll(w.h1, (li + 1) & 1, C), C, EPI_RES, 0);
+    // MLP. For batches of 3 and 4 sequences the MLP is cut into nsub K-chunk sub-ops (a down_proj row of I elements is
+    // nsub ring slots long):
+    //   gate_up_0 .. gate_up_{nsub-1}  produce act[j*kc, (j+1)*kc) (gate_up_0 stages the normed input, the others keep it)
+    //   down_0 .. down_{nsub-1}        each a [C, kc] slice of down_w (row pitch I); the row sums accumulate in shared
+    //                                  memory, the last one adds the residual and broadcasts the new hidden state
+    // The activation vectors staged per op shrink from B * I to B * kc elements, which is what leaves room for a ring
+    // at those batch sizes (B = 4: 4 -> 10 slots, 6.36 -> 5.40 ms per step; B = 3: 5.02 -> 4.42). At B = 1 the same cut
+    // is 9 % SLOWER (2.71 -> 2.96 ms) although down_j never waits for gate_up_j: every extra op costs ~1.8 us of staging
+    // and barriers plus its own ramp and tail, so fewer, longer ops win whenever the ring is deep enough; B = 2 is a tie.
+    int kc = I;
+    int nsub = ((long long)I * 2 > slot_bytes) ? pick_ksplit(I, slot_bytes, 1, &kc) : 1;
+    const bool want_sub = (d->scalar_gemv & 8) ? true : (d->scalar_gemv & 4) ? false : B >= 3;  // bits 2/3: A/B overrides
+    if (nsub > kMaxSub || kc % 8 != 0 || !want_sub) nsub = 1;
+    if (nsub <= 1) {
+      const int i_gu = gemv(d->gate_up_w[li], 2 * I, C, ll(w.h2, par, C), C, i_o, d->ln2[li], nullptr, ll(w.act, par, I), I,
+                            EPI_SWIGLU, 0);
+      prev = gemv(d->down_w[li], C, I, ll(w.act, par, I), I, i_gu, nullptr, nullptr, ll(w.h1, (li + 1) & 1, C), C, EPI_RES, 0);
+    } else {
+      int i_gu[kMaxSub];
+      for (int j = 0; j < nsub; ++j) {
+        const int a0 = j * kc, len = I - a0 < kc ? I - a0 : kc;
+        i_gu[j] = gemv(static_cast<const bf16*>(d->gate_up_w[li]) + (size_t)2 * a0 * C, 2 * len, C, ll(w.h2, par, C), C, i_o,
+                       d->ln2[li], nullptr, ll(w.act, par, I) + a0, I, EPI_SWIGLU, j > 0 ? F_X_KEEP : 0);
+      }
+      for (int j = 0; j < nsub; ++j) {
+        const int a0 = j * kc, len = I - a0 < kc ? I - a0 : kc;
+        const bool last = (j == nsub - 1);
+        prev = gemv(static_cast<const bf16*>(d->down_w[li]) + a0, C, len, ll(w.act, par, I) + a0, I, i_gu[j], nullptr, nullptr,
+                    last ? ll(w.h1, (li + 1) & 1, C) : nullptr, C, last ? EPI_RES : (j == 0 ? EPI_PART_SET : EPI_PART_ADD),
+                    last ? F_ADD_PART : 0, I);
+      }
+    }
     ops[prev].xslot = (uint8_t)(3 + par);
   }
   const int i_head = gemv(d->lm_head, d->vocab, C, d->n_layers == 0 ? nullptr : ll(w.h1, d->n_layers & 1, C), C, prev,
@@ -1445,10 +1518,23 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
   if (region_a < (B + 1) * knorm * 2) region_a = (B + 1) * knorm * 2;  // normed ops stage the norm weights behind x
   if (region_a < kAttnScratchBytes) region_a = kAttnScratchBytes;
   region_a = (region_a + 127) & ~127;
-  const int ops_bytes = front_bytes_of(n);  // plan header + op list + slab table
+  const int ops_bytes = kHdrBytes;  // plan header, context, ring barriers, op window + slab window
+  // the refill path may look nslots stages ahead: that must stay inside the op window, so no GEMV op may be empty for
+  // a CTA (every op then contributes >= 1 stage and 16 stages span at most 16 GEMV ops + their attention ops)
+  for (int i = 0; i < n; ++i)
+    if (ops[i].type == OP_GEMV && ops[i].N / ops[i].gran < d->grid)
+      return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: a weight matrix has fewer row groups than the grid has CTAs");
   const int meta_bytes = kMetaFixed + bt_bytes_of(B, d->max_pages);
   int nslots = (kSmemLimit - ops_bytes - meta_bytes - region_a) / slot_bytes;
   if (nslots > kMaxSlots) nslots = kMaxSlots;
+  {
+    // a split-K op streams its rows as ksplit consecutive stages consumed by one warp: the ring works in whole rows.
+    // Measured on down_proj (3 chunks per row): 12 slots 21.3 us, 13 slots 26.8 us, 10 slots 31.5 us per layer.
+    int ksp_max = 1;
+    for (int i = 0; i < n; ++i)
+      if (ops[i].type == OP_GEMV && ops[i].ksplit > ksp_max) ksp_max = ops[i].ksplit;
+    if (ksp_max > 1 && nslots >= 2 * ksp_max) nslots -= nslots % ksp_max;
+  }
   if (((d->scalar_gemv >> 4) & 15) >= 2 && nslots > ((d->scalar_gemv >> 4) & 15)) nslots = (d->scalar_gemv >> 4) & 15;  // experiment
   if (nslots < 2) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: activations leave no room for the weight ring");
   P->nslots = nslots; P->region_a_bytes = region_a;

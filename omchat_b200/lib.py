@@ -330,6 +330,35 @@ def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None, workspace: 
 
 
 # ----------------------------------------------------------------------------------------------- persistent decode step
+_MEGA_PLAN_BYTES, _MEGA_OP_BYTES = 256, 96  # sizeof(MegaPlan), sizeof(MegaOp) in csrc/decode_mega.cu (profiling tools only)
+
+
+def mega_op_kinds(plan) -> list:
+    """Names of the ops of a built decode plan, for tools/prof_mega.py: parsed from the host copy of the op list
+    (MegaOp: 7 pointers, N, K, ldx, ldo, kc0, ldw, int16 in_op, then uint8 type, epi, R, ksplit, gran, flags, ...)."""
+    raw, names, prev_attn = plan.host.raw, [], False
+    for i in range(plan.n_ops):
+        o = _MEGA_PLAN_BYTES + i * _MEGA_OP_BYTES
+        typ, epi, flags = raw[o + 82], raw[o + 83], raw[o + 87]
+        if typ == 2:
+            name = "attn"
+        elif typ == 3:
+            name = "final"
+        elif flags & 1:
+            name = "lm_head"
+        elif epi == 3:
+            name = "gate_up"
+        elif epi in (8, 9) or (epi == 2 and not prev_attn):
+            name = "down"
+        elif epi == 2:
+            name = "o"
+        else:
+            name = "qkv"
+        prev_attn = typ == 2
+        names.append(name)
+    return names
+
+
 class DecodeDesc(ctypes.Structure):
     """Mirror of `omc_decode_desc` (include/omchat_b200.h)."""
     _fields_ = ([(n, ctypes.c_int32) for n in ("n_layers", "batch", "hidden", "q_heads", "kv_heads", "inter", "vocab",
@@ -452,17 +481,21 @@ class DecodePlan:
         d.workspace = self.workspace.data_ptr()
         self.status = torch.zeros(4, dtype=torch.int32).pin_memory()  # watchdog record, readable after a device trap
         d.status = self.status.data_ptr()
+        nbytes = lib.omc_decode_plan_bytes(n_layers)
         self.prof = None
         if os.environ.get("OMCHAT_B200_MEGA_PROF", "0") == "1":
-            self.prof = torch.zeros(self.grid, 5 * n_layers + 2, 8, device=dev, dtype=torch.int64)
-            d.prof = self.prof.data_ptr()
+            # sized for the longest op list the plan builder may produce; viewed as [grid, n_ops, 8] once n_ops is known
+            self._prof_flat = torch.zeros(self.grid * (nbytes // _MEGA_OP_BYTES + 1) * 8, device=dev, dtype=torch.int64)
+            d.prof = self._prof_flat.data_ptr()
         self.desc = d
-        nbytes = lib.omc_decode_plan_bytes(n_layers)
         self.host = ctypes.create_string_buffer(nbytes)
         rc = lib.omc_decode_plan_build(ctypes.byref(d), self.host)
         if rc != 0:
             raise OmcError(f"omc_decode_plan_build failed ({rc}): {lib.omc_last_error().decode(errors='replace')}")
         self.dev = torch.frombuffer(bytearray(self.host.raw), dtype=torch.uint8).to(dev)
+        self.n_ops = int.from_bytes(self.host.raw[0:4], "little")  # MegaPlan.n_ops
+        if d.prof:
+            self.prof = self._prof_flat[: self.grid * self.n_ops * 8].view(self.grid, self.n_ops, 8)
         self._keep = (layers, embed, final_norm, lm_head, rope_cs, kv_pool, block_table, ctx_lens, tokens, token_hist,
                       hist_pos, h, qkv, attn, act, logits)
 
