@@ -226,3 +226,40 @@ def test_end_to_end_image_bytes_to_tokens(sd_bf16):
             top2 = torch.topk(step_logits[i], 2).values
             assert float(top2[0] - top2[1]) < 0.05 * float(step_logits[i].abs().max()), (i, got, want)
             break
+
+
+def test_multi_image_batch_generate_c5_shape(sd_bf16):
+    """BASELINE.json config 5 at tiny size: a batch of prompts with several images each, pixel-shuffle 0.5 (every image
+    becomes (grid/2)^2 tokens), ragged prompt lengths behind an attention mask, batched greedy decode (the persistent
+    kernel at batch 2) - every row against the oracle's batch-1 greedy loop on the same images."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from omchat_b200.model.omchat import OmChatQwen2ForCausalLM
+    sd = dict(sd_bf16)
+    g = torch.Generator().manual_seed(3)
+    sd["model.mm_projector.0.weight"] = (torch.randn(TINY["hidden"], TINY["vit_hidden"] * 4, generator=g) * 0.03).to(torch.bfloat16).float()
+    m = OmChatQwen2ForCausalLM.from_state_dict(sd, tiny_cfgs(mm_pixel_shuffle_ratio=0.5), device="cuda")
+    pixels = torch.randn(5, 3, TINY["image_size"], TINY["image_size"], generator=g).to(torch.bfloat16).float()
+    S = 30
+    ids = torch.randint(1, TINY["vocab"], (2, S), generator=g)
+    mask = torch.ones(2, S, dtype=torch.bool)
+    for p in (2, 11, 25):        # row 0: three images, full length
+        ids[0, p] = -200
+    for p in (0, 13):            # row 1: two images (one at the very start), 22 valid tokens then padding
+        ids[1, p] = -200
+    mask[1, 22:] = False
+    ids[1, 22:] = 0
+    new = 6
+    out = m.generate(ids, images=pixels, attention_mask=mask, max_new_tokens=new, do_sample=False, eos_token_id=-1)
+    assert out.shape == (2, S + new)
+    per_img = (TINY["image_size"] // TINY["patch_size"] // 2) ** 2
+    for row, (n_valid, img0, img1) in enumerate([(S, 0, 3), (22, 3, 5)]):
+        want, step_logits = O.greedy_generate(ids[row:row + 1, :n_valid], pixels[img0:img1], sd,
+                                              oracle_cfg(pixel_shuffle_down=2), max_new_tokens=new)
+        assert len(want) == new and n_valid - (img1 - img0) + (img1 - img0) * per_img > n_valid
+        got = out[row, S:].tolist()
+        for i in range(new):
+            if got[i] != want[i]:
+                top2 = torch.topk(step_logits[i], 2).values
+                assert float(top2[0] - top2[1]) < 0.05 * float(step_logits[i].abs().max()), (row, i, got, want)
+                break
