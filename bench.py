@@ -235,7 +235,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--new-tokens", type=int, default=NEW_TOKENS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -270,6 +270,9 @@ def main():
     if args.workload == "c4":
         from tools.bench_workloads import run_c4
         return run_c4(args, rank, world, local)
+    if args.workload == "c5":
+        from tools.bench_workloads import run_c5
+        return run_c5(args, rank, world, local)
 
     from omchat_b200.model.omchat import OmChatQwen2ForCausalLM
     cfg = OmChatQwen2Config(mm_pixel_shuffle_ratio=args.pixel_shuffle, eos_token_id=-1)

@@ -174,7 +174,9 @@ typedef struct omc_decode_desc {
   int32_t l2_prefetch_stages; /* how many ring stages (one slot each, per CTA) the L2 prefetch runs ahead; 0 = off */
   int32_t ring_slot_bytes;    /* bytes of one shared-memory ring slot (multiple of 128); 0 = default (14336 = 2 rows of
                                  K = 3584; longer rows travel as equal K chunks of at most one slot) */
-  int32_t scalar_gemv;        /* A/B switch: 1 = compute the dot products with FFMA instead of mma.sync (default 0) */
+  int32_t tune;               /* A/B switches for measurements, 0 = defaults. bit 0: FFMA dot products instead of mma.sync;
+                                 bit 1: two-row stages for split-K ops; bit 2 / bit 3: never / always cut the MLP into
+                                 K-chunk sub-ops (default: batch >= 3); bits 4-7: cap on the number of ring slots */
   float eps, attn_scale;
   const void* embed;
   const void* final_norm;

@@ -111,7 +111,7 @@ struct MegaPlan {  // header, followed by n_ops MegaOp
   int32_t grid, nsplit_max, vocab_offset, hist_capacity, kmax, nslots, region_a_bytes, smem_bytes;
   float eps, scale_log2;
   int32_t pf_stages, slot_bytes;
-  int32_t scalar_gemv, prof_mode, poll_ns, pad2;  // prof_mode: which breakdown warp 0 records (0 phases, 1 refill issue, 2 epilogue)  // scalar_gemv: A/B switch, 1 = FFMA dot products instead of the mma.sync path
+  int32_t scalar_gemv, pad2[3];  // scalar_gemv: A/B switch, 1 = FFMA dot products instead of the mma.sync path
   const bf16* embed;
   const float* rope_cs;  // [positions][64][2] fp32 (cos, sin)
   const int32_t* block_table;
@@ -273,8 +273,6 @@ struct MegaCtx {
   float* s_xp;           // [kHRows][4] own partial sums of a row-parallel op (tensor parallelism)
   uint8_t* region_a;     // activation vectors / attention scratch
   int cta, grid, n_ops, pf_stages, scalar_gemv;
-  int prof_mode;
-  unsigned int poll_ns;  // back-off between failed polls of a flag-in-data vector (0 = spin)
   unsigned long long* prof_op;  // this CTA's profile record of the current op (null = profiling off)
   uint32_t epoch;
 };
@@ -418,10 +416,7 @@ __device__ void stage_x(MegaCtx& c, const MegaOp& op, int op_idx, int ctid) {
             const int i = base + u * kMegaThreads;
             if (i < n4 && !ll4_ok(v[u], tag)) ok = false;
           }
-          if (!ok) {
-            wd.tick(P.err_flag, 5, op.in_op);
-            if (c.poll_ns) __nanosleep(c.poll_ns);
-          }
+          if (!ok) wd.tick(P.err_flag, 5, op.in_op);  // (a nanosleep back-off here was measured: no change)
         } while (!ok);
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
@@ -1159,7 +1154,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
   if (tid == 0) {
   c.P = s_plan; c.gops = gops; c.red = red; c.am_v = am_v; c.am_i = am_i; c.s_ctx = s_ctx;
   c.s_h = s_h; c.s_bias = s_bias; c.s_bt = s_bt; c.s_xp = s_xp; c.region_a = region_a; c.cta = blockIdx.x;
-  c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch; c.pf_stages = P.pf_stages; c.scalar_gemv = P.scalar_gemv; c.prof_mode = P.prof_mode; c.poll_ns = (unsigned int)P.poll_ns;
+  c.grid = gridDim.x; c.n_ops = n_ops; c.epoch = epoch; c.pf_stages = P.pf_stages; c.scalar_gemv = P.scalar_gemv;
   c.prof_op = nullptr;
   }
   __syncthreads();
@@ -1439,7 +1434,7 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
       // activation fragments shared by both rows - measured 0.5 % slower: the ring is latency-bound, not LDS-bound.)
       R = 1;
       ksp = pick_ksplit(K, slot_bytes, 1, &o.kc0);
-      if (d->scalar_gemv & 2) {
+      if (d->tune & 2) {
         R = 2;
         ksp = pick_ksplit(K, slot_bytes, 2, &o.kc0);
       }
@@ -1478,7 +1473,7 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
     // and barriers plus its own ramp and tail, so fewer, longer ops win whenever the ring is deep enough; B = 2 is a tie.
     int kc = I;
     int nsub = ((long long)I * 2 > slot_bytes) ? pick_ksplit(I, slot_bytes, 1, &kc) : 1;
-    const bool want_sub = (d->scalar_gemv & 8) ? true : (d->scalar_gemv & 4) ? false : B >= 3;  // bits 2/3: A/B overrides
+    const bool want_sub = (d->tune & 8) ? true : (d->tune & 4) ? false : B >= 3;  // bits 2/3: A/B overrides
     if (nsub > kMaxSub || kc % 8 != 0 || !want_sub) nsub = 1;
     if (nsub <= 1) {
       const int i_gu = gemv(d->gate_up_w[li], 2 * I, C, ll(w.h2, par, C), C, i_o, d->ln2[li], nullptr, ll(w.act, par, I), I,
@@ -1535,14 +1530,12 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
       if (ops[i].type == OP_GEMV && ops[i].ksplit > ksp_max) ksp_max = ops[i].ksplit;
     if (ksp_max > 1 && nslots >= 2 * ksp_max) nslots -= nslots % ksp_max;
   }
-  if (((d->scalar_gemv >> 4) & 15) >= 2 && nslots > ((d->scalar_gemv >> 4) & 15)) nslots = (d->scalar_gemv >> 4) & 15;  // experiment
+  if (((d->tune >> 4) & 15) >= 2 && nslots > ((d->tune >> 4) & 15)) nslots = (d->tune >> 4) & 15;  // A/B: cap on the ring depth
   if (nslots < 2) return set_error(OMC_ERR_SHAPE, "omc_decode_plan_build: activations leave no room for the weight ring");
   P->nslots = nslots; P->region_a_bytes = region_a;
   P->pf_stages = d->l2_prefetch_stages < 0 ? 0 : d->l2_prefetch_stages;
   P->slot_bytes = slot_bytes;
-  P->scalar_gemv = d->scalar_gemv & 1;  // (bit 1: one-row stages for split-K ops, an A/B switch of the plan builder)
-  P->prof_mode = (d->scalar_gemv >> 8) & 0xff;  // tools/prof_mega.py: which breakdown warp 0 records
-  P->poll_ns = (d->scalar_gemv >> 16) & 0x7fff; // experiment: back-off between failed polls
+  P->scalar_gemv = d->tune & 1;
   P->smem_bytes = ops_bytes + meta_bytes + region_a + nslots * slot_bytes;
   P->eps = d->eps; P->scale_log2 = d->attn_scale * 1.4426950408889634f;
   P->embed = (const bf16*)d->embed; P->rope_cs = d->rope_cs; P->block_table = d->block_table; P->ctx_lens = d->ctx_lens;

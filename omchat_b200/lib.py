@@ -363,7 +363,7 @@ class DecodeDesc(ctypes.Structure):
     """Mirror of `omc_decode_desc` (include/omchat_b200.h)."""
     _fields_ = ([(n, ctypes.c_int32) for n in ("n_layers", "batch", "hidden", "q_heads", "kv_heads", "inter", "vocab",
                                                  "vocab_offset", "page_size", "max_pages", "grid", "hist_capacity",
-                                                 "rope_positions", "l2_prefetch_stages", "ring_slot_bytes", "scalar_gemv")]
+                                                 "rope_positions", "l2_prefetch_stages", "ring_slot_bytes", "tune")]
                 + [("eps", c_float), ("attn_scale", c_float)]
                 + [(n, c_void_p) for n in ("embed", "final_norm", "lm_head", "rope_cs", "ln1", "qkv_w", "qkv_b", "o_w",
                                            "ln2", "gate_up_w", "down_w", "kv_pool")]
@@ -456,9 +456,7 @@ class DecodePlan:
         d.eps, d.attn_scale = eps, scale
         d.l2_prefetch_stages = int(os.environ.get("OMCHAT_B200_MEGA_PF", "0"))
         d.ring_slot_bytes = int(os.environ.get("OMCHAT_B200_MEGA_SLOT", "0"))  # 0 = the library's default
-        d.scalar_gemv = (int(os.environ.get("OMCHAT_B200_MEGA_SCALAR", "0"))  # A/B: 1 = FFMA dots, 2 = one-row split-K stages
-                         | int(os.environ.get("OMCHAT_B200_MEGA_PROFMODE", "0")) << 8  # profiling detail (tools/prof_mega.py)
-                         | int(os.environ.get("OMCHAT_B200_MEGA_POLLNS", "0")) << 16)  # experiment: poll back-off (ns)
+        d.tune = int(os.environ.get("OMCHAT_B200_MEGA_TUNE", "0"))  # A/B switches of omc_decode_desc.tune (measurements)
         d.embed, d.final_norm, d.lm_head, d.rope_cs = embed.data_ptr(), final_norm.data_ptr(), lm_head.data_ptr(), rope_cs.data_ptr()
         assert rope_cs.dtype == torch.float32 and rope_cs.is_contiguous() and rope_cs.shape[1:] == (64, 2)
         d.rope_positions = rope_cs.shape[0]

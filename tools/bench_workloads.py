@@ -1,4 +1,4 @@
-"""The two multi-GPU workloads of BASELINE.json besides the headline request (bench.py --workload c3 | c4).
+"""The multi-GPU workloads of BASELINE.json besides the headline request (bench.py --workload c3 | c4 | c5).
 
 c3 (configs[2]): InternViT-6B tower + mm_projector only, 64 synthetic 448x448 crops, DATA-parallel: rank r encodes crops
     r, r+N, r+2N, ... with replicated weights and NO collective on the data path (SURVEY.md §8e "independent crops").
@@ -7,7 +7,12 @@ c4 (configs[3]): Qwen2-7B decoder TENSOR-parallel over N ranks: 32 sequences x 1
     ids + one placeholder -> 256 image tokens, i.e. pixel-shuffle 0.5 features, synthetic) and batch-32 greedy decode
     over the paged KV cache. value = decode tokens/s (all 32 sequences); prefill tokens/s is reported beside it.
 
-Both print ONE JSON line on rank 0 with the same keys as bench.py's main line.
+c5 (configs[4]): OmChat-2.1-8B-style multi-image requests: 16 prompts x 8 images x 256 image tokens (pixel-shuffle 0.5)
+    + 2048 text ids = 4096-token contexts, greedy decode. DATA-parallel replicas: rank r serves prompts r, r+N, ... in
+    mini-batches of 2 (the per-GPU share at N = 8) through the public generate() call; no collective on the data path.
+    value = generated tokens/s over all ranks; crops/s of the vision phase is reported beside it.
+
+All print ONE JSON line on rank 0 with the same keys as bench.py's main line.
 """
 from __future__ import annotations
 
@@ -220,6 +225,91 @@ def run_c4(args, rank, world, local, n_seq: int = 32, text_tokens: int = 768, im
                      "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                      "traffic": None, "peak_source": peaks["source"], "bytes_per_step_per_gpu": step_bytes,
                      "avg_step_us": us},
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        _finish(torch, dist)
+
+
+# ------------------------------------------------------------------------------------------------------------ c5
+def run_c5(args, rank, world, local, n_prompts: int = 16, images_per_prompt: int = 8, text_tokens: int = 2048, mb: int = 2):
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler
+    from omchat_b200 import lib
+    from omchat_b200.config import IMAGE_TOKEN_INDEX, OmChatQwen2Config
+    from omchat_b200.model.omchat import OmChatQwen2ForCausalLM
+
+    dev = torch.device("cuda", local)
+    cfg = OmChatQwen2Config(mm_pixel_shuffle_ratio=0.5, eos_token_id=-1)
+    model = OmChatQwen2ForCausalLM(cfg, device=f"cuda:{local}", seed=0)
+    new_tokens = min(args.new_tokens, 64)
+    L = cfg.image_tokens_per_crop  # 256
+    T = text_tokens + images_per_prompt * L
+    mine = list(range(rank, n_prompts, world))
+    g = torch.Generator().manual_seed(2)
+    ids = torch.randint(0, 151643, (n_prompts, text_tokens + images_per_prompt), generator=g)
+    step = (text_tokens + images_per_prompt) // images_per_prompt
+    for j in range(images_per_prompt):
+        ids[:, 8 + j * step] = IMAGE_TOKEN_INDEX  # placeholders evenly spaced
+    g1 = torch.Generator().manual_seed(1)
+    pixels = torch.randn(len(mine) * images_per_prompt, 3, 448, 448, generator=g1).to(torch.bfloat16)
+    ids_host, px_host = ids[mine].contiguous().pin_memory(), pixels.pin_memory()
+    groups = [list(range(i, min(i + mb, len(mine)))) for i in range(0, len(mine), mb)]
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def serve(ids_src, px_src):
+        outs = []
+        for grp in groups:
+            i_d = ids_src[grp[0]:grp[-1] + 1].to(dev, non_blocking=True)
+            p_d = px_src[grp[0] * images_per_prompt:(grp[-1] + 1) * images_per_prompt].to(dev, non_blocking=True)
+            outs.append(model.generate(i_d, images=p_d, max_new_tokens=new_tokens, do_sample=False))
+        return outs
+
+    ids_dev, px_dev = ids_host.to(dev), px_host.to(dev)
+    for _ in range(max(args.warmup, 3) if len(groups) <= 2 else 1):
+        serve(ids_dev, px_dev)
+    _barrier(torch, dist, world)
+    n0 = lib.launch_count()
+    t0e, t1e, v0, v1 = ev(), ev(), ev(), ev()
+    with ClockSampler(local) as clocks:
+        _barrier(torch, dist, world)
+        t0e.record()
+        for _ in range(args.steps):
+            serve(ids_dev, px_dev)
+        t1e.record()
+        _barrier(torch, dist, world)
+    launches = lib.launch_count() - n0
+    v0.record()
+    for grp in groups:
+        model.encode_images(px_dev[grp[0] * images_per_prompt:(grp[-1] + 1) * images_per_prompt])
+    v1.record()
+    torch.cuda.synchronize()
+    tot, vis = _max_over_ranks(torch, dist, world, [t0e.elapsed_time(t1e) / args.steps, v0.elapsed_time(v1)], dev)
+    _barrier(torch, dist, world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_host = [o.cpu() for o in serve(ids_host, px_host)]
+    _barrier(torch, dist, world)
+    (e2e_s,) = _max_over_ranks(torch, dist, world, [(time.perf_counter() - t0) / args.steps], dev)
+    gen = n_prompts * new_tokens
+    crops = n_prompts * images_per_prompt
+    line = {
+        "metric": "tokens/sec", "value": gen / (tot * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3) if len(groups) <= 2 else 1, "ms_per_step": tot, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"c5: {n_prompts} prompts x {images_per_prompt} images x {L} image tokens (pixel-shuffle 0.5) + "
+                               f"{text_tokens} text ids = {T}-token contexts, {new_tokens} greedy tokens each",
+                   "parallelism": f"dp{world} replicas, mini-batches of {mb} prompts per GPU (no collective)",
+                   "kv_cache": f"paged, page {cfg.kv_page_size}",
+                   "l2": "no flush needed: every mini-batch streams 26 GB of weights"},
+        "phases": {"vision_ms_per_rank": vis, "crops_per_sec_vision": crops / (vis * 1e-3),
+                   "prompt_tokens_per_sec": n_prompts * T / (tot * 1e-3)},
+        "e2e": {"value": gen / e2e_s, "unit": "tokens/s",
+                "h2d_bytes_per_step": ids_host.numel() * 8 + px_host.numel() * 2,
+                "d2h_bytes_per_step": sum(o.numel() for o in out_host) * 8},
+        "gpu_launches": launches, "clocks": clocks.summary(),
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
