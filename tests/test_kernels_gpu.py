@@ -113,8 +113,9 @@ def test_gemm_swiglu(L, cg):
 @pytest.mark.parametrize("M", [1, 9, 16, 17, 32, 33, 64])
 @pytest.mark.parametrize("N,K", [(256, 64), (3584, 1792), (1000, 4104), (37888 // 8, 512)])
 def test_gemm_skinny(L, M, N, K):
-    """Swapped-operand tcgen05 GEMM for M <= 64 (csrc/gemm_skinny.cu): split-K with the red.add reduction for small N,
-    ragged N / K tails, every epilogue; the workspace must come back zeroed (second call = same result)."""
+    """Swapped-operand tcgen05 GEMM for M <= 64 (csrc/gemm_skinny.cu): split-K over a thread-block cluster (partials summed
+    in rank order through distributed shared memory: bit-identical from call to call) for small N, ragged N / K tails,
+    every epilogue."""
     g = torch.Generator().manual_seed(M * 7 + N + K)
     x = bf(torch.randn(M, K, generator=g)).cuda()
     w = bf(torch.randn(N, K, generator=g) * 0.1).cuda()
@@ -123,8 +124,11 @@ def test_gemm_skinny(L, M, N, K):
     res = bf(torch.randn(M, N, generator=g)).cuda()
     lin = ref_linear(x, w, bias)
     assert L.SKINNY_ENABLED and M <= L.SKINNY_MAX_M
+    outs = []
     for rep in range(2):
-        assert_close(L.gemm(x, w), ref_linear(x, w), what=f"skinny plain rep {rep}")
+        outs.append(L.gemm(x, w))
+        assert_close(outs[-1], ref_linear(x, w), what=f"skinny plain rep {rep}")
+    assert torch.equal(outs[0], outs[1]), "the split-K reduction must be deterministic"
     assert_close(L.gemm(x, w, bias=bias, epi=L.EPI_GELU), torch.nn.functional.gelu(lin), what="skinny gelu")
     want = res.float().cpu() + scale.float().cpu() * lin
     assert_close(L.gemm(x, w, bias=bias, scale=scale, res=res, epi=L.EPI_RES), want, what="skinny res")
