@@ -168,13 +168,16 @@ class Qwen2Decoder:
     # ------------------------------------------------------------------------------------------------ prefill
     @torch.no_grad()
     def prefill(self, embeds: torch.Tensor, pos_ids: torch.Tensor, seq_ids: torch.Tensor, offsets: Sequence[int],
-                cache: PagedKVCache, logits: str = "last", collect_hidden: bool = False):
+                cache: PagedKVCache, logits: str = "last", collect_hidden: bool = False,
+                slots: Optional[Sequence[int]] = None):
         """embeds [T, C] bf16 packed; pos_ids/seq_ids int32 [T]; offsets: host list of n_seq+1 row offsets.
         Fills the cache for every sequence (fresh prefill from position 0) and returns fp32 logits:
-        'last' -> [n_seq, V_local] of each sequence's final token, 'all' -> [T, V_local], 'none' -> None."""
+        'last' -> [n_seq, V_local] of each sequence's final token, 'all' -> [T, V_local], 'none' -> None.
+        slots: cache rows the packed sequences go to (seq_ids must already hold these row numbers) when only SOME rows of
+        the cache are (re)filled - continuous batching; the other rows keep their state."""
         n_seq = len(offsets) - 1
         T = offsets[-1]
-        assert embeds.shape[0] >= T and n_seq == cache.n_seq
+        assert embeds.shape[0] >= T and (n_seq == cache.n_seq if slots is None else len(slots) == n_seq)
         lens = [offsets[i + 1] - offsets[i] for i in range(n_seq)]
         assert max(lens) <= cache.capacity, "KV cache too small for this prefill"
         dev = embeds.device
@@ -201,8 +204,13 @@ class Qwen2Decoder:
             self._row_parallel(act, l.down_w, h, use_gemv=False)
             if collect_hidden:
                 hiddens.append(h.clone())
-        cache.host_lens = list(lens)
-        cache.ctx_lens.copy_(torch.tensor(lens, dtype=torch.int32), non_blocking=True)
+        if slots is None:
+            cache.host_lens = list(lens)
+            cache.ctx_lens.copy_(torch.tensor(lens, dtype=torch.int32), non_blocking=True)
+        else:
+            for s_, n_ in zip(slots, lens):
+                cache.host_lens[s_] = n_
+            cache.ctx_lens.copy_(torch.tensor(cache.host_lens, dtype=torch.int32), non_blocking=True)
         out = None
         if logits == "last":
             last_rows = torch.tensor([offsets[i + 1] - 1 for i in range(n_seq)], dtype=torch.int64).to(dev)
@@ -257,7 +265,7 @@ class Qwen2Decoder:
 
     def use_mega(self, B: int) -> bool:
         """Small-batch decode runs as ONE persistent cooperative kernel per token (csrc/decode_mega.cu)."""
-        return (self.mega_enabled and B <= MEGA_MAX_B and self.C <= 4096 and len(self.w.layers) * 5 + 2 <= 192
+        return (self.mega_enabled and B <= MEGA_MAX_B and self.C <= 4096 and len(self.w.layers) <= 32
                 and (self.tp.size == 1 or (self.tp.size <= 8 and self.tp_mega_enabled)))
 
     def _peer_exchange(self, B: int):
