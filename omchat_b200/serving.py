@@ -47,7 +47,8 @@ class ContinuousBatcher:
         self.model, self.dec = model, model.model.decoder
         self.slots, self.chunk = slots, chunk
         ps = model.config.kv_page_size
-        self.cache: PagedKVCache = self.dec.new_cache(slots, max_ctx, shuffle_pages=False)
+        # one page more per slot than max_ctx needs: the pool then holds every slot at full length PLUS the scratch page
+        self.cache: PagedKVCache = self.dec.new_cache(slots, max_ctx + ps, shuffle_pages=False)
         self.max_pages = self.cache.max_pages
         n_pool = self.cache.pool.shape[1]
         total = n_pool if total_pages is None else min(total_pages, n_pool)
