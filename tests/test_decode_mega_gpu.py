@@ -87,6 +87,15 @@ def test_mega_matches_per_op_path_full_width(lens):
             assert (va.float() - vb.float()).abs().max().item() <= 0.02 * vb.float().abs().max().item()
 
 
+@pytest.mark.parametrize("tune,lens", [(1, [130, 77]), (8, [200]), (2, [64, 300, 129])])
+def test_mega_plan_variants_match_per_op_path(monkeypatch, tune, lens):
+    """The plan variants behind omc_decode_desc.tune that are not the default at these batch sizes but ARE the code path of
+    other shapes: 1 = FFMA dot products (what K chunks that are not a multiple of 128 elements fall back to, e.g. the
+    448-wide o_proj shard at TP 8), 8 = MLP cut into K-chunk sub-ops (default from batch 3), 2 = two-row split-K stages."""
+    monkeypatch.setenv("OMCHAT_B200_MEGA_TUNE", str(tune))
+    test_mega_matches_per_op_path_full_width(lens)
+
+
 def test_mega_generate_history_and_repeatability():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
