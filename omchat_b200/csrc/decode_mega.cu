@@ -3,14 +3,18 @@
 //   (SwiGLU), down GEMV (+res)] -> final RMSNorm + lm_head GEMV -> greedy argmax (+ token history, ctx_lens += 1)
 // with one CTA per SM. A decode step is HBM-bound weight streaming (14.1 GB per token for Qwen2-7B in bf16), so the
 // kernel is organised around keeping HBM busy across op boundaries:
-//   weight ring  this CTA's row slab of every weight matrix, op after op, is one long sequence of "stages" streamed into a
-//                shared-memory ring with cp.async.bulk (TMA, mbarrier complete_tx, L2 evict-first). The ring refills
-//                itself: the warp that finishes reading a slot immediately issues the copy of the stage that will
-//                occupy it next (stage + nslots), whichever op that belongs to. Weights are immutable, so the stream runs
-//                ahead across op boundaries while the CTA waits for activations or runs the attention phase.
+//   weight ring  this CTA's row slab of every weight matrix, op after op, is one long sequence of "stages" (2 whole rows
+//                of K = 3584, or one K chunk of a longer row: <= one 14 KB slot) streamed into a 12-slot shared-memory
+//                ring with cp.async.bulk (TMA, mbarrier complete_tx, L2 evict-first). The ring refills itself: the warp
+//                that finishes reading a slot immediately issues the copy of the stage that will occupy it next
+//                (stage + nslots), whichever op that belongs to. Weights are immutable, so the stream runs ahead across
+//                op boundaries while the CTA waits for activations or runs the attention phase. The ring is latency-
+//                bound (step time follows the bytes in flight), so the rest of shared memory is kept small: the op list
+//                is a 32-entry sliding window, everything the refill path reads sits at a compile-time offset.
 //   8 warps      per op: gather the activation vector(s) into shared memory (RMSNorm fused) -> each warp owns whole
-//                "units" (R weight rows x full K) of the ring, dot products with fp32 accumulation, warp-shuffle
-//                reduction, fused epilogue (bias / residual / SwiGLU / fp32 logits + running argmax).
+//                "units" (R weight rows x a K chunk) of the ring; dot products on the tensor pipe (ldmatrix + mma.sync
+//                with the diagonal trick of mma_rows), fp32 accumulation, warp-shuffle reduction, fused epilogue (bias /
+//                residual / SwiGLU / fp32 logits + running argmax).
 //   no barriers  there is no grid-wide barrier. Every activation that crosses CTAs travels in a flag-in-data buffer (the
 //                LL idea of NCCL): each 32-bit word is {16-bit sequence tag, bf16 value} (64-bit {tag, fp32} for the
 //                attention partials), written with one store and polled by the readers, so "data has arrived" is the
@@ -18,9 +22,11 @@
 //                layer parity; a writer can only reach a buffer again after every reader of its previous contents has
 //                moved two phases on (it needs their outputs first), so tags never alias. The residual stream stays in
 //                the shared memory of the CTA that owns those rows (o_proj and down_proj partition rows identically).
-// Attention runs inside the same kernel: (sequence, kv-head) items are split over all CTAs by key range, K/V loads are
-// issued before the CTA waits for q, the 7 query heads of a group share each K/V row read, and partial (m, l, O) are
-// merged head by head by designated CTAs that poll the partials (no counters).
+// Attention runs inside the same kernel, on the tensor pipe too: (sequence, kv-head) items are split over all CTAs by key
+// range, the K/V rows are fetched with cp.async into swizzled tiles before the CTA waits for q, the 7 query heads of a
+// group are the rows of mma.sync fragments (S = Q K^T, softmax in registers, O = P V with every warp owning 16 output
+// dims), and partial (m, l, O) are merged head by head by designated CTAs that poll the partials (no counters).
+// DESIGN.md section 4.3 has the measurements behind each of these choices and the variants that were rejected.
 //
 // Reference call sites replaced: transformers models/qwen2/modeling_qwen2.py:280-310 (decoder layer), :206-246 (attention,
 // RoPE :124-146, cache update :227), :46-48 (MLP), :258-263 (RMSNorm), :411,470-472 (final norm + lm_head) and the HF
