@@ -38,9 +38,9 @@ def _prefill(dec, cfg, lens, seed=1):
 
 # the last three cases reach the multi-tile branch of the in-kernel attention (> 48 keys per CTA): a long single sequence,
 # two sequences whose new token lands in the second tile, and four sequences whose key ranges end exactly on, one short
-# of and one past a tile boundary (batch 4: 9 key splits per kv head, 432 = 9 * 48)
+# of and one past a tile boundary (batch 4: 9 key splits per kv head, 432 = 9 * 48; 576 = 9 * 64 = two 32-key tiles + the new token)
 @pytest.mark.parametrize("lens", [[200], [130, 77], [64, 300, 129], [1, 5, 257, 40], [2500], [700, 900],
-                                  [432, 431, 433, 100]])
+                                  [432, 431, 433, 100], [576, 575, 577, 64]])
 def test_mega_matches_per_op_path_full_width(lens):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
