@@ -45,6 +45,23 @@ def test_mega_matches_per_op_path_full_width(lens):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     cfg, w, dec = _decoder(2)
+    _check_mega_vs_per_op(cfg, dec, lens, n_layers=2)
+
+
+@pytest.mark.parametrize("layers,kw,lens", [
+    # deeper than the 32-entry op window of the kernel (5 ops per layer + 2): the window has to slide
+    (7, {}, [150]),                                                        # full width, 37 ops
+    (9, dict(hidden_size=256, num_attention_heads=2, num_key_value_heads=1, intermediate_size=512, vocab_size=1000),
+     [40, 90, 17]),                                                        # tiny: 1-2 stages per op, refills run ~16 ops ahead
+])
+def test_mega_deep_stacks_slide_the_op_window(layers, kw, lens):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg, w, dec = _decoder(layers, **kw)
+    _check_mega_vs_per_op(cfg, dec, lens, n_layers=layers)
+
+
+def _check_mega_vs_per_op(cfg, dec, lens, n_layers):
     B, steps = len(lens), 6
     cache_a, first = _prefill(dec, cfg, lens)
     cache_b, first_b = _prefill(dec, cfg, lens)
@@ -78,7 +95,7 @@ def test_mega_matches_per_op_path_full_width(lens):
         dec.mega_enabled = True
     assert cache_a.ctx_lens.tolist() == cache_b.ctx_lens.tolist() == [n + steps for n in lens]
     # appended K/V rows: same bf16 inputs, same rounding -> compare closely (different reduction order upstream)
-    for li in range(2):
+    for li in range(n_layers):
         for s in range(B):
             ka, va = cache_a.gather(li, s)
             kb, vb = cache_b.gather(li, s)
