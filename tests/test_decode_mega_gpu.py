@@ -51,6 +51,7 @@ def test_mega_matches_per_op_path_full_width(lens):
 @pytest.mark.parametrize("layers,kw,lens", [
     # deeper than the 32-entry op window of the kernel (5 ops per layer + 2): the window has to slide
     (7, {}, [150]),                                                        # full width, 37 ops
+    (28, {}, [1100]),                                                      # the benchmarked shape: Qwen2-7B depth, c2 context
     (9, dict(hidden_size=256, num_attention_heads=2, num_key_value_heads=1, intermediate_size=512, vocab_size=1000),
      [40, 90, 17]),                                                        # tiny: 1-2 stages per op, refills run ~16 ops ahead
 ])
@@ -63,6 +64,10 @@ def test_mega_deep_stacks_slide_the_op_window(layers, kw, lens):
 
 def _check_mega_vs_per_op(cfg, dec, lens, n_layers):
     B, steps = len(lens), 6
+    # bf16 rounding differences between two correct paths are amplified layer by layer on random-init weights: the FFMA and
+    # mma.sync variants of the SAME kernel differ by 0.3 % of the logit scale at 2 layers, 1.2 % at 7 and 3.2 % at 28
+    # (tools/debug_depth.py), so the max-abs bound follows the depth; the cosine bound does not move
+    rel_tol = 0.02 if n_layers <= 8 else 0.06
     cache_a, first = _prefill(dec, cfg, lens)
     cache_b, first_b = _prefill(dec, cfg, lens)
     assert torch.equal(first, first_b)
@@ -84,7 +89,7 @@ def _check_mega_vs_per_op(cfg, dec, lens, n_layers):
             ref_tok = lg.argmax(-1)
             cos = torch.nn.functional.cosine_similarity(logits_a[i], lg, dim=-1).min().item()
             err = (logits_a[i] - lg).abs().max().item() / lg.abs().max().item()
-            assert cos >= 0.999 and err <= 0.02, (i, cos, err)
+            assert cos >= 0.999 and err <= rel_tol, (i, cos, err)
             # feed the mega path's token so both caches see the same sequence even if a near-tie flipped an argmax
             top2 = torch.topk(lg, 2, dim=-1).values
             for b in range(B):
@@ -100,8 +105,8 @@ def _check_mega_vs_per_op(cfg, dec, lens, n_layers):
             ka, va = cache_a.gather(li, s)
             kb, vb = cache_b.gather(li, s)
             assert torch.equal(ka[:, :lens[s]], kb[:, :lens[s]])  # prefill part untouched
-            assert (ka.float() - kb.float()).abs().max().item() <= 0.02 * kb.float().abs().max().item()
-            assert (va.float() - vb.float()).abs().max().item() <= 0.02 * vb.float().abs().max().item()
+            assert (ka.float() - kb.float()).abs().max().item() <= rel_tol * kb.float().abs().max().item()
+            assert (va.float() - vb.float()).abs().max().item() <= rel_tol * vb.float().abs().max().item()
 
 
 @pytest.mark.parametrize("tune,lens", [(1, [130, 77]), (8, [200]), (2, [64, 300, 129])])
