@@ -129,6 +129,15 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const int n = nt * 128 + quarter * 32 + lane;
   const bool n_ok = epi_warp && n < p.N;
   float acc[MPAD];
+  // residual of the rows this thread will write (EPI_RES, leader CTA only): fetched NOW, while the weights stream. In the
+  // epilogue loop a load of res[m+1] may not be hoisted above the store of out[m] (the decoder calls this in place,
+  // out == res), so 32 dependent L2 round trips - ~20 us - used to sit at the end of every o_proj / down_proj kernel.
+  float resv[MPAD];
+  if (epi_warp && p.epi == EPI_RES && ks == 0) {
+#pragma unroll
+    for (int m = 0; m < MPAD; ++m)
+      resv[m] = (m < p.M && n < p.N) ? __bfloat162float(p.res[(long long)m * p.ldr + n]) : 0.f;
+  }
   if (epi_warp) {
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
@@ -187,7 +196,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         continue;
       }
       if (p.epi == EPI_GELU) v = sk_gelu(v);
-      else if (p.epi == EPI_RES && n_ok) v = __bfloat162float(p.res[(long long)m * p.ldr + n]) + scale_n * v;
+      else if (p.epi == EPI_RES && n_ok) v = resv[m] + scale_n * v;
       if (n_ok) {
         if (p.out_f32 != nullptr) p.out_f32[(long long)m * p.ldo + n] = v;
         else p.out[(long long)m * p.ldo + n] = __float2bfloat16(v);
