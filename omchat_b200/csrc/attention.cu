@@ -231,10 +231,13 @@ __global__ void __launch_bounds__(kAttThreads) attention_fwd_kernel(const AttnPa
 // ==================================================================================================== paged decode
 constexpr int kDecThreads = 128;
 constexpr int kDecTile = 16;  // keys per warp tile (page_size must be a multiple)
-constexpr int kDecWarpBuf = 2 * 2 * kDecTile * kRowBytes;  // 2 stages x (K,V) x 16 rows = 16 KB per warp
+constexpr int kDecStages = 3;  // cp.async stages per warp: a warp is latency-bound on its own tile stream (2 stages: one
+                               // 8 KB tile in flight per warp, batch-32 attention at 2.4 TB/s)
+constexpr int kDecWarpBuf = kDecStages * 2 * kDecTile * kRowBytes;  // stages x (K,V) x 16 rows = 24 KB per warp
 constexpr int kDecQBytes = 16 * kRowBytes;
 constexpr int kDecPartStride = kHD + 2;  // O[128], m, l
-constexpr int kDecSmem = kDecQBytes + 4 * kDecWarpBuf + 4 * 8 * kDecPartStride * 4;
+constexpr int kDecSmem = kDecQBytes + 4 * kDecWarpBuf;  // 100 KB: two CTAs per SM (the warp-merge scratch aliases warp 0's tiles)
+static_assert(4 * 8 * kDecPartStride * 4 <= kDecWarpBuf, "merge scratch must fit the tile buffer of warp 0");
 
 struct DecParams {
   const bf16* qkv;  // [B, ldq]: q heads | k heads | v heads of the NEW token (pre-RoPE) when fused != 0, else q only
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(kDecThreads) paged_decode_attn_kernel(const De
   extern __shared__ __align__(128) uint8_t dec_smem[];
   uint8_t* sQ = dec_smem;
   uint8_t* sKV = dec_smem + kDecQBytes;
-  float* sPart = reinterpret_cast<float*>(dec_smem + kDecQBytes + 4 * kDecWarpBuf);  // [4 warps][8 rows][130]
+  float* sPart = reinterpret_cast<float*>(dec_smem + kDecQBytes);  // [4 warps][8 rows][130], aliases warp 0's K/V tiles
   __shared__ int s_is_last;
 
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -321,13 +324,16 @@ __global__ void __launch_bounds__(kDecThreads) paged_decode_attn_kernel(const De
   float m_run = -INFINITY, l_run = 0.f;  // row g only (rows >= 8 are padding)
 
   int tile = t_begin + warp, it = 0;
-  if (tile < t_end) issue(tile, 0);
-  cp_async_commit();
-  for (; tile < t_end; tile += 4, ++it) {
-    const int st = it & 1;
-    if (tile + 4 < t_end) issue(tile + 4, st ^ 1);
+#pragma unroll
+  for (int s = 0; s < kDecStages - 1; ++s) {  // one commit group per stage, empty groups keep the count uniform
+    if (tile + 4 * s < t_end) issue(tile + 4 * s, s);
     cp_async_commit();
-    cp_async_wait<1>();
+  }
+  for (; tile < t_end; tile += 4, ++it) {
+    const int st = it % kDecStages;
+    if (tile + 4 * (kDecStages - 1) < t_end) issue(tile + 4 * (kDecStages - 1), (it + kDecStages - 1) % kDecStages);
+    cp_async_commit();
+    cp_async_wait<kDecStages - 1>();
     __syncwarp();
     const int key0 = tile * kDecTile;
     if (fused && pos_new >= key0 && pos_new < key0 + kDecTile) {
@@ -393,6 +399,7 @@ __global__ void __launch_bounds__(kDecThreads) paged_decode_attn_kernel(const De
     __syncwarp();
   }
   cp_async_wait<0>();
+  __syncthreads();  // every warp is done with its tiles: the merge scratch may overwrite warp 0's
 
   // ---- merge the 4 warps through shared memory
   l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
@@ -535,7 +542,7 @@ extern "C" int omc_attention_fwd(const void* q, long long ldq, const void* k, lo
 extern "C" int omc_decode_attn_splits(int B, int Hkv, int max_ctx) {
   if (B <= 0 || Hkv <= 0 || max_ctx <= 0) return 1;
   const int tiles = (max_ctx + kDecTile - 1) / kDecTile;
-  int by_fill = (2 * num_sms() + B * Hkv - 1) / (B * Hkv);
+  int by_fill = (2 * num_sms()) / (B * Hkv);  // two 100 KB CTAs per SM: fill ONE wave (rounding up made 1.3 waves at batch 32)
   int by_work = (tiles + 7) / 8;  // >= 2 tiles per warp
   int s = by_fill < by_work ? by_fill : by_work;
   if (s < 1) s = 1;
