@@ -47,9 +47,10 @@ int omc_gemm_bf16(const void* X, long long ldx, const void* W, long long ldw, vo
                   int tile_cfg, void* stream);
 
 /* Skinny variant for M <= 64 (batched decode steps too large for the GEMV kernels; HBM-bound): operands swapped so the
- * 128-row tcgen05 tile runs along N (all TMA bytes are weight bytes), small N split along K over CTAs with an fp32
- * red.global.add reduction in `workspace` (omc_gemm_skinny_workspace_bytes(max N) bytes, ZERO-INITIALISED once by the caller;
- * the kernel leaves it zeroed). Same epilogues and argument meaning as omc_gemm_bf16. workspace may be NULL (no split-K). */
+ * 128-row tcgen05 tile runs along N (all TMA bytes are weight bytes), small N split along K over the CTAs of a thread-block
+ * cluster whose fp32 partial tiles are summed in rank order through distributed shared memory (bit-identical from call to
+ * call). Same epilogues and argument meaning as omc_gemm_bf16; out may alias res. `workspace` / `workspace_bytes` are
+ * kept for ABI stability and ignored (the first version reduced through a global workspace); NULL / 0 are fine. */
 long long omc_gemm_skinny_workspace_bytes(int max_n);
 int omc_gemm_skinny_bf16(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M, int N,
                          int K, const void* bias, const void* scale, const void* res, long long ldr, int epi,
