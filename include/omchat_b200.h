@@ -177,7 +177,8 @@ typedef struct omc_decode_desc {
                                  K = 3584; longer rows travel as equal K chunks of at most one slot) */
   int32_t tune;               /* A/B switches for measurements, 0 = defaults. bit 0: FFMA dot products instead of mma.sync;
                                  bit 1: two-row stages for split-K ops; bit 2 / bit 3: never / always cut the MLP into
-                                 K-chunk sub-ops (default: batch >= 3); bits 4-7: cap on the number of ring slots */
+                                 K-chunk sub-ops (default: batch >= 3); bits 4-7: cap on the number of ring slots;
+                                 bit 8: cut only down_proj into K-chunk sub-ops */
   float eps, attn_scale;
   const void* embed;
   const void* final_norm;

@@ -1468,19 +1468,24 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
     const int i_attn = n++;
     const int i_o = gemv(d->o_w[li], C, aw, ll(w.attn, par, aw), aw, i_attn, nullptr, nullptr, ll(w.h2, par, C), C, EPI_RES, 0);
     ops[i_o].xslot = (uint8_t)(1 + par);  // row-parallel under TP: partial sums cross the GPUs through exchange slot par
-    // MLP. For batches of 3 and 4 sequences the MLP is cut into nsub K-chunk sub-ops (a down_proj row of I elements is
-    // nsub ring slots long):
-    //   gate_up_0 .. gate_up_{nsub-1}  produce act[j*kc, (j+1)*kc) (gate_up_0 stages the normed input, the others keep it)
-    //   down_0 .. down_{nsub-1}        each a [C, kc] slice of down_w (row pitch I); the row sums accumulate in shared
-    //                                  memory, the last one adds the residual and broadcasts the new hidden state
-    // The activation vectors staged per op shrink from B * I to B * kc elements, which is what leaves room for a ring
-    // at those batch sizes (B = 4: 4 -> 10 slots, 6.36 -> 5.40 ms per step; B = 3: 5.02 -> 4.42). At B = 1 the same cut
-    // is 9 % SLOWER (2.71 -> 2.96 ms) although down_j never waits for gate_up_j: every extra op costs ~1.8 us of staging
-    // and barriers plus its own ramp and tail, so fewer, longer ops win whenever the ring is deep enough; B = 2 is a tie.
+    // MLP. For batches of 3 and 4 sequences down_proj is cut into nsub K-chunk sub-ops (a down_proj row of I elements is
+    // nsub ring slots long): down_0 .. down_{nsub-1} are [C, kc] slices of down_w (row pitch I) whose row sums accumulate
+    // in shared memory; the last one adds the residual and broadcasts the new hidden state. The activation vectors staged
+    // per op shrink from B * I to B * kc elements, which is what leaves room for a ring at those batch sizes (B = 4: 4 -> 10
+    // slots, 6.36 -> 5.27 ms per step; B = 3: 5.02 -> 4.29). gate_up can be cut the same way (gate_up_j produces
+    // act[j*kc, (j+1)*kc), gate_up_0 stages the normed input and the others keep it) so that down_j only waits for
+    // gate_up_j - measured 3 % slower than cutting down_proj alone, and at B = 1 either cut costs 9 % (2.71 -> 2.95 ms):
+    // every extra op costs ~1.8 us of staging and barriers plus its own ramp and tail, so fewer, longer ops win whenever
+    // the ring is deep enough. B = 2: 3.20 ms uncut (9 slots), 3.53 with down_proj cut (13 slots).
     int kc = I;
     int nsub = ((long long)I * 2 > slot_bytes) ? pick_ksplit(I, slot_bytes, 1, &kc) : 1;
-    const bool want_sub = (d->tune & 8) ? true : (d->tune & 4) ? false : B >= 3;  // bits 2/3: A/B overrides
-    if (nsub > kMaxSub || kc % 8 != 0 || !want_sub) nsub = 1;
+    // cut: 0 = one gate_up and one down op, 1 = both cut into sub-ops, 2 = only down_proj cut (gate_up stays whole; the
+    // staged activation vector still shrinks to kc elements). tune bits 2 / 3 / 8 force 0 / 1 / 2.
+    int cut = B >= 3 ? 2 : 0;
+    if (d->tune & 4) cut = 0;
+    else if (d->tune & 8) cut = 1;
+    else if (d->tune & 256) cut = 2;
+    if (nsub > kMaxSub || kc % 8 != 0 || cut == 0) nsub = 1;
     if (nsub <= 1) {
       const int i_gu = gemv(d->gate_up_w[li], 2 * I, C, ll(w.h2, par, C), C, i_o, d->ln2[li], nullptr, ll(w.act, par, I), I,
                             EPI_SWIGLU, 0);
@@ -1488,7 +1493,8 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
     } else {
       int i_gu[kMaxSub];
       for (int j = 0; j < nsub; ++j) {
-        const int a0 = j * kc, len = I - a0 < kc ? I - a0 : kc;
+        if (cut == 2 && j > 0) { i_gu[j] = i_gu[0]; continue; }
+        const int a0 = j * kc, len = cut == 2 ? I : (I - a0 < kc ? I - a0 : kc);
         i_gu[j] = gemv(static_cast<const bf16*>(d->gate_up_w[li]) + (size_t)2 * a0 * C, 2 * len, C, ll(w.h2, par, C), C, i_o,
                        d->ln2[li], nullptr, ll(w.act, par, I) + a0, I, EPI_SWIGLU, j > 0 ? F_X_KEEP : 0);
       }

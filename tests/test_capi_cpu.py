@@ -98,17 +98,24 @@ def test_decode_plan_build_is_host_only(built):
     assert kinds[:5] == ["qkv", "attn", "o", "gate_up", "down"] and kinds[-2:] == ["lm_head", "final"]
     assert l.omc_decode_workspace_bytes(ctypes.byref(d)) > 2 * 148 * 8 * 130 * 8
     # batch 4 still leaves a ring; batch 5 is refused; SwiGLU pair that cannot fit a ring stage is refused
-    # batch 4: the MLP is cut into 3 K-chunk sub-ops (a down_proj row of 18944 elements is 3 ring slots long) so that the
-    # staged activations leave room for the ring: gate_up_0..2, down_0..2 with K chunks 6400 + 6400 + 6144 = 18944
+    # batch 4: down_proj is cut into 3 K-chunk sub-ops (a row of 18944 elements is 3 ring slots long) so that the staged
+    # activations leave room for the ring: down_0..2 with K chunks 6400 + 6400 + 6144 = 18944 and row pitch 18944
     d4, _k4 = _fake_desc(lib, batch=4)
     assert l.omc_decode_plan_build(ctypes.byref(d4), buf) == 0
     h4 = struct.unpack_from("16i", buf.raw, 0)
-    assert h4[0] == 28 * 9 + 2 and h4[13] >= 8
+    assert h4[0] == 28 * 7 + 2 and h4[13] >= 8
     kinds = lib.mega_op_kinds(type("P", (), {"host": buf, "n_ops": h4[0]}))
-    assert kinds[:9] == ["qkv", "attn", "o", "gate_up", "gate_up", "gate_up", "down", "down", "down"]
+    assert kinds[:7] == ["qkv", "attn", "o", "gate_up", "down", "down", "down"]
     op = lambda i: struct.unpack_from("6i", buf.raw, 256 + 96 * i + 56)  # N, K, ldx, ldo, kc0, ldw
-    assert [op(i)[1] for i in (6, 7, 8)] == [6400, 6400, 6144] and all(op(i)[5] == 18944 for i in (6, 7, 8))
-    assert [op(i)[0] for i in (3, 4, 5)] == [12800, 12800, 12288] and all(op(i)[5] == 3584 for i in (3, 4, 5))
+    assert [op(i)[1] for i in (4, 5, 6)] == [6400, 6400, 6144] and all(op(i)[5] == 18944 for i in (4, 5, 6))
+    assert op(3)[0] == 2 * 18944 and op(3)[5] == 3584
+    # tune bit 3: gate_up cut as well (gate_up_0..2, down_0..2)
+    d4.tune = 8
+    assert l.omc_decode_plan_build(ctypes.byref(d4), buf) == 0
+    h4 = struct.unpack_from("16i", buf.raw, 0)
+    kinds = lib.mega_op_kinds(type("P", (), {"host": buf, "n_ops": h4[0]}))
+    assert h4[0] == 28 * 9 + 2 and kinds[3:9] == ["gate_up"] * 3 + ["down"] * 3
+    assert [op(i)[0] for i in (3, 4, 5)] == [12800, 12800, 12288]
     d5, _k5 = _fake_desc(lib, batch=5)
     assert l.omc_decode_plan_build(ctypes.byref(d5), buf) == -2
     dbad, _kb = _fake_desc(lib, hidden=8192)

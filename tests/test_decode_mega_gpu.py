@@ -109,11 +109,12 @@ def _check_mega_vs_per_op(cfg, dec, lens, n_layers):
             assert (va.float() - vb.float()).abs().max().item() <= rel_tol * vb.float().abs().max().item()
 
 
-@pytest.mark.parametrize("tune,lens", [(1, [130, 77]), (8, [200]), (2, [64, 300, 129])])
+@pytest.mark.parametrize("tune,lens", [(1, [130, 77]), (8, [200]), (256, [200, 31]), (2, [64, 300, 129])])
 def test_mega_plan_variants_match_per_op_path(monkeypatch, tune, lens):
     """The plan variants behind omc_decode_desc.tune that are not the default at these batch sizes but ARE the code path of
     other shapes: 1 = FFMA dot products (what K chunks that are not a multiple of 128 elements fall back to, e.g. the
-    448-wide o_proj shard at TP 8), 8 = MLP cut into K-chunk sub-ops (default from batch 3), 2 = two-row split-K stages."""
+    448-wide o_proj shard at TP 8), 8 = gate_up and down_proj cut into K-chunk sub-ops, 256 = down_proj alone (the default from
+    batch 3), 2 = two-row split-K stages."""
     monkeypatch.setenv("OMCHAT_B200_MEGA_TUNE", str(tune))
     test_mega_matches_per_op_path_full_width(lens)
 
