@@ -130,6 +130,56 @@ def _skinny_workspace(device, n: int) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------- wrappers
+# ---- tile choice for mid-sized M (one crop, one prompt: M ~ 1000): with 5-9 tiles along M and a 148-SM device the
+# number of WAVES decides, not the per-tile efficiency - the library default (2-CTA pairs, widest BN dividing N) is up to
+# 35 % off the best configuration there (tools/bench_gemm.py --small). Every configuration accumulates along K in the same
+# order, so the choice does not change the result bits; it is made once per (M, N, K, epilogue) by timing the six
+# instantiations on the caller's operands (scratch output, L2 flushed between launches) and cached.
+GEMM_AUTOTUNE = os.environ.get("OMCHAT_B200_GEMM_AUTOTUNE", "1") != "0"
+GEMM_AUTOTUNE_MAX_M = 2048
+_GEMM_CFGS = [256 | (2 << 16), 192 | (2 << 16), 160 | (2 << 16), 128 | (2 << 16), 256 | (1 << 16), 128 | (1 << 16)]
+_gemm_tuned: dict = {}
+_l2_flush = None
+
+
+def _gemm_autotune(x, w, out, bias, scale, res, epi, out_f32) -> int:
+    global _l2_flush
+    M, K = x.shape
+    N = w.shape[0]
+    key = (M, N, K, epi, out_f32, bias is not None, scale is not None)
+    cfg = _gemm_tuned.get(key)
+    if cfg is not None:
+        return cfg
+    if torch.cuda.is_current_stream_capturing():
+        return 0
+    if _l2_flush is None or _l2_flush.device != x.device:
+        _l2_flush = torch.empty(256 << 20, device=x.device, dtype=torch.uint8)
+    scratch = torch.empty_like(out)
+    cands = [c for c in _GEMM_CFGS if epi != EPI_SWIGLU or (c & 0xFFFF) == 256]
+    best, best_t = 0, float("inf")
+    for c in cands:
+        ts = []
+        for i in range(4):
+            _l2_flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = load().omc_gemm_bf16(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(scratch), scratch.stride(0), M, N, K,
+                                      _ptr(bias), _ptr(scale), _ptr(res), res.stride(0) if res is not None else 0, epi,
+                                      1 if out_f32 else 0, c, _stream())
+            e1.record()
+            if rc != 0:
+                break
+            if i > 0:
+                ts.append((e0, e1))
+        else:
+            torch.cuda.synchronize()
+            t = sorted(a.elapsed_time(b) for a, b in ts)[len(ts) // 2]
+            if t < best_t:
+                best, best_t = c, t
+    _gemm_tuned[key] = best
+    return best
+
+
 def gemm(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, scale=None, res=None,
          epi: int = EPI_NONE, out_f32: bool = False, tile_cfg: int = 0) -> torch.Tensor:
     """out[M,N] = epi(x[M,K] @ w[N,K]^T). x/out may be row-strided 2-D views (last dim contiguous)."""
@@ -148,6 +198,8 @@ def gemm(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *
                                          1 if out_f32 else 0, ws.data_ptr(), ws.numel(), _stream())
         _check(rc, "omc_gemm_skinny_bf16")
         return out
+    if tile_cfg == 0 and GEMM_AUTOTUNE and M <= GEMM_AUTOTUNE_MAX_M:
+        tile_cfg = _gemm_autotune(x, w, out, bias, scale, res, epi, out_f32)
     rc = load().omc_gemm_bf16(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
                               _ptr(bias), _ptr(scale), _ptr(res), res.stride(0) if res is not None else 0, epi,
                               1 if out_f32 else 0, tile_cfg, _stream())

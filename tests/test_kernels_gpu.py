@@ -387,3 +387,28 @@ def test_gemv_variants(L, B):
     x3 = bf(torch.randn(B, K2, generator=g)).cuda()
     w3 = bf(torch.randn(72, K2, generator=g) * 0.02).cuda()
     assert_close(L.gemv(x3, w3), ref_linear(x3, w3), what="gemv long K")
+
+
+def test_gemm_autotune_picks_a_config_and_keeps_the_bits(L):
+    """Mid-sized M (one crop / one prompt): lib.gemm times the tile configurations once per shape and caches the choice.
+    Every configuration accumulates along K in the same order, so the output bits must not depend on it."""
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 1025, 3200, 640
+    x = bf(torch.randn(M, K, generator=g)).cuda()
+    w = bf(torch.randn(N, K, generator=g) * 0.1).cuda()
+    res = bf(torch.randn(M, N, generator=g)).cuda()
+    bias = bf(torch.randn(N, generator=g)).cuda()
+    L._gemm_tuned.clear()
+    assert L.GEMM_AUTOTUNE and M <= L.GEMM_AUTOTUNE_MAX_M
+    tuned = L.gemm(x, w, bias=bias, res=res, epi=L.EPI_RES)
+    assert len(L._gemm_tuned) == 1 and next(iter(L._gemm_tuned.values())) in L._GEMM_CFGS
+    assert_close(tuned, res.float().cpu() + ref_linear(x, w, bias), what="autotuned gemm")
+    for cfg in L._GEMM_CFGS:
+        assert torch.equal(L.gemm(x, w, bias=bias, res=res, epi=L.EPI_RES, tile_cfg=cfg), tuned), hex(cfg)
+    again = L.gemm(x, w, bias=bias, res=res, epi=L.EPI_RES)
+    assert torch.equal(again, tuned) and len(L._gemm_tuned) == 1
+    # in place (out == res, how the decoder calls it): tuning must not touch the caller's buffers
+    h = res.clone()
+    L._gemm_tuned.clear()
+    L.gemm(x, w, out=h, bias=bias, res=h, epi=L.EPI_RES)
+    assert torch.equal(h, tuned)

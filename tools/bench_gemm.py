@@ -19,7 +19,14 @@ SHAPES = {
     "llm_gateup_t1088": (1088, 37888, 3584, "swiglu"),
     "llm_down_t1088": (1088, 3584, 18944, "res"),
     "llm_qkv_t1088": (1088, 4608, 3584, "none"),
+    # the single-request shapes (c2): one crop, one 1088-token prefill; "--small" runs only these
+    "vit_qkv_b1": (1025, 9600, 3200, "none"),
+    "vit_proj_b1": (1025, 3200, 3200, "res"),
+    "llm_o_t1088": (1088, 3584, 3584, "res"),
+    "proj_fc1_b1": (1024, 3584, 3200, "gelu"),
 }
+SMALL = ("vit_qkv_b1", "vit_proj_b1", "vit_fc1_b1", "vit_fc2_b1", "llm_qkv_t1088", "llm_o_t1088", "llm_gateup_t1088",
+         "llm_down_t1088")
 CFGS = [(256, 1), (128, 1), (256, 2), (192, 2), (160, 2), (128, 2)]
 
 
@@ -39,10 +46,13 @@ def time_fn(fn, nbuf, iters=12, warm=3):
 
 def main():
     quick = "--quick" in sys.argv
+    small = "--small" in sys.argv
     lib.load()
     res = []
     for name, (M, N, K, epi) in SHAPES.items():
         if quick and not name.endswith("b8"):
+            continue
+        if small and name not in SMALL:
             continue
         bytes_per = (M * K + N * K + M * N) * 2
         nbuf = max(2, int(300e6 // bytes_per) + 1)
@@ -54,8 +64,8 @@ def main():
         flops = 2.0 * M * N * K
         t = time_fn(lambda i: torch.matmul(xs[i], ws[i].t()), nbuf)
         row = {"shape": name, "M": M, "N": N, "K": K, "cublas_tflops": round(flops / t / 1e9, 1)}
-        for bn, cg in CFGS:
-            if epi == "swiglu" and bn != 256:
+        for bn, cg in [(0, 0)] + CFGS:  # (0, 0) = the library's own choice
+            if epi == "swiglu" and bn not in (0, 256):
                 continue
             cfg = bn | (cg << 16)
             kw = {}
@@ -70,7 +80,7 @@ def main():
                     t = time_fn(lambda i: lib.gemm(xs[i], ws[i], out=outs[i], res=outs[i], tile_cfg=cfg, **kw), nbuf)
                 else:
                     t = time_fn(lambda i: lib.gemm(xs[i], ws[i], out=outs[i], tile_cfg=cfg, **kw), nbuf)
-                row[f"bn{bn}_cg{cg}"] = round(flops / t / 1e9, 1)
+                row["auto" if bn == 0 else f"bn{bn}_cg{cg}"] = round(flops / t / 1e9, 1)
             except Exception as e:  # noqa: BLE001
                 row[f"bn{bn}_cg{cg}"] = f"ERR {e}"
         print(json.dumps(row), flush=True)
