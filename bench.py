@@ -112,42 +112,96 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+_TEARDOWN = []  # callables that release what still references the communicator (captured graphs, peer mappings)
+
+
 def _finish(torch, dist):
-    """End of a multi-rank run: all ranks are done (barrier + device idle), then leave without tearing NCCL down —
-    destroy_process_group() after CUDA-graph-captured collectives was seen to hang at exit on the 2-GPU box."""
+    """End of a multi-rank run. destroy_process_group() hung in round 1 because CUDA graphs that had captured NCCL
+    collectives (the batched decode step) were still alive when the communicator was torn down: release them first (and
+    close the CUDA-IPC peer mappings of the tensor-parallel decode kernel), drain the device, then destroy the group. A
+    watchdog turns a teardown that still blocks into a loud message on stderr + exit instead of a silent hang."""
     dist.barrier()
+    torch.cuda.synchronize()
+    for fn in _TEARDOWN:
+        try:
+            fn()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] teardown step failed: {e!r}", file=sys.stderr, flush=True)
+    _TEARDOWN.clear()
+    import gc
+    gc.collect()
     torch.cuda.synchronize()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
+
+    def _watchdog():
+        print("[bench] destroy_process_group() did not return within 60 s; exiting", file=sys.stderr, flush=True)
+        os._exit(0)
+
+    t = threading.Timer(60.0, _watchdog)
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()
+
+
+def _release_decoder(dec):
+    """Drop the captured decode graphs / plans and close the peer exchange buffers of a decoder."""
+    for st in dec._dec.values():
+        st.graphs.clear()
+        st.plans.clear()
+    dec._dec.clear()
+    for px in dec._xchg.values():
+        px.close()
+    dec._xchg.clear()
 
 
 # --------------------------------------------------------------------------------------------------- reference arm
+def host_threads() -> int:
+    """All host threads this process may use (cgroup / affinity aware). torch.distributed.run exports OMP_NUM_THREADS=1
+    to its workers; the reference arm runs alone on rank 0, so it takes the whole host regardless."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:  # noqa: BLE001
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
-    """The reference's own CPU fp32 implementation of the path, timed on the host cores (oracle port; see
-    oracle/cpu_baseline.py for why it is a port and what the bounded sample is). Rank 0 only."""
+    """The reference's own CPU fp32 implementation of the path, timed on ALL host cores (oracle port; see
+    oracle/cpu_baseline.py for why it is a port). The full c2 request in fp32 is ~52 GB of weights and minutes of CPU time
+    per step, so each step times a BOUNDED SAMPLE of it - a few full-width layers of each tower at the real sequence
+    lengths + real decode steps + the full lm_head - and the full-depth request time is that sample scaled by the layer
+    and token counts. Both are in the line: `ms_per_step` / `measured_seconds_per_step` are MEASURED wall time of the
+    sample, `value` is the extrapolation and says so (`extrapolated: true`, `extrapolated_request_ms`). Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    import torch
     from oracle.cpu_baseline import time_c2_sample
-    vals, last = [], None
+    cores = host_threads()
+    torch.set_num_threads(cores)  # overrides the OMP_NUM_THREADS=1 that torchrun puts in the environment
+    vals, walls = [], []
     for i in range(args.warmup + args.steps):
         quick = i < args.warmup
-        r = time_c2_sample(vit_layers=1, llm_layers=1, decode_steps=2 if quick else 3)
+        t0 = time.perf_counter()
+        r = time_c2_sample(vit_layers=1 if quick else 2, llm_layers=1 if quick else 2, decode_steps=2 if quick else 4,
+                           threads=cores)
         if not quick:
             vals.append(r)
-        last = r
-    if not vals:
-        vals = [last]
+            walls.append(time.perf_counter() - t0)
     v = sum(x["tokens_per_sec_request"] for x in vals) / len(vals)
-    ms = 1000.0 * sum(x["seconds"]["request"] for x in vals) / len(vals)
+    req_ms = 1000.0 * sum(x["seconds"]["request"] for x in vals) / len(vals)
+    wall = sum(walls) / len(walls)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_C2, "device": "cpu", "note": "ms_per_step is the full-depth request time "
-                   "extrapolated from the bounded sample each step times"},
+        "warmup": args.warmup, "ms_per_step": 1000.0 * wall, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "extrapolated": True, "measured_seconds_per_step": wall, "extrapolated_request_ms": req_ms,
+        "config": {"workload": WORKLOAD_C2, "device": "cpu", "threads": cores,
+                   "note": "ms_per_step = measured wall time of one bounded sample (weight generation included); value = "
+                           "256 tokens / extrapolated_request_ms, the sample's per-layer and per-token times scaled to 45 "
+                           "ViT blocks, 28 decoder layers and 255 decode steps"},
         "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": vals[-1]["cores"], "kind": "port",
-                         "sample": vals[-1]["sample"],
+                         "sample": vals[-1]["sample"], "extrapolated": True,
                          "decode_tokens_per_sec": vals[-1]["decode_tokens_per_sec"],
                          "images_per_sec_vit_prefill": vals[-1]["images_per_sec_vit_prefill"]},
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -238,6 +292,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--new-tokens", type=int, default=NEW_TOKENS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c5-mode", default="dp", choices=["dp", "tp"], help="c5: data-parallel replicas, or vision-DP -> "
+                    "feature all-gather -> decoder-TP over all GPUs")
+    ap.add_argument("--c5-mb", type=int, default=0, help="c5: prompts per mini-batch (0 = default of the mode)")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the c3 / c4 legs of the main line (`workloads`)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--pixel-shuffle", type=float, default=1.0, help="mm_pixel_shuffle_ratio (1.0 = reference behaviour)")
     args = ap.parse_args()
@@ -256,9 +314,7 @@ def main():
         raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL_DEBUG=VERSION/INFO writes to stdout: keep the ONE JSON line clean
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and os.environ.get("OMCHAT_B200_KEEP_NCCL_DEBUG") != "1":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL's environment (NCCL_DEBUG & co) is left exactly as the launcher set it: its log lines go where NCCL puts them
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from omchat_b200 import lib
     from omchat_b200.config import OmChatQwen2Config
@@ -374,7 +430,7 @@ def main():
                    f"decoder tp{world} (all-reduce x56/forward: NCCL at prefill, in-kernel NVLink exchange at decode), vision replicated",
                    "kv_cache": f"paged, page {cfg.kv_page_size}, shuffled block table",
                    "decode": "persistent megakernel, 1 launch/token" if dec.use_mega(1) else ("cuda graph" if not args.no_graph else "eager"),
-                   "l2": "no flush needed: every step streams 26 GB of weights (>> 126 MB L2)"},
+                   "l2": "no flush needed: every decode step streams 14.2 GB of weights, the ViT pass 11 GB (>> 126 MB L2)"},
         "phases": {"vit_projector_prefill_ms": vp_ms, "images_per_sec_vit_prefill": 1000.0 / vp_ms,
                    "decode_ms": dec_ms, "decode_tokens_per_sec": (new_tokens - 1) / (dec_ms * 1e-3),
                    "decode_ms_per_token": dec_ms / (new_tokens - 1)},
@@ -418,18 +474,32 @@ def main():
                                    "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long train)",
                                    "flops_per_launch": gm["flops_per_launch"], "avg_launch_us": gm["avg_launch_us"],
                                    "shapes": "ViT block GEMMs, 8 crops (M=8200)"}
+    # ---- the workloads that shard naturally, on the same weights, each with its own timing:
+    # c3 = 64 crops data-parallel over the N towers (images/s, tensor roofline), c4 = 32 x 1024-token prefill + batch-32
+    # decode with the decoder tensor-parallel over the N GPUs (tokens/s, HBM roofline)
+    if not args.no_workloads:
+        from tools.bench_workloads import measure_c3, measure_c4
+        del one_request.cache
+        torch.cuda.empty_cache()
+        wl = {}
+        wl["c3"] = measure_c3(args, rank, world, local, cfg, model.get_vision_tower(), model.get_model().mm_projector)
+        torch.cuda.empty_cache()
+        wl["c4"] = measure_c4(args, rank, world, local, cfg, dec)
+        keep = ("metric", "value", "unit", "ms_per_step", "scaling", "config", "phases", "e2e", "gpu_launches", "roofline")
+        line["workloads"] = {k: {kk: v[kk] for kk in keep if kk in v} for k, v in wl.items()}
     if world > 1:
         dist.barrier()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             from oracle.cpu_baseline import time_c2_sample
-            r = time_c2_sample(new_tokens=new_tokens, vit_layers=1, llm_layers=1, decode_steps=3)
+            r = time_c2_sample(new_tokens=new_tokens, vit_layers=1, llm_layers=1, decode_steps=3, threads=host_threads())
             line["cpu_baseline"] = {"value": r["tokens_per_sec_request"], "unit": "tokens/s", "cores": r["cores"],
-                                    "kind": "port", "sample": r["sample"],
+                                    "kind": "port", "sample": r["sample"], "extrapolated": True,
                                     "decode_tokens_per_sec": r["decode_tokens_per_sec"],
                                     "images_per_sec_vit_prefill": r["images_per_sec_vit_prefill"]}
         print(json.dumps(line), flush=True)
     if world > 1:
+        _TEARDOWN.append(lambda: _release_decoder(dec))
         _finish(torch, dist)
 
 

@@ -139,7 +139,8 @@ int omc_paged_decode_attn(const void* qkv, long long ldq, const float* inv_freq,
                           int Hq, int Hkv, int splits, float scale, void* out, long long ldo, void* workspace,
                           void* stream);
 /* embed_tokens gather (omchat_arch.py:139): out[t,:] = table[ids[t],:]; ids int64. */
-int omc_embed_lookup(const int64_t* ids, int T, const void* table, int C, void* out, long long ldo, void* stream);
+int omc_embed_lookup(const int64_t* ids, int T, const void* table, int C, void* out, long long ldo, int vocab,
+                     void* stream);
 /* Image-token splice (omchat_arch.py:115-195), integer placement on device, bit-exact.
  * ids: packed int64 [S_total]; seq_offsets int32 [n_seq+1] into ids; every id == image_token (-200) is replaced,
  * in batch-major order, by the L rows of the next image feature block feats[img, L, C]; all other ids gather
@@ -147,11 +148,12 @@ int omc_embed_lookup(const int64_t* ids, int T, const void* table, int C, void* 
  * [T_total], out_offsets int32 [n_seq+1]. max_len > 0 truncates each spliced sequence (omchat_arch.py:161-164).
  * A sequence without placeholders still consumes one feature block (omchat_arch.py:122-129).
  * workspace: int32 [S_total + n_seq + 2]. T_capacity is the row capacity of the outputs
- * (S_total + n_img*(L-1) always suffices). */
+ * (S_total + n_img*(L-1) always suffices). vocab > 0: text ids outside [0, vocab) yield zero rows (omc_embed_lookup too)
+ * instead of an out-of-bounds read - nn.Embedding raises there (omchat_arch.py:139); vocab <= 0 disables the check. */
 int omc_splice(const int64_t* ids, const int32_t* seq_offsets, int n_seq, int S_total, long long image_token,
                const void* table, const void* feats, int n_img, int L, int C, int max_len, void* embeds,
                int32_t* pos_ids, int32_t* seq_ids, int32_t* out_offsets, int32_t* workspace, int T_capacity,
-               void* stream);
+               int vocab, void* stream);
 /* greedy sampling (HF GenerationMixin argmax as driven by cli.py:60-70): next[b] = argmax_v logits[b, v]
  * (lowest index on ties), logits fp32 [B, V] with row stride ldl. workspace: 128*B floats. */
 int omc_argmax(const float* logits, long long ldl, int B, int V, int64_t* next, float* workspace, void* stream);

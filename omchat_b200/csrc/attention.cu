@@ -515,7 +515,8 @@ extern "C" int omc_attention_fwd(const void* q, long long ldq, const void* k, lo
   if (num_seqs <= 0 || max_seqlen <= 0) return OMC_OK;
   if (Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0) return set_error(OMC_ERR_SHAPE, "omc_attention_fwd: Hq must be a multiple of Hkv");
   if ((ldq | ldk | ldv | ldo) % 8 != 0) return set_error(OMC_ERR_ALIGN, "omc_attention_fwd: row strides must be multiples of 8");
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
     if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
@@ -564,7 +565,8 @@ extern "C" int omc_paged_decode_attn(const void* qkv, long long ldq, const float
   if (Hq % Hkv != 0 || Hq / Hkv > 8) return set_error(OMC_ERR_SHAPE, "omc_paged_decode_attn: group size must be <= 8");
   if (page_size % kDecTile != 0) return set_error(OMC_ERR_SHAPE, "omc_paged_decode_attn: page_size must be a multiple of 16");
   if (splits < 1) return set_error(OMC_ERR_ARG, "omc_paged_decode_attn: splits < 1");
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(paged_decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmem);
     if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));

@@ -825,7 +825,8 @@ int launch_fa_sm100(const void* q, long long ldq, const void* k, long long ldk, 
   if (rc) return rc;
   rc = make_tmap_2d(&tmV, v, total_rows, (long long)Hkv * 128, ldv, kv_box);
   if (rc) return rc;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(fa_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem);
     if (e == cudaSuccess)

@@ -1276,6 +1276,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
           }
+          if (bi == 0x7fffffff) bi = 0;  // all-NaN logits: index 0 like torch.argmax, never the sentinel (embed row out of range)
           if (TP) {
             // vocab-parallel lm_head: every rank pushes its (max, global index) to all ranks (itself included), then
             // picks the best of the tp_size candidates — lowest index among equal maxima, like a single argmax would
@@ -1307,6 +1308,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
               const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
               if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
+            if (bi == 0x7fffffff) bi = P.vocab_offset;
             bi -= P.vocab_offset;  // the shared tail below adds it back
           }
           if (lane == 0) {
@@ -1564,7 +1566,8 @@ extern "C" int omc_decode_plan_build(const omc_decode_desc* d, void* plan_host) 
 
 template <int NB, int G, bool TP>
 static int launch_mega(const MegaPlan* host, const void* plan_dev, uint32_t epoch, cudaStream_t st) {
-  static int attr_smem = 0;
+  static int attr_smem_dev[kMaxDevices] = {};
+  int& attr_smem = attr_smem_dev[cur_device()];
   if (host->smem_bytes > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<NB, G, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, host->smem_bytes);
     if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));

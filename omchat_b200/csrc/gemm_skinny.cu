@@ -220,9 +220,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 // one wave. Cached per (MPAD, splitk); 0 = unknown / not launchable.
 template <int MPAD>
 static int max_clusters(int splitk) {
-  static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+  static int cache_dev[kMaxDevices][9];  // 0 = not probed yet, else clusters + 1
   if (splitk < 1 || splitk > 8) return 0;
-  if (cache[splitk] >= 0) return cache[splitk];
+  int* cache = cache_dev[cur_device()];
+  if (cache[splitk] > 0) return cache[splitk] - 1;
   constexpr int smem = sk_stages(MPAD) * (kSkWBytes + MPAD * kSkBK * 2) + 2048;
   cudaFuncSetAttribute(gemm_skinny_kernel<MPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaLaunchConfig_t cfg{};
@@ -241,14 +242,15 @@ static int max_clusters(int splitk) {
     cudaGetLastError();
     n = 0;
   }
-  cache[splitk] = n;
+  cache[splitk] = n + 1;
   return n;
 }
 
 template <int MPAD>
 static int launch_skinny(const CUtensorMap& tmW, const CUtensorMap& tmX, const SkinnyParams& p, int ctas, cudaStream_t st) {
   constexpr int smem = sk_stages(MPAD) * (kSkWBytes + MPAD * kSkBK * 2) + 2048;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_skinny_kernel<MPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));

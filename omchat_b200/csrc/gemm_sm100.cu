@@ -329,15 +329,14 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long long co
   return OMC_OK;
 }
 
-static int g_num_sms = 0;
+static int g_num_sms[kMaxDevices] = {};
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  const int dev = cur_device();
+  if (g_num_sms[dev] == 0) {
+    cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms[dev] <= 0) g_num_sms[dev] = 148;
   }
-  return g_num_sms;
+  return g_num_sms[dev];
 }
 
 template <int BN, int CG>
@@ -351,7 +350,8 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
   if (rc) return rc;
   p.num_m_tiles = (p.M + kBM * CG - 1) / (kBM * CG);
   p.num_n_tiles = (p.N + BN - 1) / BN;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);

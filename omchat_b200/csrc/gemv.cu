@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_bf16_kernel(const GemvParam
 template <int NB>
 static int launch_gemv(const GemvParams& p, cudaStream_t st) {
   const size_t smem = (size_t)NB * p.K * 2;
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[kMaxDevices] = {};
+  size_t& attr_smem = attr_smem_dev[cur_device()];
   if (smem > 48 * 1024 && smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(gemv_bf16_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));

@@ -12,6 +12,19 @@ enum { EPI_NONE = OMC_EPI_NONE, EPI_GELU = OMC_EPI_GELU, EPI_RES = OMC_EPI_RES, 
 int set_error(int code, const char* msg);
 int num_sms();
 
+// Ordinal of the calling thread's current device, clamped to [0, kMaxDevices): index of the per-device caches below.
+// cudaFuncSetAttribute and the SM count are per device, so "done once" flags must be kept per ordinal (a process may
+// drive several GPUs: OmChatQwen2ForCausalLM(cfg, device="cuda:1")).
+constexpr int kMaxDevices = 16;
+inline int cur_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    dev = 0;
+  }
+  return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -132,13 +132,16 @@ __global__ void select_pixel_shuffle_kernel(const bf16* __restrict__ hidden, bf1
 }
 
 // ------------------------------------------------------------------------------------------------ embed lookup
+// ids outside [0, vocab) (vocab > 0) produce a zero row instead of an out-of-bounds read (nn.Embedding raises there).
 __global__ void embed_lookup_kernel(const int64_t* __restrict__ ids, int T, const bf16* __restrict__ table, int C,
-                                    bf16* __restrict__ out, long long ldo) {
+                                    bf16* __restrict__ out, long long ldo, int vocab) {
   const int nvec = C >> 3;
   for (int t = blockIdx.x; t < T; t += gridDim.x) {
-    const uint4* src = reinterpret_cast<const uint4*>(table + ids[t] * (long long)C);
+    const long long id = ids[t];
+    const bool ok = vocab <= 0 || (id >= 0 && id < vocab);
+    const uint4* src = reinterpret_cast<const uint4*>(table + (ok ? id : 0) * (long long)C);
     uint4* dst = reinterpret_cast<uint4*>(out + (long long)t * ldo);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = ok ? src[i] : make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -202,7 +205,8 @@ __global__ void splice_gather_kernel(const int64_t* __restrict__ ids, const int3
                                      const bf16* __restrict__ feats, int n_img, int L, int C,
                                      const int32_t* __restrict__ gcount, const int32_t* __restrict__ img_base,
                                      const int32_t* __restrict__ out_offsets, bf16* __restrict__ embeds,
-                                     int32_t* __restrict__ pos_ids, int32_t* __restrict__ seq_ids, int T_capacity) {
+                                     int32_t* __restrict__ pos_ids, int32_t* __restrict__ seq_ids, int T_capacity,
+                                     int vocab) {
   const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int T_total = out_offsets[n_seq];
@@ -231,9 +235,9 @@ __global__ void splice_gather_kernel(const int64_t* __restrict__ ids, const int3
     if (id == image_token) {
       const int img = img_base[s] + gcount[i];
       if (img < n_img) src = reinterpret_cast<const uint4*>(feats + ((long long)img * L + r) * C);
-    } else {
+    } else if (vocab <= 0 || (id >= 0 && id < vocab)) {
       src = reinterpret_cast<const uint4*>(table + id * (long long)C);
-    }
+    }  // else: id outside the vocabulary -> zero row, never an out-of-bounds read
     uint4* dst = reinterpret_cast<uint4*>(embeds + (long long)t * C);
     for (int v = lane; v < nvec; v += 32) dst[v] = src ? src[v] : make_uint4(0, 0, 0, 0);
     if (lane == 0) {
@@ -341,7 +345,7 @@ __global__ void argmax_final_kernel(const float* __restrict__ pv, const int* __r
     int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     argmax_merge(bv, bi, ov, oi);
   }
-  if (threadIdx.x == 0) next[b] = (int64_t)bi;
+  if (threadIdx.x == 0) next[b] = bi == 0x7fffffff ? 0 : (int64_t)bi;  // all-NaN row: index 0 like torch.argmax, never the sentinel
 }
 
 static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
@@ -401,18 +405,18 @@ extern "C" int omc_select_pixel_shuffle(const void* hidden, void* out, int B, in
 }
 
 extern "C" int omc_embed_lookup(const int64_t* ids, int T, const void* table, int C, void* out, long long ldo,
-                                void* stream) {
+                                int vocab, void* stream) {
   if (T <= 0) return OMC_OK;
   if (C % 8 != 0 || ldo % 8 != 0) return set_error(OMC_ERR_SHAPE, "omc_embed_lookup: C, ldo must be multiples of 8");
   int grid = T < num_sms() * 8 ? T : num_sms() * 8;
-  embed_lookup_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(ids, T, (const bf16*)table, C, (bf16*)out, ldo);
+  embed_lookup_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(ids, T, (const bf16*)table, C, (bf16*)out, ldo, vocab);
   return check_launch("embed_lookup");
 }
 
 extern "C" int omc_splice(const int64_t* ids, const int32_t* seq_offsets, int n_seq, int S_total, long long image_token,
                           const void* table, const void* feats, int n_img, int L, int C, int max_len, void* embeds,
                           int32_t* pos_ids, int32_t* seq_ids, int32_t* out_offsets, int32_t* workspace, int T_capacity,
-                          void* stream) {
+                          int vocab, void* stream) {
   if (n_seq <= 0 || S_total <= 0) return set_error(OMC_ERR_SHAPE, "omc_splice: empty input");
   if (C % 8 != 0) return set_error(OMC_ERR_SHAPE, "omc_splice: C % 8 != 0");
   if (L < 1) return set_error(OMC_ERR_SHAPE, "omc_splice: L < 1");
@@ -425,7 +429,7 @@ extern "C" int omc_splice(const int64_t* ids, const int32_t* seq_offsets, int n_
   int grid = grid_for((long long)T_capacity * 32, 256);
   splice_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ids, seq_offsets, n_seq, image_token, (const bf16*)table,
                                                                (const bf16*)feats, n_img, L, C, gcount, img_base,
-                                                               out_offsets, (bf16*)embeds, pos_ids, seq_ids, T_capacity);
+                                                               out_offsets, (bf16*)embeds, pos_ids, seq_ids, T_capacity, vocab);
   return check_launch("splice_gather");
 }
 

@@ -40,8 +40,8 @@ SIGNATURES = {
     "omc_decode_attn_splits": (_I, [_I, _I, _I]),
     "omc_decode_attn_workspace_bytes": (_L, [_I, _I, _I, _I]),
     "omc_paged_decode_attn": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _F, _P, _L, _P, _P]),
-    "omc_embed_lookup": (_I, [_P, _I, _P, _I, _P, _L, _P]),
-    "omc_splice": (_I, [_P, _P, _I, _I, _L, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P]),
+    "omc_embed_lookup": (_I, [_P, _I, _P, _I, _P, _L, _I, _P]),
+    "omc_splice": (_I, [_P, _P, _I, _I, _L, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
     "omc_argmax": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "omc_decode_plan_bytes": (_L, [_I]),
     "omc_decode_workspace_bytes": (_L, [_P]),
@@ -108,9 +108,17 @@ def _stream() -> int:
 
 
 def _need_cuda(*ts):
+    """Every kernel is launched on torch.cuda.current_stream() of the CURRENT device: a tensor living on another GPU would
+    be dereferenced there (illegal access or silent peer traffic), so that is an error, not a convention."""
+    cur = torch.cuda.current_device()
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise OmcError("omchat_b200 kernels need CUDA tensors (no CPU fallback)")
+        if t.device.index != cur:
+            raise OmcError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: run the call under "
+                           f"`with torch.cuda.device({t.device.index}):` (the model classes do this themselves)")
 
 
 SKINNY_MAX_M = 64  # rows up to which gemm() streams the weights through the swapped-operand skinny kernel
@@ -341,7 +349,7 @@ def embed_lookup(ids: torch.Tensor, table: torch.Tensor, out: Optional[torch.Ten
     T, C = ids.numel(), table.shape[1]
     if out is None:
         out = torch.empty(T, C, device=table.device, dtype=torch.bfloat16)
-    rc = load().omc_embed_lookup(_ptr(ids), T, _ptr(table), C, _ptr(out), out.stride(0), _stream())
+    rc = load().omc_embed_lookup(_ptr(ids), T, _ptr(table), C, _ptr(out), out.stride(0), table.shape[0], _stream())
     _check(rc, "omc_embed_lookup")
     return out
 
@@ -363,7 +371,7 @@ def splice(ids: torch.Tensor, seq_offsets: torch.Tensor, table: torch.Tensor, fe
     ws = torch.empty(S + n_seq + 2, device=dev, dtype=torch.int32)
     rc = load().omc_splice(_ptr(ids), _ptr(seq_offsets), n_seq, S, image_token, _ptr(table), _ptr(feats), n_img, L, C,
                            max_len, _ptr(embeds), _ptr(pos_ids), _ptr(seq_ids), _ptr(out_off), _ptr(ws), T_capacity,
-                           _stream())
+                           table.shape[0], _stream())
     _check(rc, "omc_splice")
     return embeds, pos_ids, seq_ids, out_off
 

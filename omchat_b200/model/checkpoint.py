@@ -108,9 +108,12 @@ def save_checkpoint(sd: Dict[str, torch.Tensor], config: OmChatQwen2Config, path
     for i, s in enumerate(shards):
         save_file(s, os.path.join(path, f"model-{i + 1:05d}-of-{len(shards):05d}.safetensors"))
     d = config.to_dict()
-    if hub_layout:
+    if hub_layout:  # omchat/hf/configuration_omchat.py:99-198: model_type "omchat", nested text / vision configs
         text = {k: d[k] for k in _TEXT_KEYS}
         d = {k: v for k, v in d.items() if k not in _TEXT_KEYS}
         d["text_config"] = text
+        d["model_type"] = "omchat"
+        d["vision_feature_layer"] = d["mm_vision_select_layer"]
+        d["image_token_index"] = -200
     with open(os.path.join(path, "config.json"), "w") as fh:
         json.dump(d, fh, indent=1)

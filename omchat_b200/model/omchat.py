@@ -15,6 +15,7 @@ Differences that are deliberate (SURVEY.md §8b "known reference bugs not to rep
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -25,6 +26,16 @@ from ..config import IGNORE_INDEX, IMAGE_TOKEN_INDEX, OmChatQwen2Config
 from .decoder import PagedKVCache, Qwen2Decoder, TPInfo
 from .vision import InternVITVisionTower, MMProjector
 from .weights import OmChatWeights, from_state_dict, random_init
+
+
+def _on_model_device(fn):
+    """Run a model method with the model's GPU as the current CUDA device (kernels launch on the current device's stream;
+    a model built with device="cuda:1" must work without the caller calling torch.cuda.set_device first)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 @dataclass
@@ -81,11 +92,14 @@ class OmChatQwen2ForCausalLM:
         lib.load()
         self.config = config
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.dtype = torch.bfloat16
         if weights is None:
             weights = random_init(config, device=device, seed=seed, tp_rank=tp_rank, tp_size=tp_size)
         self.weights = weights
         self.tp = TPInfo(rank=tp_rank, size=tp_size, group=tp_group)
+        self.vision_dp = True  # under tensor parallelism: crops data-parallel over the ranks + one feature all-gather
         self.model = OmChatQwen2Model(config, weights, self.tp)
         self.vocab_size = config.vocab_size
         self.generation_config = _GenerationConfig(config)
@@ -93,6 +107,8 @@ class OmChatQwen2ForCausalLM:
     # ------------------------------------------------------------------------------------------------ construction
     @classmethod
     def from_state_dict(cls, sd, config: OmChatQwen2Config, device="cuda", **kw):
+        if not torch.cuda.is_available():
+            raise lib.OmcError("omchat_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         w = from_state_dict(sd, config, device=device, tp_rank=kw.get("tp_rank", 0), tp_size=kw.get("tp_size", 1))
         return cls(config, w, device=device, **kw)
 
@@ -117,28 +133,56 @@ class OmChatQwen2ForCausalLM:
     def to(self, *a, **k):
         return self
 
+    @_on_model_device
     def encode_images(self, images: torch.Tensor) -> torch.Tensor:
-        """omchat_arch.py:50-53: vision tower -> (pixel shuffle) -> mm_projector. [n,3,S,S] -> [n, L, hidden]."""
-        images = self._to_dev(images)
-        feats = self.get_vision_tower()(images, self.config.pixel_shuffle_down)
-        return self.get_model().mm_projector(feats)
+        """omchat_arch.py:50-53: vision tower -> (pixel shuffle) -> mm_projector. [n,3,S,S] -> [n, L, hidden].
 
-    def process_images(self, images):
+        With the decoder tensor-parallel over tp ranks (one process per GPU, every rank holding the whole tower) the crops
+        are independent: rank r encodes the r-th contiguous share of them and ONE all-gather of the
+        projected features [share, L, hidden] gives every rank the full, identically ordered tensor the splice needs -
+        vision data-parallel -> feature all-gather -> decoder tensor-parallel. `vision_dp = False` replicates instead."""
+        images = self._to_dev(images)
+        n, tp = images.shape[0], self.tp.size
+        if tp == 1 or not self.vision_dp or n < 2:
+            feats = self.get_vision_tower()(images, self.config.pixel_shuffle_down)
+            return self.get_model().mm_projector(feats)
+        import torch.distributed as dist
+        share = (n + tp - 1) // tp
+        lo, hi = min(n, self.tp.rank * share), min(n, (self.tp.rank + 1) * share)
+        L, H = self.config.image_tokens_per_crop, self.config.hidden_size
+        mine = torch.zeros(share, L, H, device=self.device, dtype=torch.bfloat16)
+        if hi > lo:
+            feats = self.get_vision_tower()(images[lo:hi], self.config.pixel_shuffle_down)
+            mine[:hi - lo] = self.get_model().mm_projector(feats)
+        out = torch.empty(tp * share, L, H, device=self.device, dtype=torch.bfloat16)
+        dist.all_gather_into_tensor(out, mine, group=self.tp.group)
+        return out[:n]
+
+    @_on_model_device
+    def process_images(self, images, flatten: bool = True):
         """GPU replacement of omchat.mm_utils.process_images / process_anyres_image (mm_utils.py:119-182) for
-        image_aspect_ratio == 'anyres': PIL images / uint8 [H,W,3] arrays -> crops [n, 3, 448, 448] on the model's device
-        (Pillow-exact bicubic, csrc/preprocess.cu), ready to be passed as `images=` together with
-        omchat_b200.prompt.image_prompt(n_crops, text)."""
+        image_aspect_ratio == 'anyres' (Pillow-exact bicubic, csrc/preprocess.cu): PIL images / uint8 [H,W,3] arrays ->
+        with flatten (default) ONE tensor [sum of crops, 3, 448, 448] in image order, ready to be passed as `images=`
+        together with one placeholder per crop (omchat_b200.prompt.image_prompt(n_crops, text)); with flatten=False the
+        reference's own return shape: [n_images, n_crops, 3, 448, 448] when every image yields the same number of crops,
+        else a list of [n_crops_i, 3, 448, 448] (mm_utils.py:176-181)."""
         from ..preprocess import AnyResPreprocessor
         pre = getattr(self, "_anyres", None)
         if pre is None:
             pre = AnyResPreprocessor(self.config.image_grid_pinpoints, crop=self.config.vision_config.image_size,
                                      device=self.device, dtype=torch.bfloat16)
             self._anyres = pre
-        return pre.process_images(images if isinstance(images, (list, tuple)) else [images])
+        out = pre.process_images(images if isinstance(images, (list, tuple)) else [images])
+        if not flatten:
+            return out
+        return out.flatten(0, 1) if isinstance(out, torch.Tensor) else torch.cat(list(out), dim=0)
 
     def _to_dev(self, t):
         if isinstance(t, (list, tuple)):
-            t = torch.stack([x for x in t])
+            # list of [3,S,S] crops (omchat_arch.py:72-75) or of per-image [n_i,3,S,S] stacks (process_images, ragged)
+            t = torch.cat([x if x.dim() == 4 else x[None] for x in t], dim=0)
+        if t.dim() == 5:  # [n_images, n_crops, 3, S, S] as process_anyres_image stacks them
+            t = t.flatten(0, 1)
         if not t.is_cuda:
             t = t.to(self.device, non_blocking=True)
         return t
@@ -205,6 +249,7 @@ class OmChatQwen2ForCausalLM:
                 out[i, :n] = packed[offsets[i]:offsets[i + 1]]
         return out
 
+    @_on_model_device
     def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
                                              images):
         """Same contract as omchat_arch.py:55-209: returns (None, position_ids, attention_mask, past_key_values,
@@ -227,7 +272,8 @@ class OmChatQwen2ForCausalLM:
         return None, new_pos, new_mask, past_key_values, inputs_embeds, new_labels
 
     def _splice_labels(self, input_ids, attention_mask, labels, lens, offsets):
-        """Label placement of omchat_arch.py:118-158: image positions get IGNORE_INDEX (training-only; host loop)."""
+        """Label placement of omchat_arch.py:116-158: labels are compacted by the attention mask like the ids, image
+        positions get IGNORE_INDEX, and the result is re-padded like the logits (training-only; host loop)."""
         L = self.config.image_tokens_per_crop
         ids_h, lab_h = input_ids.cpu(), labels.cpu()
         mh = attention_mask.cpu().bool() if attention_mask is not None else torch.ones_like(ids_h, dtype=torch.bool)
@@ -242,6 +288,7 @@ class OmChatQwen2ForCausalLM:
 
     # ------------------------------------------------------------------------------------------------ forward
     @torch.no_grad()
+    @_on_model_device
     def forward(self, input_ids: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
                 position_ids: Optional[torch.Tensor] = None, past_key_values: Optional[PagedKVCache] = None,
                 inputs_embeds: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
@@ -256,13 +303,11 @@ class OmChatQwen2ForCausalLM:
         if output_attentions:
             raise NotImplementedError("attention probabilities are never materialised by the flash kernels")
         dec = self.model.decoder
-        if self.tp.size > 1 and logits_to_keep != 1 and past_key_values is None:
-            raise NotImplementedError("full-sequence logits are vocab-sharded under tensor parallelism; use generate()")
         # ---- decode step (omchat_arch.py:59-70 short-circuit)
         if past_key_values is not None and past_key_values.get_seq_length() > 0:
             if inputs_embeds is not None or input_ids is None or input_ids.shape[1] != 1:
                 raise ValueError("with a populated cache, forward() takes exactly one new token per sequence")
-            logits = dec.decode_step(input_ids.to(self.device).reshape(-1), past_key_values).clone()
+            logits = self._gather_vocab(dec.decode_step(input_ids.to(self.device).reshape(-1), past_key_values).clone())
             return self._output(logits[:, None, :], past_key_values, None, return_dict)
         # ---- prefill
         if inputs_embeds is None:
@@ -272,9 +317,9 @@ class OmChatQwen2ForCausalLM:
             embeds, pos, seq, offsets = self._splice_packed(input_ids, attention_mask, images)
             spliced_labels = None
             if labels is not None:
+                # always compact labels by the mask and re-pad them like the logits (omchat_arch.py:116), images or not
                 lens = [offsets[i + 1] - offsets[i] for i in range(len(offsets) - 1)]
-                spliced_labels = self._splice_labels(input_ids, attention_mask, labels, lens, offsets) \
-                    if images is not None else labels.to(self.device)
+                spliced_labels = self._splice_labels(input_ids, attention_mask, labels, lens, offsets)
         else:
             inputs_embeds = inputs_embeds.to(device=self.device, dtype=torch.bfloat16)
             b, T, _ = inputs_embeds.shape
@@ -291,7 +336,11 @@ class OmChatQwen2ForCausalLM:
             pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(self.device)
             seq = torch.cat([torch.full((n,), i, dtype=torch.int32) for i, n in enumerate(lens)]).to(self.device)
             embeds = embeds.contiguous().clone()
-            spliced_labels = labels.to(self.device) if labels is not None else None
+            spliced_labels = None
+            if labels is not None:  # same compaction by the mask + re-padding as the logits get
+                lab = labels.to(self.device)
+                packed = lab.reshape(-1) if attention_mask is None else lab[attention_mask.to(self.device).bool()]
+                spliced_labels = self._pad(packed, offsets, fill=IGNORE_INDEX)
         n_seq = len(offsets) - 1
         max_len = max(offsets[i + 1] - offsets[i] for i in range(n_seq))
         if past_key_values is None:
@@ -300,6 +349,7 @@ class OmChatQwen2ForCausalLM:
         mode = "last" if logits_to_keep == 1 else "all"
         res = dec.prefill(embeds, pos, seq, offsets, past_key_values, logits=mode, collect_hidden=bool(output_hidden_states))
         logits, hiddens = res if output_hidden_states else (res, None)
+        logits = self._gather_vocab(logits)
         if mode == "last":
             logits = logits[:, None, :]
         else:
@@ -316,6 +366,17 @@ class OmChatQwen2ForCausalLM:
         return self._output(logits, past_key_values if use_cache is not False else None, loss, return_dict, hs)
 
     __call__ = forward
+
+    def _gather_vocab(self, logits: torch.Tensor) -> torch.Tensor:
+        """Under tensor parallelism lm_head is vocab-parallel: every rank holds [rows, V / tp]. forward() returns FULL
+        logits like the reference does, so the shards are all-gathered along the vocabulary (rank order = vocab order)."""
+        if self.tp.size == 1:
+            return logits
+        import torch.distributed as dist
+        flat = logits.reshape(-1, logits.shape[-1]).contiguous()
+        parts = torch.empty(self.tp.size, *flat.shape, device=flat.device, dtype=flat.dtype)
+        dist.all_gather_into_tensor(parts, flat, group=self.tp.group)
+        return parts.permute(1, 0, 2).reshape(*logits.shape[:-1], self.tp.size * logits.shape[-1])
 
     @staticmethod
     def _output(logits, cache, loss, return_dict, hidden_states=None):
@@ -337,13 +398,17 @@ class OmChatQwen2ForCausalLM:
 
     # ------------------------------------------------------------------------------------------------ generate
     @torch.no_grad()
+    @_on_model_device
     def generate(self, input_ids: Optional[torch.Tensor] = None, images: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, max_new_tokens: Optional[int] = None,
                  do_sample: bool = False, temperature: Optional[float] = None, eos_token_id=None, pad_token_id=None,
                  use_cache: bool = True, streamer=None, inputs: Optional[torch.Tensor] = None, use_graph: bool = True,
-                 **unused):
+                 stopping_criteria=None, **unused):
         """Greedy generation with the reference's call shape (cli.py:60-70, hf_example.py:13-18):
-        returns LongTensor [b, S + new] = the prompt ids followed by the generated ids (pad_token_id after EOS)."""
+        returns LongTensor [b, S + new] = the prompt ids followed by the generated ids (pad_token_id after a row has
+        finished). A row finishes at its first EOS token or when `stopping_criteria` (a callable or a list of callables
+        `crit(ids [b, len], scores) -> bool | BoolTensor[b]`, e.g. prompt.KeywordsStoppingCriteria, mm_utils.py:242-274;
+        HF StoppingCriteriaList semantics: any criterion firing stops) says so; generation ends when every row has."""
         if input_ids is None:
             input_ids = inputs
         if input_ids is None:
@@ -355,6 +420,12 @@ class OmChatQwen2ForCausalLM:
         eos = gc.eos_token_id if eos_token_id is None else eos_token_id
         eos_set = set(eos) if isinstance(eos, (list, tuple)) else ({eos} if eos is not None and eos >= 0 else set())
         pad = pad_token_id if pad_token_id is not None else (gc.pad_token_id if gc.pad_token_id is not None else 0)
+        if stopping_criteria is None:
+            criteria = []
+        elif callable(stopping_criteria):
+            criteria = [stopping_criteria]
+        else:
+            criteria = list(stopping_criteria)
         dec = self.model.decoder
         input_ids = input_ids.to(self.device)
         b = input_ids.shape[0]
@@ -378,35 +449,54 @@ class OmChatQwen2ForCausalLM:
         if streamer is not None:
             streamer.put(first.cpu())
             hook = lambda i, toks: streamer.put(toks.cpu())  # noqa: E731
-        # decode in chunks; EOS is checked on the host once per chunk (tokens past EOS are discarded -> same result)
+        # Decode in chunks; EOS and the stopping criteria are evaluated on the host once per chunk, token by token, and
+        # whatever was generated past a row's end is discarded -> the same ids as a per-token loop, without a sync per token.
+        check_stop = bool(eos_set or criteria)
+        prompt_host = input_ids.cpu() if criteria else None
+        new_host = torch.empty(b, 0, dtype=torch.int64)
+        ends: List[Optional[int]] = [None] * b  # number of generated tokens row i keeps, once it has finished
+
+        def scan(from_col: int):
+            """Mark rows finished by the tokens new_host[:, from_col:]. Returns True when every row has finished."""
+            for j in range(from_col, new_host.shape[1]):
+                live = [i for i in range(b) if ends[i] is None]
+                if not live:
+                    break
+                for i in live:
+                    if int(new_host[i, j]) in eos_set:
+                        ends[i] = j + 1
+                if criteria:
+                    prefix = torch.cat([prompt_host, new_host[:, :j + 1]], dim=1)
+                    for crit in criteria:
+                        r = crit(prefix, None)
+                        hit = [bool(r)] * b if not isinstance(r, torch.Tensor) or r.dim() == 0 else [bool(x) for x in r.tolist()]
+                        for i in live:
+                            if hit[i] and ends[i] is None:
+                                ends[i] = j + 1
+            return all(e is not None for e in ends)
+
         chunks = [first.view(b, 1)]
-        done = torch.zeros(b, dtype=torch.bool)
-        produced, cur = 1, first
-        if eos_set:
-            done |= torch.tensor([int(t) in eos_set for t in first.tolist()])
-        chunk = 1 if streamer is not None else 32
-        while produced < max_new and not bool(done.all()):
+        produced, cur, done = 1, first, False
+        if check_stop:
+            new_host = first.view(b, 1).cpu()
+            done = scan(0)
+        chunk = 1 if streamer is not None else (8 if criteria else 32)
+        while produced < max_new and not done:
             n = min(chunk, max_new - produced)
             toks = dec.generate_greedy(cur, cache, n, use_graph=use_graph, on_token=hook)
             chunks.append(toks)
-            produced += n
             cur = toks[:, -1].contiguous()
-            if eos_set:
-                th = toks.cpu()
-                for e in eos_set:
-                    done |= (th == e).any(dim=1)
+            if check_stop:
+                new_host = torch.cat([new_host, toks.cpu()], dim=1)
+                done = scan(produced)
+            produced += n
         new = torch.cat(chunks, dim=1)
-        if eos_set:
-            nh = new.cpu()
-            keep = new.shape[1]
-            ends = []
-            for i in range(b):
-                hit = [j for j, t in enumerate(nh[i].tolist()) if t in eos_set]
-                ends.append(hit[0] + 1 if hit else keep)
-            keep = max(ends)
-            nh = nh[:, :keep].clone()
+        if check_stop and any(e is not None for e in ends):
+            keep = max(e if e is not None else new.shape[1] for e in ends)
+            nh = new_host[:, :keep].clone()
             for i, e in enumerate(ends):
-                nh[i, e:] = pad
+                if e is not None:
+                    nh[i, e:] = pad
             new = nh.to(self.device)
         if streamer is not None:
             streamer.end()

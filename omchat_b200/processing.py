@@ -45,8 +45,16 @@ class OmChatImageProcessor:
         self.image_grid_pinpoints = image_grid_pinpoints if image_grid_pinpoints is not None else DEFAULT_PINPOINTS
         self.size = {"shortest_edge": size}
         self.crop_size = {"height": size, "width": size}
-        self._pre = AnyResPreprocessor(self.image_grid_pinpoints, crop=size, device=device, dtype=dtype, mean=image_mean,
-                                       std=image_std)
+        self._pre_args = dict(crop=size, device=device, dtype=dtype, mean=image_mean, std=image_std)
+        self._pre_obj = None
+
+    @property
+    def _pre(self) -> AnyResPreprocessor:
+        """Built on first use: the processor object itself (tokenizer + geometry) loads on a host without a GPU, the pixel
+        work does not - AnyResPreprocessor raises there (no CPU fallback)."""
+        if self._pre_obj is None:
+            self._pre_obj = AnyResPreprocessor(self.image_grid_pinpoints, **self._pre_args)
+        return self._pre_obj
 
     def preprocess(self, images, return_tensors="pt", **unused) -> BatchFeature:
         if not isinstance(images, (list, tuple)):

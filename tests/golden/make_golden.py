@@ -101,6 +101,38 @@ def main():
         last = r2.logits[0, -1]
     out["greedy_tokens"] = toks
     out["greedy_margins"] = margins
+    # D2. north_star: greedy ids must match for the first 32 generated tokens. Random-init logits are nearly flat, so the
+    # prompt is SEARCHED (seeds 100, 101, ...) for the one whose smallest of 32 top-1 margins is largest relative to the logit scale (>= 2 %, bf16 noise at this
+    # depth is ~0.3 %): then a
+    # mismatch on the bf16 path is an error, not a tie, and the GPU test can assert the 32 ids without a margin escape.
+    best = None
+    for seed in range(100, 260):
+        g = torch.Generator().manual_seed(seed)
+        ids_d = torch.randint(0, TINY["vocab"] - 10, (1, 24), generator=g)
+        ids_d[0, 7] = -200
+        res = model(input_ids=ids_d, images=pixels[1:2], use_cache=True)
+        past, last = res.past_key_values, res.logits[0, -1]
+        toks32, margins32, scales32 = [], [], []
+        for step in range(32):
+            top2 = torch.topk(last, 2).values
+            margins32.append(float(top2[0] - top2[1]))
+            scales32.append(float(last.abs().max()))
+            tok = int(torch.argmax(last))
+            toks32.append(tok)
+            r2 = model(input_ids=torch.tensor([[tok]]), past_key_values=past, use_cache=True)
+            past, last = r2.past_key_values, r2.logits[0, -1]
+        worst = min(m / s for m, s in zip(margins32, scales32))
+        if best is None or worst > best[0]:
+            best = (worst, seed, ids_d, toks32, margins32, scales32)
+    worst, seed, ids_d, toks32, margins32, scales32 = best
+    assert worst >= 0.02, f"no prompt with 32 comfortable margins found (best {worst})"
+    out["greedy32_seed"] = seed
+    out["greedy32_ids"] = ids_d
+    out["greedy32_image"] = 1
+    out["greedy32_tokens"] = toks32
+    out["greedy32_margins"] = margins32
+    out["greedy32_scales"] = scales32
+    print("greedy32 seed", seed, toks32, "min margin/scale", min(m / s for m, s in zip(margins32, scales32)))
 
     # E. splice semantics: batch of 3 with padding, 2 / 0 / 1 placeholders (the image-less row still consumes a block)
     ids_e = ids.clone()

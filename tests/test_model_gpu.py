@@ -121,6 +121,30 @@ def test_greedy_ids_match_reference_and_oracle(model, golden, sd_bf16):
     assert toks == got
 
 
+def test_32_greedy_ids_match_reference(model, golden, sd_bf16):
+    """north_star: the first 32 greedy ids equal the REAL reference's (fp32, tests/golden/make_golden.py D2). The prompt was
+    searched so that every one of the 32 top-1 margins is >= 2 % of the logit scale (bf16 noise at this depth: ~0.3 %),
+    so the ids are asserted outright - no margin escape."""
+    pixels, _ = tiny_inputs(1)
+    ids, im, want = golden["greedy32_ids"], golden["greedy32_image"], golden["greedy32_tokens"]
+    assert len(want) == 32
+    out = model.generate(ids, images=pixels[im:im + 1], max_new_tokens=32, do_sample=False, eos_token_id=-1)
+    got = out[0, ids.shape[1]:].tolist()
+    print("cuda:", got, "\nreference:", want, "\nmin margin/scale:",
+          min(m / s for m, s in zip(golden["greedy32_margins"], golden["greedy32_scales"])))
+    assert got == want
+    # per-step logits through the forward() API against the oracle on the same bf16-rounded weights: cosine >= 0.999
+    owant, step_logits = O.greedy_generate(ids, pixels[im:im + 1], sd_bf16, oracle_cfg(), max_new_tokens=32)
+    assert owant == want
+    res = model(input_ids=ids, images=pixels[im:im + 1], logits_to_keep=1, max_cache_len=512)
+    cache, last = res.past_key_values, res.logits[:, -1]
+    for i in range(32):
+        check(last, step_logits[i][None], f"step {i} logits", rel=0.02)
+        tok = last.argmax(-1)
+        assert int(tok) == want[i]
+        last = model(input_ids=tok.view(1, 1), past_key_values=cache).logits[:, -1]
+
+
 @pytest.mark.parametrize("side", ["right", "left"])
 @pytest.mark.parametrize("max_len", [None, 300])
 def test_splice_placement_vs_reference_golden(sd_bf16, golden, side, max_len):
@@ -209,16 +233,19 @@ def test_end_to_end_image_bytes_to_tokens(sd_bf16):
     pins = [[S, 2 * S], [2 * S, S], [2 * S, 2 * S]]
     m = OmChatQwen2ForCausalLM.from_state_dict(sd_bf16, tiny_cfgs(image_grid_pinpoints=pins), device="cuda")
     img = synthetic_image(2, 500, 230)
-    crops = m.process_images([img])  # [1, n, 3, S, S] bf16
+    crops = m.process_images([img])  # [n, 3, S, S] bf16: ready for images=
     want_crops = torch.from_numpy(PO.process_anyres(img, pins, crop=S))
-    assert crops.shape[0] == 1 and torch.equal(crops[0].cpu(), want_crops.to(torch.bfloat16))
-    n = crops.shape[1]
+    assert crops.dim() == 4 and torch.equal(crops.cpu(), want_crops.to(torch.bfloat16))
+    stacked = m.process_images([img, img], flatten=False)  # the reference's own shape [n_images, n_crops, 3, S, S]
+    assert stacked.shape == (2,) + tuple(crops.shape) and torch.equal(stacked[1], crops)
+    assert torch.equal(m.encode_images(stacked)[crops.shape[0]:], m.encode_images(crops))  # 5-D input is flattened
+    n = crops.shape[0]
     _, ids = P.make_context(ToyTokenizer(), P.image_prompt(n, "What is this?"), None, "You are a helpful assistant.")
     ids = [t if t == -200 else (t % 997) + 1 for t in ids]  # the toy tokenizer's ids folded into the tiny vocabulary
     assert ids.count(-200) == n
     ids = torch.tensor([ids])
     new = 6
-    out = m.generate(ids, images=crops[0], max_new_tokens=new, do_sample=False, eos_token_id=-1)
+    out = m.generate(ids, images=crops, max_new_tokens=new, do_sample=False, eos_token_id=-1)
     got = out[0, ids.shape[1]:].tolist()
     want, step_logits = O.greedy_generate(ids, want_crops.to(torch.bfloat16).float(), sd_bf16, oracle_cfg(), max_new_tokens=new)
     for i in range(new):

@@ -54,6 +54,18 @@ def test_prefill_logits_and_greedy_match_reference(golden, tiny_sd):
     assert toks == golden["greedy_tokens"]
 
 
+def test_32_greedy_ids_match_reference(golden, tiny_sd):
+    """north_star: 'greedy token IDs must match for the first 32 generated tokens' - the oracle against the REAL
+    reference's manual greedy loop (tests/golden/make_golden.py D2; prompt searched for comfortable top-1 margins)."""
+    pixels, _ = tiny_inputs(1)
+    im = golden["greedy32_image"]
+    toks, step_logits = O.greedy_generate(golden["greedy32_ids"], pixels[im:im + 1], tiny_sd, tiny_cfg(), max_new_tokens=32)
+    assert len(golden["greedy32_tokens"]) == 32 and toks == golden["greedy32_tokens"]
+    for lg, m in zip(step_logits, golden["greedy32_margins"]):
+        top2 = torch.topk(lg, 2).values
+        assert abs(float(top2[0] - top2[1]) - m) < 2e-3
+
+
 @pytest.mark.parametrize("side", ["right", "left"])
 @pytest.mark.parametrize("max_len", [None, 300])
 def test_splice_matches_reference(golden, tiny_sd, side, max_len):

@@ -31,9 +31,11 @@ def _peaks():
     return load_peaks()
 
 
-def _finish(torch, dist):
-    from bench import _finish as f
-    f(torch, dist)
+def _finish(torch, dist, dec=None):
+    import bench
+    if dec is not None:
+        bench._TEARDOWN.append(lambda: bench._release_decoder(dec))
+    bench._finish(torch, dist)
 
 
 def _barrier(torch, dist, world):
@@ -53,8 +55,6 @@ def _max_over_ranks(torch, dist, world, vals, dev):
 def run_c3(args, rank, world, local, total_crops: int = 64):
     import torch
     import torch.distributed as dist
-    from bench import ClockSampler
-    from omchat_b200 import lib
     from omchat_b200.config import OmChatQwen2Config
     from omchat_b200.model.vision import InternVITVisionTower, MMProjector
     from omchat_b200.model.weights import random_init
@@ -62,7 +62,21 @@ def run_c3(args, rank, world, local, total_crops: int = 64):
     dev = torch.device("cuda", local)
     cfg = OmChatQwen2Config(mm_pixel_shuffle_ratio=args.pixel_shuffle)
     w = random_init(cfg, device=dev, seed=0, vision=True, text=False)
-    tower, proj = InternVITVisionTower(cfg, w.vit), MMProjector(w.proj)
+    line = measure_c3(args, rank, world, local, cfg, InternVITVisionTower(cfg, w.vit), MMProjector(w.proj), total_crops)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        _finish(torch, dist)
+
+
+def measure_c3(args, rank, world, local, cfg, tower, proj, total_crops: int = 64) -> dict:
+    """Times config c3 on an existing tower + projector (also called by bench.py's main line: `workloads.c3`)."""
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler
+    from omchat_b200 import lib
+
+    dev = torch.device("cuda", local)
     mine = list(range(rank, total_crops, world))  # crop i -> GPU i mod N
     g = torch.Generator().manual_seed(1)
     pixels_all = torch.randn(total_crops, 3, 448, 448, generator=g)
@@ -118,10 +132,7 @@ def run_c3(args, rank, world, local, total_crops: int = 64):
                      "traffic": None, "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
                      "flops_per_crop": flop_crop},
     }
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        _finish(torch, dist)
+    return line
 
 
 # ------------------------------------------------------------------------------------------------------------ c4
@@ -138,6 +149,23 @@ def run_c4(args, rank, world, local, n_seq: int = 32, text_tokens: int = 768, im
     cfg = OmChatQwen2Config(mm_pixel_shuffle_ratio=0.5, eos_token_id=-1)
     w = random_init(cfg, device=dev, seed=0, vision=False, text=True, tp_rank=rank, tp_size=world)
     dec = Qwen2Decoder(cfg, w.llm, TPInfo(rank=rank, size=world, group=dist.group.WORLD if world > 1 else None))
+    line = measure_c4(args, rank, world, local, cfg, dec, n_seq, text_tokens, image_tokens)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        _finish(torch, dist, dec)
+
+
+def measure_c4(args, rank, world, local, cfg, dec, n_seq: int = 32, text_tokens: int = 768, image_tokens: int = 256) -> dict:
+    """Times config c4 on an existing (tensor-parallel) decoder (also called by bench.py's main line: `workloads.c4`)."""
+    import torch
+    import torch.distributed as dist
+    from bench import ClockSampler
+    from omchat_b200 import lib
+    from omchat_b200.config import IMAGE_TOKEN_INDEX
+
+    dev = torch.device("cuda", local)
+    w_llm = dec.w
     new_tokens = min(args.new_tokens, 256)
     T = text_tokens + image_tokens
     g = torch.Generator().manual_seed(2)
@@ -155,7 +183,7 @@ def run_c4(args, rank, world, local, n_seq: int = 32, text_tokens: int = 768, im
         e = [ev() for _ in range(3)] if timing is not None else None
         if e:
             e[0].record()
-        embeds, pos, seq, _ = lib.splice(ids_d.reshape(-1), seq_off, w.llm.embed, feats_d, IMAGE_TOKEN_INDEX, 0, n_seq * T)
+        embeds, pos, seq, _ = lib.splice(ids_d.reshape(-1), seq_off, w_llm.embed, feats_d, IMAGE_TOKEN_INDEX, 0, n_seq * T)
         logits = dec.prefill(embeds, pos, seq, offsets, cache, logits="last")
         st = dec._decode_state(n_seq, cache.capacity)
         st.logits.copy_(logits)
@@ -197,14 +225,14 @@ def run_c4(args, rank, world, local, n_seq: int = 32, text_tokens: int = 768, im
     peaks = _peaks()
     gen = n_seq * new_tokens
     # decode bytes per step per GPU: local weights + local KV at the mean context
-    wbytes = sum(l.qkv_w.numel() + l.o_w.numel() + l.gate_up_w.numel() + l.down_w.numel() for l in w.llm.layers) * 2 \
-        + w.llm.lm_head.numel() * 2
-    kv_tok = 2 * len(w.llm.layers) * dec.Hkv * 128 * 2
+    wbytes = sum(l.qkv_w.numel() + l.o_w.numel() + l.gate_up_w.numel() + l.down_w.numel() for l in w_llm.layers) * 2 \
+        + w_llm.lm_head.numel() * 2
+    kv_tok = 2 * len(w_llm.layers) * dec.Hkv * 128 * 2
     step_bytes = wbytes + n_seq * (T + new_tokens / 2.0) * kv_tok
     us = 1000.0 * dc / max(new_tokens - 1, 1)
     gbs = step_bytes / (us * 1e-6) / 1e9
-    p_mm = sum(l.qkv_w.numel() + l.o_w.numel() + l.gate_up_w.numel() + l.down_w.numel() for l in w.llm.layers)
-    pf_flop = 2.0 * p_mm * n_seq * T + 2.0 * len(w.llm.layers) * dec.Hq * 128 * T * T * n_seq
+    p_mm = sum(l.qkv_w.numel() + l.o_w.numel() + l.gate_up_w.numel() + l.down_w.numel() for l in w_llm.layers)
+    pf_flop = 2.0 * p_mm * n_seq * T + 2.0 * len(w_llm.layers) * dec.Hq * 128 * T * T * n_seq
     line = {
         "metric": "tokens/sec", "value": gen / (tot * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": tot, "higher_is_better": True, "scaling": "strong",
@@ -226,10 +254,7 @@ def run_c4(args, rank, world, local, n_seq: int = 32, text_tokens: int = 768, im
                      "traffic": None, "peak_source": peaks["source"], "bytes_per_step_per_gpu": step_bytes,
                      "avg_step_us": us},
     }
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        _finish(torch, dist)
+    return line
 
 
 # ------------------------------------------------------------------------------------------------------------ c5
@@ -243,11 +268,19 @@ def run_c5(args, rank, world, local, n_prompts: int = 16, images_per_prompt: int
 
     dev = torch.device("cuda", local)
     cfg = OmChatQwen2Config(mm_pixel_shuffle_ratio=0.5, eos_token_id=-1)
-    model = OmChatQwen2ForCausalLM(cfg, device=f"cuda:{local}", seed=0)
+    tp_mode = getattr(args, "c5_mode", "dp") == "tp" and world > 1
+    if tp_mode:
+        # SURVEY.md §8e row 3, second variant: ONE model over all GPUs - the 128 crops data-parallel over the N towers, one
+        # all-gather of the projected features, then the decoder tensor-parallel N ways over all 16 prompts
+        model = OmChatQwen2ForCausalLM(cfg, device=f"cuda:{local}", seed=0, tp_rank=rank, tp_size=world,
+                                       tp_group=dist.group.WORLD)
+        mb = getattr(args, "c5_mb", 0) or 8
+    else:
+        model = OmChatQwen2ForCausalLM(cfg, device=f"cuda:{local}", seed=0)
     new_tokens = min(args.new_tokens, 64)
     L = cfg.image_tokens_per_crop  # 256
     T = text_tokens + images_per_prompt * L
-    mine = list(range(rank, n_prompts, world))
+    mine = list(range(n_prompts)) if tp_mode else list(range(rank, n_prompts, world))
     g = torch.Generator().manual_seed(2)
     ids = torch.randint(0, 151643, (n_prompts, text_tokens + images_per_prompt), generator=g)
     step = (text_tokens + images_per_prompt) // images_per_prompt
@@ -301,7 +334,8 @@ def run_c5(args, rank, world, local, n_prompts: int = 16, images_per_prompt: int
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"c5: {n_prompts} prompts x {images_per_prompt} images x {L} image tokens (pixel-shuffle 0.5) + "
                                f"{text_tokens} text ids = {T}-token contexts, {new_tokens} greedy tokens each",
-                   "parallelism": f"dp{world} replicas, mini-batches of {mb} prompts per GPU (no collective)",
+                   "parallelism": (f"vision dp{world} -> feature all-gather -> decoder tp{world}, mini-batches of {mb} prompts"
+                                   if tp_mode else f"dp{world} replicas, mini-batches of {mb} prompts per GPU (no collective)"),
                    "kv_cache": f"paged, page {cfg.kv_page_size}",
                    "l2": "no flush needed: every mini-batch streams 26 GB of weights"},
         "phases": {"vision_ms_per_rank": vis, "crops_per_sec_vision": crops / (vis * 1e-3),
@@ -314,4 +348,4 @@ def run_c5(args, rank, world, local, n_prompts: int = 16, images_per_prompt: int
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        _finish(torch, dist)
+        _finish(torch, dist, model.model.decoder)
