@@ -110,12 +110,14 @@ def _stream() -> int:
 def _need_cuda(*ts):
     """Every kernel is launched on torch.cuda.current_stream() of the CURRENT device: a tensor living on another GPU would
     be dereferenced there (illegal access or silent peer traffic), so that is an error, not a convention."""
-    cur = torch.cuda.current_device()
+    cur = None
     for t in ts:
         if t is None:
             continue
         if not t.is_cuda:
             raise OmcError("omchat_b200 kernels need CUDA tensors (no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
         if t.device.index != cur:
             raise OmcError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: run the call under "
                            f"`with torch.cuda.device({t.device.index}):` (the model classes do this themselves)")
