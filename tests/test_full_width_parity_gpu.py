@@ -15,8 +15,8 @@ oracle's; a differing id is accepted only where it is arithmetically forced - if
 the argmax can only move when the oracle's top-1 margin is <= 2e - with e the max-abs logit error MEASURED at that step
 (teacher-forced on the oracle's ids), and the margins are printed.
 
-The full-DEPTH variant (45 + 28 layers = config c1, ~52 GB of fp32 weights staged tower -> decoder on the host) runs with
-OMCHAT_FULL_PARITY=1.
+The full-DEPTH variant (45 + 28 layers = config c1: the tower's fp32 weights staged one block at a time, the decoder's
+30 GB held on the host) runs with OMCHAT_FULL_PARITY=1; its log is committed under profiles/.
 """
 import os
 import time
@@ -68,17 +68,41 @@ def _build(vit_layers, llm_layers, seed=0, peaked_head=True):
         # every run of 32 steps), which would make "32 equal ids" a coin toss under ANY bf16 rounding. Give the rows of
         # lm_head log-normal norms (a trained head is not isotropic either): the winner then leads by a visible margin.
         g = torch.Generator(device="cuda").manual_seed(1234)
-        s = torch.exp(0.8 * torch.randn(cfg.vocab_size, 1, generator=g, device="cuda"))
+        s = torch.exp(1.2 * torch.randn(cfg.vocab_size, 1, generator=g, device="cuda"))
         model.weights.llm.lm_head.mul_(s.to(torch.bfloat16))
     return cfg, model
 
 
-def _inputs():
-    g1, g2 = torch.Generator().manual_seed(1), torch.Generator().manual_seed(2)
+def _inputs(prompt_seed=2):
+    g1, g2 = torch.Generator().manual_seed(1), torch.Generator().manual_seed(prompt_seed)
     pixels = torch.randn(1, 3, 448, 448, generator=g1)
     ids = torch.randint(0, 151643, (1, TEXT_TOKENS + 1), generator=g2)
     ids[0, PLACEHOLDER_AT] = -200
     return pixels, ids
+
+
+def _pick_prompt(model, candidates=range(2, 34), good=0.04):
+    """Input selection, not checking: among the candidate prompt seeds take the one whose 32 greedy steps on the CUDA path
+    have the largest minimum top-1 margin relative to the logit scale (early exit at `good`). Random-init logits tie within
+    bf16 noise somewhere in most 32-step runs; on a prompt without such ties the 32 ids can be asserted outright. The
+    oracle then runs on the chosen prompt only, and every comparison against it is unconditional on this choice."""
+    best = (-1.0, None)
+    for seed in candidates:
+        pixels, ids = _inputs(seed)
+        r = model(input_ids=ids, images=pixels, logits_to_keep=1, max_cache_len=TEXT_TOKENS + 1024 + NEW_TOKENS + 8)
+        cache, last, worst = r.past_key_values, r.logits[:, -1], 1.0
+        for _ in range(NEW_TOKENS):
+            top2 = torch.topk(last[0], 2).values
+            worst = min(worst, float((top2[0] - top2[1]) / last.abs().max()))
+            if worst < best[0]:
+                break
+            last = model(input_ids=last.argmax(-1).view(1, 1), past_key_values=cache).logits[:, -1]
+        if worst > best[0]:
+            best = (worst, seed)
+        if worst >= good:
+            break
+    print(f"prompt seed {best[1]}: smallest top-1 margin of its 32 steps on the CUDA path = {best[0]:.4f} of the logit scale")
+    return best[1]
 
 
 def _oracle_cfg(cfg):
@@ -91,7 +115,7 @@ def test_full_width_reduced_depth_vs_oracle():
     from omchat_b200.model.weights import to_reference_state_dict
     cfg, model = _build(3, 3)
     ocfg = _oracle_cfg(cfg)
-    pixels, ids = _inputs()
+    pixels, ids = _inputs(_pick_prompt(model))
     # the pixels the tower sees are bf16 (im2col output dtype): hand the oracle the same bf16-representable values
     pixels = pixels.to(torch.bfloat16).float()
     sd = {k: v.float().cpu() for k, v in to_reference_state_dict(model.weights, cfg).items()}
@@ -174,7 +198,7 @@ def _compare_ids(got, teacher_forced, want, margins, errs):
 
 
 @pytest.mark.skipif(os.environ.get("OMCHAT_FULL_PARITY") != "1", reason="config c1 at full depth: set OMCHAT_FULL_PARITY=1 "
-                    "(needs ~40 GB of host RAM and several minutes of CPU time)")
+                    "(needs ~45 GB of host RAM and a few minutes of CPU time)")
 def test_full_depth_c1_vs_oracle():
     """BASELINE.json configs[0]: the OmChat-2.0-13B arch (45 ViT blocks + 28 decoder layers), 1 crop + 64-token prompt,
     32 greedy tokens, fp32 on the CPU - staged: the oracle walks the towers one layer at a time, taking
@@ -185,7 +209,7 @@ def test_full_depth_c1_vs_oracle():
     from omchat_b200.model.weights import to_reference_state_dict
     cfg, model = _build(45, 28)
     ocfg = _oracle_cfg(cfg)
-    pixels, ids = _inputs()
+    pixels, ids = _inputs(_pick_prompt(model, candidates=range(2, 18)))
     pixels = pixels.to(torch.bfloat16).float()
     sd_dev = to_reference_state_dict(model.weights, cfg)  # bf16 views on the device
 
@@ -213,12 +237,14 @@ def test_full_depth_c1_vs_oracle():
     table = sd_dev["model.embed_tokens.weight"].float().cpu()
     emb_o, mask_o, pos_o, lens = O.splice(ids, None, enc_o, table, ocfg)
     T = lens[0]
-    host = {k: v.cpu() for k, v in sd_dev.items() if k.startswith("model.layers.")}
-    one = O.OracleConfig(layers=1)
+    # fp32 host copy of the decoder (30 GB; the GPU box has 196 GB of host RAM), keyed per layer under a layer-0 prefix
+    layers_host = []
+    for li in range(28):
+        p = f"model.layers.{li}."
+        layers_host.append({"model.layers.0." + k[len(p):]: v.float().cpu() for k, v in sd_dev.items() if k.startswith(p)})
 
     def layer_sd(li):
-        p = f"model.layers.{li}."
-        return {"model.layers.0." + k[len(p):]: v.float() for k, v in host.items() if k.startswith(p)}
+        return layers_host[li]
 
     head = {"model.norm.weight": sd_dev["model.norm.weight"].float().cpu(), "lm_head.weight": sd_dev["lm_head.weight"].float().cpu()}
 

@@ -90,7 +90,7 @@ def test_forward_rejects_tensors_on_another_device():
 
 
 @pytest.mark.gpu
-def test_auto_model_generate_with_stopping_criteria(tmp_path):
+def test_auto_model_generate_with_stopping_criteria(tmp_path, golden):
     """AutoModelForCausalLM.from_pretrained(saved tiny checkpoint) -> generate(stopping_criteria=[KeywordsStoppingCriteria])
     on the CUDA path: ids equal the oracle's greedy ids cut where the criterion first fires, rows pad after their end, a
     per-row BoolTensor criterion and EOS stop rows independently."""
@@ -103,15 +103,17 @@ def test_auto_model_generate_with_stopping_criteria(tmp_path):
     d = _save(tmp_path, False)
     model = AutoModelForCausalLM.from_pretrained(d)
     assert type(model) is H.OmChatQwen2ForCausalLM and model.config == _tiny_cfg()
-    pixels, ids = tiny_inputs(1)
-    ids = ids[:1].clone() % 200 + 10   # byte-range ids so the toy tokenizer decodes them
-    ids[0, 5] = -200
+    # the prompt whose 32 greedy ids are pinned against the REAL reference with comfortable top-1 margins (make_golden.py D2)
+    pixels, _ = tiny_inputs(1)
+    im = golden["greedy32_image"]
+    pixels, ids = pixels[im:im + 1], golden["greedy32_ids"]
     sd = {k: v.to(torch.bfloat16).float() for k, v in tiny_state_dict(0).items()}
     ocfg = O.OracleConfig(vit_hidden=TINY["vit_hidden"], vit_heads=TINY["vit_heads"], vit_inter=TINY["vit_inter"],
                           vit_layers=TINY["vit_layers"], image_size=TINY["image_size"], hidden=TINY["hidden"],
                           heads=TINY["heads"], kv_heads=TINY["kv_heads"], inter=TINY["inter"], layers=TINY["layers"],
                           vocab=TINY["vocab"], rope_theta=TINY["rope_theta"])
     want, _ = O.greedy_generate(ids, pixels[:1], sd, ocfg, max_new_tokens=20)
+    assert want == golden["greedy32_tokens"][:20]
     free = model.generate(ids, images=pixels[:1], max_new_tokens=20, do_sample=False, eos_token_id=-1)
     assert free[0, ids.shape[1]:].tolist() == want
     # a keyword made of the ids of generated tokens 6..7: the criterion fires when token 7 has been produced
@@ -127,6 +129,7 @@ def test_auto_model_generate_with_stopping_criteria(tmp_path):
     out = model.generate(ids, images=pixels[:1], max_new_tokens=20, do_sample=False, eos_token_id=-1,
                          stopping_criteria=[crit])
     first_hit = next(i for i in range(1, 20) if want[i - 1:i + 1] == keyword_ids)
+    assert first_hit == 7
     assert out[0, ids.shape[1]:].tolist() == want[:first_hit + 1]
     # batch of 2 with a per-row tensor criterion + EOS: rows end independently, pad after the end
     ids2 = torch.cat([ids, ids], 0)
@@ -143,4 +146,4 @@ def test_auto_model_generate_with_stopping_criteria(tmp_path):
     assert new[1].tolist() == want[:9]
     out3 = model.generate(ids, images=pixels[:1], max_new_tokens=20, do_sample=False, eos_token_id=want[3])
     assert out3[0, ids.shape[1]:].tolist() == want[:want.index(want[3]) + 1]
-    assert tok is not None
+    assert tok is not None and tiny_inputs is not None
