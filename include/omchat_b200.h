@@ -158,6 +158,33 @@ int omc_splice(const int64_t* ids, const int32_t* seq_offsets, int n_seq, int S_
  * (lowest index on ties), logits fp32 [B, V] with row stride ldl. workspace: 128*B floats. */
 int omc_argmax(const float* logits, long long ldl, int B, int V, int64_t* next, float* workspace, void* stream);
 
+/* ---- weight-streaming GEMM of the batched decode step (omchat_b200/csrc/gemm_stream.cu) --------------------------------
+ * Replaces, for M <= 64 rows, the nn.Linear calls of Qwen2Attention / Qwen2MLP / lm_head (transformers modeling_qwen2.py:
+ * 46-48, 219-221, 245, 470-472) together with the Qwen2RMSNorm in front of them (:258-263): Y[M,N] = epi(rstd[m] * (X W'^T)).
+ * omc_pack_weight re-lays an [N, K] row-major bf16 weight once, at load time, as [N/128][K/64] tiles of 128 x 64 elements in
+ * the shared-memory image of the MMA (128-byte swizzle), optionally scaling column k by col_scale[k] (the RMSNorm weight that
+ * precedes the layer). `packed` must be 1024-byte aligned and omc_packed_weight_bytes(N, K) long.
+ * omc_gemm_stream: X bf16 [M, K] (row stride ldx), packed weights, out bf16 (or fp32) [M, N or N/2 for SwiGLU].
+ *   ssq_in  != NULL: fp32 [ssq_parts][64] partial sums of squares of X's rows over norm_dim columns; row m of the product is
+ *                    scaled by rsqrt(sum_parts / norm_dim + eps) before bias / activation  (the folded RMSNorm)
+ *   ssq_out != NULL: (bf16 output, not SwiGLU) fp32 [ceil(N/128)][64] partial sums of squares of the rows written
+ *   workspace: omc_gemm_stream_workspace_bytes() bytes, zeroed once by the caller, shared by consecutive launches of a stream
+ *   pdl != 0: launch with programmatic stream serialization (the kernel prefetches weights before it waits for its
+ *             predecessor; every access to activations happens after griddepcontrol.wait).
+ * omc_row_ssq: sums of squares of rows that were not produced by an EPI_RES epilogue (embedding rows; all-reduced rows
+ *   under tensor parallelism): ssq[0][m] = sum_k x[m,k]^2, ssq[1..parts-1][m] = 0. */
+long long omc_packed_weight_bytes(int N, int K);
+int omc_pack_weight(const void* W, long long ldw, int N, int K, const void* col_scale, void* packed, void* stream);
+long long omc_gemm_stream_workspace_bytes(void);
+int omc_gemm_stream(const void* X, long long ldx, int M, const void* Wp, int N, int K, void* out, long long ldo,
+                    int out_is_f32, const void* bias, const void* res, long long ldr, int epi, const float* ssq_in,
+                    int ssq_parts, int norm_dim, float eps, float* ssq_out, void* workspace, int pdl, void* stream);
+int omc_row_ssq(const void* x, long long ldx, int rows, int C, float* ssq, int parts, int pdl, void* stream);
+/* profiling hook: the next max_launches omc_gemm_stream launches write %globaltimer stamps [2 * SMs][8] each into buf
+ * (entry, weights issued, dependency satisfied, first stage landed, last MMA issued, accumulator read, partials summed,
+ * stores issued); buf = NULL switches it off. Measurement only (tools/prof_stream.py). */
+int omc_gemm_stream_set_prof(void* buf, int max_launches);
+
 /* ---- persistent decode step ("megakernel", omchat_b200/csrc/decode_mega.cu) ------------------------------------------
  * One cooperative launch = one whole Qwen2 decode step for 1..4 sequences: embed_tokens (omchat_arch.py:139), every
  * Qwen2DecoderLayer (modeling_qwen2.py:280-310: RMSNorm, q/k/v + bias, RoPE, paged KV append + GQA attention, o_proj,

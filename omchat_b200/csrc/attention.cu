@@ -266,6 +266,10 @@ __global__ void __launch_bounds__(kDecThreads) paged_decode_attn_kernel(const De
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
   const int G = p.G;
+  // programmatic dependent launch (csrc/gemm_stream.cu): let the next kernel's CTAs move in as ours retire, and do not
+  // read the qkv rows / context lengths of this step before the kernel that produced them has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int ctx = p.ctx_lens[b];
   const int pos_new = ctx - 1;
   const bool fused = p.inv_freq != nullptr;
@@ -580,7 +584,17 @@ extern "C" int omc_paged_decode_attn(const void* qkv, long long ldq, const float
   const int G = Hq / Hkv;
   p.ws = (float*)workspace;
   p.counters = reinterpret_cast<unsigned int*>((float*)workspace + (long long)B * Hkv * splits * G * kDecPartStride);
-  dim3 grid(splits, Hkv, B);
-  paged_decode_attn_kernel<<<grid, kDecThreads, kDecSmem, (cudaStream_t)stream>>>(p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(splits, Hkv, B);
+  cfg.blockDim = dim3(kDecThreads);
+  cfg.dynamicSmemBytes = kDecSmem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // a no-op unless the previous kernel triggers early
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, paged_decode_attn_kernel, p);
+  if (le != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(le));
   return check_launch("paged_decode_attn");
 }

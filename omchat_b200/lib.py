@@ -26,6 +26,12 @@ SIGNATURES = {
     "omc_gemm_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _L, _I, _I, _I, _P]),
     "omc_gemm_skinny_workspace_bytes": (_L, [_I]),
     "omc_gemm_skinny_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _L, _I, _I, _P, _L, _P]),
+    "omc_packed_weight_bytes": (_L, [_I, _I]),
+    "omc_pack_weight": (_I, [_P, _L, _I, _I, _P, _P, _P]),
+    "omc_gemm_stream_workspace_bytes": (_L, []),
+    "omc_gemm_stream": (_I, [_P, _L, _I, _P, _I, _I, _P, _L, _I, _P, _P, _L, _I, _P, _I, _I, _F, _P, _P, _I, _P]),
+    "omc_row_ssq": (_I, [_P, _L, _I, _I, _P, _I, _I, _P]),
+    "omc_gemm_stream_set_prof": (_I, [_P, _I]),
     "omc_gemv_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _L, _I, _I, _P]),
     "omc_rmsnorm": (_I, [_P, _L, _P, _P, _L, _I, _I, _F, _P]),
     "omc_vit_im2col": (_I, [_P, _I, _P, _L, _I, _I, _I, _P]),
@@ -215,6 +221,74 @@ def gemm(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *
                               1 if out_f32 else 0, tile_cfg, _stream())
     _check(rc, "omc_gemm_bf16")
     return out
+
+
+# ---- weight-streaming GEMM of the batched decode step (csrc/gemm_stream.cu): packed weights, stream-K, PDL, folded RMSNorm
+PDL_ENABLED = os.environ.get("OMCHAT_B200_PDL", "1") != "0"
+_stream_ws = {}
+
+
+class PackedWeight:
+    """An [N, K] weight re-laid as 16 KB swizzled tiles (omc_pack_weight); `data` is the 1024-byte aligned byte view."""
+
+    def __init__(self, w: torch.Tensor, col_scale: Optional[torch.Tensor] = None):
+        _need_cuda(w, col_scale)
+        assert w.dim() == 2 and w.stride(1) == 1 and w.dtype == torch.bfloat16
+        self.N, self.K = w.shape
+        nbytes = load().omc_packed_weight_bytes(self.N, self.K)
+        self._buf = torch.empty(nbytes + 1024, device=w.device, dtype=torch.uint8)
+        off = (-self._buf.data_ptr()) % 1024
+        self.data = self._buf[off:off + nbytes]
+        rc = load().omc_pack_weight(_ptr(w), w.stride(0), self.N, self.K, _ptr(col_scale), self.data.data_ptr(), _stream())
+        _check(rc, "omc_pack_weight")
+
+
+def _stream_workspace(device) -> torch.Tensor:
+    key = str(device)
+    ws = _stream_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(load().omc_gemm_stream_workspace_bytes(), device=device, dtype=torch.uint8)
+        _stream_ws[key] = ws
+    return ws
+
+
+def ssq_parts(C: int) -> int:
+    """Number of 128-column tiles of a C-wide row = number of sum-of-squares partials an EPI_RES epilogue writes."""
+    return (C + 127) // 128
+
+
+def gemm_stream(x: torch.Tensor, wp: PackedWeight, out: Optional[torch.Tensor] = None, *, bias=None, res=None,
+                epi: int = EPI_NONE, out_f32: bool = False, ssq_in: Optional[torch.Tensor] = None, ssq_in_parts: int = 0,
+                norm_dim: int = 0, eps: float = 1e-6, ssq_out: Optional[torch.Tensor] = None, pdl: Optional[bool] = None):
+    """out[M, N] = epi(rstd[m] * (x[M, K] @ W'^T)) for M <= 64 (see include/omchat_b200.h, omc_gemm_stream)."""
+    _need_cuda(x, out, bias, res, ssq_in, ssq_out)
+    M, K = x.shape
+    assert K == wp.K and x.stride(1) == 1 and M <= 64
+    N = wp.N
+    n_out = N // 2 if epi == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty(M, n_out, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    if ssq_in is not None:
+        assert ssq_in.dtype == torch.float32 and ssq_in.numel() >= ssq_in_parts * 64 and norm_dim > 0
+    if ssq_out is not None:
+        assert ssq_out.dtype == torch.float32 and ssq_out.numel() >= ssq_parts(N) * 64
+    ws = _stream_workspace(x.device)
+    rc = load().omc_gemm_stream(_ptr(x), x.stride(0), M, wp.data.data_ptr(), N, K, _ptr(out), out.stride(0), 1 if out_f32 else 0,
+                                _ptr(bias), _ptr(res), res.stride(0) if res is not None else 0, epi, _ptr(ssq_in),
+                                ssq_in_parts, norm_dim, eps, _ptr(ssq_out), ws.data_ptr(),
+                                1 if (PDL_ENABLED if pdl is None else pdl) else 0, _stream())
+    _check(rc, "omc_gemm_stream")
+    return out
+
+
+def row_ssq(x: torch.Tensor, ssq: torch.Tensor, parts: int = 1, pdl: Optional[bool] = None):
+    _need_cuda(x, ssq)
+    assert x.dim() == 2 and x.stride(1) == 1 and ssq.dtype == torch.float32 and ssq.numel() >= parts * 64
+    rc = load().omc_row_ssq(_ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(ssq), parts,
+                            1 if (PDL_ENABLED if pdl is None else pdl) else 0, _stream())
+    _check(rc, "omc_row_ssq")
+    return ssq
 
 
 def gemv(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, norm_w=None, eps: float = 1e-6,

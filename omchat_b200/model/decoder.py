@@ -18,6 +18,11 @@ gate/up GEMM(SwiGLU), down GEMM(+residual). Decode (B <= 8) = 5 launches: qkv GE
 (RoPE + append fused), o GEMV(+residual), gate/up GEMV (RMSNorm + SwiGLU fused), down GEMV(+residual); the whole step
 including lm_head, argmax and the next embedding lookup is captured in one CUDA graph.
 
+Batched decode (B > 4) = per layer 5 launches chained by programmatic dependent launch (csrc/gemm_stream.cu): qkv GEMM
+(RMSNorm folded in: packed weights carry the norm weight, the epilogue applies rstd), paged attention (RoPE + append
+fused), o GEMM (+residual, emits the row sums of squares), gate/up GEMM (folded RMSNorm + SwiGLU), down GEMM (+residual,
+sums of squares); one CUDA graph per step.
+
 Tensor parallelism (tp > 1, one process per GPU): q/k/v and gate/up are column-parallel, o and down row-parallel with
 one NCCL all-reduce each (56 per forward); rank 0 alone folds the residual into its partial sum so the all-reduce
 result is the new residual stream. lm_head is vocab-parallel; greedy sampling all-gathers one (max, index) pair per rank.
@@ -114,6 +119,9 @@ class Qwen2Decoder:
         self.scale = cfg.head_dim ** -0.5
         self.eps = cfg.rms_norm_eps
         self.mega_enabled = os.environ.get("OMCHAT_B200_NO_MEGA", "0") != "1"
+        # batched decode steps (B > 4): weight-streaming GEMMs on packed weights (0 = the round-1 skinny GEMM / GEMV path)
+        self.stream_enabled = os.environ.get("OMCHAT_B200_NO_STREAM", "0") != "1"
+        self._packed = None  # lazily built packed copies of the decoder weights (csrc/gemm_stream.cu)
         # tp > 1: all-reduce inside the persistent kernel over NVLink peer memory (0 = per-op kernels + NCCL all-reduce)
         self.tp_mega_enabled = os.environ.get("OMCHAT_B200_TP_MEGA", "1") != "0"
         self._xchg = {}  # batch -> lib.PeerExchange (tensor-parallel persistent decode kernel)
@@ -164,6 +172,31 @@ class Qwen2Decoder:
     @staticmethod
     def _gemv_ok(B: int, K: int) -> bool:
         return B <= GEMV_MAX_B and B * K * 2 <= GEMV_MAX_SMEM
+
+    # ------------------------------------------------------------------------------------------------ packed weights
+    class _Packed:
+        pass
+
+    def packed_weights(self):
+        """The decoder's matrices re-laid for the weight-streaming GEMM (built once, on the first batched decode step):
+        q|k|v and gate|up carry the RMSNorm weight in front of them, lm_head the final norm (modeling_qwen2.py:258-263
+        folded into :219-221, :46-48, :470-472). Costs one more copy of the decoder weights in HBM (14 GB of 180)."""
+        if self._packed is None:
+            P = Qwen2Decoder._Packed()
+            P.layers = []
+            for l in self.w.layers:
+                e = Qwen2Decoder._Packed()
+                e.qkv = lib.PackedWeight(l.qkv_w, col_scale=l.ln1)
+                e.o = lib.PackedWeight(l.o_w)
+                e.gate_up = lib.PackedWeight(l.gate_up_w, col_scale=l.ln2)
+                e.down = lib.PackedWeight(l.down_w)
+                P.layers.append(e)
+            P.lm_head = lib.PackedWeight(self.w.lm_head, col_scale=self.w.norm)
+            self._packed = P
+        return self._packed
+
+    def use_stream(self, B: int) -> bool:
+        return self.stream_enabled and not self.use_mega(B) and B <= 64
 
     # ------------------------------------------------------------------------------------------------ prefill
     @torch.no_grad()
@@ -249,6 +282,8 @@ class Qwen2Decoder:
         st.act = torch.empty(B, self.I_local, device=dev, dtype=torch.bfloat16)
         st.logits = torch.empty(B, self.V_local, device=dev, dtype=torch.float32)
         st.arg_ws = torch.empty(128 * B, device=dev, dtype=torch.float32)
+        st.ssq_a = torch.zeros(lib.ssq_parts(self.C) * 64, device=dev, dtype=torch.float32)  # row sums of squares entering a layer
+        st.ssq_b = torch.zeros(lib.ssq_parts(self.C) * 64, device=dev, dtype=torch.float32)  # ... entering its MLP
         st.splits = lib.decode_attn_splits(B, self.Hkv, max_ctx)
         st.attn_ws = lib.decode_attn_workspace(B, self.Hq, self.Hkv, st.splits, dev)
         if self.tp.size > 1:
@@ -323,6 +358,11 @@ class Qwen2Decoder:
             # embed + all layers + lm_head + argmax + ctx_lens += 1 in one launch (always samples into st.tokens)
             self._mega_step(self._mega_plan(st, cache))
             return
+        if self.use_stream(B):
+            self._decode_body_stream(st, cache)
+            if sample:
+                self._greedy(st)
+            return
         cache.ctx_lens.add_(1)  # context length INCLUDING the token being processed
         lib.embed_lookup(st.tokens, self.w.embed, out=st.h)
         h = st.h
@@ -347,6 +387,36 @@ class Qwen2Decoder:
         self.lm_head(h, out=st.logits)
         if sample:
             self._greedy(st)
+
+    def _decode_body_stream(self, st, cache: PagedKVCache):
+        """Batched decode step on the weight-streaming GEMMs: 5 kernels per layer, each launched as a programmatic
+        dependent of the previous one; no stand-alone RMSNorm (folded into the GEMMs that follow it)."""
+        P = self.packed_weights()
+        C, eps = self.C, self.eps
+        tp = self.tp.size > 1
+        parts = 1 if tp else lib.ssq_parts(C)
+        cache.ctx_lens.add_(1)  # context length INCLUDING the token being processed
+        lib.embed_lookup(st.tokens, self.w.embed, out=st.h)
+        lib.row_ssq(st.h, st.ssq_a, parts=parts, pdl=False)
+        h = st.h
+        fold = (not tp) or self.tp.rank == 0  # under TP rank 0 alone adds the residual; the all-reduce completes the sum
+        for li, (l, p) in enumerate(zip(self.w.layers, P.layers)):
+            lib.gemm_stream(h, p.qkv, out=st.qkv, bias=l.qkv_b, ssq_in=st.ssq_a, ssq_in_parts=parts, norm_dim=C, eps=eps)
+            lib.paged_decode_attn(st.qkv, self.inv_freq, cache.pool[li], cache.block_table, cache.page_size,
+                                  cache.ctx_lens, self.Hq, self.Hkv, st.splits, self.scale, st.attn, st.attn_ws)
+            lib.gemm_stream(st.attn, p.o, out=h, res=h if fold else None, epi=lib.EPI_RES if fold else lib.EPI_NONE,
+                            ssq_out=None if tp else st.ssq_b)
+            if tp:
+                self._all_reduce(h)
+                lib.row_ssq(h, st.ssq_b, parts=1, pdl=False)
+            lib.gemm_stream(h, p.gate_up, out=st.act, epi=lib.EPI_SWIGLU, ssq_in=st.ssq_b, ssq_in_parts=parts, norm_dim=C,
+                            eps=eps)
+            lib.gemm_stream(st.act, p.down, out=h, res=h if fold else None, epi=lib.EPI_RES if fold else lib.EPI_NONE,
+                            ssq_out=None if tp else st.ssq_a)
+            if tp:
+                self._all_reduce(h)
+                lib.row_ssq(h, st.ssq_a, parts=1, pdl=False)
+        lib.gemm_stream(h, P.lm_head, out=st.logits, out_f32=True, ssq_in=st.ssq_a, ssq_in_parts=parts, norm_dim=C, eps=eps)
 
     def _greedy(self, st):
         """HF GenerationMixin greedy argmax (cli.py:60-70); vocab-parallel under TP."""

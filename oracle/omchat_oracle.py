@@ -16,6 +16,10 @@ outputs in tests/golden/*.pt; tests/test_oracle.py checks this restatement again
 (ratio 0.5) has NO reference symbol ("parity unpinned" for that one function): it is pinned against the InternVL
 view/permute formulation quoted in SURVEY.md §8 a7.
 
+The tower / projector / decoder functions are device- and dtype-agnostic plain torch: the parity tests also run them with
+bf16 CUDA tensors ("what the reference's own 16-bit PyTorch path gives on this box") to calibrate how much of an error
+against the fp32 gold is bf16 itself.
+
 Weights are passed as a flat dict keyed by the reference's own state-dict names
 (`model.vision_tower.vision_tower.*`, `model.mm_projector.{0,2}.*`, `model.layers.*`, `model.norm.weight`,
 `model.embed_tokens.weight`, `lm_head.weight`).
@@ -238,7 +242,7 @@ def rope_inv_freq(cfg: OracleConfig) -> torch.Tensor:
 
 def rope_cos_sin(position_ids: torch.Tensor, cfg: OracleConfig, dtype: torch.dtype):
     """Qwen2RotaryEmbedding.forward modeling_qwen2.py:102-113: fp32 angles, emb = cat(freqs, freqs), cast to dtype."""
-    inv = rope_inv_freq(cfg)
+    inv = rope_inv_freq(cfg).to(position_ids.device)
     freqs = position_ids.to(torch.float32)[..., None] * inv  # [b, T, d/2]
     emb = torch.cat([freqs, freqs], dim=-1)
     return emb.cos().to(dtype), emb.sin().to(dtype)
@@ -275,8 +279,8 @@ def qwen2_attention(x: torch.Tensor, sd, pre: str, cfg: OracleConfig, cos, sin, 
     kr = k[:, :, None].expand(b, KV, H // KV, ctx, D).reshape(b, H, ctx, D)
     vr = v[:, :, None].expand(b, KV, H // KV, ctx, D).reshape(b, H, ctx, D)
     w = (q @ kr.transpose(2, 3)) * (D ** -0.5)
-    qpos = torch.arange(ctx - T, ctx)[:, None]
-    causal = torch.arange(ctx)[None, :] <= qpos  # [T, ctx]
+    qpos = torch.arange(ctx - T, ctx, device=q.device)[:, None]
+    causal = torch.arange(ctx, device=q.device)[None, :] <= qpos  # [T, ctx]
     allow = causal[None, None]
     if key_mask is not None:
         allow = allow & key_mask[:, None, None, :].bool()

@@ -36,18 +36,35 @@ def _cos_rows(a, b):
 
 
 class Report:
+    """Collects one line per compared tensor and asserts at the end, so one run shows every number. `calib` is the same
+    quantity computed by plain torch in bf16 on the GPU (the oracle's functions on bf16 CUDA tensors = what the reference's
+    own 16-bit PyTorch path gives): its error against the fp32 gold is printed beside ours. strict=False rows (intermediate
+    states of the full-depth run, where bf16 rounding is amplified layer by layer on random-init weights) are bounded by
+    cosine >= 0.99 and by 2 x the calibration's own error instead of the north_star tolerance."""
+
     def __init__(self):
         self.rows, self.fail = [], []
 
-    def add(self, what, got, ref, rel=0.03, cos_min=0.999):
+    def add(self, what, got, ref, rel=0.03, cos_min=0.999, calib=None, strict=True):
         got, ref = got.float().cpu(), ref.float().cpu()
         assert got.shape == ref.shape, (what, got.shape, ref.shape)
         err = (got - ref).abs().max().item()
         scale = ref.abs().max().item()
         cos = _cos_rows(got, ref).min().item()
-        ok = bool(torch.isfinite(got).all()) and err <= rel * scale and cos >= cos_min
-        self.rows.append(f"{what:34s} max-abs err {err:9.4g}  scale {scale:9.4g}  rel {err / scale:8.5f}  min cosine/token {cos:.6f}"
-                         + ("" if ok else "   <-- FAIL"))
+        line = f"{what:34s} max-abs err {err:9.4g}  scale {scale:9.4g}  rel {err / scale:8.5f}  min cosine/token {cos:.6f}"
+        ok = bool(torch.isfinite(got).all())
+        if calib is not None:
+            cal = calib.float().cpu()
+            cerr = (cal - ref).abs().max().item()
+            ccos = _cos_rows(cal, ref).min().item()
+            line += f"   | torch bf16: err {cerr:9.4g} cosine {ccos:.6f}"
+            if not strict:
+                ok = ok and cos >= 0.99 and err <= 2.0 * cerr + 0.01 * scale and (1 - cos) <= 3.0 * (1 - ccos) + 1e-4
+        if strict:
+            ok = ok and err <= rel * scale and cos >= cos_min
+        elif calib is None:
+            ok = ok and cos >= 0.99
+        self.rows.append(line + ("" if ok else "   <-- FAIL"))
         if not ok:
             self.fail.append(what)
         return err
@@ -200,10 +217,12 @@ def _compare_ids(got, teacher_forced, want, margins, errs):
 @pytest.mark.skipif(os.environ.get("OMCHAT_FULL_PARITY") != "1", reason="config c1 at full depth: set OMCHAT_FULL_PARITY=1 "
                     "(needs ~45 GB of host RAM and a few minutes of CPU time)")
 def test_full_depth_c1_vs_oracle():
-    """BASELINE.json configs[0]: the OmChat-2.0-13B arch (45 ViT blocks + 28 decoder layers), 1 crop + 64-token prompt,
-    32 greedy tokens, fp32 on the CPU - staged: the oracle walks the towers one layer at a time, taking
-    each layer's fp32 weights from the CUDA model's bf16 tensors, so the host never holds more than the decoder's bf16
-    copy + one fp32 layer."""
+    """BASELINE.json configs[0]: the OmChat-2.0-13B arch (45 ViT blocks + 28 decoder layers), 1 crop + 64-token prompt
+    (T = 1088), 32 greedy tokens, fp32 on the CPU - staged: the oracle walks the tower one block at a time
+    taking each block's fp32 weights from the CUDA model's bf16 tensors, the decoder's fp32 copy (30 GB) stays on the host.
+    north_star tolerances are asserted on the quantities it names - vision features, projector output, logits (cosine >=
+    0.999 per token), 32 greedy ids - and every intermediate state is printed with its max-abs error beside the error of
+    plain torch in bf16 on the same GPU (Report)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from omchat_b200.model.weights import to_reference_state_dict
@@ -213,47 +232,48 @@ def test_full_depth_c1_vs_oracle():
     pixels = pixels.to(torch.bfloat16).float()
     sd_dev = to_reference_state_dict(model.weights, cfg)  # bf16 views on the device
 
-    def take(prefix):
-        return {k: v.float().cpu() for k, v in sd_dev.items() if k.startswith(prefix)}
+    def take(prefix, dev=False):
+        return {k: (v if dev else v.float().cpu()) for k, v in sd_dev.items() if k.startswith(prefix)}
 
     rep = Report()
     t0 = time.time()
-    # ---- tower, layer by layer
+    # ---- tower, block by block: fp32 gold on the CPU, torch bf16 on the GPU, ours
     S = cfg.vision_config.num_patches + 1
     tower = model.get_vision_tower()
     _, states = tower.hidden_states(pixels.cuda(), collect=True)
     h = O.vit_embeddings(pixels, take(O.VT + "embeddings."), ocfg)
-    rep.add("ViT hidden state  0", states[0].view(1, S, -1), h)
+    hb = O.vit_embeddings(pixels.cuda().to(torch.bfloat16), take(O.VT + "embeddings.", True), ocfg)
+    rep.add("ViT hidden state  0", states[0].view(1, S, -1), h, calib=hb, strict=False)
     for li in range(45):
         h = O.vit_layer(h, take(f"{O.VT}encoder.layers.{li}."), li, ocfg)
-        rep.add(f"ViT hidden state {li + 1:2d}", states[li + 1].view(1, S, -1), h)
+        hb = O.vit_layer(hb, take(f"{O.VT}encoder.layers.{li}.", True), li, ocfg)
+        rep.add(f"ViT hidden state {li + 1:2d}", states[li + 1].view(1, S, -1), h, calib=hb, strict=False)
     del states
     feats_o = h[:, 1:]
-    rep.add("vision features", tower(pixels.cuda()), feats_o)
+    rep.add("vision features", tower(pixels.cuda()), feats_o, rel=0.06, calib=hb[:, 1:])
     enc_o = O.projector(feats_o, take("model.mm_projector."))
-    rep.add("mm_projector out", model.encode_images(pixels), enc_o)
+    enc_b = O.projector(hb[:, 1:], take("model.mm_projector.", True))
+    rep.add("mm_projector out", model.encode_images(pixels), enc_o, rel=0.06, calib=enc_b)
     print(f"tower done {time.time() - t0:.0f} s", flush=True)
-    # ---- decoder: bf16 host copy, one fp32 layer at a time
+    # ---- decoder
     table = sd_dev["model.embed_tokens.weight"].float().cpu()
     emb_o, mask_o, pos_o, lens = O.splice(ids, None, enc_o, table, ocfg)
     T = lens[0]
-    # fp32 host copy of the decoder (30 GB; the GPU box has 196 GB of host RAM), keyed per layer under a layer-0 prefix
-    layers_host = []
+    layers_host, layers_dev = [], []
     for li in range(28):
         p = f"model.layers.{li}."
-        layers_host.append({"model.layers.0." + k[len(p):]: v.float().cpu() for k, v in sd_dev.items() if k.startswith(p)})
+        layers_dev.append({"model.layers.0." + k[len(p):]: v for k, v in sd_dev.items() if k.startswith(p)})
+        layers_host.append({k: v.float().cpu() for k, v in layers_dev[-1].items()})
+    head_dev = {"model.norm.weight": sd_dev["model.norm.weight"], "lm_head.weight": sd_dev["lm_head.weight"]}
+    head_host = {k: v.float().cpu() for k, v in head_dev.items()}
 
-    def layer_sd(li):
-        return layers_host[li]
-
-    head = {"model.norm.weight": sd_dev["model.norm.weight"].float().cpu(), "lm_head.weight": sd_dev["lm_head.weight"].float().cpu()}
-
-    def run(embeds, pos, past, key_mask):
-        """qwen2_forward staged per layer (a 1-layer oracle call per layer; the final norm + lm_head are applied once)."""
+    def run(embeds, pos, past, key_mask, layers, head):
+        """qwen2_forward staged per layer (the oracle's own attention / MLP / norm functions; final norm + lm_head applied
+        to the last position only). Works on CPU fp32 (gold) and on CUDA bf16 (calibration) alike."""
         x, new_past, hid = embeds, [], [embeds]
         cos, sin = O.rope_cos_sin(pos, ocfg, embeds.dtype)
         for li in range(28):
-            lsd = layer_sd(li)
+            lsd = layers[li]
             a, kv = O.qwen2_attention(O.rms_norm(x, lsd["model.layers.0.input_layernorm.weight"], ocfg.rms_eps), lsd,
                                       "model.layers.0.", ocfg, cos, sin, None if past is None else past[li], key_mask)
             x = x + a
@@ -264,18 +284,21 @@ def test_full_depth_c1_vs_oracle():
         xl = O.rms_norm(x[:, -1:], head["model.norm.weight"], ocfg.rms_eps)
         return torch.nn.functional.linear(xl, head["lm_head.weight"])[0, 0], new_past, hid
 
-    last_o, past, hid_o = run(emb_o, pos_o, None, mask_o)
+    last_o, past, hid_o = run(emb_o, pos_o, None, mask_o, layers_host, head_host)
+    # the calibration pipeline is torch bf16 end to end: its decoder starts from ITS OWN projector output, like ours does
+    emb_b = O.splice(ids, None, enc_b.float().cpu(), table.to(torch.bfloat16).float(), ocfg)[0]
+    last_b, past_b, hid_b = run(emb_b.cuda().to(torch.bfloat16), pos_o.cuda(), None, mask_o.cuda(), layers_dev, head_dev)
     res = model(input_ids=ids, images=pixels, output_hidden_states=True, logits_to_keep=1, max_cache_len=T + NEW_TOKENS + 8)
     for li, (mine, ref) in enumerate(zip(res.hidden_states, hid_o)):
-        rep.add(f"decoder hidden state {li:2d}", mine, ref, rel=0.06)
-    del hid_o
+        rep.add(f"decoder hidden state {li:2d}", mine, ref, calib=hid_b[li], strict=False)
+    del hid_o, hid_b
     cache, last = res.past_key_values, res.logits[:, -1]
     print(f"prefill done {time.time() - t0:.0f} s", flush=True)
     out = model.generate(ids, images=pixels, max_new_tokens=NEW_TOKENS, do_sample=False, eos_token_id=-1)
     got = out[0, ids.shape[1]:].tolist()
     want, margins, errs, tf = [], [], [], []
     for i in range(NEW_TOKENS):
-        errs.append(rep.add(f"decode step {i:2d} logits", last, last_o[None], rel=0.06))
+        errs.append(rep.add(f"decode step {i:2d} logits", last, last_o[None], rel=0.06, calib=last_b[None]))
         tf.append(int(last.argmax(-1)))
         top2 = torch.topk(last_o, 2).values
         margins.append(float(top2[0] - top2[1]))
@@ -283,7 +306,9 @@ def test_full_depth_c1_vs_oracle():
         want.append(tok)
         if i == NEW_TOKENS - 1:
             break
-        last_o, past, _ = run(table[torch.tensor([[tok]])], torch.tensor([[T + i]]), past, None)
+        last_o, past, _ = run(table[torch.tensor([[tok]])], torch.tensor([[T + i]]), past, None, layers_host, head_host)
+        last_b, past_b, _ = run(table[torch.tensor([[tok]])].cuda().to(torch.bfloat16), torch.tensor([[T + i]]).cuda(), past_b,
+                                None, layers_dev, head_dev)
         last = model(input_ids=torch.tensor([[tok]]), past_key_values=cache).logits[:, -1]
     print(f"\noracle ids: {want}\ncuda ids  : {got}\nmargins: {[round(m, 4) for m in margins]}")
     _compare_ids(got, tf, want, margins, errs)

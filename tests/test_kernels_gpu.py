@@ -144,6 +144,58 @@ def test_gemm_skinny(L, M, N, K):
         assert int(ws.count_nonzero()) == 0, "split-K workspace must be left zeroed"
 
 
+@pytest.mark.parametrize("M", [1, 9, 16, 17, 32, 33, 64])
+@pytest.mark.parametrize("N,K", [(256, 64), (3584, 1792), (1000, 4104), (37888 // 8, 512), (4608, 3584), (152064 // 8, 3584)])
+def test_gemm_stream(L, M, N, K):
+    """Weight-streaming GEMM of the batched decode step (csrc/gemm_stream.cu): packed 16 KB weight tiles, stream-K over
+    2 CTAs per SM with tiles cut across CTAs (partials summed in CTA order: bit-identical from call to call), ragged N / K
+    tails, every epilogue, and the folded RMSNorm: y = rstd[m] * (x @ (W * g)^T) with the sums of squares taken from an
+    EPI_RES epilogue's partials. Reference: fp32 on the CPU from the same bf16 inputs; the folded-norm case against
+    Qwen2RMSNorm + Linear of the oracle (the norm weight's bf16 rounding moves from the activations into W': tolerance 2^-6)."""
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    x = bf(torch.randn(M, K, generator=g)).cuda()
+    w = bf(torch.randn(N, K, generator=g) * 0.1).cuda()
+    bias = bf(torch.randn(N, generator=g)).cuda()
+    res = bf(torch.randn(M, N, generator=g)).cuda()
+    wp = L.PackedWeight(w)
+    lin = ref_linear(x, w, bias)
+    outs = []
+    for rep in range(2):
+        outs.append(L.gemm_stream(x, wp, pdl=bool(rep)))
+        assert_close(outs[-1], ref_linear(x, w), what=f"stream plain rep {rep}")
+    assert torch.equal(outs[0], outs[1]), "the stream-K reduction must be deterministic (and PDL must not change results)"
+    assert_close(L.gemm_stream(x, wp, bias=bias, epi=L.EPI_GELU), torch.nn.functional.gelu(lin), what="stream gelu")
+    assert_close(L.gemm_stream(x, wp, out_f32=True), ref_linear(x, w), what="stream f32 out")
+    # residual in place + sums of squares of the rows written
+    h = res.clone()
+    ssq = torch.full((L.ssq_parts(N) * 64,), float("nan"), device="cuda")
+    L.gemm_stream(x, wp, out=h, res=h, bias=bias, epi=L.EPI_RES, ssq_out=ssq)
+    assert_close(h, res.float().cpu() + lin, what="stream res in place")
+    got_ssq = ssq.view(-1, 64)[:, :M].sum(0).cpu()
+    want_ssq = h.float().pow(2).sum(-1).cpu()
+    assert torch.allclose(got_ssq, want_ssq, rtol=1e-4), "sum of squares must be that of the bf16 rows actually written"
+    if N % 16 == 0:
+        gate, up = w[0::2].cpu(), w[1::2].cpu()
+        wantg = torch.nn.functional.silu(ref_linear(x, gate)) * ref_linear(x, up)
+        assert_close(L.gemm_stream(x, wp, epi=L.EPI_SWIGLU), wantg, what="stream swiglu")
+    # folded RMSNorm: next layer consumes h (K2 = N) through W2 * g
+    if N % 8 == 0 and N <= 8192:
+        N2 = 384
+        gw = bf(torch.randn(N, generator=g) * 0.1 + 1.0).cuda()
+        w2 = bf(torch.randn(N2, N, generator=g) * 0.1).cuda()
+        wp2 = L.PackedWeight(w2, col_scale=gw)
+        y = L.gemm_stream(h, wp2, ssq_in=ssq, ssq_in_parts=L.ssq_parts(N), norm_dim=N, eps=1e-6)
+        want = ref_linear(O.rms_norm(h.cpu(), gw.cpu(), 1e-6), w2)
+        assert_close(y, want, rel=2 ** -6, what="stream folded rmsnorm")
+        ssq1 = torch.empty(64, device="cuda")
+        L.row_ssq(h, ssq1, parts=1)
+        assert torch.allclose(ssq1[:M].cpu(), want_ssq, rtol=1e-4)
+        y1 = L.gemm_stream(h, wp2, ssq_in=ssq1, ssq_in_parts=1, norm_dim=N, eps=1e-6)
+        assert_close(y1, want, rel=2 ** -6, what="stream folded rmsnorm (row_ssq)")
+    flags = L._stream_workspace(x.device)[-(2 * L.num_sms() * 4 + 256):-256]
+    assert int(flags.count_nonzero()) == 0, "every partial-tile flag must have been consumed"
+
+
 def test_gemm_strided_views_and_errors(L):
     g = torch.Generator().manual_seed(11)
     big = bf(torch.randn(200, 1024, generator=g)).cuda()
