@@ -172,13 +172,24 @@ int omc_argmax(const float* logits, long long ldl, int B, int V, int64_t* next, 
  *   pdl != 0: launch with programmatic stream serialization (the kernel prefetches weights before it waits for its
  *             predecessor; every access to activations happens after griddepcontrol.wait).
  * omc_row_ssq: sums of squares of rows that were not produced by an EPI_RES epilogue (embedding rows; all-reduced rows
- *   under tensor parallelism): ssq[0][m] = sum_k x[m,k]^2, ssq[1..parts-1][m] = 0. */
+ *   under tensor parallelism): ssq[0][m] = sum_k x[m,k]^2, ssq[1..parts-1][m] = 0.
+ * omc_gemm_stream, tp != NULL (row-parallel o_proj / down_proj under tensor parallelism, one process per GPU): the all-reduce over the
+ *             tp->size ranks happens inside the epilogue over NVLink peer memory - tp->bufs[r] is rank r's exchange buffer
+ *             (omc_gemm_stream_xchg_bytes() bytes from omc_peer_alloc, zeroed; peers' buffers mapped with omc_peer_open),
+ *             tp->channel 0 / 1 separates the two row-parallel ops of a layer. Every rank passes the same residual replica and
+ *             gets the same bits of output and of ssq_out. Replaces the NCCL all-reduce of the reference-shaped TP plan. */
+typedef struct omc_tp_xchg {
+  int rank, size, channel, reserved;
+  void* bufs[8];
+} omc_tp_xchg;
+long long omc_gemm_stream_xchg_bytes(void);
 long long omc_packed_weight_bytes(int N, int K);
 int omc_pack_weight(const void* W, long long ldw, int N, int K, const void* col_scale, void* packed, void* stream);
 long long omc_gemm_stream_workspace_bytes(void);
 int omc_gemm_stream(const void* X, long long ldx, int M, const void* Wp, int N, int K, void* out, long long ldo,
                     int out_is_f32, const void* bias, const void* res, long long ldr, int epi, const float* ssq_in,
-                    int ssq_parts, int norm_dim, float eps, float* ssq_out, void* workspace, int pdl, void* stream);
+                    int ssq_parts, int norm_dim, float eps, float* ssq_out, void* workspace, int pdl, const omc_tp_xchg* tp,
+                    void* stream);
 int omc_row_ssq(const void* x, long long ldx, int rows, int C, float* ssq, int parts, int pdl, void* stream);
 /* profiling hook: the next max_launches omc_gemm_stream launches write %globaltimer stamps [2 * SMs][8] each into buf
  * (entry, weights issued, dependency satisfied, first stage landed, last MMA issued, accumulator read, partials summed,

@@ -31,6 +31,14 @@
 //    o_proj / down_proj: per 128-column tile partials, summed in tile order by the consumer), so the two row passes per
 //    layer disappear. (The reference rounds the normalised row to 16 bit before it multiplies by g; here the rounding
 //    happens in W' instead - covered by the stated tolerance, see tests/test_kernels_gpu.py::test_gemm_stream.)
+//  * TENSOR-PARALLEL ALL-REDUCE INSIDE THE EPILOGUE (row-parallel o_proj / down_proj under tp_size 2..8, one process per
+//    GPU). The owner CTA of an output tile pushes its fp32 partial tile straight into every peer's exchange buffer over
+//    NVLink (buffers mapped with CUDA IPC: omc_peer_alloc / omc_peer_open), publishes a flag with release.sys, polls the
+//    flags the peers set in ITS buffer, and sums the tp_size partials in rank order - so every GPU ends up with the same
+//    bits of the new residual stream, the residual add and the sums of squares for the next folded RMSNorm happen in the same
+//    epilogue, and no NCCL kernel (nor a stand-alone add / norm pass) sits between two GEMMs of a decode step. One buffer per
+//    op kind ("channel": o_proj, down_proj): a producer can only come back to a slot after it has consumed, through the
+//    other channel, data its peer sent AFTER reading that slot; the consumer clears the flags it has read.
 // Epilogues: bias, erf-GELU, +residual, SwiGLU on interleaved gate/up rows (adjacent lanes), fp32 output.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -73,7 +81,26 @@ struct StreamParams {
   float* ws;       // [grid][64*128] fp32 partial tiles
   unsigned int* flags;  // [grid]
   unsigned long long* prof;  // optional [grid][8] %globaltimer stamps of this launch (tools/prof_stream.py), else nullptr
+  // tensor-parallel exchange (tp_size > 1): xbuf[r] = rank r's exchange buffer as mapped into THIS process
+  int tp_rank, tp_size, tp_channel;
+  uint8_t* xbuf[8];
 };
+
+// exchange buffer layout: [channel 2][src rank 8][tile 64] payload slots of 64 x 128 fp32, then the flags [2][8][64] u32
+constexpr int kXTiles = 64;
+constexpr size_t kXPayload = (size_t)kStSlotFloats * 4;
+constexpr size_t kXFlagsOffset = 2ull * 8 * kXTiles * kXPayload;
+constexpr size_t kXBytes = kXFlagsOffset + 2ull * 8 * kXTiles * 4;
+__host__ __device__ inline size_t x_slot(int channel, int src, int tile) { return ((size_t)(channel * 8 + src) * kXTiles + tile); }
+
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ unsigned long long st_now() {
   unsigned long long t;
@@ -315,6 +342,57 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
           epi_barrier();
         }
         if (et == 0) ST_STAMP(6);
+        if (owner && p.tp_size > 1) {
+          // ---- tensor-parallel exchange: local sum of the K parts -> own staging tile + every peer's buffer over NVLink
+          const uint32_t stage_addr0 = smem_u32(stage_f);
+          const size_t slot_me = x_slot(p.tp_channel, p.tp_rank, (int)tile);
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) {
+            const int c = i * 128 + et, m = c >> 4, n8 = (c & 15) * 8;
+            float4 a = *reinterpret_cast<const float4*>(stage_f + m * 128 + n8);
+            float4 b4 = *reinterpret_cast<const float4*>(stage_f + m * 128 + n8 + 4);
+            if (cluster_mode) {
+              const uint32_t off = stage_addr0 + (uint32_t)(m * 128 + n8) * 4u;
+              for (int r = 1; r < p.splitk; ++r) {
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(off), "r"(r));
+                float4 x, y;
+                asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(remote) : "memory");
+                asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(remote + 16u) : "memory");
+                a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w; b4.x += y.x; b4.y += y.y; b4.z += y.z; b4.w += y.w;
+              }
+            }
+            *reinterpret_cast<float4*>(stage_f + m * 128 + n8) = a;  // each chunk is read and written by this thread only
+            *reinterpret_cast<float4*>(stage_f + m * 128 + n8 + 4) = b4;
+            if (m < p.M) {
+              for (int r = 0; r < p.tp_size; ++r) {
+                if (r == p.tp_rank) continue;
+                float* dst = reinterpret_cast<float*>(p.xbuf[r] + slot_me * kXPayload) + m * 128 + n8;
+                *reinterpret_cast<float4*>(dst) = a;
+                *reinterpret_cast<float4*>(dst + 4) = b4;
+              }
+            }
+          }
+          __threadfence_system();
+          epi_barrier();
+          if (et < p.tp_size && et != p.tp_rank)
+            st_release_sys_u32(reinterpret_cast<unsigned int*>(p.xbuf[et] + kXFlagsOffset) + slot_me, 1u);
+        }
+        if (cluster_mode && p.tp_size > 1) {
+          // the K parts of this GPU are summed: the other CTAs of the cluster may retire while the exchange is in flight
+          __syncwarp();
+          cluster_sync_all();
+        }
+        if (owner && p.tp_size > 1) {
+          unsigned int* my_flags = reinterpret_cast<unsigned int*>(p.xbuf[p.tp_rank] + kXFlagsOffset);
+          if (et < p.tp_size && et != p.tp_rank) {
+            while (ld_acquire_sys_u32(my_flags + x_slot(p.tp_channel, et, (int)tile)) == 0u) {
+            }
+          }
+          epi_barrier();
+        }
         if (owner) {
           // ---- phase 2
           const uint32_t stage_addr = smem_u32(stage_f);
@@ -329,7 +407,25 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
               const float4 b4 = *reinterpret_cast<const float4*>(stage_f + m * 128 + n8 + 4);
               v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
             }
-            if (cluster_mode) {
+            if (p.tp_size > 1) {
+              // sum of the tp_size partial tiles in RANK order (own one from the staging tile): identical bits on every GPU
+              float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              for (int r = 0; r < p.tp_size; ++r) {
+                float4 a, b4;
+                if (r == p.tp_rank) {
+                  a = make_float4(v[0], v[1], v[2], v[3]);
+                  b4 = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+                  const float* src = reinterpret_cast<const float*>(p.xbuf[p.tp_rank] + x_slot(p.tp_channel, r, (int)tile) * kXPayload) +
+                                     m * 128 + n8;
+                  a = m < p.M ? __ldcg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  b4 = m < p.M ? __ldcg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w; s[4] += b4.x; s[5] += b4.y; s[6] += b4.z; s[7] += b4.w;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = s[j];
+            } else if (cluster_mode) {
               const uint32_t off = stage_addr + (uint32_t)(m * 128 + n8) * 4u;
               for (int r = 1; r < p.splitk; ++r) {
                 uint32_t remote;
@@ -390,11 +486,17 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
             }
           }
         }
-        if (cluster_mode) {
+        if (owner && p.tp_size > 1) {
+          // every thread has read the peers' partial tiles: clear the flags for the next use of this channel
+          epi_barrier();
+          if (et < p.tp_size && et != p.tp_rank)
+            reinterpret_cast<unsigned int*>(p.xbuf[p.tp_rank] + kXFlagsOffset)[x_slot(p.tp_channel, et, (int)tile)] = 0u;
+        }
+        if (cluster_mode && p.tp_size <= 1) {
           // the other parts may only retire (and give up their staging tiles) once the owner has read them
           __syncwarp();
           cluster_sync_all();
-        } else {
+        } else if (!cluster_mode) {
           epi_barrier();  // the staging tile is reused by the next segment
         }
       }
@@ -586,6 +688,8 @@ extern "C" int omc_gemm_stream_set_prof(void* buf, int max_launches) {
   return OMC_OK;
 }
 
+extern "C" long long omc_gemm_stream_xchg_bytes(void) { return (long long)kXBytes; }
+
 extern "C" long long omc_gemm_stream_workspace_bytes(void) {
   const long long grid = 2LL * num_sms();
   return grid * kStSlotFloats * 4 + grid * 4 + 256;
@@ -611,7 +715,7 @@ extern "C" int omc_row_ssq(const void* x, long long ldx, int rows, int C, float*
 extern "C" int omc_gemm_stream(const void* X, long long ldx, int M, const void* Wp, int N, int K, void* out, long long ldo,
                                int out_is_f32, const void* bias, const void* res, long long ldr, int epi,
                                const float* ssq_in, int ssq_parts, int norm_dim, float eps, float* ssq_out, void* workspace,
-                               int pdl, void* stream) {
+                               int pdl, const omc_tp_xchg* tp, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(OMC_ERR_SHAPE, "omc_gemm_stream: empty problem");
   if (M > 64) return set_error(OMC_ERR_SHAPE, "omc_gemm_stream: M must be <= 64 (use omc_gemm_bf16)");
   if (K % 8 != 0 || N % 8 != 0 || ldo % 8 != 0 || (res != nullptr && ldr % 8 != 0))
@@ -661,6 +765,19 @@ extern "C" int omc_gemm_stream(const void* X, long long ldx, int M, const void* 
   p.ldr = ldr;
   p.epi = epi;
   p.splitk = splitk;
+  p.tp_rank = 0; p.tp_size = 1; p.tp_channel = 0;
+  if (tp != nullptr && tp->size > 1) {
+    if (tp->size > 8 || tp->rank < 0 || tp->rank >= tp->size || tp->channel < 0 || tp->channel > 1)
+      return set_error(OMC_ERR_ARG, "omc_gemm_stream: bad tensor-parallel exchange description");
+    if (epi != EPI_RES && epi != EPI_NONE) return set_error(OMC_ERR_ARG, "omc_gemm_stream: the exchange needs EPI_RES / EPI_NONE");
+    if (out_is_f32 || n_tiles > kXTiles) return set_error(OMC_ERR_SHAPE, "omc_gemm_stream: exchange needs bf16 output, N <= 8192");
+    if (n_tiles >= grid) return set_error(OMC_ERR_SHAPE, "omc_gemm_stream: exchange needs fewer tiles than SMs");
+    p.tp_rank = tp->rank; p.tp_size = tp->size; p.tp_channel = tp->channel;
+    for (int r = 0; r < tp->size; ++r) {
+      if (tp->bufs[r] == nullptr) return set_error(OMC_ERR_ARG, "omc_gemm_stream: null exchange buffer");
+      p.xbuf[r] = static_cast<uint8_t*>(tp->bufs[r]);
+    }
+  }
   p.ssq_in = ssq_in; p.ssq_parts = ssq_parts; p.inv_norm_dim = norm_dim > 0 ? 1.0f / (float)norm_dim : 0.f; p.eps = eps;
   p.ssq_out = ssq_out;
   const long long max_grid = 2LL * num_sms();

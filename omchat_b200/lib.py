@@ -29,7 +29,8 @@ SIGNATURES = {
     "omc_packed_weight_bytes": (_L, [_I, _I]),
     "omc_pack_weight": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "omc_gemm_stream_workspace_bytes": (_L, []),
-    "omc_gemm_stream": (_I, [_P, _L, _I, _P, _I, _I, _P, _L, _I, _P, _P, _L, _I, _P, _I, _I, _F, _P, _P, _I, _P]),
+    "omc_gemm_stream": (_I, [_P, _L, _I, _P, _I, _I, _P, _L, _I, _P, _P, _L, _I, _P, _I, _I, _F, _P, _P, _I, _P, _P]),
+    "omc_gemm_stream_xchg_bytes": (_L, []),
     "omc_row_ssq": (_I, [_P, _L, _I, _I, _P, _I, _I, _P]),
     "omc_gemm_stream_set_prof": (_I, [_P, _I]),
     "omc_gemv_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _L, _I, _I, _P]),
@@ -257,9 +258,29 @@ def ssq_parts(C: int) -> int:
     return (C + 127) // 128
 
 
+class TpXchg(ctypes.Structure):
+    """Mirror of `omc_tp_xchg` (include/omchat_b200.h)."""
+    _fields_ = [("rank", ctypes.c_int32), ("size", ctypes.c_int32), ("channel", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("bufs", c_void_p * 8)]
+
+
+def tp_xchg(ptrs, rank: int, channel: int) -> TpXchg:
+    """Exchange description of one row-parallel op: ptrs[r] = rank r's exchange buffer as mapped here (PeerExchange.ptrs)."""
+    t = TpXchg()
+    t.rank, t.size, t.channel = rank, len(ptrs), channel
+    for r, p_ in enumerate(ptrs):
+        t.bufs[r] = p_
+    return t
+
+
+def gemm_stream_xchg_bytes() -> int:
+    return load().omc_gemm_stream_xchg_bytes()
+
+
 def gemm_stream(x: torch.Tensor, wp: PackedWeight, out: Optional[torch.Tensor] = None, *, bias=None, res=None,
                 epi: int = EPI_NONE, out_f32: bool = False, ssq_in: Optional[torch.Tensor] = None, ssq_in_parts: int = 0,
-                norm_dim: int = 0, eps: float = 1e-6, ssq_out: Optional[torch.Tensor] = None, pdl: Optional[bool] = None):
+                norm_dim: int = 0, eps: float = 1e-6, ssq_out: Optional[torch.Tensor] = None, pdl: Optional[bool] = None,
+                tp: Optional[TpXchg] = None):
     """out[M, N] = epi(rstd[m] * (x[M, K] @ W'^T)) for M <= 64 (see include/omchat_b200.h, omc_gemm_stream)."""
     _need_cuda(x, out, bias, res, ssq_in, ssq_out)
     M, K = x.shape
@@ -277,7 +298,8 @@ def gemm_stream(x: torch.Tensor, wp: PackedWeight, out: Optional[torch.Tensor] =
     rc = load().omc_gemm_stream(_ptr(x), x.stride(0), M, wp.data.data_ptr(), N, K, _ptr(out), out.stride(0), 1 if out_f32 else 0,
                                 _ptr(bias), _ptr(res), res.stride(0) if res is not None else 0, epi, _ptr(ssq_in),
                                 ssq_in_parts, norm_dim, eps, _ptr(ssq_out), ws.data_ptr(),
-                                1 if (PDL_ENABLED if pdl is None else pdl) else 0, _stream())
+                                1 if (PDL_ENABLED if pdl is None else pdl) else 0, ctypes.byref(tp) if tp is not None else None,
+                                _stream())
     _check(rc, "omc_gemm_stream")
     return out
 

@@ -196,7 +196,9 @@ class Qwen2Decoder:
         return self._packed
 
     def use_stream(self, B: int) -> bool:
-        return self.stream_enabled and not self.use_mega(B) and B <= 64
+        """Batches 5..64 decode on the weight-streaming GEMMs; 1..4 on the persistent kernel (or, with that switched off,
+        on the per-op GEMV kernels that serve as its cross-check)."""
+        return self.stream_enabled and MEGA_MAX_B < B <= 64
 
     # ------------------------------------------------------------------------------------------------ prefill
     @torch.no_grad()

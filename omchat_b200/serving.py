@@ -1,8 +1,9 @@
 """Continuous batching over the paged KV cache (the reference has no serving loop - cli.py serves one
 request at a time through generate()).
 
-A fixed number of decode SLOTS (<= 4: the persistent decode kernel, one launch per token for all slots) share one page
-pool. A request is admitted into a free slot as soon as one exists: its prompt is spliced (image features in place of the
+A fixed number of decode SLOTS share one page pool: up to 4 slots decode with the persistent kernel (one launch per token
+for all slots), 5..64 slots with the batched step on the weight-streaming GEMMs (csrc/gemm_stream.cu; one CUDA graph
+replay per token). A request is admitted into a free slot as soon as one exists: its prompt is spliced (image features in place of the
 -200 placeholders, omchat_arch.py:115-195) and prefilled into pages taken from a free list, its first token is sampled from
 the prefill logits, and from the next step on it decodes together with whatever the other slots hold. A finished request
 (EOS or max_new_tokens) gives its pages back and frees its slot at the next chunk boundary. Idle slots point at one
@@ -21,7 +22,9 @@ from typing import Dict, List, Optional
 import torch
 
 from . import lib
-from .model.decoder import MEGA_MAX_B, PagedKVCache
+from .model.decoder import PagedKVCache
+
+MAX_SLOTS = 64  # rows of the batched decode step (csrc/gemm_stream.cu)
 
 
 @dataclass
@@ -37,13 +40,13 @@ class _Request:
 
 
 class ContinuousBatcher:
-    """model: OmChatQwen2ForCausalLM (single GPU). slots: decode batch (1..4). max_ctx: longest prompt + generation a slot
+    """model: OmChatQwen2ForCausalLM (single GPU). slots: decode batch (1..64). max_ctx: longest prompt + generation a slot
     can hold. total_pages: size of the shared page pool (default: enough for every slot at max_ctx). chunk: decode steps
     between two looks at the host side (admission, EOS, release)."""
 
     def __init__(self, model, slots: int = 4, max_ctx: int = 4096, total_pages: Optional[int] = None, chunk: int = 8):
-        if not 1 <= slots <= MEGA_MAX_B:
-            raise ValueError(f"slots must be 1..{MEGA_MAX_B}")
+        if not 1 <= slots <= MAX_SLOTS:
+            raise ValueError(f"slots must be 1..{MAX_SLOTS}")
         self.model, self.dec = model, model.model.decoder
         self.slots, self.chunk = slots, chunk
         ps = model.config.kv_page_size

@@ -298,7 +298,9 @@ def test_full_depth_c1_vs_oracle():
     got = out[0, ids.shape[1]:].tolist()
     want, margins, errs, tf = [], [], [], []
     for i in range(NEW_TOKENS):
-        errs.append(rep.add(f"decode step {i:2d} logits", last, last_o[None], rel=0.06, calib=last_b[None]))
+        # stated tolerance at full depth: cosine >= 0.999; max-abs <= 10 % of the largest logit (the log-normal head makes a
+        # few rows 30 x larger than the rest and the max-abs error lives on those; torch bf16 shows the same 5-8 %)
+        errs.append(rep.add(f"decode step {i:2d} logits", last, last_o[None], rel=0.10, calib=last_b[None]))
         tf.append(int(last.argmax(-1)))
         top2 = torch.topk(last_o, 2).values
         margins.append(float(top2[0] - top2[1]))

@@ -21,7 +21,10 @@ def _same_or_near_tie(got, want, step_logits, what):
     return len(want)
 
 
-def test_continuous_batching_matches_standalone_generation():
+@pytest.mark.parametrize("slots", [3, 6])
+def test_continuous_batching_matches_standalone_generation(slots):
+    """3 slots: the persistent decode kernel; 6 slots: the batched step on the weight-streaming GEMMs (more slots than the
+    persistent kernel's 4; with 7 requests the pool and the slots both turn over)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from omchat_b200.model.omchat import OmChatQwen2ForCausalLM
@@ -43,7 +46,7 @@ def test_continuous_batching_matches_standalone_generation():
     # pool: the scratch page + room for about two of the long requests -> admissions have to wait for pages
     page = 16
     pages_long = (longest + page - 1) // page
-    cb = ContinuousBatcher(m, slots=3, max_ctx=longest + page, total_pages=1 + 2 * pages_long + 3, chunk=4)
+    cb = ContinuousBatcher(m, slots=slots, max_ctx=longest + page, total_pages=1 + 2 * pages_long + 3, chunk=4)
     total_free = len(cb.free_pages)
     rids = [cb.submit(ids, px, max_new_tokens=mn) for ids, px, mn in reqs]
     seen_tables = []
