@@ -154,6 +154,9 @@ def _release_decoder(dec):
     for px in dec._xchg.values():
         px.close()
     dec._xchg.clear()
+    if getattr(dec, "_stream_xchg", None) is not None:
+        dec._stream_xchg.close()
+        dec._stream_xchg = None
 
 
 # --------------------------------------------------------------------------------------------------- reference arm

@@ -245,7 +245,9 @@ class PackedWeight:
 
 
 def _stream_workspace(device) -> torch.Tensor:
-    key = str(device)
+    """Partial-tile slots + flags of the stream-K GEMM: consecutive launches of ONE stream share them (they are ordered),
+    launches on different streams may overlap and get their own."""
+    key = (str(device), torch.cuda.current_stream().cuda_stream)
     ws = _stream_ws.get(key)
     if ws is None:
         ws = torch.zeros(load().omc_gemm_stream_workspace_bytes(), device=device, dtype=torch.uint8)

@@ -125,6 +125,10 @@ class Qwen2Decoder:
         # tp > 1: all-reduce inside the persistent kernel over NVLink peer memory (0 = per-op kernels + NCCL all-reduce)
         self.tp_mega_enabled = os.environ.get("OMCHAT_B200_TP_MEGA", "1") != "0"
         self._xchg = {}  # batch -> lib.PeerExchange (tensor-parallel persistent decode kernel)
+        # tp > 1, batched step: all-reduce fused into the o_proj / down_proj epilogues over NVLink peer memory
+        # (csrc/gemm_stream.cu; 0 = NCCL all-reduce between the kernels)
+        self.tp_stream_fused = os.environ.get("OMCHAT_B200_TP_STREAM_FUSED", "1") != "0"
+        self._stream_xchg = None  # lib.PeerExchange of the batched step (or a test's emulation object with .ptrs)
         self._mega_epoch = 1  # shared by every plan that uses the peer exchange buffers: identical on all ranks
         self._dec = {}  # decode state per batch size
         self._caches = {}  # reusable caches for generate(), keyed by (n_seq, capacity)
@@ -390,9 +394,19 @@ class Qwen2Decoder:
         if sample:
             self._greedy(st)
 
+    def stream_exchange(self):
+        """Exchange buffers of the batched step's fused all-reduce (collective: every rank calls this at the same point -
+        the first batched decode step)."""
+        if self._stream_xchg is None:
+            self._stream_xchg = lib.PeerExchange(lib.gemm_stream_xchg_bytes(), self.tp.rank, self.tp.size, self.tp.group)
+        return self._stream_xchg
+
     def _decode_body_stream(self, st, cache: PagedKVCache):
         """Batched decode step on the weight-streaming GEMMs: 5 kernels per layer, each launched as a programmatic
-        dependent of the previous one; no stand-alone RMSNorm (folded into the GEMMs that follow it)."""
+        dependent of the previous one; no stand-alone RMSNorm (folded into the GEMMs that follow it). Under tensor
+        parallelism the two all-reduces per layer happen inside the o_proj / down_proj epilogues over NVLink."""
+        if self.tp.size > 1 and self.tp_stream_fused:
+            return self._decode_body_stream_tp(st, cache)
         P = self.packed_weights()
         C, eps = self.C, self.eps
         tp = self.tp.size > 1
@@ -418,6 +432,26 @@ class Qwen2Decoder:
             if tp:
                 self._all_reduce(h)
                 lib.row_ssq(h, st.ssq_a, parts=1, pdl=False)
+        lib.gemm_stream(h, P.lm_head, out=st.logits, out_f32=True, ssq_in=st.ssq_a, ssq_in_parts=parts, norm_dim=C, eps=eps)
+
+    def _decode_body_stream_tp(self, st, cache: PagedKVCache):
+        P = self.packed_weights()
+        C, eps = self.C, self.eps
+        parts = lib.ssq_parts(C)
+        ptrs = self.stream_exchange().ptrs
+        x_o, x_down = lib.tp_xchg(ptrs, self.tp.rank, 0), lib.tp_xchg(ptrs, self.tp.rank, 1)
+        cache.ctx_lens.add_(1)
+        lib.embed_lookup(st.tokens, self.w.embed, out=st.h)
+        lib.row_ssq(st.h, st.ssq_a, parts=parts, pdl=False)
+        h = st.h
+        for li, (l, p) in enumerate(zip(self.w.layers, P.layers)):
+            lib.gemm_stream(h, p.qkv, out=st.qkv, bias=l.qkv_b, ssq_in=st.ssq_a, ssq_in_parts=parts, norm_dim=C, eps=eps)
+            lib.paged_decode_attn(st.qkv, self.inv_freq, cache.pool[li], cache.block_table, cache.page_size,
+                                  cache.ctx_lens, self.Hq, self.Hkv, st.splits, self.scale, st.attn, st.attn_ws)
+            lib.gemm_stream(st.attn, p.o, out=h, res=h, epi=lib.EPI_RES, ssq_out=st.ssq_b, tp=x_o)
+            lib.gemm_stream(h, p.gate_up, out=st.act, epi=lib.EPI_SWIGLU, ssq_in=st.ssq_b, ssq_in_parts=parts, norm_dim=C,
+                            eps=eps)
+            lib.gemm_stream(st.act, p.down, out=h, res=h, epi=lib.EPI_RES, ssq_out=st.ssq_a, tp=x_down)
         lib.gemm_stream(h, P.lm_head, out=st.logits, out_f32=True, ssq_in=st.ssq_a, ssq_in_parts=parts, norm_dim=C, eps=eps)
 
     def _greedy(self, st):

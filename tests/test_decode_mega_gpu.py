@@ -244,3 +244,19 @@ def test_batched_decode_stream_vs_oracle_full_width(lens):
     lg_new = dec.decode_step(first, cache_d)
     cos = torch.nn.functional.cosine_similarity(lg_new, lg_old, dim=-1).min().item()
     assert cos >= 0.9995, cos
+
+
+@pytest.mark.parametrize("tp", [2, 4])
+def test_stream_tensor_parallel_fused_allreduce_emulated_on_one_gpu(tp):
+    """The all-reduce fused into the epilogues of the row-parallel GEMMs of the batched decode step (csrc/gemm_stream.cu),
+    with the ranks emulated as host threads + streams on one GPU (tests/tp_stream_emulation.py; a subprocess with a timeout
+    so that a protocol deadlock stays contained)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import os
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tp_stream_emulation.py")
+    r = subprocess.run([sys.executable, script, str(tp)], capture_output=True, text=True, timeout=150)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert f"tp{tp} stream emulation ok" in r.stdout

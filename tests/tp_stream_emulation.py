@@ -1,0 +1,154 @@
+"""Single-GPU emulation of the tensor-parallel batched decode step with the all-reduce fused into the o_proj / down_proj
+epilogues (csrc/gemm_stream.cu; run as a script by test_decode_mega_gpu.py so that a deadlock or device trap cannot poison
+the pytest process).
+
+The tp "ranks" live in ONE process on ONE GPU: each is a host thread with its own CUDA stream driving the product's own
+Qwen2Decoder on its Megatron shard of the same seed-0 full-width weights; their exchange buffers are plain device buffers of
+this process, so the cross-"GPU" protocol (partial tiles pushed into every peer's buffer, release / acquire flags at system
+scope, sums in rank order, flags cleared by the consumer) is exactly the one that runs over NVLink between processes.
+Programmatic dependent launch is switched off here: on ONE GPU the early-launched next kernel of rank 0 could take the SM
+slots rank 1's exchange partner needs (on separate GPUs that cannot happen).
+
+Checks: (1) kernel level - a row-parallel GEMM chain alternating the two channels, outputs and sums of squares bit-identical
+on every rank and equal to the fp32 reference within bf16 tolerance; (2) decoder level - 4 decode steps at batch 9 / 32: the
+ranks' residual streams are bit-identical, the concatenated vocab-shard logits match the unsharded decoder's (cosine >=
+0.999, max-abs <= 2 % of scale)."""
+import os
+import sys
+import threading
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from omchat_b200 import lib  # noqa: E402
+from omchat_b200.config import OmChatQwen2Config  # noqa: E402
+from omchat_b200.model.decoder import Qwen2Decoder, TPInfo  # noqa: E402
+from omchat_b200.model.weights import random_init, tp_plan  # noqa: E402
+
+
+class FakeExchange:
+    def __init__(self, ptrs):
+        self.ptrs = ptrs
+
+    def close(self):
+        pass
+
+
+def run_ranks(fns):
+    errs = []
+
+    def wrap(f, r):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                f(r)
+                torch.cuda.current_stream().synchronize()
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    th = [threading.Thread(target=wrap, args=(f, r)) for r, f in enumerate(fns)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    torch.cuda.synchronize()
+
+
+def kernel_level(tp: int):
+    dev = "cuda"
+    M, N, K = 19, 3584, 1024 * tp
+    g = torch.Generator(device=dev).manual_seed(3)
+    xbufs = [torch.zeros(lib.gemm_stream_xchg_bytes(), device=dev, dtype=torch.uint8) for _ in range(tp)]
+    ptrs = [b.data_ptr() for b in xbufs]
+    x = (torch.randn(M, K, generator=g, device=dev) * 0.5).to(torch.bfloat16)
+    ws = [(torch.randn(N, K, generator=g, device=dev) * 0.05).to(torch.bfloat16) for _ in range(4)]
+    res0 = torch.randn(M, N, generator=g, device=dev).to(torch.bfloat16)
+    Ks = K // tp
+    packed = [[lib.PackedWeight(w[:, r * Ks:(r + 1) * Ks].contiguous()) for w in ws] for r in range(tp)]
+    hs = [res0.clone() for _ in range(tp)]
+    ssqs = [torch.zeros(lib.ssq_parts(N) * 64, device=dev) for _ in range(tp)]
+
+    def rank(r):
+        xr = x[:, r * Ks:(r + 1) * Ks].contiguous()
+        for i in range(4):  # channels 0,1,0,1: the second round reuses slots whose flags the consumer cleared
+            lib.gemm_stream(xr, packed[r][i], out=hs[r], res=hs[r], epi=lib.EPI_RES, ssq_out=ssqs[r], pdl=False,
+                            tp=lib.tp_xchg(ptrs, r, i & 1))
+
+    run_ranks([rank] * tp)
+    want = res0.float().cpu()
+    for w in ws:
+        want = (want + x.float().cpu() @ w.float().cpu().t()).to(torch.bfloat16).float()
+    for r in range(1, tp):
+        assert torch.equal(hs[0], hs[r]) and torch.equal(ssqs[0], ssqs[r]), f"rank {r} differs from rank 0"
+    err = (hs[0].float().cpu() - want).abs().max().item() / want.abs().max().item()
+    assert err <= 2 ** -6, err
+    got = ssqs[0].view(-1, 64)[:, :M].sum(0).cpu()
+    assert torch.allclose(got, hs[0].float().pow(2).sum(-1).cpu(), rtol=1e-4)
+    for b in xbufs:
+        flags = b[-(2 * 8 * 64 * 4):]
+        assert int(flags.count_nonzero()) == 0, "exchange flags must be cleared by their consumer"
+    print(f"kernel level tp{tp} ok (rel err {err:.5f})")
+
+
+def decoder_level(tp: int, lens):
+    dev = "cuda"
+    cfg = OmChatQwen2Config(num_hidden_layers=2)
+    B, steps = len(lens), 4
+    full = Qwen2Decoder(cfg, random_init(cfg, device=dev, seed=0, vision=False).llm)
+    ranks = [Qwen2Decoder(cfg, random_init(cfg, device=dev, seed=0, vision=False, tp_rank=r, tp_size=tp).llm,
+                          TPInfo(rank=r, size=tp)) for r in range(tp)]
+    g = torch.Generator(device=dev).manual_seed(1)
+    T = sum(lens)
+    emb = (torch.randn(T, cfg.hidden_size, generator=g, device=dev) * 0.02).to(torch.bfloat16)
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens]).to(dev)
+    seq = torch.cat([torch.full((n,), i, dtype=torch.int32) for i, n in enumerate(lens)]).to(dev)
+    offs = [0]
+    for n in lens:
+        offs.append(offs[-1] + n)
+    cache = full.new_cache(B, max(lens) + 40)
+    first = full.prefill(emb, pos, seq, offs, cache, logits="last").argmax(-1)
+    xbufs = [torch.zeros(lib.gemm_stream_xchg_bytes(), device=dev, dtype=torch.uint8) for _ in range(tp)]
+    fake = FakeExchange([b.data_ptr() for b in xbufs])
+    caches = []
+    for r, d in enumerate(ranks):
+        assert d.use_stream(B) and d.tp_stream_fused
+        d._stream_xchg = fake
+        c = d.new_cache(B, max(lens) + 40)
+        assert torch.equal(c.block_table, cache.block_table)
+        c.pool.copy_(cache.pool[:, :, :, tp_plan(cfg, r, tp).kv_heads])
+        c.ctx_lens.copy_(cache.ctx_lens)
+        c.host_lens = list(cache.host_lens)
+        caches.append(c)
+    cur = first.clone()
+    for s in range(steps):
+        ref = full.decode_step(cur, cache).clone()
+        outs = [None] * tp
+
+        def rank(r):
+            outs[r] = ranks[r].decode_step(cur, caches[r]).clone()
+
+        run_ranks([rank] * tp)
+        hs = [d._decode_state(B, caches[r].capacity).h for r, d in enumerate(ranks)]
+        for r in range(1, tp):
+            assert torch.equal(hs[0], hs[r]), f"step {s}: residual streams of rank 0 and {r} differ"
+        lg = torch.cat(outs, dim=1)
+        cos = torch.nn.functional.cosine_similarity(lg, ref, dim=-1).min().item()
+        err = (lg - ref).abs().max().item() / ref.abs().max().item()
+        assert cos >= 0.999 and err <= 0.02, (s, cos, err)
+        print(f"tp{tp} batch {B} step {s}: cos {cos:.6f} err {err:.4f}")
+        cur = ref.argmax(-1)
+    print(f"decoder level tp{tp} batch {B} ok")
+
+
+if __name__ == "__main__":
+    tp = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    lib.PDL_ENABLED = False
+    torch.cuda.set_device(0)
+    lib.load()
+    kernel_level(tp)
+    decoder_level(tp, [40 + 3 * i for i in range(9)])
+    if tp == 2:
+        decoder_level(tp, [30 + 2 * i for i in range(32)])
+    print(f"tp{tp} stream emulation ok")
