@@ -191,10 +191,14 @@ int omc_gemm_stream(const void* X, long long ldx, int M, const void* Wp, int N, 
                     int ssq_parts, int norm_dim, float eps, float* ssq_out, void* workspace, int pdl, const omc_tp_xchg* tp,
                     void* stream);
 int omc_row_ssq(const void* x, long long ldx, int rows, int C, float* ssq, int parts, int pdl, void* stream);
-/* profiling hook: the next max_launches omc_gemm_stream launches write %globaltimer stamps [2 * SMs][8] each into buf
- * (entry, weights issued, dependency satisfied, first stage landed, last MMA issued, accumulator read, partials summed,
- * stores issued); buf = NULL switches it off. Measurement only (tools/prof_stream.py). */
+/* profiling hook: the next max_launches omc_gemm_stream launches write %globaltimer stamps [2 * SMs][16] each into buf
+ * (0 entry, 1 weights issued, 2 dependency satisfied, 3 first stage landed, 4 last MMA issued, 5 accumulator read, 6 K parts
+ * staged, 7 stores issued, 8 partial tile pushed to the peers, 9 peers' tiles arrived); buf = NULL switches it off.
+ * Measurement only (tools/prof_stream.py). */
 int omc_gemm_stream_set_prof(void* buf, int max_launches);
+/* spin-wait watchdog record: 8 ints of pinned, device-mapped host memory (or NULL). A wait that lasts 10 s writes
+ * {kind (1 = stream-K partial, 2 + 16 * rank = tensor-parallel exchange), tile, peer / part, channel, block, grid} and traps. */
+int omc_gemm_stream_set_debug(void* pinned_host_record);
 
 /* ---- persistent decode step ("megakernel", omchat_b200/csrc/decode_mega.cu) ------------------------------------------
  * One cooperative launch = one whole Qwen2 decode step for 1..4 sequences: embed_tokens (omchat_arch.py:139), every

@@ -82,7 +82,8 @@ struct StreamParams {
   unsigned int* flags;  // [grid]
   unsigned long long* prof;  // optional [grid][8] %globaltimer stamps of this launch (tools/prof_stream.py), else nullptr
   // tensor-parallel exchange (tp_size > 1): xbuf[r] = rank r's exchange buffer as mapped into THIS process
-  int tp_rank, tp_size, tp_channel;
+  int* dbg;  // optional pinned host record for the spin-wait watchdog
+  int tp_rank, tp_size, tp_channel, tp_fence_all;
   uint8_t* xbuf[8];
 };
 
@@ -107,7 +108,7 @@ __device__ __forceinline__ unsigned long long st_now() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define ST_STAMP(i) do { if (p.prof != nullptr) p.prof[(size_t)blockIdx.x * 8 + (i)] = st_now(); } while (0)
+#define ST_STAMP(i) do { if (p.prof != nullptr) p.prof[(size_t)blockIdx.x * 16 + (i)] = st_now(); } while (0)
 
 __device__ __forceinline__ void st_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -135,8 +136,58 @@ __device__ __forceinline__ long long st_range_start(const StreamParams& p, long 
   }
   return total * j / grid;
 }
+// Spin-wait guard: a partner that never shows up (a rank that died, a protocol bug) must not hang the GPU - after ~10 s of
+// polling the kernel traps, which surfaces as a CUDA error in the host process instead of a dead box.
+struct StWatchdog {
+  unsigned long long t0 = 0;
+  unsigned int n = 0;
+  // dbg: optional pinned host record {kind, a, b, c} written before the trap (readable after the context died)
+  __device__ __forceinline__ void tick(int* dbg, int kind, int a, int b, int c) {
+    if ((++n & 0xFFFFu) == 0u) {
+      const unsigned long long now = st_now();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 10000000000ull) {
+        if (dbg != nullptr && atomicCAS(dbg, 0, kind) == 0) {
+          dbg[1] = a; dbg[2] = b; dbg[3] = c; dbg[4] = (int)blockIdx.x; dbg[5] = (int)gridDim.x;
+          __threadfence_system();
+        }
+        __trap();
+      }
+    }
+  }
+};
 __device__ __forceinline__ float st_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float st_silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// Sum of the K parts 1..splitk-1 of one (m, 8-feature) chunk, read from the staging tiles of the other CTAs of the cluster
+// over distributed shared memory. All loads of a group of four peers are issued before the first add (an add behind
+// every load would serialise the ~0.3 us DSMEM round trips: 5 peers x 2 loads x 4 chunks used to cost ~10 us per epilogue).
+__device__ __forceinline__ void st_dsmem_add8(uint32_t local_addr, int splitk, float4& a, float4& b4) {
+#pragma unroll
+  for (int base = 1; base < 8; base += 4) {
+    if (base >= splitk) break;
+    float4 x[4], y[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = base + q;
+      if (r < splitk) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(r));
+        asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(x[q].x), "=f"(x[q].y), "=f"(x[q].z), "=f"(x[q].w) : "r"(remote));
+        asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(y[q].x), "=f"(y[q].y), "=f"(y[q].z), "=f"(y[q].w) : "r"(remote + 16u));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (base + q < splitk) {  // rank order: bit-identical from launch to launch
+        a.x += x[q].x; a.y += x[q].y; a.z += x[q].z; a.w += x[q].w;
+        b4.x += y[q].x; b4.y += y[q].y; b4.z += y[q].z; b4.w += y[q].w;
+      }
+    }
+  }
+}
 
 template <int MPAD>
 __global__ void __launch_bounds__(kStThreads, 2)
@@ -318,8 +369,8 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
           unsigned int nparts = 0;
           for (unsigned int j = blockIdx.x + 1; j < gridDim.x && st_range_start(p, total, j, gridDim.x) < tile_end; ++j) ++nparts;
           for (unsigned int i = (unsigned int)et; i < nparts; i += 128u) {
-            while (ld_acquire_u32(p.flags + blockIdx.x + 1 + i) == 0u) {
-            }
+            StWatchdog wd;
+            while (ld_acquire_u32(p.flags + blockIdx.x + 1 + i) == 0u) wd.tick(p.dbg, 1, (int)tile, (int)i, 0);
           }
           epi_barrier();
           for (unsigned int i = 0; i < nparts; ++i) {
@@ -351,19 +402,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
             const int c = i * 128 + et, m = c >> 4, n8 = (c & 15) * 8;
             float4 a = *reinterpret_cast<const float4*>(stage_f + m * 128 + n8);
             float4 b4 = *reinterpret_cast<const float4*>(stage_f + m * 128 + n8 + 4);
-            if (cluster_mode) {
-              const uint32_t off = stage_addr0 + (uint32_t)(m * 128 + n8) * 4u;
-              for (int r = 1; r < p.splitk; ++r) {
-                uint32_t remote;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(off), "r"(r));
-                float4 x, y;
-                asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
-                             : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(remote) : "memory");
-                asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
-                             : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(remote + 16u) : "memory");
-                a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w; b4.x += y.x; b4.y += y.y; b4.z += y.z; b4.w += y.w;
-              }
-            }
+            if (cluster_mode) st_dsmem_add8(stage_addr0 + (uint32_t)(m * 128 + n8) * 4u, p.splitk, a, b4);
             *reinterpret_cast<float4*>(stage_f + m * 128 + n8) = a;  // each chunk is read and written by this thread only
             *reinterpret_cast<float4*>(stage_f + m * 128 + n8 + 4) = b4;
             if (m < p.M) {
@@ -375,10 +414,13 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
               }
             }
           }
-          __threadfence_system();
+          // the CTA barrier orders every thread's peer stores before the flag writers; their release at system scope is
+          // cumulative, so one release store per peer publishes the whole tile (no per-thread system fence)
+          if (p.tp_fence_all) __threadfence_system();
           epi_barrier();
           if (et < p.tp_size && et != p.tp_rank)
             st_release_sys_u32(reinterpret_cast<unsigned int*>(p.xbuf[et] + kXFlagsOffset) + slot_me, 1u);
+          if (et == 0) ST_STAMP(8);
         }
         if (cluster_mode && p.tp_size > 1) {
           // the K parts of this GPU are summed: the other CTAs of the cluster may retire while the exchange is in flight
@@ -388,10 +430,12 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
         if (owner && p.tp_size > 1) {
           unsigned int* my_flags = reinterpret_cast<unsigned int*>(p.xbuf[p.tp_rank] + kXFlagsOffset);
           if (et < p.tp_size && et != p.tp_rank) {
-            while (ld_acquire_sys_u32(my_flags + x_slot(p.tp_channel, et, (int)tile)) == 0u) {
-            }
+            StWatchdog wd;
+            while (ld_acquire_sys_u32(my_flags + x_slot(p.tp_channel, et, (int)tile)) == 0u)
+              wd.tick(p.dbg, 2 + 16 * p.tp_rank, (int)tile, et, p.tp_channel);
           }
           epi_barrier();
+          if (et == 0) ST_STAMP(9);
         }
         if (owner) {
           // ---- phase 2
@@ -426,17 +470,9 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = s[j];
             } else if (cluster_mode) {
-              const uint32_t off = stage_addr + (uint32_t)(m * 128 + n8) * 4u;
-              for (int r = 1; r < p.splitk; ++r) {
-                uint32_t remote;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(off), "r"(r));
-                float4 a, b4;
-                asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
-                             : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(remote) : "memory");
-                asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
-                             : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(remote + 16u) : "memory");
-                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b4.x; v[5] += b4.y; v[6] += b4.z; v[7] += b4.w;
-              }
+              float4 a = make_float4(v[0], v[1], v[2], v[3]), b4 = make_float4(v[4], v[5], v[6], v[7]);
+              st_dsmem_add8(stage_addr + (uint32_t)(m * 128 + n8) * 4u, p.splitk, a, b4);
+              v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
             }
             if (p.ssq_in != nullptr) {
               const float r = s_rstd[m < 64 ? m : 0];
@@ -669,6 +705,7 @@ extern "C" int omc_pack_weight(const void* W, long long ldw, int N, int K, const
 }
 
 // profiling hook (tools/prof_stream.py): consecutive launches stamp consecutive [296][8] blocks of `buf`
+static int* g_dbg = nullptr;
 static unsigned long long* g_prof_buf = nullptr;
 static int g_prof_max = 0, g_prof_next = 0;
 
@@ -679,6 +716,11 @@ static int st_max_grid() {
     ctas_per_sm = (e != nullptr && e[0] == '2') ? 2 : 1;
   }
   return ctas_per_sm * num_sms();
+}
+
+extern "C" int omc_gemm_stream_set_debug(void* pinned_host_record) {
+  g_dbg = static_cast<int*>(pinned_host_record);
+  return OMC_OK;
 }
 
 extern "C" int omc_gemm_stream_set_prof(void* buf, int max_launches) {
@@ -772,7 +814,7 @@ extern "C" int omc_gemm_stream(const void* X, long long ldx, int M, const void* 
     if (epi != EPI_RES && epi != EPI_NONE) return set_error(OMC_ERR_ARG, "omc_gemm_stream: the exchange needs EPI_RES / EPI_NONE");
     if (out_is_f32 || n_tiles > kXTiles) return set_error(OMC_ERR_SHAPE, "omc_gemm_stream: exchange needs bf16 output, N <= 8192");
     if (n_tiles >= grid) return set_error(OMC_ERR_SHAPE, "omc_gemm_stream: exchange needs fewer tiles than SMs");
-    p.tp_rank = tp->rank; p.tp_size = tp->size; p.tp_channel = tp->channel;
+    p.tp_rank = tp->rank; p.tp_size = tp->size; p.tp_channel = tp->channel; p.tp_fence_all = tp->reserved & 1;
     for (int r = 0; r < tp->size; ++r) {
       if (tp->bufs[r] == nullptr) return set_error(OMC_ERR_ARG, "omc_gemm_stream: null exchange buffer");
       p.xbuf[r] = static_cast<uint8_t*>(tp->bufs[r]);
@@ -783,7 +825,8 @@ extern "C" int omc_gemm_stream(const void* X, long long ldx, int M, const void* 
   const long long max_grid = 2LL * num_sms();
   p.ws = static_cast<float*>(workspace);
   p.flags = reinterpret_cast<unsigned int*>(static_cast<float*>(workspace) + max_grid * kStSlotFloats);
-  p.prof = (g_prof_buf != nullptr && g_prof_next < g_prof_max) ? g_prof_buf + (size_t)(g_prof_next++) * max_grid * 8 : nullptr;
+  p.dbg = g_dbg;
+  p.prof = (g_prof_buf != nullptr && g_prof_next < g_prof_max) ? g_prof_buf + (size_t)(g_prof_next++) * max_grid * 16 : nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mpad == 16) return launch_stream<16>(tmX, p, (int)grid, pdl != 0, st);
   if (mpad == 32) return launch_stream<32>(tmX, p, (int)grid, pdl != 0, st);

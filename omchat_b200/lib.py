@@ -33,6 +33,7 @@ SIGNATURES = {
     "omc_gemm_stream_xchg_bytes": (_L, []),
     "omc_row_ssq": (_I, [_P, _L, _I, _I, _P, _I, _I, _P]),
     "omc_gemm_stream_set_prof": (_I, [_P, _I]),
+    "omc_gemm_stream_set_debug": (_I, [_P]),
     "omc_gemv_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _L, _I, _I, _P]),
     "omc_rmsnorm": (_I, [_P, _L, _P, _P, _L, _I, _I, _F, _P]),
     "omc_vit_im2col": (_I, [_P, _I, _P, _L, _I, _I, _I, _P]),
@@ -270,6 +271,7 @@ def tp_xchg(ptrs, rank: int, channel: int) -> TpXchg:
     """Exchange description of one row-parallel op: ptrs[r] = rank r's exchange buffer as mapped here (PeerExchange.ptrs)."""
     t = TpXchg()
     t.rank, t.size, t.channel = rank, len(ptrs), channel
+    t.reserved = int(os.environ.get("OMCHAT_B200_XCHG_FENCE_ALL", "0"))  # A/B switch: per-thread system fence before the flag
     for r, p_ in enumerate(ptrs):
         t.bufs[r] = p_
     return t

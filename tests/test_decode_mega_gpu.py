@@ -250,7 +250,8 @@ def test_batched_decode_stream_vs_oracle_full_width(lens):
 def test_stream_tensor_parallel_fused_allreduce_emulated_on_one_gpu(tp):
     """The all-reduce fused into the epilogues of the row-parallel GEMMs of the batched decode step (csrc/gemm_stream.cu),
     with the ranks emulated as host threads + streams on one GPU (tests/tp_stream_emulation.py; a subprocess with a timeout
-    so that a protocol deadlock stays contained)."""
+    so that a protocol deadlock stays contained): 2 ranks at kernel and decoder level, 4 ranks at kernel level (why: see the
+    script's header; the 4- and 8-GPU runs on real hardware are under profiles/)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import os

@@ -25,33 +25,44 @@ def main():
     ap.add_argument("--ctx", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=4)
     a = ap.parse_args()
-    torch.cuda.set_device(0)
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
     L = lib.load()
     cfg = OmChatQwen2Config(num_hidden_layers=a.layers)
-    w = random_init(cfg, device="cuda:0", vision=False)
-    dec = Qwen2Decoder(cfg, w.llm)
+    if world > 1:  # tensor-parallel step (torchrun): the timeline of rank 0 includes the waits for the peers' partial tiles
+        import torch.distributed as dist
+        from omchat_b200.model.decoder import TPInfo
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        w = random_init(cfg, device=f"cuda:{local}", vision=False, tp_rank=rank, tp_size=world)
+        dec = Qwen2Decoder(cfg, w.llm, TPInfo(rank=rank, size=world, group=dist.group.WORLD))
+    else:
+        w = random_init(cfg, device="cuda:0", vision=False)
+        dec = Qwen2Decoder(cfg, w.llm)
     B = a.batch
     cache = dec.new_cache(B, a.ctx + 64)
     cache.host_lens = [a.ctx] * B
     cache.ctx_lens.fill_(a.ctx)
     cache.pool.normal_(0, 0.5)
-    toks = torch.randint(0, cfg.vocab_size, (B,), device="cuda:0")
+    toks = torch.randint(0, cfg.vocab_size, (B,), device=f"cuda:{local}")
     for _ in range(3):
         dec.decode_step(toks, cache, sample=True)
     torch.cuda.synchronize()
     per_step = 4 * a.layers + 1
     grid = 2 * lib.num_sms()
-    buf = torch.zeros(2 * per_step, grid, 8, device="cuda:0", dtype=torch.int64)
+    buf = torch.zeros(2 * per_step, grid, 16, device=f"cuda:{local}", dtype=torch.int64)
     L.omc_gemm_stream_set_prof(buf.data_ptr(), 2 * per_step)
     for _ in range(2):
         dec.decode_step(toks, cache, sample=True)
     torch.cuda.synchronize()
     L.omc_gemm_stream_set_prof(None, 0)
+    if rank != 0:
+        torch.distributed.barrier()
+        return
     t = buf[per_step:].cpu().double()  # second profiled step
     names = (["qkv", "o", "gate_up", "down"] * a.layers) + ["lm_head"]
     t0 = t[t > 0].min()
     print(f"{'launch':10s} {'ctas':>4s} {'entry':>15s} {'w issued':>9s} {'dep ok':>15s} {'1st stage':>15s} {'last mma':>15s} "
-          f"{'acc read':>15s} {'gathered':>9s} {'done':>15s}   (us since the step's first stamp; first..last CTA)")
+          f"{'acc read':>15s} {'gathered':>9s} {'pushed':>15s} {'peers in':>15s} {'done':>15s}   (us since the step's first stamp; first..last CTA)")
     for i, name in enumerate(names):
         x = t[i]
         live = x[:, 0] > 0
@@ -68,7 +79,9 @@ def main():
             v = v[v > 0]
             return f"{(v.max() - t0) / 1e3:9.1f}" if v.numel() else "        -"
 
-        print(f"{name:10s} {n:4d} {rng(0)} {mx(1)} {rng(2)} {rng(3)} {rng(4)} {rng(5)} {mx(6)} {rng(7)}")
+        print(f"{name:10s} {n:4d} {rng(0)} {mx(1)} {rng(2)} {rng(3)} {rng(4)} {rng(5)} {mx(6)} {rng(8)} {rng(9)} {rng(7)}")
+    if world > 1:
+        torch.distributed.barrier()
 
 
 if __name__ == "__main__":
