@@ -273,6 +273,56 @@ int omc_decode_plan_build(const omc_decode_desc* desc, void* plan_host);
 int omc_decode_step(const void* plan_host, const void* plan_dev, unsigned int epoch, void* stream);
 long long omc_decode_xchg_bytes(const omc_decode_desc* desc); /* uses batch, hidden, tp_size */
 
+/* ---- model-level entry points (omchat_b200/csrc/model_capi.cu): the layer loops in C++, for hosts that are not Python ----
+ * omc_vit_forward = OmChatMetaForCausalLM.encode_images (omchat/model/omchat_arch.py:50-53): InternVITVisionTower.forward
+ * (multimodal_encoder/internVIT_encoder.py:45-56 -> intern_vit_6b/modeling_intern_vit.py:90-102,138-222,268-279), feature
+ * select 'patch' (:35-43) (+ pixel shuffle), mm_projector mlp2x_gelu (multimodal_projector/builder.py:54-61).
+ *   pixels [n, 3, S, S] fp32 or bf16 -> feats_out bf16 [n, (S/patch/down)^2, proj_hidden]. Weight pointers are bf16 device
+ *   tensors in nn.Linear's [out, in] layout (patch_w: [hidden, patch_k] = the conv weight flattened, K zero-padded to patch_k);
+ *   per-layer pointers are arrays of n_layers. workspace: omc_vit_workspace_bytes(desc, n) bytes, 256-byte aligned.
+ * omc_decoder_prefill = Qwen2Model.forward on PACKED sequences (transformers modeling_qwen2.py:280-310,353-414) + final norm
+ *   and lm_head on each sequence's last row (:411,470-472), writing K/V into the paged cache. Uses the omc_decode_desc
+ *   fields n_layers, hidden, q_heads, kv_heads, inter, vocab, page_size, max_pages, eps, attn_scale, final_norm, lm_head,
+ *   ln1 .. down_w, kv_pool, kv_layer_stride, block_table. embeds [T, hidden] bf16 is the residual stream (updated in place),
+ *   pos_ids / seq_ids int32 [T], cu_seqlens int32 [n_seq + 1], last_rows int64 [n_seq] (packed row of each sequence's last
+ *   token), last_logits fp32 [n_seq, vocab] (NULL: cache fill only). workspace: omc_decoder_prefill_workspace_bytes().
+ * Neither allocates nor synchronises: both can be captured in a CUDA graph. Same kernels, same order, same bits as the Python
+ * host path (omchat_b200/model/vision.py, decoder.py). The decode step's model-level entry is omc_decode_step above. */
+typedef struct omc_vit_desc {
+  int32_t n_layers, hidden, heads, inter, image_size, patch_size, patch_k, qk_norm;
+  int32_t pixel_shuffle_down, proj_hidden;
+  float eps;
+  int32_t reserved;
+  const void* patch_w;
+  const void* patch_b;
+  const void* cls;
+  const void* pos;
+  const void* const* norm1;
+  const void* const* qkv_w;
+  const void* const* q_norm;
+  const void* const* k_norm;
+  const void* const* proj_w;
+  const void* const* proj_b;
+  const void* const* ls1;
+  const void* const* norm2;
+  const void* const* fc1_w;
+  const void* const* fc1_b;
+  const void* const* fc2_w;
+  const void* const* fc2_b;
+  const void* const* ls2;
+  const void* p_w0;
+  const void* p_b0;
+  const void* p_w2;
+  const void* p_b2;
+} omc_vit_desc;
+long long omc_vit_workspace_bytes(const omc_vit_desc* desc, int max_crops);
+int omc_vit_forward(const omc_vit_desc* desc, const void* pixels, int pixels_are_f32, int n_crops, void* workspace,
+                    void* feats_out, void* stream);
+long long omc_decoder_prefill_workspace_bytes(const omc_decode_desc* desc, int T, int n_seq);
+int omc_decoder_prefill(const omc_decode_desc* desc, const float* inv_freq, void* embeds, const int32_t* pos_ids,
+                        const int32_t* seq_ids, const int32_t* cu_seqlens, int n_seq, int T, int max_len,
+                        const int64_t* last_rows, void* workspace, float* last_logits, void* stream);
+
 /* ---- peer (NVLink) memory for the tensor-parallel decode step ------------------------------------------------------
  * Replaces the NCCL communicator a Megatron-style decoder would hand to its all-reduce: one exchange buffer per rank,
  * visible to every rank of the node. omc_peer_alloc: cudaMalloc + zero-fill on the current device and export a 64-byte

@@ -51,6 +51,10 @@ SIGNATURES = {
     "omc_embed_lookup": (_I, [_P, _I, _P, _I, _P, _L, _I, _P]),
     "omc_splice": (_I, [_P, _P, _I, _I, _L, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
     "omc_argmax": (_I, [_P, _L, _I, _I, _P, _P, _P]),
+    "omc_vit_workspace_bytes": (_L, [_P, _I]),
+    "omc_vit_forward": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "omc_decoder_prefill_workspace_bytes": (_L, [_P, _I, _I]),
+    "omc_decoder_prefill": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "omc_decode_plan_bytes": (_L, [_I]),
     "omc_decode_workspace_bytes": (_L, [_P]),
     "omc_decode_plan_build": (_I, [_P, _P]),
@@ -667,3 +671,75 @@ class DecodePlan:
             self.epoch += 1
         rc = load().omc_decode_step(self.host, self.dev.data_ptr(), epoch & 0xFFFFFF, _stream())
         _check(rc, "omc_decode_step")
+
+
+# ----------------------------------------------------------------------------------------------- model-level entry points
+class VitDesc(ctypes.Structure):
+    """Mirror of `omc_vit_desc` (include/omchat_b200.h)."""
+    _fields_ = ([(n, ctypes.c_int32) for n in ("n_layers", "hidden", "heads", "inter", "image_size", "patch_size", "patch_k",
+                                                 "qk_norm", "pixel_shuffle_down", "proj_hidden")]
+                + [("eps", c_float), ("reserved", ctypes.c_int32)]
+                + [(n, c_void_p) for n in ("patch_w", "patch_b", "cls", "pos", "norm1", "qkv_w", "q_norm", "k_norm", "proj_w",
+                                           "proj_b", "ls1", "norm2", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2", "p_w0", "p_b0",
+                                           "p_w2", "p_b2")])
+
+
+class VitForward:
+    """omc_vit_forward on a model's weights: the whole encode_images (tower + select / pixel shuffle + projector) as ONE
+    C call - what a non-Python host binds. `vit` / `proj` are weights.VitW / ProjW, vc an InternVisionConfig."""
+
+    def __init__(self, vit, proj, vc, pixel_shuffle_down: int = 1):
+        n = len(vit.layers)
+        d = VitDesc()
+        d.n_layers, d.hidden, d.heads, d.inter = n, vc.hidden_size, vc.num_attention_heads, vc.intermediate_size
+        d.image_size, d.patch_size, d.patch_k, d.qk_norm = vc.image_size, vc.patch_size, vit.patch_w.shape[1], int(vc.qk_normalization)
+        d.pixel_shuffle_down, d.proj_hidden, d.eps = pixel_shuffle_down, proj.w2.shape[0], vc.layer_norm_eps
+        d.patch_w, d.patch_b, d.cls, d.pos = (t.data_ptr() for t in (vit.patch_w, vit.patch_b, vit.cls, vit.pos))
+        names = {"norm1": "norm1", "qkv_w": "qkv", "q_norm": "q_norm", "k_norm": "k_norm", "proj_w": "proj_w", "proj_b": "proj_b",
+                 "ls1": "ls1", "norm2": "norm2", "fc1_w": "fc1_w", "fc1_b": "fc1_b", "fc2_w": "fc2_w", "fc2_b": "fc2_b", "ls2": "ls2"}
+        self._arrays = {}
+        for field, attr in names.items():
+            arr = (c_void_p * max(n, 1))(*[getattr(l, attr).data_ptr() for l in vit.layers])
+            self._arrays[field] = arr
+            setattr(d, field, ctypes.cast(arr, c_void_p))
+        d.p_w0, d.p_b0, d.p_w2, d.p_b2 = (t.data_ptr() for t in (proj.w0, proj.b0, proj.w2, proj.b2))
+        self.desc, self._keep, self._ws = d, (vit, proj), None
+        self.tokens = (vc.image_size // vc.patch_size // pixel_shuffle_down) ** 2
+
+    def __call__(self, pixels: torch.Tensor) -> torch.Tensor:
+        _need_cuda(pixels)
+        assert pixels.dim() == 4 and pixels.is_contiguous() and pixels.dtype in (torch.float32, torch.bfloat16)
+        n = pixels.shape[0]
+        need = load().omc_vit_workspace_bytes(ctypes.byref(self.desc), n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, device=pixels.device, dtype=torch.uint8)
+        out = torch.empty(n, self.tokens, self.desc.proj_hidden, device=pixels.device, dtype=torch.bfloat16)
+        rc = load().omc_vit_forward(ctypes.byref(self.desc), _ptr(pixels), 1 if pixels.dtype == torch.float32 else 0, n,
+                                    self._ws.data_ptr(), _ptr(out), _stream())
+        add_launches(4 + self.desc.n_layers * (9 if self.desc.qk_norm else 7) + 3 - 1)
+        _check(rc, "omc_vit_forward")
+        return out
+
+
+def decoder_prefill(layers, final_norm, lm_head, dims, eps, scale, inv_freq, embeds, pos_ids, seq_ids, cu_seqlens, max_len,
+                    kv_pool, block_table, page_size, last_rows=None):
+    """omc_decoder_prefill: embeds [T, C] (updated in place) -> fp32 logits [n_seq, V] of each sequence's last row (None if
+    last_rows is None); fills the paged cache. dims = (hidden, q_heads, kv_heads, inter, vocab)."""
+    _need_cuda(embeds, pos_ids, seq_ids, cu_seqlens, kv_pool, block_table, inv_freq)
+    n_layers, T, n_seq = len(layers), embeds.shape[0], cu_seqlens.numel() - 1
+    d = DecodeDesc()
+    d.n_layers = n_layers
+    d.hidden, d.q_heads, d.kv_heads, d.inter, d.vocab = dims
+    d.page_size, d.max_pages, d.eps, d.attn_scale = page_size, block_table.shape[1], eps, scale
+    d.final_norm, d.lm_head = final_norm.data_ptr(), lm_head.data_ptr()
+    arrays = [(c_void_p * max(n_layers, 1))(*[getattr(l, k).data_ptr() for l in layers]) for k in
+              ("ln1", "qkv_w", "qkv_b", "o_w", "ln2", "gate_up_w", "down_w")]
+    (d.ln1, d.qkv_w, d.qkv_b, d.o_w, d.ln2, d.gate_up_w, d.down_w) = [ctypes.cast(a, c_void_p) for a in arrays]
+    d.kv_pool, d.kv_layer_stride, d.block_table = kv_pool.data_ptr(), kv_pool.stride(0), block_table.data_ptr()
+    ws = torch.empty(load().omc_decoder_prefill_workspace_bytes(ctypes.byref(d), T, n_seq), device=embeds.device, dtype=torch.uint8)
+    logits = torch.empty(n_seq, dims[4], device=embeds.device, dtype=torch.float32) if last_rows is not None else None
+    rc = load().omc_decoder_prefill(ctypes.byref(d), _ptr(inv_freq), _ptr(embeds), _ptr(pos_ids), _ptr(seq_ids), _ptr(cu_seqlens),
+                                    n_seq, T, max_len, _ptr(last_rows), ws.data_ptr(), _ptr(logits), _stream())
+    add_launches(8 * n_layers + (3 if last_rows is not None else 0) - 1)
+    _check(rc, "omc_decoder_prefill")
+    return logits

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_model_capi_gpu.py -m gpu -x -q 2>&1 | tail -15
