@@ -189,6 +189,36 @@ __device__ __forceinline__ void st_dsmem_add8(uint32_t local_addr, int splitk, f
   }
 }
 
+// Sum over ALL splitk staging tiles of the cluster (own one included, through its cluster address) in rank order.
+__device__ __forceinline__ void st_dsmem_sum8(uint32_t local_addr, int splitk, float4& a, float4& b4) {
+  a = make_float4(0.f, 0.f, 0.f, 0.f);
+  b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int base = 0; base < 8; base += 4) {
+    if (base >= splitk) break;
+    float4 x[4], y[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = base + q;
+      if (r < splitk) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(r));
+        asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(x[q].x), "=f"(x[q].y), "=f"(x[q].z), "=f"(x[q].w) : "r"(remote));
+        asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(y[q].x), "=f"(y[q].y), "=f"(y[q].z), "=f"(y[q].w) : "r"(remote + 16u));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (base + q < splitk) {
+        a.x += x[q].x; a.y += x[q].y; a.z += x[q].z; a.w += x[q].w;
+        b4.x += y[q].x; b4.y += y[q].y; b4.z += y[q].z; b4.w += y[q].w;
+      }
+    }
+  }
+}
+
 template <int MPAD>
 __global__ void __launch_bounds__(kStThreads, 2)
 gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p) {
@@ -207,6 +237,13 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_rstd = reinterpret_cast<float*>(tmem_slot + 2);  // [64]
   const bool cluster_mode = p.splitk > 1;  // the splitk K parts of a tile = the CTAs of one thread-block cluster
+  // cluster mode on one GPU: phase 2 of the epilogue is SHARED by the CTAs of the cluster - CTA r finalises the rows
+  // m = r, r + splitk, ... of the tile (sum of all parts over DSMEM, epilogue math, stores, sums of squares), so the
+  // hand-off to the next kernel waits for 1 / splitk of the work. (Under tensor parallelism the tile's owner does it all: it
+  // is the one talking to the peers.)
+  const bool dist = cluster_mode && p.tp_size <= 1;
+  const int row_step = dist ? p.splitk : 1;
+  const int row_base = dist ? (int)(blockIdx.x % (unsigned int)p.splitk) : 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)p.n_tiles * p.num_kb;
@@ -329,11 +366,11 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
       const uint32_t buf = seg & 1u;
       // residual chunks of phase 2 fetched NOW, while the weights stream (out may alias res)
       uint4 resq[kIters];
-      if (owner && p.epi == EPI_RES) {
+      if ((owner || dist) && p.epi == EPI_RES) {
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
-          const int c = i * 128 + et, m = c >> 4, n = (int)tile * 128 + (c & 15) * 8;
-          resq[i] = (m < p.M && n < p.N) ? __ldcg(reinterpret_cast<const uint4*>(p.res + (long long)m * p.ldr + n))
+          const int c = i * 128 + et, m = row_base + row_step * (c >> 4), n = (int)tile * 128 + (c & 15) * 8;
+          resq[i] = (m < p.M && m < MPAD && n < p.N) ? __ldcg(reinterpret_cast<const uint4*>(p.res + (long long)m * p.ldr + n))
                                          : make_uint4(0, 0, 0, 0);
         }
       }
@@ -437,16 +474,25 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
           epi_barrier();
           if (et == 0) ST_STAMP(9);
         }
-        if (owner) {
+        if (owner || dist) {
           // ---- phase 2
           const uint32_t stage_addr = smem_u32(stage_f);
 #pragma unroll
           for (int i = 0; i < kIters; ++i) {
-            const int c = i * 128 + et, m = c >> 4, n8 = (c & 15) * 8;
+            const int c = i * 128 + et, n8 = (c & 15) * 8;
+            // a warp covers two rows (lanes 0-15 / 16-31): leave the loop only when BOTH are past the tile (warp-uniform: the
+            // sums of squares below shuffle with a full mask); a lane whose own row is past it computes on row 0 and stores nothing
+            if (row_base + row_step * ((i * 128 + (et & ~31)) >> 4) >= MPAD) break;
+            const int m_raw = row_base + row_step * (c >> 4);
+            const int m = m_raw < MPAD ? m_raw : 0;
             const int n = (int)tile * 128 + n8;
-            const bool ok = m < p.M && n < p.N;  // N % 8 == 0: a chunk is entirely inside or outside
+            const bool ok = m_raw < p.M && n < p.N;  // N % 8 == 0: a chunk is entirely inside or outside
             float v[8];
-            {
+            if (dist) {
+              float4 a, b4;
+              st_dsmem_sum8(stage_addr + (uint32_t)(m * 128 + n8) * 4u, p.splitk, a, b4);
+              v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+            } else {
               const float4 a = *reinterpret_cast<const float4*>(stage_f + m * 128 + n8);
               const float4 b4 = *reinterpret_cast<const float4*>(stage_f + m * 128 + n8 + 4);
               v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
@@ -469,10 +515,6 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
               }
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = s[j];
-            } else if (cluster_mode) {
-              float4 a = make_float4(v[0], v[1], v[2], v[3]), b4 = make_float4(v[4], v[5], v[6], v[7]);
-              st_dsmem_add8(stage_addr + (uint32_t)(m * 128 + n8) * 4u, p.splitk, a, b4);
-              v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
             }
             if (p.ssq_in != nullptr) {
               const float r = s_rstd[m < 64 ? m : 0];
@@ -517,7 +559,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
                                  q3.x * q3.x + q3.y * q3.y) : 0.f;
 #pragma unroll
                 for (int d = 8; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
-                if ((lane & 15) == 0 && m < p.M) p.ssq_out[(long long)tile * 64 + m] = sq;
+                if ((lane & 15) == 0 && m_raw < p.M) p.ssq_out[(long long)tile * 64 + m] = sq;
               }
             }
           }
