@@ -236,6 +236,7 @@ constexpr int kDecStages = 3;  // cp.async stages per warp: a warp is latency-bo
 constexpr int kDecWarpBuf = kDecStages * 2 * kDecTile * kRowBytes;  // stages x (K,V) x 16 rows = 24 KB per warp
 constexpr int kDecQBytes = 16 * kRowBytes;
 constexpr int kDecPartStride = kHD + 2;  // O[128], m, l
+constexpr int kDecMaxStagedPages = 1024;  // page ids of one sequence staged in shared memory (longer tables: global look-ups)
 constexpr int kDecSmem = kDecQBytes + 4 * kDecWarpBuf;  // 100 KB: two CTAs per SM (the warp-merge scratch aliases warp 0's tiles)
 static_assert(4 * 8 * kDecPartStride * 4 <= kDecWarpBuf, "merge scratch must fit the tile buffer of warp 0");
 
@@ -266,18 +267,54 @@ __global__ void __launch_bounds__(kDecThreads) paged_decode_attn_kernel(const De
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
   const int G = p.G;
-  // programmatic dependent launch (csrc/gemm_stream.cu): let the next kernel's CTAs move in as ours retire, and do not
-  // read the qkv rows / context lengths of this step before the kernel that produced them has completed
+  // Programmatic dependent launch (csrc/gemm_stream.cu): let the next kernel's CTAs move in as ours retire. Everything that
+  // does not depend on THIS step's qkv rows runs before griddepcontrol.wait, i.e. while the qkv GEMM is still streaming: the
+  // context length (incremented at the top of the step, several completed kernels ago), the sequence's page ids (staged in
+  // shared memory: no dependent table look-up in front of every tile fetch) and the first K/V tiles of every warp's pipeline
+  // (the cache rows of earlier tokens are immutable; the new token's slot is patched in shared memory below).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int ctx = p.ctx_lens[b];
   const int pos_new = ctx - 1;
   const bool fused = p.inv_freq != nullptr;
   const bf16* qrow = p.qkv + (long long)b * p.ldq;
-
+  __shared__ int s_pages[kDecMaxStagedPages];
+  {
+    const int n_pages = (ctx + p.page_size - 1) / p.page_size;
+    for (int i = tid; i < n_pages && i < kDecMaxStagedPages; i += kDecThreads) s_pages[i] = p.block_table[(long long)b * p.max_pages + i];
+  }
   // ---- Q tile [16][128]: rows 0..G-1 = query heads of this KV group (rotated), rest zero
   for (int c = tid; c < 16 * 16; c += kDecThreads) *reinterpret_cast<uint4*>(sQ + swz(c >> 4, c & 15)) = make_uint4(0, 0, 0, 0);
   __syncthreads();
+
+  // ---- this CTA's key-tile range, tiles dealt round-robin to the 4 warps
+  const int tiles_ctx = (ctx + kDecTile - 1) / kDecTile;
+  const int per_split = (tiles_ctx + p.splits - 1) / p.splits;
+  const int t_begin = split * per_split;
+  const int t_end = min(tiles_ctx, t_begin + per_split);
+
+  uint8_t* wbuf = sKV + warp * kDecWarpBuf;
+  auto stage_k = [&](int st) { return wbuf + st * (2 * kDecTile * kRowBytes); };
+  auto stage_v = [&](int st) { return wbuf + st * (2 * kDecTile * kRowBytes) + kDecTile * kRowBytes; };
+  auto issue = [&](int tile, int st) {
+    const int key0 = tile * kDecTile;
+    const int pi = key0 / p.page_size;
+    const int page = pi < kDecMaxStagedPages ? s_pages[pi] : p.block_table[(long long)b * p.max_pages + pi];
+    const int slot = key0 % p.page_size;
+    const bf16* kg = p.pool + ((((long long)page * 2 + 0) * p.Hkv + kvh) * p.page_size + slot) * kHD;
+    const bf16* vg = p.pool + ((((long long)page * 2 + 1) * p.Hkv + kvh) * p.page_size + slot) * kHD;
+    for (int c = lane; c < kDecTile * 16; c += 32) {
+      const int r = c >> 4, ch = c & 15;
+      cp_async16(stage_k(st) + swz(r, ch), kg + r * kHD + ch * 8, true);
+      cp_async16(stage_v(st) + swz(r, ch), vg + r * kHD + ch * 8, true);
+    }
+  };
+  int tile = t_begin + warp, it = 0;
+#pragma unroll
+  for (int s = 0; s < kDecStages - 1; ++s) {  // one commit group per stage, empty groups keep the count uniform
+    if (tile + 4 * s < t_end) issue(tile + 4 * s, s);
+    cp_async_commit();
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // from here on: this step's q / k / v rows
   for (int e = tid; e < G * 64; e += kDecThreads) {
     const int r = e >> 6, i = e & 63;
     const bf16* hp = qrow + (kvh * G + r) * kHD;
@@ -300,39 +337,11 @@ __global__ void __launch_bounds__(kDecThreads) paged_decode_attn_kernel(const De
     ldmatrix_x4(smem_u32(sQ) + swz(r, ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
   }
 
-  // ---- this CTA's key-tile range, tiles dealt round-robin to the 4 warps
-  const int tiles_ctx = (ctx + kDecTile - 1) / kDecTile;
-  const int per_split = (tiles_ctx + p.splits - 1) / p.splits;
-  const int t_begin = split * per_split;
-  const int t_end = min(tiles_ctx, t_begin + per_split);
-
-  uint8_t* wbuf = sKV + warp * kDecWarpBuf;
-  auto stage_k = [&](int st) { return wbuf + st * (2 * kDecTile * kRowBytes); };
-  auto stage_v = [&](int st) { return wbuf + st * (2 * kDecTile * kRowBytes) + kDecTile * kRowBytes; };
-  auto issue = [&](int tile, int st) {
-    const int key0 = tile * kDecTile;
-    const int page = p.block_table[(long long)b * p.max_pages + key0 / p.page_size];
-    const int slot = key0 % p.page_size;
-    const bf16* kg = p.pool + ((((long long)page * 2 + 0) * p.Hkv + kvh) * p.page_size + slot) * kHD;
-    const bf16* vg = p.pool + ((((long long)page * 2 + 1) * p.Hkv + kvh) * p.page_size + slot) * kHD;
-    for (int c = lane; c < kDecTile * 16; c += 32) {
-      const int r = c >> 4, ch = c & 15;
-      cp_async16(stage_k(st) + swz(r, ch), kg + r * kHD + ch * 8, true);
-      cp_async16(stage_v(st) + swz(r, ch), vg + r * kHD + ch * 8, true);
-    }
-  };
-
   float o[16][4];
 #pragma unroll
   for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;  // row g only (rows >= 8 are padding)
 
-  int tile = t_begin + warp, it = 0;
-#pragma unroll
-  for (int s = 0; s < kDecStages - 1; ++s) {  // one commit group per stage, empty groups keep the count uniform
-    if (tile + 4 * s < t_end) issue(tile + 4 * s, s);
-    cp_async_commit();
-  }
   for (; tile < t_end; tile += 4, ++it) {
     const int st = it % kDecStages;
     if (tile + 4 * (kDecStages - 1) < t_end) issue(tile + 4 * (kDecStages - 1), (it + kDecStages - 1) % kDecStages);

@@ -43,6 +43,13 @@ from .weights import LlmW
 GEMV_MAX_B = 8
 GEMV_MAX_SMEM = 200 * 1024
 MEGA_MAX_B = 4  # the persistent decode kernel (csrc/decode_mega.cu) handles 1..4 sequences
+# Smallest batch that decodes on the weight-streaming GEMMs (csrc/gemm_stream.cu); below it: the persistent kernel
+# (csrc/decode_mega.cu). Measured on one B200, ctx 1024 (profiles/r02_decode_small_batch_stream_vs_mega.jsonl), ms per step,
+# persistent kernel / streaming GEMMs: batch 1: 2.68 / 2.82, batch 2: 3.18 / 2.85, batch 4: 5.24 / 2.89 - the persistent
+# kernel re-reads its activation fragments for every weight byte from batch 2 on, the tcgen05 tile does not care.
+# Under tensor parallelism the persistent kernel keeps batches 1..4 (its in-kernel exchange moves 8-byte words, not tiles).
+STREAM_MIN_B = 2
+STREAM_MIN_B_TP = 5
 MEGA_HIST = 4096  # token-history rows kept on the device between host reads
 
 
@@ -121,6 +128,8 @@ class Qwen2Decoder:
         self.mega_enabled = os.environ.get("OMCHAT_B200_NO_MEGA", "0") != "1"
         # batched decode steps (B > 4): weight-streaming GEMMs on packed weights (0 = the round-1 skinny GEMM / GEMV path)
         self.stream_enabled = os.environ.get("OMCHAT_B200_NO_STREAM", "0") != "1"
+        self.stream_min_b = int(os.environ.get("OMCHAT_B200_STREAM_MIN_B",
+                                               str(STREAM_MIN_B if self.tp.size == 1 else STREAM_MIN_B_TP)))
         self._packed = None  # lazily built packed copies of the decoder weights (csrc/gemm_stream.cu)
         # tp > 1: all-reduce inside the persistent kernel over NVLink peer memory (0 = per-op kernels + NCCL all-reduce)
         self.tp_mega_enabled = os.environ.get("OMCHAT_B200_TP_MEGA", "1") != "0"
@@ -200,9 +209,9 @@ class Qwen2Decoder:
         return self._packed
 
     def use_stream(self, B: int) -> bool:
-        """Batches 5..64 decode on the weight-streaming GEMMs; 1..4 on the persistent kernel (or, with that switched off,
-        on the per-op GEMV kernels that serve as its cross-check)."""
-        return self.stream_enabled and MEGA_MAX_B < B <= 64
+        """Batches stream_min_b..64 decode on the weight-streaming GEMMs; smaller ones on the persistent kernel (or, with
+        that switched off, on the per-op GEMV kernels that serve as its cross-check)."""
+        return self.stream_enabled and self.stream_min_b <= B <= 64
 
     # ------------------------------------------------------------------------------------------------ prefill
     @torch.no_grad()
@@ -306,7 +315,7 @@ class Qwen2Decoder:
 
     def use_mega(self, B: int) -> bool:
         """Small-batch decode runs as ONE persistent cooperative kernel per token (csrc/decode_mega.cu)."""
-        return (self.mega_enabled and B <= MEGA_MAX_B and self.C <= 4096 and len(self.w.layers) <= 32
+        return (self.mega_enabled and B <= MEGA_MAX_B and B < self.stream_min_b and self.C <= 4096 and len(self.w.layers) <= 32
                 and (self.tp.size == 1 or (self.tp.size <= 8 and self.tp_mega_enabled)))
 
     def _peer_exchange(self, B: int):

@@ -19,7 +19,9 @@ def _decoder(layers, seed=0, **kw):
     from omchat_b200.model.weights import random_init
     cfg = OmChatQwen2Config(num_hidden_layers=layers, **kw)
     w = random_init(cfg, device="cuda", seed=seed, vision=False)
-    return cfg, w, Qwen2Decoder(cfg, w.llm)
+    dec = Qwen2Decoder(cfg, w.llm)
+    dec.stream_min_b = 5  # these tests exercise the persistent kernel at batches 1..4 (the default routes 2..4 to the stream GEMMs)
+    return cfg, w, dec
 
 
 def _prefill(dec, cfg, lens, seed=1):
@@ -186,9 +188,10 @@ def test_mega_tensor_parallel_emulated_on_one_gpu(tp, lens):
     assert f"tp{tp} emulation ok" in r.stdout
 
 
-@pytest.mark.parametrize("lens", [[40, 7, 90, 33, 64, 1, 20], [30 + 3 * i for i in range(32)], [5 + 2 * i for i in range(40)]])
+@pytest.mark.parametrize("lens", [[50, 9], [20, 33, 70, 5], [40, 7, 90, 33, 64, 1, 20], [30 + 3 * i for i in range(32)],
+                                  [5 + 2 * i for i in range(40)]])
 def test_batched_decode_stream_vs_oracle_full_width(lens):
-    """Batched decode steps (B = 7 / 32 / 40 -> 16 / 32 / 64-row activation tiles) on the weight-streaming GEMMs
+    """Batched decode steps (B = 2 / 4 / 7 / 32 / 40 -> 16 / 32 / 64-row activation tiles) on the weight-streaming GEMMs
     (csrc/gemm_stream.cu: packed weights, stream-K, programmatic dependent launch, RMSNorm folded into the GEMMs) at full
     Qwen2-7B width, 2 layers, against the CPU oracle run sequence by sequence on the same weights, teacher-forced on the
     CUDA path's own tokens: logits cosine >= 0.999 and max-abs <= 2 % of scale per row; the eager step, the CUDA-graph
@@ -197,6 +200,7 @@ def test_batched_decode_stream_vs_oracle_full_width(lens):
         pytest.skip("no CUDA device")
     from omchat_b200.model.weights import OmChatWeights, to_reference_state_dict
     cfg, w, dec = _decoder(2)
+    dec.stream_min_b = 2  # the product default on one GPU: batches 2..64 on the stream GEMMs
     assert dec.use_stream(len(lens)) and not dec.use_mega(len(lens))
     sd = {k: v.float().cpu() for k, v in to_reference_state_dict(OmChatWeights(None, None, w.llm), cfg).items()}
     ocfg = O.OracleConfig(layers=2)

@@ -33,6 +33,7 @@ def main(tp: int, lens, steps: int = 6, layers: int = 2):
                                 intermediate_size=8192, vocab_size=32000)
     B = len(lens)
     full = Qwen2Decoder(cfg, random_init(cfg, device=dev, seed=0, vision=False).llm)
+    full.stream_min_b = 5  # the reference here is the single-GPU PERSISTENT kernel (batches 2..4 default to the stream GEMMs)
     ranks = [Qwen2Decoder(cfg, random_init(cfg, device=dev, seed=0, vision=False, tp_rank=r, tp_size=tp).llm,
                           TPInfo(rank=r, size=tp)) for r in range(tp)]
     # prefill once on the unsharded decoder; every rank's cache = its kv heads of that cache (same block table: same seed)

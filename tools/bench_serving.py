@@ -50,7 +50,7 @@ def main():
     serve_sequential()
     torch.cuda.synchronize()
     out["sequential_generate_tokens_per_s"] = total / (time.perf_counter() - t0)
-    for slots in sorted({1, 2, a.slots}):
+    for slots in sorted({1, 2, 4, 8, a.slots}):
         serve_batched(slots)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
