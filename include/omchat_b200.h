@@ -45,6 +45,30 @@ int omc_num_sms(void);
 int omc_gemm_bf16(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M, int N,
                   int K, const void* bias, const void* scale, const void* res, long long ldr, int epi, int out_is_f32,
                   int tile_cfg, void* stream);
+/* The same GEMM with the RMSNorm in front of the layer FOLDED in (InternRMSNorm norm1 / norm2, modeling_intern_vit.py:39-44,
+ * 218-220; Qwen2RMSNorm input / post-attention / final norm, modeling_qwen2.py:258-263,280-310,411): the caller multiplies the
+ * norm weight into W's columns once at load time, X is the RAW residual stream, and the epilogue scales row m by
+ * rsqrt(sum_q ssq_in[q][m] / norm_dim + eps) before bias / activation. The sums of squares come from the EPI_RES GEMM that
+ * wrote X: with ssq_out set, every N tile of that GEMM stores the sum of squares of the bf16 values it wrote for each row
+ * (ssq_out[tile][m], fp32) and reports how many tiles there were in ssq_out_parts (host-side, at launch time: it depends on
+ * the tile configuration). For rows that no GEMM produced (embeddings) use omc_row_ssq_rows. */
+typedef struct omc_gemm_norm {
+  const float* ssq_in;    /* [ssq_in_parts][ssq_in_ld] or NULL */
+  long long ssq_in_ld;    /* >= M */
+  int ssq_in_parts, norm_dim;
+  float eps;
+  int ssq_out_max_parts;  /* capacity of ssq_out in parts */
+  float* ssq_out;         /* [ssq_out_max_parts][ssq_out_ld] or NULL (EPI_RES / EPI_NONE with bf16 output) */
+  long long ssq_out_ld;   /* >= M */
+  int ssq_out_parts;      /* OUT: parts written by this launch */
+  int reserved;
+} omc_gemm_norm;
+int omc_gemm_bf16_norm(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M, int N,
+                       int K, const void* bias, const void* scale, const void* res, long long ldr, int epi, int out_is_f32,
+                       int tile_cfg, omc_gemm_norm* nf, void* stream);
+/* ssq[m] = sum_k x[m,k]^2 for any number of rows (one warp per row). */
+int omc_row_ssq_rows(const void* x, long long ldx, long long rows, int C, float* ssq, void* stream);
+
 
 /* Skinny variant for M <= 64 (batched decode steps too large for the GEMV kernels; HBM-bound): operands swapped so the
  * 128-row tcgen05 tile runs along N (all TMA bytes are weight bytes), small N split along K over the CTAs of a thread-block
@@ -292,7 +316,8 @@ typedef struct omc_vit_desc {
   int32_t n_layers, hidden, heads, inter, image_size, patch_size, patch_k, qk_norm;
   int32_t pixel_shuffle_down, proj_hidden;
   float eps;
-  int32_t reserved;
+  int32_t norm_folded; /* 1: qkv_w / fc1_w carry norm1 / norm2 in their columns (W * g): the loop uses omc_gemm_bf16_norm and no
+                          stand-alone RMSNorm in front of them (the product's default path); 0: plain weights + omc_rmsnorm */
   const void* patch_w;
   const void* patch_b;
   const void* cls;
@@ -321,7 +346,9 @@ int omc_vit_forward(const omc_vit_desc* desc, const void* pixels, int pixels_are
 long long omc_decoder_prefill_workspace_bytes(const omc_decode_desc* desc, int T, int n_seq);
 int omc_decoder_prefill(const omc_decode_desc* desc, const float* inv_freq, void* embeds, const int32_t* pos_ids,
                         const int32_t* seq_ids, const int32_t* cu_seqlens, int n_seq, int T, int max_len,
-                        const int64_t* last_rows, void* workspace, float* last_logits, void* stream);
+                        const int64_t* last_rows, void* workspace, float* last_logits, int norm_folded, void* stream);
+/* norm_folded = 1: desc->qkv_w / gate_up_w carry the input / post-attention RMSNorm weights in their columns (ln1 / ln2 are
+ * then unused); final_norm + lm_head stay separate. */
 
 /* ---- peer (NVLink) memory for the tensor-parallel decode step ------------------------------------------------------
  * Replaces the NCCL communicator a Megatron-style decoder would hand to its all-reduce: one exchange buffer per rank,

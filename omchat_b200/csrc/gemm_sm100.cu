@@ -31,6 +31,13 @@ struct GemmParams {
   float* out_f32;  // if non-null, EPI_NONE writes fp32 here instead of bf16
   int epi;
   int num_m_tiles, num_n_tiles;
+  // folded RMSNorm (the norm weight lives in W; see omc_gemm_bf16_norm): row scale rstd[m] = rsqrt(sum_parts / norm_dim + eps)
+  const float* ssq_in;   // [ssq_in_parts][ssq_in_ld] partial sums of squares of X's rows, or null
+  long long ssq_in_ld;
+  int ssq_in_parts;
+  float inv_norm_dim, eps;
+  float* ssq_out;        // [num_n_tiles][ssq_out_ld]: sums of squares of the bf16 rows written, per N tile, or null
+  long long ssq_out_ld;
 };
 
 constexpr int kBM = 128;
@@ -176,10 +183,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int mt, nt;
       tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
       const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
-      mbar_wait_cluster(&tfull_bar[acc], acc_ph);
-      tc_fence_after();
       const long long row = (long long)(mt * CG + (int)cta_rank) * kBM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
+      // folded RMSNorm: this row's scale, fetched while the MMAs of the tile are still running
+      float rstd = 1.0f;
+      if (p.ssq_in != nullptr) {
+        float ss = 0.f;
+        if (row_ok)
+          for (int q = 0; q < p.ssq_in_parts; ++q) ss += __ldcg(p.ssq_in + q * p.ssq_in_ld + row);
+        rstd = rsqrtf(ss * p.inv_norm_dim + p.eps);
+      }
+      float ssq_acc = 0.f;
+      mbar_wait_cluster(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * Cfg::kAccStride + ((uint32_t)(quarter * 32) << 16);
 
       if (p.epi == EPI_SWIGLU) {
@@ -195,8 +211,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float a0 = silu(__uint_as_float(v[4 * j])) * __uint_as_float(v[4 * j + 1]);
-            float a1 = silu(__uint_as_float(v[4 * j + 2])) * __uint_as_float(v[4 * j + 3]);
+            float a0 = silu(__uint_as_float(v[4 * j]) * rstd) * (__uint_as_float(v[4 * j + 1]) * rstd);
+            float a1 = silu(__uint_as_float(v[4 * j + 2]) * rstd) * (__uint_as_float(v[4 * j + 3]) * rstd);
             o[j] = pack_bf16(a0, a1);
           }
           if (row_ok) {
@@ -215,7 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (col >= p.N) break;
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * rstd;
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -270,12 +286,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   uint4 o = make_uint4(pack_bf16(f[8 * j + 0], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                                        pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
                   *reinterpret_cast<uint4*>(dst + 8 * j) = o;
+                  if (p.ssq_out != nullptr) {  // of the bf16 values actually stored
+                    const float2 q0 = unpack_bf16(o.x), q1 = unpack_bf16(o.y), q2 = unpack_bf16(o.z), q3 = unpack_bf16(o.w);
+                    ssq_acc += q0.x * q0.x + q0.y * q0.y + q1.x * q1.x + q1.y * q1.y + q2.x * q2.x + q2.y * q2.y +
+                               q3.x * q3.x + q3.y * q3.y;
+                  }
                 }
               }
             }
           }
         }
       }
+      if (p.ssq_out != nullptr && row_ok) p.ssq_out[(long long)nt * p.ssq_out_ld + row] = ssq_acc;
       // accumulator drained -> hand the TMEM buffer back to the MMA issuer (in the leader CTA)
       tc_fence_before();
       __syncwarp();
@@ -384,9 +406,27 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
 
 using namespace omc;
 
+static int gemm_impl(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M, int N, int K,
+                     const void* bias, const void* scale, const void* res, long long ldr, int epi, int out_is_f32,
+                     int tile_cfg, const omc_gemm_norm* nf, void* stream);
+
 extern "C" int omc_gemm_bf16(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo,
                              int M, int N, int K, const void* bias, const void* scale, const void* res,
                              long long ldr, int epi, int out_is_f32, int tile_cfg, void* stream) {
+  return gemm_impl(X, ldx, W, ldw, out, ldo, M, N, K, bias, scale, res, ldr, epi, out_is_f32, tile_cfg, nullptr, stream);
+}
+
+extern "C" int omc_gemm_bf16_norm(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo,
+                                  int M, int N, int K, const void* bias, const void* scale, const void* res,
+                                  long long ldr, int epi, int out_is_f32, int tile_cfg, omc_gemm_norm* nf, void* stream) {
+  if (nf == nullptr) return set_error(OMC_ERR_ARG, "omc_gemm_bf16_norm: null norm description");
+  return gemm_impl(X, ldx, W, ldw, out, ldo, M, N, K, bias, scale, res, ldr, epi, out_is_f32, tile_cfg, nf, stream);
+}
+
+static int gemm_impl(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M, int N, int K,
+                     const void* bias, const void* scale, const void* res, long long ldr, int epi, int out_is_f32,
+                     int tile_cfg, const omc_gemm_norm* nf_c, void* stream) {
+  omc_gemm_norm* nf = const_cast<omc_gemm_norm*>(nf_c);
   if (M <= 0 || N <= 0 || K <= 0) return set_error(OMC_ERR_SHAPE, "omc_gemm_bf16: empty problem");
   if (N % 8 != 0 || K % 8 != 0) return set_error(OMC_ERR_SHAPE, "omc_gemm_bf16: N and K must be multiples of 8");
   if (epi < EPI_NONE || epi > EPI_SWIGLU) return set_error(OMC_ERR_ARG, "omc_gemm_bf16: unknown epilogue");
@@ -412,6 +452,22 @@ extern "C" int omc_gemm_bf16(const void* X, long long ldx, const void* W, long l
     bn = (N % 256 == 0) ? 256 : (N % 160 == 0) ? 160 : (N % 192 == 0) ? 192 : (N % 128 == 0) ? 128 : 256;
   }
   if (cg == 0) cg = 2;
+  if (nf != nullptr) {
+    if (nf->ssq_in != nullptr) {
+      if (nf->ssq_in_parts < 1 || nf->norm_dim < 1 || nf->ssq_in_ld < M)
+        return set_error(OMC_ERR_ARG, "omc_gemm_bf16_norm: bad ssq_in description");
+      p.ssq_in = nf->ssq_in; p.ssq_in_parts = nf->ssq_in_parts; p.ssq_in_ld = nf->ssq_in_ld;
+      p.inv_norm_dim = 1.0f / (float)nf->norm_dim; p.eps = nf->eps;
+    }
+    if (nf->ssq_out != nullptr) {
+      if (out_is_f32 || epi == EPI_SWIGLU || nf->ssq_out_ld < M)
+        return set_error(OMC_ERR_ARG, "omc_gemm_bf16_norm: sums of squares need a bf16 row output");
+      p.ssq_out = nf->ssq_out; p.ssq_out_ld = nf->ssq_out_ld;
+      nf->ssq_out_parts = (N + bn - 1) / bn;  // one partial per N tile of the configuration that runs
+      if (nf->ssq_out_parts > nf->ssq_out_max_parts)
+        return set_error(OMC_ERR_ARG, "omc_gemm_bf16_norm: ssq_out buffer holds too few parts");
+    }
+  }
 #define OMC_GEMM_CASE(BN_, CG_) \
   if (bn == BN_ && cg == CG_) return launch_gemm<BN_, CG_>(X, ldx, W, ldw, p, max_ctas, st);
   OMC_GEMM_CASE(256, 1)

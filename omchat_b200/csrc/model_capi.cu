@@ -19,6 +19,7 @@
 using namespace omc;
 
 namespace {
+constexpr int kSsqParts = 32;  // capacity (in N tiles) of a sums-of-squares buffer: hidden 3200 / 3584 at 128-wide tiles = 25 / 28
 inline long long align256(long long x) { return (x + 255) & ~255LL; }
 struct Carver {
   uint8_t* p;
@@ -51,13 +52,14 @@ static void vit_sizes(const omc_vit_desc* d, int n, long long* rows, long long* 
   sizes[7] = (long long)n * L * d->hidden * down * down * 2;     // selected (+ shuffled) features
   sizes[8] = (long long)n * L * d->proj_hidden * 2;              // projector hidden
   sizes[9] = ((long long)n + 1) * 4;                             // cu_seqlens
+  sizes[10] = d->norm_folded ? 2 * kSsqParts * *rows * 4 : 0;    // two [parts][rows] fp32 sums-of-squares buffers
 }
 
 extern "C" long long omc_vit_workspace_bytes(const omc_vit_desc* d, int max_crops) {
   if (d == nullptr || max_crops <= 0 || d->patch_size <= 0) return -1;
-  long long rows, s[10], total = 0;
+  long long rows, s[11], total = 0;
   vit_sizes(d, max_crops, &rows, s);
-  for (int i = 0; i < 10; ++i) total += align256(s[i]);
+  for (int i = 0; i < 11; ++i) total += align256(s[i]);
   return total + 256;
 }
 
@@ -76,7 +78,7 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
   const int G = d->image_size / d->patch_size, P = G * G, C = d->hidden, S = P + 1;
   const int down = d->pixel_shuffle_down;
   if (down < 1 || G % down != 0) return set_error(OMC_ERR_SHAPE, "omc_vit_forward: bad pixel_shuffle_down");
-  long long rows, s[10];
+  long long rows, s[11];
   vit_sizes(d, n_crops, &rows, s);
   Carver cv{static_cast<uint8_t*>(workspace) + ((256 - (reinterpret_cast<uintptr_t>(workspace) & 255)) & 255)};
   void* cols = cv.take(s[0]);
@@ -89,6 +91,8 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
   void* sel = cv.take(s[7]);
   void* ph = cv.take(s[8]);
   int32_t* cu = static_cast<int32_t*>(cv.take(s[9]));
+  float* ssq_a = static_cast<float*>(cv.take(s[10] / 2));
+  float* ssq_b = static_cast<float*>(cv.take(s[10] / 2));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   iota_scaled_kernel<<<(n_crops + 1 + 127) / 128, 128, 0, st>>>(cu, n_crops + 1, S);
   OMC_TRY(check_launch("iota"));
@@ -99,22 +103,54 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
   OMC_TRY(omc_vit_assemble(patch, d->cls, d->pos, h, n_crops, P, C, stream));
   const float scale = 1.0f / sqrtf(128.0f);
   const int M = (int)rows;
+  const bool fold = d->norm_folded != 0;
+  int parts_a = 1, parts_b = 1;  // sums-of-squares partials the last producer of each buffer wrote
+  if (fold) OMC_TRY(omc_row_ssq_rows(h, C, rows, C, ssq_a, stream));
+  auto norm_in = [&](const float* ssq, int parts) {
+    omc_gemm_norm nf{};
+    nf.ssq_in = ssq; nf.ssq_in_ld = rows; nf.ssq_in_parts = parts; nf.norm_dim = C; nf.eps = d->eps;
+    return nf;
+  };
+  auto norm_out = [&](float* ssq) {
+    omc_gemm_norm nf{};
+    nf.ssq_out = ssq; nf.ssq_out_ld = rows; nf.ssq_out_max_parts = kSsqParts;
+    return nf;
+  };
   for (int li = 0; li < d->n_layers; ++li) {
     // h += ls1 * proj(attn(qk_norm(qkv(norm1(h)))));  h += ls2 * fc2(gelu(fc1(norm2(h))))   (:138-155, 187-191, 218-220)
-    OMC_TRY(omc_rmsnorm(h, C, d->norm1[li], xn, C, M, C, d->eps, stream));
-    OMC_TRY(omc_gemm_bf16(xn, C, d->qkv_w[li], C, qkv, 3LL * C, M, 3 * C, C, nullptr, nullptr, nullptr, 0, OMC_EPI_NONE, 0, 0, stream));
+    if (fold) {
+      omc_gemm_norm nf = norm_in(ssq_a, parts_a);
+      OMC_TRY(omc_gemm_bf16_norm(h, C, d->qkv_w[li], C, qkv, 3LL * C, M, 3 * C, C, nullptr, nullptr, nullptr, 0, OMC_EPI_NONE, 0, 0,
+                                 &nf, stream));
+    } else {
+      OMC_TRY(omc_rmsnorm(h, C, d->norm1[li], xn, C, M, C, d->eps, stream));
+      OMC_TRY(omc_gemm_bf16(xn, C, d->qkv_w[li], C, qkv, 3LL * C, M, 3 * C, C, nullptr, nullptr, nullptr, 0, OMC_EPI_NONE, 0, 0, stream));
+    }
     if (d->qk_norm) {
       OMC_TRY(omc_rmsnorm(qkv, 3LL * C, d->q_norm[li], qkv, 3LL * C, M, C, d->eps, stream));
       OMC_TRY(omc_rmsnorm(qkv + C, 3LL * C, d->k_norm[li], qkv + C, 3LL * C, M, C, d->eps, stream));
     }
     OMC_TRY(omc_attention_fwd(qkv, 3LL * C, qkv + C, 3LL * C, qkv + 2 * C, 3LL * C, attn, C, cu, n_crops, S, rows, d->heads,
                               d->heads, 0, scale, stream));
-    OMC_TRY(omc_gemm_bf16(attn, C, d->proj_w[li], C, h, C, M, C, C, d->proj_b[li], d->ls1[li], h, C, OMC_EPI_RES, 0, 0, stream));
-    OMC_TRY(omc_rmsnorm(h, C, d->norm2[li], xn, C, M, C, d->eps, stream));
-    OMC_TRY(omc_gemm_bf16(xn, C, d->fc1_w[li], C, act, d->inter, M, d->inter, C, d->fc1_b[li], nullptr, nullptr, 0, OMC_EPI_GELU,
-                          0, 0, stream));
-    OMC_TRY(omc_gemm_bf16(act, d->inter, d->fc2_w[li], d->inter, h, C, M, C, d->inter, d->fc2_b[li], d->ls2[li], h, C, OMC_EPI_RES,
-                          0, 0, stream));
+    if (fold) {
+      omc_gemm_norm no = norm_out(ssq_b);
+      OMC_TRY(omc_gemm_bf16_norm(attn, C, d->proj_w[li], C, h, C, M, C, C, d->proj_b[li], d->ls1[li], h, C, OMC_EPI_RES, 0, 0, &no, stream));
+      parts_b = no.ssq_out_parts;
+      omc_gemm_norm nf = norm_in(ssq_b, parts_b);
+      OMC_TRY(omc_gemm_bf16_norm(h, C, d->fc1_w[li], C, act, d->inter, M, d->inter, C, d->fc1_b[li], nullptr, nullptr, 0,
+                                 OMC_EPI_GELU, 0, 0, &nf, stream));
+      omc_gemm_norm no2 = norm_out(ssq_a);
+      OMC_TRY(omc_gemm_bf16_norm(act, d->inter, d->fc2_w[li], d->inter, h, C, M, C, d->inter, d->fc2_b[li], d->ls2[li], h, C,
+                                 OMC_EPI_RES, 0, 0, &no2, stream));
+      parts_a = no2.ssq_out_parts;
+    } else {
+      OMC_TRY(omc_gemm_bf16(attn, C, d->proj_w[li], C, h, C, M, C, C, d->proj_b[li], d->ls1[li], h, C, OMC_EPI_RES, 0, 0, stream));
+      OMC_TRY(omc_rmsnorm(h, C, d->norm2[li], xn, C, M, C, d->eps, stream));
+      OMC_TRY(omc_gemm_bf16(xn, C, d->fc1_w[li], C, act, d->inter, M, d->inter, C, d->fc1_b[li], nullptr, nullptr, 0, OMC_EPI_GELU,
+                            0, 0, stream));
+      OMC_TRY(omc_gemm_bf16(act, d->inter, d->fc2_w[li], d->inter, h, C, M, C, d->inter, d->fc2_b[li], d->ls2[li], h, C, OMC_EPI_RES,
+                            0, 0, stream));
+    }
   }
   // feature select 'patch' (+ pixel shuffle), then the mlp2x_gelu projector (internVIT_encoder.py:35-43, builder.py:54-61)
   OMC_TRY(omc_select_pixel_shuffle(h, sel, n_crops, G, C, down, stream));
@@ -129,12 +165,14 @@ extern "C" long long omc_decoder_prefill_workspace_bytes(const omc_decode_desc* 
   if (d == nullptr || T <= 0 || n_seq <= 0) return -1;
   const long long C = d->hidden, qw = (long long)(d->q_heads + 2 * d->kv_heads) * 128;
   return align256((long long)T * C * 2) + align256((long long)T * qw * 2) + align256((long long)T * d->q_heads * 128 * 2) +
-         align256((long long)T * d->inter * 2) + 2 * align256((long long)n_seq * C * 2) + 256;
+         align256((long long)T * d->inter * 2) + 2 * align256((long long)n_seq * C * 2) +
+         2 * align256((long long)kSsqParts * T * 4) + 256;
 }
 
 extern "C" int omc_decoder_prefill(const omc_decode_desc* d, const float* inv_freq, void* embeds, const int32_t* pos_ids,
                                    const int32_t* seq_ids, const int32_t* cu_seqlens, int n_seq, int T, int max_len,
-                                   const int64_t* last_rows, void* workspace, float* last_logits, void* stream) {
+                                   const int64_t* last_rows, void* workspace, float* last_logits, int norm_folded,
+                                   void* stream) {
   if (d == nullptr || inv_freq == nullptr || embeds == nullptr || workspace == nullptr)
     return set_error(OMC_ERR_ARG, "omc_decoder_prefill: null argument");
   if (T <= 0 || n_seq <= 0) return OMC_OK;
@@ -147,20 +185,54 @@ extern "C" int omc_decoder_prefill(const omc_decode_desc* d, const float* inv_fr
   void* act = cv.take((long long)T * I * 2);
   void* hl = cv.take((long long)n_seq * C * 2);
   void* hn = cv.take((long long)n_seq * C * 2);
+  float* ssq_a = static_cast<float*>(cv.take((long long)kSsqParts * T * 4));
+  float* ssq_b = static_cast<float*>(cv.take((long long)kSsqParts * T * 4));
   void* h = embeds;  // the residual stream is updated in place
+  const bool fold = norm_folded != 0;
+  int parts_a = 1, parts_b = 1;
+  if (fold) OMC_TRY(omc_row_ssq_rows(h, C, T, C, ssq_a, stream));
+  auto norm_in = [&](const float* ssq, int parts) {
+    omc_gemm_norm nf{};
+    nf.ssq_in = ssq; nf.ssq_in_ld = T; nf.ssq_in_parts = parts; nf.norm_dim = C; nf.eps = d->eps;
+    return nf;
+  };
+  auto norm_out = [&](float* ssq) {
+    omc_gemm_norm nf{};
+    nf.ssq_out = ssq; nf.ssq_out_ld = T; nf.ssq_out_max_parts = kSsqParts;
+    return nf;
+  };
   for (int li = 0; li < d->n_layers; ++li) {
     // Qwen2DecoderLayer.forward modeling_qwen2.py:280-310
     __nv_bfloat16* pool = static_cast<__nv_bfloat16*>(d->kv_pool) + (long long)li * d->kv_layer_stride;
-    OMC_TRY(omc_rmsnorm(h, C, d->ln1[li], xn, C, T, C, d->eps, stream));
-    OMC_TRY(omc_gemm_bf16(xn, C, d->qkv_w[li], C, qkv, qw, T, (int)qw, C, d->qkv_b[li], nullptr, nullptr, 0, OMC_EPI_NONE, 0, 0, stream));
+    if (fold) {
+      omc_gemm_norm nf = norm_in(ssq_a, parts_a);
+      OMC_TRY(omc_gemm_bf16_norm(h, C, d->qkv_w[li], C, qkv, qw, T, (int)qw, C, d->qkv_b[li], nullptr, nullptr, 0, OMC_EPI_NONE, 0, 0,
+                                 &nf, stream));
+    } else {
+      OMC_TRY(omc_rmsnorm(h, C, d->ln1[li], xn, C, T, C, d->eps, stream));
+      OMC_TRY(omc_gemm_bf16(xn, C, d->qkv_w[li], C, qkv, qw, T, (int)qw, C, d->qkv_b[li], nullptr, nullptr, 0, OMC_EPI_NONE, 0, 0, stream));
+    }
     OMC_TRY(omc_rope_kv_store(qkv, qw, pos_ids, seq_ids, T, Hq, Hkv, inv_freq, pool, d->block_table, d->max_pages, d->page_size, stream));
     OMC_TRY(omc_attention_fwd(qkv, qw, qkv + (long long)Hq * 128, qw, qkv + (long long)(Hq + Hkv) * 128, qw, attn, (long long)Hq * 128,
                               cu_seqlens, n_seq, max_len, T, Hq, Hkv, 1, d->attn_scale, stream));
-    OMC_TRY(omc_gemm_bf16(attn, (long long)Hq * 128, d->o_w[li], (long long)Hq * 128, h, C, T, C, Hq * 128, nullptr, nullptr, h, C,
-                          OMC_EPI_RES, 0, 0, stream));
-    OMC_TRY(omc_rmsnorm(h, C, d->ln2[li], xn, C, T, C, d->eps, stream));
-    OMC_TRY(omc_gemm_bf16(xn, C, d->gate_up_w[li], C, act, I, T, 2 * I, C, nullptr, nullptr, nullptr, 0, OMC_EPI_SWIGLU, 0, 0, stream));
-    OMC_TRY(omc_gemm_bf16(act, I, d->down_w[li], I, h, C, T, C, I, nullptr, nullptr, h, C, OMC_EPI_RES, 0, 0, stream));
+    if (fold) {
+      omc_gemm_norm no = norm_out(ssq_b);
+      OMC_TRY(omc_gemm_bf16_norm(attn, (long long)Hq * 128, d->o_w[li], (long long)Hq * 128, h, C, T, C, Hq * 128, nullptr, nullptr, h,
+                                 C, OMC_EPI_RES, 0, 0, &no, stream));
+      parts_b = no.ssq_out_parts;
+      omc_gemm_norm nf = norm_in(ssq_b, parts_b);
+      OMC_TRY(omc_gemm_bf16_norm(h, C, d->gate_up_w[li], C, act, I, T, 2 * I, C, nullptr, nullptr, nullptr, 0, OMC_EPI_SWIGLU, 0, 0,
+                                 &nf, stream));
+      omc_gemm_norm no2 = norm_out(ssq_a);
+      OMC_TRY(omc_gemm_bf16_norm(act, I, d->down_w[li], I, h, C, T, C, I, nullptr, nullptr, h, C, OMC_EPI_RES, 0, 0, &no2, stream));
+      parts_a = no2.ssq_out_parts;
+    } else {
+      OMC_TRY(omc_gemm_bf16(attn, (long long)Hq * 128, d->o_w[li], (long long)Hq * 128, h, C, T, C, Hq * 128, nullptr, nullptr, h, C,
+                            OMC_EPI_RES, 0, 0, stream));
+      OMC_TRY(omc_rmsnorm(h, C, d->ln2[li], xn, C, T, C, d->eps, stream));
+      OMC_TRY(omc_gemm_bf16(xn, C, d->gate_up_w[li], C, act, I, T, 2 * I, C, nullptr, nullptr, nullptr, 0, OMC_EPI_SWIGLU, 0, 0, stream));
+      OMC_TRY(omc_gemm_bf16(act, I, d->down_w[li], I, h, C, T, C, I, nullptr, nullptr, h, C, OMC_EPI_RES, 0, 0, stream));
+    }
   }
   if (last_logits != nullptr && last_rows != nullptr) {
     // final norm + lm_head on each sequence's last position (modeling_qwen2.py:411,470-472); the row gather is the

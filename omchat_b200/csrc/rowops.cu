@@ -298,6 +298,28 @@ __global__ void __launch_bounds__(256) rope_kv_store_kernel(bf16* __restrict__ q
   }
 }
 
+// ------------------------------------------------------------------------------------------------ row sums of squares
+// One warp per row: ssq[m] = sum_k x[m,k]^2 (fp32), for the folded RMSNorm of the GEMM that consumes x (omc_gemm_bf16_norm).
+__global__ void __launch_bounds__(256) row_ssq_rows_kernel(const bf16* __restrict__ x, long long ldx, long long rows, int C,
+                                                           float* __restrict__ ssq) {
+  const int lane = threadIdx.x & 31;
+  for (long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); m < rows; m += (long long)gridDim.x * 8) {
+    const bf16* row = x + m * ldx;
+    float s = 0.f;
+    for (int i = lane * 8; i < C; i += 32 * 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(row + i);
+      const uint32_t* a = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack_bf16(a[q]);
+        s += f.x * f.x + f.y * f.y;
+      }
+    }
+    s = warp_sum(s);
+    if (lane == 0) ssq[m] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ argmax
 __device__ __forceinline__ void argmax_merge(float& bv, int& bi, float v, int i) {
   if (v > bv || (v == bv && i < bi)) {
@@ -359,6 +381,13 @@ static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
 }  // namespace omc
 
 using namespace omc;
+
+extern "C" int omc_row_ssq_rows(const void* x, long long ldx, long long rows, int C, float* ssq, void* stream) {
+  if (rows <= 0) return OMC_OK;
+  if (C % 8 != 0 || ldx % 8 != 0) return set_error(OMC_ERR_SHAPE, "omc_row_ssq_rows: C, ldx must be multiples of 8");
+  row_ssq_rows_kernel<<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, rows, C, ssq);
+  return check_launch("row_ssq_rows");
+}
 
 extern "C" int omc_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, int rows, int C,
                            float eps, void* stream) {

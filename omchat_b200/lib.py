@@ -24,6 +24,8 @@ SIGNATURES = {
     "omc_version": (_I, []),
     "omc_num_sms": (_I, []),
     "omc_gemm_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _L, _I, _I, _I, _P]),
+    "omc_gemm_bf16_norm": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _L, _I, _I, _I, _P, _P]),
+    "omc_row_ssq_rows": (_I, [_P, _L, _L, _I, _P, _P]),
     "omc_gemm_skinny_workspace_bytes": (_L, [_I]),
     "omc_gemm_skinny_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _L, _I, _I, _P, _L, _P]),
     "omc_packed_weight_bytes": (_L, [_I, _I]),
@@ -54,7 +56,7 @@ SIGNATURES = {
     "omc_vit_workspace_bytes": (_L, [_P, _I]),
     "omc_vit_forward": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "omc_decoder_prefill_workspace_bytes": (_L, [_P, _I, _I]),
-    "omc_decoder_prefill": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "omc_decoder_prefill": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
     "omc_decode_plan_bytes": (_L, [_I]),
     "omc_decode_workspace_bytes": (_L, [_P]),
     "omc_decode_plan_build": (_I, [_P, _P]),
@@ -202,9 +204,38 @@ def _gemm_autotune(x, w, out, bias, scale, res, epi, out_f32) -> int:
     return best
 
 
+class GemmNorm(ctypes.Structure):
+    """Mirror of `omc_gemm_norm` (include/omchat_b200.h)."""
+    _fields_ = [("ssq_in", c_void_p), ("ssq_in_ld", c_longlong), ("ssq_in_parts", c_int), ("norm_dim", c_int), ("eps", c_float),
+                ("ssq_out_max_parts", c_int), ("ssq_out", c_void_p), ("ssq_out_ld", c_longlong), ("ssq_out_parts", c_int),
+                ("reserved", c_int)]
+
+
+class RowSsq:
+    """Per-row sums of squares of a residual stream, as per-N-tile partials [max_parts, rows] fp32 (+ how many parts the
+    last producer wrote): what an EPI_RES GEMM leaves behind for the folded RMSNorm of the GEMM that reads the rows next."""
+    MAX_PARTS = 32
+
+    def __init__(self, rows: int, device):
+        self.buf = torch.empty(self.MAX_PARTS, rows, device=device, dtype=torch.float32)
+        self.rows, self.parts = rows, 0
+
+    def from_rows(self, x: torch.Tensor):
+        """Rows no GEMM produced (embeddings, all-reduced rows): one warp per row."""
+        _need_cuda(x)
+        assert x.dim() == 2 and x.stride(1) == 1 and x.shape[0] <= self.rows
+        rc = load().omc_row_ssq_rows(_ptr(x), x.stride(0), x.shape[0], x.shape[1], self.buf.data_ptr(), _stream())
+        _check(rc, "omc_row_ssq_rows")
+        self.parts = 1
+        return self
+
+
 def gemm(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, scale=None, res=None,
-         epi: int = EPI_NONE, out_f32: bool = False, tile_cfg: int = 0) -> torch.Tensor:
-    """out[M,N] = epi(x[M,K] @ w[N,K]^T). x/out may be row-strided 2-D views (last dim contiguous)."""
+         epi: int = EPI_NONE, out_f32: bool = False, tile_cfg: int = 0, ssq_in: Optional[RowSsq] = None, norm_dim: int = 0,
+         eps: float = 1e-6, ssq_out: Optional[RowSsq] = None) -> torch.Tensor:
+    """out[M,N] = epi(x[M,K] @ w[N,K]^T). x/out may be row-strided 2-D views (last dim contiguous).
+    ssq_in: the RMSNorm in front of this layer is folded into w's columns; rows are scaled by rsqrt(sum / norm_dim + eps) in
+    the epilogue (omc_gemm_bf16_norm). ssq_out: leave the sums of squares of the rows written for the next such GEMM."""
     _need_cuda(x, w)
     assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1] and x.stride(1) == 1 and w.stride(1) == 1
     M, K = x.shape
@@ -213,6 +244,23 @@ def gemm(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *
     if out is None:
         out = torch.empty(M, n_out, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     assert out.shape == (M, n_out) and out.stride(1) == 1
+    if ssq_in is not None or ssq_out is not None:
+        if tile_cfg == 0 and GEMM_AUTOTUNE and M <= GEMM_AUTOTUNE_MAX_M:
+            tile_cfg = _gemm_autotune(x, w, out, bias, scale, res, epi, out_f32)
+        nf = GemmNorm()
+        if ssq_in is not None:
+            assert ssq_in.parts >= 1 and ssq_in.rows >= M and norm_dim > 0
+            nf.ssq_in, nf.ssq_in_ld, nf.ssq_in_parts, nf.norm_dim, nf.eps = ssq_in.buf.data_ptr(), ssq_in.rows, ssq_in.parts, norm_dim, eps
+        if ssq_out is not None:
+            assert ssq_out.rows >= M
+            nf.ssq_out, nf.ssq_out_ld, nf.ssq_out_max_parts = ssq_out.buf.data_ptr(), ssq_out.rows, RowSsq.MAX_PARTS
+        rc = load().omc_gemm_bf16_norm(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
+                                       _ptr(bias), _ptr(scale), _ptr(res), res.stride(0) if res is not None else 0, epi,
+                                       1 if out_f32 else 0, tile_cfg, ctypes.byref(nf), _stream())
+        _check(rc, "omc_gemm_bf16_norm")
+        if ssq_out is not None:
+            ssq_out.parts = nf.ssq_out_parts
+        return out
     if M <= SKINNY_MAX_M and tile_cfg == 0 and SKINNY_ENABLED:
         ws = _skinny_workspace(x.device, N)
         rc = load().omc_gemm_skinny_bf16(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), M, N, K,
@@ -678,7 +726,7 @@ class VitDesc(ctypes.Structure):
     """Mirror of `omc_vit_desc` (include/omchat_b200.h)."""
     _fields_ = ([(n, ctypes.c_int32) for n in ("n_layers", "hidden", "heads", "inter", "image_size", "patch_size", "patch_k",
                                                  "qk_norm", "pixel_shuffle_down", "proj_hidden")]
-                + [("eps", c_float), ("reserved", ctypes.c_int32)]
+                + [("eps", c_float), ("norm_folded", ctypes.c_int32)]
                 + [(n, c_void_p) for n in ("patch_w", "patch_b", "cls", "pos", "norm1", "qkv_w", "q_norm", "k_norm", "proj_w",
                                            "proj_b", "ls1", "norm2", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2", "p_w0", "p_b0",
                                            "p_w2", "p_b2")])
@@ -688,9 +736,13 @@ class VitForward:
     """omc_vit_forward on a model's weights: the whole encode_images (tower + select / pixel shuffle + projector) as ONE
     C call - what a non-Python host binds. `vit` / `proj` are weights.VitW / ProjW, vc an InternVisionConfig."""
 
-    def __init__(self, vit, proj, vc, pixel_shuffle_down: int = 1):
+    def __init__(self, vit, proj, vc, pixel_shuffle_down: int = 1, folded=None):
+        """folded: [(qkv * norm1, fc1 * norm2)] per layer (InternVITVisionTower._folded()) -> the norm-folded loop the
+        product runs by default; None -> plain weights + stand-alone RMSNorm kernels."""
         n = len(vit.layers)
         d = VitDesc()
+        d.norm_folded = 1 if folded is not None else 0
+        self._folded = folded
         d.n_layers, d.hidden, d.heads, d.inter = n, vc.hidden_size, vc.num_attention_heads, vc.intermediate_size
         d.image_size, d.patch_size, d.patch_k, d.qk_norm = vc.image_size, vc.patch_size, vit.patch_w.shape[1], int(vc.qk_normalization)
         d.pixel_shuffle_down, d.proj_hidden, d.eps = pixel_shuffle_down, proj.w2.shape[0], vc.layer_norm_eps
@@ -699,7 +751,11 @@ class VitForward:
                  "ls1": "ls1", "norm2": "norm2", "fc1_w": "fc1_w", "fc1_b": "fc1_b", "fc2_w": "fc2_w", "fc2_b": "fc2_b", "ls2": "ls2"}
         self._arrays = {}
         for field, attr in names.items():
-            arr = (c_void_p * max(n, 1))(*[getattr(l, attr).data_ptr() for l in vit.layers])
+            if folded is not None and field in ("qkv_w", "fc1_w"):
+                ptrs = [f[0 if field == "qkv_w" else 1].data_ptr() for f in folded]
+            else:
+                ptrs = [getattr(l, attr).data_ptr() for l in vit.layers]
+            arr = (c_void_p * max(n, 1))(*ptrs)
             self._arrays[field] = arr
             setattr(d, field, ctypes.cast(arr, c_void_p))
         d.p_w0, d.p_b0, d.p_w2, d.p_b2 = (t.data_ptr() for t in (proj.w0, proj.b0, proj.w2, proj.b2))
@@ -716,13 +772,13 @@ class VitForward:
         out = torch.empty(n, self.tokens, self.desc.proj_hidden, device=pixels.device, dtype=torch.bfloat16)
         rc = load().omc_vit_forward(ctypes.byref(self.desc), _ptr(pixels), 1 if pixels.dtype == torch.float32 else 0, n,
                                     self._ws.data_ptr(), _ptr(out), _stream())
-        add_launches(4 + self.desc.n_layers * (9 if self.desc.qk_norm else 7) + 3 - 1)
+        add_launches(4 + self.desc.norm_folded + self.desc.n_layers * ((9 if self.desc.qk_norm else 7) - 2 * self.desc.norm_folded) + 3 - 1)
         _check(rc, "omc_vit_forward")
         return out
 
 
 def decoder_prefill(layers, final_norm, lm_head, dims, eps, scale, inv_freq, embeds, pos_ids, seq_ids, cu_seqlens, max_len,
-                    kv_pool, block_table, page_size, last_rows=None):
+                    kv_pool, block_table, page_size, last_rows=None, folded=None):
     """omc_decoder_prefill: embeds [T, C] (updated in place) -> fp32 logits [n_seq, V] of each sequence's last row (None if
     last_rows is None); fills the paged cache. dims = (hidden, q_heads, kv_heads, inter, vocab)."""
     _need_cuda(embeds, pos_ids, seq_ids, cu_seqlens, kv_pool, block_table, inv_freq)
@@ -732,14 +788,19 @@ def decoder_prefill(layers, final_norm, lm_head, dims, eps, scale, inv_freq, emb
     d.hidden, d.q_heads, d.kv_heads, d.inter, d.vocab = dims
     d.page_size, d.max_pages, d.eps, d.attn_scale = page_size, block_table.shape[1], eps, scale
     d.final_norm, d.lm_head = final_norm.data_ptr(), lm_head.data_ptr()
-    arrays = [(c_void_p * max(n_layers, 1))(*[getattr(l, k).data_ptr() for l in layers]) for k in
-              ("ln1", "qkv_w", "qkv_b", "o_w", "ln2", "gate_up_w", "down_w")]
+    def ptrs(k):
+        if folded is not None and k in ("qkv_w", "gate_up_w"):  # [(q|k|v * ln1, gate|up * ln2)] per layer
+            return [f[0 if k == "qkv_w" else 1].data_ptr() for f in folded]
+        return [getattr(l, k).data_ptr() for l in layers]
+
+    arrays = [(c_void_p * max(n_layers, 1))(*ptrs(k)) for k in ("ln1", "qkv_w", "qkv_b", "o_w", "ln2", "gate_up_w", "down_w")]
     (d.ln1, d.qkv_w, d.qkv_b, d.o_w, d.ln2, d.gate_up_w, d.down_w) = [ctypes.cast(a, c_void_p) for a in arrays]
     d.kv_pool, d.kv_layer_stride, d.block_table = kv_pool.data_ptr(), kv_pool.stride(0), block_table.data_ptr()
     ws = torch.empty(load().omc_decoder_prefill_workspace_bytes(ctypes.byref(d), T, n_seq), device=embeds.device, dtype=torch.uint8)
     logits = torch.empty(n_seq, dims[4], device=embeds.device, dtype=torch.float32) if last_rows is not None else None
     rc = load().omc_decoder_prefill(ctypes.byref(d), _ptr(inv_freq), _ptr(embeds), _ptr(pos_ids), _ptr(seq_ids), _ptr(cu_seqlens),
-                                    n_seq, T, max_len, _ptr(last_rows), ws.data_ptr(), _ptr(logits), _stream())
-    add_launches(8 * n_layers + (3 if last_rows is not None else 0) - 1)
+                                    n_seq, T, max_len, _ptr(last_rows), ws.data_ptr(), _ptr(logits), 1 if folded is not None else 0,
+                                    _stream())
+    add_launches((6 if folded is not None else 8) * n_layers + (1 if folded is not None else 0) + (3 if last_rows is not None else 0) - 1)
     _check(rc, "omc_decoder_prefill")
     return logits

@@ -130,6 +130,10 @@ class Qwen2Decoder:
         self.stream_enabled = os.environ.get("OMCHAT_B200_NO_STREAM", "0") != "1"
         self.stream_min_b = int(os.environ.get("OMCHAT_B200_STREAM_MIN_B",
                                                str(STREAM_MIN_B if self.tp.size == 1 else STREAM_MIN_B_TP)))
+        # prefill: RMSNorms folded into the GEMMs that follow them (0 = stand-alone RMSNorm kernels, the round-1 path)
+        self.fold_norms = os.environ.get("OMCHAT_B200_FOLD_NORMS", "1") != "0"
+        self._folded_w = None
+        self._ssq_bufs = None
         self._packed = None  # lazily built packed copies of the decoder weights (csrc/gemm_stream.cu)
         # tp > 1: all-reduce inside the persistent kernel over NVLink peer memory (0 = per-op kernels + NCCL all-reduce)
         self.tp_mega_enabled = os.environ.get("OMCHAT_B200_TP_MEGA", "1") != "0"
@@ -166,13 +170,26 @@ class Qwen2Decoder:
         if self.tp.size > 1:
             torch.distributed.all_reduce(t, group=self.tp.group)
 
-    def _row_parallel(self, x, w, h, use_gemv: bool):
-        """h <- h + x @ w^T summed over TP ranks (o_proj / down_proj; modeling_qwen2.py:245,296,303)."""
+    def _folded_prefill(self):
+        """(q|k|v * input_layernorm, gate|up * post_attention_layernorm) per layer, row-major for the prefill GEMM; built once."""
+        if self._folded_w is None:
+            from .weights import fold_norm
+            self._folded_w = [(fold_norm(l.qkv_w, l.ln1), fold_norm(l.gate_up_w, l.ln2)) for l in self.w.layers]
+        return self._folded_w
+
+    def _prefill_ssq(self, rows: int, device):
+        if self._ssq_bufs is None or self._ssq_bufs[0].rows < rows:
+            self._ssq_bufs = (lib.RowSsq(rows, device), lib.RowSsq(rows, device))
+        return self._ssq_bufs
+
+    def _row_parallel(self, x, w, h, use_gemv: bool, ssq_out=None):
+        """h <- h + x @ w^T summed over TP ranks (o_proj / down_proj; modeling_qwen2.py:245,296,303). ssq_out: leave the
+        rows' sums of squares for the folded RMSNorm of the next GEMM."""
         if self.tp.size == 1:
             if use_gemv:
                 lib.gemv(x, w, out=h, res=h, epi=lib.EPI_RES)
             else:
-                lib.gemm(x, w, out=h, res=h, epi=lib.EPI_RES)
+                lib.gemm(x, w, out=h, res=h, epi=lib.EPI_RES, ssq_out=ssq_out)
             return
         # TP: rank 0 folds the residual into its partial product, then the all-reduce yields the new residual stream
         fold = self.tp.rank == 0
@@ -181,6 +198,8 @@ class Qwen2Decoder:
         else:
             lib.gemm(x, w, out=h, res=h if fold else None, epi=lib.EPI_RES if fold else lib.EPI_NONE)
         self._all_reduce(h)
+        if ssq_out is not None:
+            ssq_out.from_rows(h)
 
     @staticmethod
     def _gemv_ok(B: int, K: int) -> bool:
@@ -239,17 +258,30 @@ class Qwen2Decoder:
         act = torch.empty(T, self.I_local, device=dev, dtype=torch.bfloat16)
         hiddens = [h.clone()] if collect_hidden else None
         max_len = max(lens)
+        fold = self.fold_norms
+        if fold:
+            # input / post-attention RMSNorm folded into the qkv / gate|up GEMMs (omc_gemm_bf16_norm): o_proj / down_proj leave
+            # the rows' sums of squares behind (under tensor parallelism: a row pass after the all-reduce)
+            folded = self._folded_prefill()
+            ssq_a, ssq_b = self._prefill_ssq(T, dev)
+            ssq_a.from_rows(h)
         for li, l in enumerate(self.w.layers):
-            lib.rmsnorm(h, l.ln1, self.eps, out=xn)
-            lib.gemm(xn, l.qkv_w, out=qkv, bias=l.qkv_b)
+            if fold:
+                lib.gemm(h, folded[li][0], out=qkv, bias=l.qkv_b, ssq_in=ssq_a, norm_dim=C, eps=self.eps)
+            else:
+                lib.rmsnorm(h, l.ln1, self.eps, out=xn)
+                lib.gemm(xn, l.qkv_w, out=qkv, bias=l.qkv_b)
             lib.rope_kv_store(qkv, pos_ids, seq_ids, Hq, Hkv, self.inv_freq, cache.pool[li], cache.block_table,
                               cache.page_size)
             lib.attention(qkv[:, :Hq * 128], qkv[:, Hq * 128:(Hq + Hkv) * 128], qkv[:, (Hq + Hkv) * 128:], attn, cu,
                           max_len, Hq, Hkv, True, self.scale)
-            self._row_parallel(attn, l.o_w, h, use_gemv=False)
-            lib.rmsnorm(h, l.ln2, self.eps, out=xn)
-            lib.gemm(xn, l.gate_up_w, out=act, epi=lib.EPI_SWIGLU)
-            self._row_parallel(act, l.down_w, h, use_gemv=False)
+            self._row_parallel(attn, l.o_w, h, use_gemv=False, ssq_out=ssq_b if fold else None)
+            if fold:
+                lib.gemm(h, folded[li][1], out=act, epi=lib.EPI_SWIGLU, ssq_in=ssq_b, norm_dim=C, eps=self.eps)
+            else:
+                lib.rmsnorm(h, l.ln2, self.eps, out=xn)
+                lib.gemm(xn, l.gate_up_w, out=act, epi=lib.EPI_SWIGLU)
+            self._row_parallel(act, l.down_w, h, use_gemv=False, ssq_out=ssq_a if fold else None)
             if collect_hidden:
                 hiddens.append(h.clone())
         if slots is None:

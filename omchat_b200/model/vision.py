@@ -8,13 +8,14 @@ All activations are bf16 [rows, C] with rows = crops * (patches + 1); the residu
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 
 from .. import lib
 from ..config import OmChatQwen2Config
-from .weights import ProjW, VitW
+from .weights import ProjW, VitW, fold_norm
 
 
 class InternVITVisionTower:
@@ -31,6 +32,10 @@ class InternVITVisionTower:
         self.image_processor = None  # CPU preprocessing (CLIPImageProcessor) is outside the hot path
         self.max_crops_per_pass = 64
         self._cu_cache = {}
+        # norm1 / norm2 folded into the GEMMs that follow them (0 = stand-alone RMSNorm kernels, the round-1 path)
+        self.fold_norms = os.environ.get("OMCHAT_B200_FOLD_NORMS", "1") != "0"
+        self._folded_w = None
+        self._ssq_bufs = None
 
     def load_model(self):
         if self.w is None:
@@ -86,6 +91,25 @@ class InternVITVisionTower:
         act = torch.empty(rows, vc.intermediate_size, device=h.device, dtype=torch.bfloat16)
         scale = (C // H) ** -0.5
         eps = vc.layer_norm_eps
+        if self.fold_norms:
+            # norm1 / norm2 folded into the qkv / fc1 GEMMs (omc_gemm_bf16_norm): the residual epilogues of proj / fc2 leave
+            # the rows' sums of squares behind, the next GEMM scales its rows by rstd - no stand-alone RMSNorm pass
+            folded = self._folded()
+            ssq_a, ssq_b = self._ssq(rows, h.device)
+            ssq_a.from_rows(h)
+            for li in range(n_layers):
+                l, (qkv_f, fc1_f) = w.layers[li], folded[li]
+                lib.gemm(h, qkv_f, out=qkv, ssq_in=ssq_a, norm_dim=C, eps=eps)
+                if vc.qk_normalization:
+                    lib.rmsnorm(qkv[:, :C], l.q_norm, eps, out=qkv[:, :C])
+                    lib.rmsnorm(qkv[:, C:2 * C], l.k_norm, eps, out=qkv[:, C:2 * C])
+                lib.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], attn, cu, S, H, H, False, scale)
+                lib.gemm(attn, l.proj_w, out=h, bias=l.proj_b, scale=l.ls1, res=h, epi=lib.EPI_RES, ssq_out=ssq_b)
+                lib.gemm(h, fc1_f, out=act, bias=l.fc1_b, epi=lib.EPI_GELU, ssq_in=ssq_b, norm_dim=C, eps=eps)
+                lib.gemm(act, l.fc2_w, out=h, bias=l.fc2_b, scale=l.ls2, res=h, epi=lib.EPI_RES, ssq_out=ssq_a)
+                if collect:
+                    states.append(h.clone())
+            return (h, states) if collect else h
         for li in range(n_layers):
             l = w.layers[li]
             lib.rmsnorm(h, l.norm1, eps, out=xn)
@@ -101,6 +125,17 @@ class InternVITVisionTower:
             if collect:
                 states.append(h.clone())
         return (h, states) if collect else h
+
+    def _folded(self):
+        """(qkv * norm1, fc1 * norm2) per layer, built once (6.5 GB more for InternViT-6B)."""
+        if self._folded_w is None:
+            self._folded_w = [(fold_norm(l.qkv, l.norm1), fold_norm(l.fc1_w, l.norm2)) for l in self.w.layers]
+        return self._folded_w
+
+    def _ssq(self, rows: int, device):
+        if self._ssq_bufs is None or self._ssq_bufs[0].rows < rows:
+            self._ssq_bufs = (lib.RowSsq(rows, device), lib.RowSsq(rows, device))
+        return self._ssq_bufs
 
     @torch.no_grad()
     def __call__(self, images: torch.Tensor, pixel_shuffle_down: int = 1) -> torch.Tensor:

@@ -55,6 +55,12 @@ def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     return torch.stack([gate, up], dim=1).reshape(2 * I, K)
 
 
+def fold_norm(w: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """W'[n, k] = W[n, k] * g[k]: the RMSNorm weight in front of a linear layer folded into its columns (fp32 product, one
+    bf16 rounding). The GEMM then runs on the raw residual stream and scales rows by rstd in its epilogue."""
+    return (w.float() * g.float()[None, :]).to(torch.bfloat16).contiguous()
+
+
 @dataclass
 class VitLayerW:
     norm1: torch.Tensor

@@ -110,6 +110,43 @@ def test_gemm_swiglu(L, cg):
     assert_close(out, want, what="swiglu")
 
 
+@pytest.mark.parametrize("bn,cg", GEMM_CFGS)
+@pytest.mark.parametrize("M,C,N2", [(300, 1920, 768), (1025, 3200, 1280), (77, 256, 512)])
+def test_gemm_folded_rmsnorm(L, bn, cg, M, C, N2):
+    """RMSNorm folded into the GEMM that follows it (omc_gemm_bf16_norm): an EPI_RES GEMM writes the residual rows and
+    their sums of squares (one fp32 partial per N tile, of the bf16 values stored), the next GEMM runs on the raw rows with
+    W * g and scales row m by rsqrt(sum / C + eps) in its epilogue. Reference: InternRMSNorm / Qwen2RMSNorm + Linear of the
+    oracle in fp32 on the same bf16 inputs (the norm-weight rounding moves from the activations into W': 2^-6)."""
+    from omchat_b200.model.weights import fold_norm
+    g = torch.Generator().manual_seed(M + C + bn)
+    x = bf(torch.randn(M, 512, generator=g)).cuda()
+    w1 = bf(torch.randn(C, 512, generator=g) * 0.05).cuda()
+    res = bf(torch.randn(M, C, generator=g)).cuda()
+    ls = bf(torch.randn(C, generator=g) * 0.05 + 0.1).cuda()
+    gw = bf(torch.randn(C, generator=g) * 0.1 + 1.0).cuda()
+    w2 = bf(torch.randn(N2, C, generator=g) * 0.05).cuda()
+    b2 = bf(torch.randn(N2, generator=g)).cuda()
+    cfg = bn | (cg << 16)
+    ssq = L.RowSsq(M + 5, "cuda")
+    h = res.clone()
+    L.gemm(x, w1, out=h, scale=ls, res=h, epi=L.EPI_RES, tile_cfg=cfg, ssq_out=ssq)
+    assert ssq.parts == (C + bn - 1) // bn
+    assert_close(h, res.float().cpu() + ls.float().cpu() * ref_linear(x, w1), what="res rows")
+    got_ssq = ssq.buf[:ssq.parts, :M].sum(0).cpu()
+    assert torch.allclose(got_ssq, h.float().pow(2).sum(-1).cpu(), rtol=1e-4), "sums of squares of the rows actually written"
+    y = L.gemm(h, fold_norm(w2, gw), bias=b2, epi=L.EPI_GELU, tile_cfg=cfg, ssq_in=ssq, norm_dim=C, eps=1e-6)
+    want = torch.nn.functional.gelu(ref_linear(O.rms_norm(h.cpu(), gw.cpu(), 1e-6), w2, b2))
+    assert_close(y, want, rel=2 ** -6, what="folded rmsnorm + gelu")
+    ssq1 = L.RowSsq(M, "cuda").from_rows(h)
+    assert ssq1.parts == 1 and torch.allclose(ssq1.buf[0, :M].cpu(), got_ssq, rtol=1e-4)
+    if bn == 256 and N2 % 16 == 0:  # SwiGLU reads the folded norm too (Qwen2 post-attention norm -> gate|up)
+        w2f = fold_norm(w2, gw)
+        y2 = L.gemm(h, w2f, epi=L.EPI_SWIGLU, tile_cfg=cfg, ssq_in=ssq1, norm_dim=C, eps=1e-6)
+        xn = O.rms_norm(h.cpu(), gw.cpu(), 1e-6)
+        want2 = torch.nn.functional.silu(ref_linear(xn, w2[0::2])) * ref_linear(xn, w2[1::2])
+        assert_close(y2, want2, rel=2 ** -6, what="folded rmsnorm + swiglu")
+
+
 @pytest.mark.parametrize("M", [1, 9, 16, 17, 32, 33, 64])
 @pytest.mark.parametrize("N,K", [(256, 64), (3584, 1792), (1000, 4104), (37888 // 8, 512)])
 def test_gemm_skinny(L, M, N, K):
