@@ -49,12 +49,13 @@ def load_peaks():
 
 def load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one decode_mega_kernel launch from the committed ncu --set full
-    capture (profiles/r01_mega_traffic.json); None if the capture is absent."""
-    p = os.path.join(ROOT, "profiles", "r01_mega_traffic.json")
-    try:
-        return json.load(open(p))["traffic_bytes_per_launch"]
-    except Exception:
-        return None
+    capture (profiles/r02_mega_traffic.json, from profiles/r02_ncu_mega.txt); None if the capture is absent."""
+    for name in ("r02_mega_traffic.json", "r01_mega_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))["traffic_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
 
 
 # --------------------------------------------------------------------------------------------------- clocks sampler
