@@ -470,6 +470,21 @@ def main():
                             "share_of_decode_step": gv["train_ms"] / (dec_ms / (new_tokens - 1)),
                             "decode_step_frac_of_hbm_peak": (gv["bytes_per_launch"] * gv["launches"]) /
                             (dec_ms / (new_tokens - 1) * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    # tensor side of the SAME timed step: algorithmic FLOPs of the c2 ViT + projector + prefill phase over
+    # its measured time - the number to quote for c2 (the probe below runs the ViT GEMM shapes at 8 crops instead)
+    vc = cfg.vision_config
+    Sv, Cv, Iv = vc.num_patches + 1, vc.hidden_size, vc.intermediate_size
+    down = cfg.pixel_shuffle_down
+    flop_vit = vc.num_hidden_layers * (2.0 * Sv * (4 * Cv * Cv + 2 * Cv * Iv) + 4.0 * Sv * Sv * Cv) + 2.0 * vc.num_patches * 588 * Cv
+    flop_proj = 2.0 * L * (Cv * down * down * cfg.hidden_size + cfg.hidden_size ** 2)
+    p_mm = sum(l.qkv_w.numel() + l.o_w.numel() + l.gate_up_w.numel() + l.down_w.numel() for l in dec.w.layers)
+    flop_prefill = 2.0 * p_mm * T + 2.0 * len(dec.w.layers) * dec.Hq * 128 * T * T + 2.0 * dec.w.lm_head.numel()
+    tf_phase = (flop_vit + flop_proj + flop_prefill) / (vp_ms * 1e-3) / 1e12
+    line["roofline_tensor_c2_phase"] = {
+        "bound": "tensor", "kernel": "ViT + projector + prefill phase of the timed request (tcgen05 GEMMs + attention, per GPU)",
+        "achieved": tf_phase, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": tf_phase / peaks["bf16_tflops_sustained"], "flops_per_step": flop_vit + flop_proj + flop_prefill,
+        "phase_ms": vp_ms, "peak_source": peaks["source"] + " (bf16_tflops_sustained)"}
     gm = probe_gemm_roofline(model, torch, lib)
     if gm:
         line["roofline_tensor"] = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256,2>", "achieved": gm["tflops"],

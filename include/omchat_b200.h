@@ -95,6 +95,10 @@ int omc_gemv_bf16(const void* x, long long ldx, const void* W, long long ldw, vo
 int omc_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, int rows, int C, float eps,
                 void* stream);
 
+/* In place on two adjacent C-wide column segments of every row - x[m, 0:C] with w_a, x[m, C:2C] with w_b - in ONE launch:
+ * InternAttention's q_norm / k_norm over all heads flattened (modeling_intern_vit.py:143-146) on the packed qkv rows. */
+int omc_rmsnorm_pair(void* x, long long ldx, const void* w_a, const void* w_b, int rows, int C, float eps, void* stream);
+
 /* ---- vision tower glue -----------------------------------------------------------------------------------------
  * im2col for the 14x14/stride-14 patch conv (modeling_intern_vit.py:73-75,92): pixels [B,3,H,W] (fp32 if
  * pixels_are_f32 else bf16) -> cols [B*(H/14)*(W/14), ldc] bf16, column index = c*196 + ky*14 + kx (the conv weight's

@@ -127,8 +127,12 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
       OMC_TRY(omc_gemm_bf16(xn, C, d->qkv_w[li], C, qkv, 3LL * C, M, 3 * C, C, nullptr, nullptr, nullptr, 0, OMC_EPI_NONE, 0, 0, stream));
     }
     if (d->qk_norm) {
-      OMC_TRY(omc_rmsnorm(qkv, 3LL * C, d->q_norm[li], qkv, 3LL * C, M, C, d->eps, stream));
-      OMC_TRY(omc_rmsnorm(qkv + C, 3LL * C, d->k_norm[li], qkv + C, 3LL * C, M, C, d->eps, stream));
+      if (fold) {
+        OMC_TRY(omc_rmsnorm_pair(qkv, 3LL * C, d->q_norm[li], d->k_norm[li], M, C, d->eps, stream));
+      } else {
+        OMC_TRY(omc_rmsnorm(qkv, 3LL * C, d->q_norm[li], qkv, 3LL * C, M, C, d->eps, stream));
+        OMC_TRY(omc_rmsnorm(qkv + C, 3LL * C, d->k_norm[li], qkv + C, 3LL * C, M, C, d->eps, stream));
+      }
     }
     OMC_TRY(omc_attention_fwd(qkv, 3LL * C, qkv + C, 3LL * C, qkv + 2 * C, 3LL * C, attn, C, cu, n_crops, S, rows, d->heads,
                               d->heads, 0, scale, stream));

@@ -18,13 +18,17 @@ typedef __nv_bfloat16 bf16;
 constexpr int kNormThreads = 128;
 constexpr int kNormMaxVec = 4;  // 4 * 128 threads * 8 elements = 4096 channels
 
+// segs = 2: every row holds TWO independent C-wide segments side by side (q | k of the ViT's packed qkv rows), normalised
+// with w and w2 in one launch (InternAttention q_norm / k_norm, modeling_intern_vit.py:143-146).
 __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const bf16* __restrict__ x, long long ldx,
-                                                               const bf16* __restrict__ w, bf16* __restrict__ out,
-                                                               long long ldo, int rows, int C, float eps) {
+                                                               const bf16* __restrict__ w, const bf16* __restrict__ w2,
+                                                               bf16* __restrict__ out, long long ldo, int rows, int C,
+                                                               float eps, int segs) {
   __shared__ float red[kNormThreads / 32];
   const int nvec = C >> 3;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  for (int vrow = blockIdx.x; vrow < rows * segs; vrow += gridDim.x) {
+    const int row = vrow / segs, seg = vrow - row * segs;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx + (long long)seg * C);
     uint4 v[kNormMaxVec];
     float ss = 0.f;
 #pragma unroll
@@ -44,8 +48,8 @@ __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const bf16* __res
     for (int i = 0; i < kNormThreads / 32; ++i) tot += red[i];
     __syncthreads();
     const float rstd = rsqrtf(tot / (float)C + eps);
-    uint4* orow = reinterpret_cast<uint4*>(out + (long long)row * ldo);
-    const uint4* wv = reinterpret_cast<const uint4*>(w);
+    uint4* orow = reinterpret_cast<uint4*>(out + (long long)row * ldo + (long long)seg * C);
+    const uint4* wv = reinterpret_cast<const uint4*>(seg == 0 ? w : w2);
 #pragma unroll
     for (int j = 0; j < kNormMaxVec; ++j) {
       int i = threadIdx.x + j * kNormThreads;
@@ -396,9 +400,22 @@ extern "C" int omc_rmsnorm(const void* x, long long ldx, const void* w, void* ou
     return set_error(OMC_ERR_SHAPE, "omc_rmsnorm: C must be a multiple of 8 and <= 4096");
   if (ldx % 8 != 0 || ldo % 8 != 0) return set_error(OMC_ERR_ALIGN, "omc_rmsnorm: leading dims must be multiples of 8");
   int grid = rows < num_sms() * 16 ? rows : num_sms() * 16;
-  rmsnorm_kernel<<<grid, kNormThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)out, ldo,
-                                                                   rows, C, eps);
+  rmsnorm_kernel<<<grid, kNormThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, nullptr, (bf16*)out,
+                                                                   ldo, rows, C, eps, 1);
   return check_launch("rmsnorm");
+}
+
+extern "C" int omc_rmsnorm_pair(void* x, long long ldx, const void* w_a, const void* w_b, int rows, int C, float eps,
+                                void* stream) {
+  if (rows <= 0) return OMC_OK;
+  if (C <= 0 || C % 8 != 0 || C > kNormThreads * kNormMaxVec * 8)
+    return set_error(OMC_ERR_SHAPE, "omc_rmsnorm_pair: C must be a multiple of 8 and <= 4096");
+  if (ldx % 8 != 0 || ldx < 2LL * C) return set_error(OMC_ERR_ALIGN, "omc_rmsnorm_pair: ldx must be a multiple of 8 and >= 2 C");
+  const long long v = 2LL * rows;
+  int grid = v < (long long)num_sms() * 16 ? (int)v : num_sms() * 16;
+  rmsnorm_kernel<<<grid, kNormThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w_a, (const bf16*)w_b,
+                                                                   (bf16*)x, ldx, rows, C, eps, 2);
+  return check_launch("rmsnorm_pair");
 }
 
 extern "C" int omc_vit_im2col(const void* pixels, int pixels_are_f32, void* cols, long long ldc, int B, int H, int W,

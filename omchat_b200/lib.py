@@ -38,6 +38,7 @@ SIGNATURES = {
     "omc_gemm_stream_set_debug": (_I, [_P]),
     "omc_gemv_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _L, _I, _I, _P]),
     "omc_rmsnorm": (_I, [_P, _L, _P, _P, _L, _I, _I, _F, _P]),
+    "omc_rmsnorm_pair": (_I, [_P, _L, _P, _P, _I, _I, _F, _P]),
     "omc_vit_im2col": (_I, [_P, _I, _P, _L, _I, _I, _I, _P]),
     "omc_vit_assemble": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "omc_select_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _P]),
@@ -393,6 +394,15 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Te
                             _stream())
     _check(rc, "omc_rmsnorm")
     return out
+
+
+def rmsnorm_pair(x: torch.Tensor, w_a: torch.Tensor, w_b: torch.Tensor, C: int, eps: float) -> torch.Tensor:
+    """In place: x[:, :C] normalised with w_a, x[:, C:2C] with w_b (q_norm / k_norm on packed qkv rows), one launch."""
+    _need_cuda(x, w_a, w_b)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.shape[1] >= 2 * C
+    rc = load().omc_rmsnorm_pair(_ptr(x), x.stride(0), _ptr(w_a), _ptr(w_b), x.shape[0], C, eps, _stream())
+    _check(rc, "omc_rmsnorm_pair")
+    return x
 
 
 def vit_im2col(pixels: torch.Tensor, ldc: int = 640) -> torch.Tensor:
@@ -772,7 +782,8 @@ class VitForward:
         out = torch.empty(n, self.tokens, self.desc.proj_hidden, device=pixels.device, dtype=torch.bfloat16)
         rc = load().omc_vit_forward(ctypes.byref(self.desc), _ptr(pixels), 1 if pixels.dtype == torch.float32 else 0, n,
                                     self._ws.data_ptr(), _ptr(out), _stream())
-        add_launches(4 + self.desc.norm_folded + self.desc.n_layers * ((9 if self.desc.qk_norm else 7) - 2 * self.desc.norm_folded) + 3 - 1)
+        per_layer = 7 + (2 if self.desc.qk_norm else 0) - (2 + (1 if self.desc.qk_norm else 0)) * self.desc.norm_folded
+        add_launches(4 + self.desc.norm_folded + self.desc.n_layers * per_layer + 3 - 1)
         _check(rc, "omc_vit_forward")
         return out
 

@@ -101,8 +101,7 @@ class InternVITVisionTower:
                 l, (qkv_f, fc1_f) = w.layers[li], folded[li]
                 lib.gemm(h, qkv_f, out=qkv, ssq_in=ssq_a, norm_dim=C, eps=eps)
                 if vc.qk_normalization:
-                    lib.rmsnorm(qkv[:, :C], l.q_norm, eps, out=qkv[:, :C])
-                    lib.rmsnorm(qkv[:, C:2 * C], l.k_norm, eps, out=qkv[:, C:2 * C])
+                    lib.rmsnorm_pair(qkv, l.q_norm, l.k_norm, C, eps)
                 lib.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], attn, cu, S, H, H, False, scale)
                 lib.gemm(attn, l.proj_w, out=h, bias=l.proj_b, scale=l.ls1, res=h, epi=lib.EPI_RES, ssq_out=ssq_b)
                 lib.gemm(h, fc1_f, out=act, bias=l.fc1_b, epi=lib.EPI_GELU, ssq_in=ssq_b, norm_dim=C, eps=eps)
