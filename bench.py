@@ -148,16 +148,7 @@ def _finish(torch, dist):
 
 def _release_decoder(dec):
     """Drop the captured decode graphs / plans and close the peer exchange buffers of a decoder."""
-    for st in dec._dec.values():
-        st.graphs.clear()
-        st.plans.clear()
-    dec._dec.clear()
-    for px in dec._xchg.values():
-        px.close()
-    dec._xchg.clear()
-    if getattr(dec, "_stream_xchg", None) is not None:
-        dec._stream_xchg.close()
-        dec._stream_xchg = None
+    dec.release()
 
 
 # --------------------------------------------------------------------------------------------------- reference arm

@@ -205,6 +205,22 @@ class Qwen2Decoder:
     def _gemv_ok(B: int, K: int) -> bool:
         return B <= GEMV_MAX_B and B * K * 2 <= GEMV_MAX_SMEM
 
+    def release(self):
+        """Drop what references the process group / peer mappings: captured decode graphs (they hold NCCL work under tensor
+        parallelism), persistent-kernel plans, CUDA-IPC exchange buffers. Call on every rank before
+        torch.distributed.destroy_process_group() - tearing the communicator down under live graphs hangs."""
+        for st in self._dec.values():
+            st.graphs.clear()
+            st.plans.clear()
+        self._dec.clear()
+        for px in self._xchg.values():
+            px.close()
+        self._xchg.clear()
+        if self._stream_xchg is not None:
+            self._stream_xchg.close()
+            self._stream_xchg = None
+        self._caches.clear()
+
     # ------------------------------------------------------------------------------------------------ packed weights
     class _Packed:
         pass

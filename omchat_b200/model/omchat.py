@@ -130,6 +130,11 @@ class OmChatQwen2ForCausalLM:
     def eval(self):
         return self
 
+    def close(self):
+        """Release captured graphs and peer memory (see Qwen2Decoder.release); under tensor parallelism call it on every
+        rank before destroy_process_group()."""
+        self.model.decoder.release()
+
     def to(self, *a, **k):
         return self
 
