@@ -32,13 +32,17 @@
 //    layer disappear. (The reference rounds the normalised row to 16 bit before it multiplies by g; here the rounding
 //    happens in W' instead - covered by the stated tolerance, see tests/test_kernels_gpu.py::test_gemm_stream.)
 //  * TENSOR-PARALLEL ALL-REDUCE INSIDE THE EPILOGUE (row-parallel o_proj / down_proj under tp_size 2..8, one process per
-//    GPU). The owner CTA of an output tile pushes its fp32 partial tile straight into every peer's exchange buffer over
-//    NVLink (buffers mapped with CUDA IPC: omc_peer_alloc / omc_peer_open), publishes a flag with release.sys, polls the
-//    flags the peers set in ITS buffer, and sums the tp_size partials in rank order - so every GPU ends up with the same
-//    bits of the new residual stream, the residual add and the sums of squares for the next folded RMSNorm happen in the same
-//    epilogue, and no NCCL kernel (nor a stand-alone add / norm pass) sits between two GEMMs of a decode step. One buffer per
-//    op kind ("channel": o_proj, down_proj): a producer can only come back to a slot after it has consumed, through the
-//    other channel, data its peer sent AFTER reading that slot; the consumer clears the flags it has read.
+//    GPU). The owner CTA of an output tile pushes its partial tile straight into every peer's exchange buffer over NVLink
+//    (buffers mapped with CUDA IPC: omc_peer_alloc / omc_peer_open) as FLAG-IN-DATA packets - 8 bytes = two bf16 values + a
+//    32-bit generation tag, the unit NVLink delivers atomically - then polls the packets the peers write into ITS buffer until
+//    they carry this use's tag, and sums the tp_size partials in rank order in fp32 (its own one rounded to bf16 like the
+//    ones that travelled), so every GPU ends up with the same bits of the new residual stream; the residual add and the sums
+//    of squares for the next folded RMSNorm happen in the same epilogue, and no NCCL kernel (nor a stand-alone add / norm
+//    pass) sits between two GEMMs of a decode step. No fence, no separate flag: the first version (fp32 tile + release.sys
+//    flag) spent 5-9 us per exchange waiting for 16 KB of peer stores to be acknowledged before the flag could go out.
+//    The tag is a per-(channel, tile) use counter every rank keeps in its own buffer (all ranks run the same launch
+//    sequence, so the counters agree). One buffer per op kind ("channel": o_proj, down_proj): a producer can only come back
+//    to a slot after it has consumed, through the other channel, data its peer sent AFTER reading that slot.
 // Epilogues: bias, erf-GELU, +residual, SwiGLU on interleaved gate/up rows (adjacent lanes), fp32 output.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -430,49 +434,41 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
           epi_barrier();
         }
         if (et == 0) ST_STAMP(6);
+        unsigned int xtag = 0;
         if (owner && p.tp_size > 1) {
-          // ---- tensor-parallel exchange: local sum of the K parts -> own staging tile + every peer's buffer over NVLink
+          // ---- tensor-parallel exchange: local sum of the K parts -> bf16 + tag packets into every peer's buffer over NVLink
           const uint32_t stage_addr0 = smem_u32(stage_f);
           const size_t slot_me = x_slot(p.tp_channel, p.tp_rank, (int)tile);
+          // this use's tag = the slot's use counter + 1 (kept in this rank's own buffer; equal on all ranks)
+          xtag = __ldcg(reinterpret_cast<const unsigned int*>(p.xbuf[p.tp_rank] + kXFlagsOffset) + slot_me) + 1u;
 #pragma unroll
           for (int i = 0; i < kIters; ++i) {
             const int c = i * 128 + et, m = c >> 4, n8 = (c & 15) * 8;
             float4 a = *reinterpret_cast<const float4*>(stage_f + m * 128 + n8);
             float4 b4 = *reinterpret_cast<const float4*>(stage_f + m * 128 + n8 + 4);
             if (cluster_mode) st_dsmem_add8(stage_addr0 + (uint32_t)(m * 128 + n8) * 4u, p.splitk, a, b4);
-            *reinterpret_cast<float4*>(stage_f + m * 128 + n8) = a;  // each chunk is read and written by this thread only
-            *reinterpret_cast<float4*>(stage_f + m * 128 + n8 + 4) = b4;
+            const uint32_t p0 = pack_bf16(a.x, a.y), p1 = pack_bf16(a.z, a.w), p2 = pack_bf16(b4.x, b4.y), p3 = pack_bf16(b4.z, b4.w);
+            // own contribution = the same bf16-rounded values the peers receive (each chunk is touched by this thread only)
+            const float2 r0 = unpack_bf16(p0), r1 = unpack_bf16(p1), r2 = unpack_bf16(p2), r3 = unpack_bf16(p3);
+            *reinterpret_cast<float4*>(stage_f + m * 128 + n8) = make_float4(r0.x, r0.y, r1.x, r1.y);
+            *reinterpret_cast<float4*>(stage_f + m * 128 + n8 + 4) = make_float4(r2.x, r2.y, r3.x, r3.y);
             if (m < p.M) {
               for (int r = 0; r < p.tp_size; ++r) {
                 if (r == p.tp_rank) continue;
-                float* dst = reinterpret_cast<float*>(p.xbuf[r] + slot_me * kXPayload) + m * 128 + n8;
-                *reinterpret_cast<float4*>(dst) = a;
-                *reinterpret_cast<float4*>(dst + 4) = b4;
+                uint4* dst = reinterpret_cast<uint4*>(p.xbuf[r] + slot_me * kXPayload + (size_t)(m * 128 + n8) * 4);
+                asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(p0), "r"(xtag), "r"(p1), "r"(xtag)
+                             : "memory");
+                asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 1), "r"(p2), "r"(xtag), "r"(p3), "r"(xtag)
+                             : "memory");
               }
             }
           }
-          // the CTA barrier orders every thread's peer stores before the flag writers; their release at system scope is
-          // cumulative, so one release store per peer publishes the whole tile (no per-thread system fence)
-          if (p.tp_fence_all) __threadfence_system();
-          epi_barrier();
-          if (et < p.tp_size && et != p.tp_rank)
-            st_release_sys_u32(reinterpret_cast<unsigned int*>(p.xbuf[et] + kXFlagsOffset) + slot_me, 1u);
           if (et == 0) ST_STAMP(8);
         }
         if (cluster_mode && p.tp_size > 1) {
           // the K parts of this GPU are summed: the other CTAs of the cluster may retire while the exchange is in flight
           __syncwarp();
           cluster_sync_all();
-        }
-        if (owner && p.tp_size > 1) {
-          unsigned int* my_flags = reinterpret_cast<unsigned int*>(p.xbuf[p.tp_rank] + kXFlagsOffset);
-          if (et < p.tp_size && et != p.tp_rank) {
-            StWatchdog wd;
-            while (ld_acquire_sys_u32(my_flags + x_slot(p.tp_channel, et, (int)tile)) == 0u)
-              wd.tick(p.dbg, 2 + 16 * p.tp_rank, (int)tile, et, p.tp_channel);
-          }
-          epi_barrier();
-          if (et == 0) ST_STAMP(9);
         }
         if (owner || dist) {
           // ---- phase 2
@@ -505,11 +501,26 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
                 if (r == p.tp_rank) {
                   a = make_float4(v[0], v[1], v[2], v[3]);
                   b4 = make_float4(v[4], v[5], v[6], v[7]);
+                } else if (m_raw < p.M) {
+                  // a peer's chunk = 4 packets {bf16 x 2, tag}: poll until all four carry this use's tag
+                  const uint4* src = reinterpret_cast<const uint4*>(p.xbuf[p.tp_rank] + x_slot(p.tp_channel, r, (int)tile) * kXPayload +
+                                                                    (size_t)(m * 128 + n8) * 4);
+                  uint4 q0, q1;
+                  StWatchdog wd;
+                  while (true) {
+                    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w) : "l"(src) : "memory");
+                    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w) : "l"(src + 1) : "memory");
+                    if (q0.y == xtag && q0.w == xtag && q1.y == xtag && q1.w == xtag) break;
+                    wd.tick(p.dbg, 2 + 16 * p.tp_rank, (int)tile, r, p.tp_channel);
+                  }
+                  const float2 r0 = unpack_bf16(q0.x), r1 = unpack_bf16(q0.z), r2 = unpack_bf16(q1.x), r3 = unpack_bf16(q1.z);
+                  a = make_float4(r0.x, r0.y, r1.x, r1.y);
+                  b4 = make_float4(r2.x, r2.y, r3.x, r3.y);
                 } else {
-                  const float* src = reinterpret_cast<const float*>(p.xbuf[p.tp_rank] + x_slot(p.tp_channel, r, (int)tile) * kXPayload) +
-                                     m * 128 + n8;
-                  a = m < p.M ? __ldcg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                  b4 = m < p.M ? __ldcg(reinterpret_cast<const float4*>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  a = make_float4(0.f, 0.f, 0.f, 0.f);
+                  b4 = a;
                 }
                 s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w; s[4] += b4.x; s[5] += b4.y; s[6] += b4.z; s[7] += b4.w;
               }
@@ -565,10 +576,11 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmX, const StreamParams p
           }
         }
         if (owner && p.tp_size > 1) {
-          // every thread has read the peers' partial tiles: clear the flags for the next use of this channel
+          if (et == 0) ST_STAMP(9);
+          // every thread holds its copy of the tag: advance this slot's use counter for the next launch on this channel
           epi_barrier();
-          if (et < p.tp_size && et != p.tp_rank)
-            reinterpret_cast<unsigned int*>(p.xbuf[p.tp_rank] + kXFlagsOffset)[x_slot(p.tp_channel, et, (int)tile)] = 0u;
+          if (et == 0)
+            reinterpret_cast<unsigned int*>(p.xbuf[p.tp_rank] + kXFlagsOffset)[x_slot(p.tp_channel, p.tp_rank, (int)tile)] = xtag;
         }
         if (cluster_mode && p.tp_size <= 1) {
           // the other parts may only retire (and give up their staging tiles) once the owner has read them

@@ -4,8 +4,8 @@ the pytest process).
 
 The tp "ranks" live in ONE process on ONE GPU: each is a host thread with its own CUDA stream driving the product's own
 Qwen2Decoder on its Megatron shard of the same seed-0 full-width weights; their exchange buffers are plain device buffers of
-this process, so the cross-"GPU" protocol (partial tiles pushed into every peer's buffer, release / acquire flags at system
-scope, sums in rank order, flags cleared by the consumer) is exactly the one that runs over NVLink between processes.
+this process, so the cross-"GPU" protocol (partial tiles pushed into every peer's buffer as {bf16 x 2, tag} packets, polling
+for the tag of this use, sums in rank order) is exactly the one that runs over NVLink between processes.
 Programmatic dependent launch is switched off here: on ONE GPU the early-launched next kernel of rank 0 could take the SM
 slots rank 1's exchange partner needs (on separate GPUs that cannot happen).
 
@@ -93,9 +93,9 @@ def kernel_level(tp: int):
     assert err <= 2 ** -6, err
     got = ssqs[0].view(-1, 64)[:, :M].sum(0).cpu()
     assert torch.allclose(got, hs[0].float().pow(2).sum(-1).cpu(), rtol=1e-4)
-    for b in xbufs:
-        flags = b[-(2 * 8 * 64 * 4):]
-        assert int(flags.count_nonzero()) == 0, "exchange flags must be cleared by their consumer"
+    counters = [b[-(2 * 8 * 64 * 4):].view(torch.int32).view(2, 8, 64) for b in xbufs]
+    for r in range(tp):  # every rank used each of its 28 slots twice per channel: the packet tags' use counters agree
+        assert counters[r][:, r, :28].eq(2).all() and int(counters[r].count_nonzero()) == 2 * 28, counters[r][:, r, :30]
     print(f"kernel level tp{tp} ok (rel err {err:.5f})")
 
 
