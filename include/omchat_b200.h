@@ -95,6 +95,12 @@ int omc_gemv_bf16(const void* x, long long ldx, const void* W, long long ldw, vo
 int omc_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, int rows, int C, float eps,
                 void* stream);
 
+/* torch.nn.LayerNorm on bf16 rows - the norm_type = 'layer_norm' option of the InternViT-300M tower
+ * (intern_vit_300m/modeling_intern_vit.py:61-64,209-210): out = bf16((x - mean) * rsqrt(var + eps) * w + b), fp32 statistics
+ * (biased variance), one rounding. b may be NULL (no bias). */
+int omc_layernorm(const void* x, long long ldx, const void* w, const void* b, void* out, long long ldo, int rows, int C,
+                  float eps, void* stream);
+
 /* In place on two adjacent C-wide column segments of every row - x[m, 0:C] with w_a, x[m, C:2C] with w_b - in ONE launch:
  * InternAttention's q_norm / k_norm over all heads flattened (modeling_intern_vit.py:143-146) on the packed qkv rows. */
 int omc_rmsnorm_pair(void* x, long long ldx, const void* w_a, const void* w_b, int rows, int C, float eps, void* stream);
@@ -343,6 +349,15 @@ typedef struct omc_vit_desc {
   const void* p_b0;
   const void* p_w2;
   const void* p_b2;
+  /* InternViT-300M variant (intern_vit_300m/modeling_intern_vit.py:61-64,131,209-210); all zero / NULL for the 6B tower */
+  int32_t norm_type;     /* 0: InternRMSNorm; 1: nn.LayerNorm with norm1_b / norm2_b (requires norm_folded = 0) */
+  int32_t attn_head_dim; /* 0: hidden / heads (must be 128). 128 with hidden / heads < 128: every head of qkv_w's rows (and of
+                            qkv_b) and of proj_w's columns is zero-padded to 128 dims by the caller, qkv_w is [3 * heads * 128,
+                            hidden], proj_w [hidden, heads * 128]; q.k and P.V are unchanged, the softmax scale stays
+                            (hidden / heads)^-0.5 */
+  const void* const* norm1_b;
+  const void* const* norm2_b;
+  const void* const* qkv_b; /* NULL: no qkv bias (config.qkv_bias = false) */
 } omc_vit_desc;
 long long omc_vit_workspace_bytes(const omc_vit_desc* desc, int max_crops);
 int omc_vit_forward(const omc_vit_desc* desc, const void* pixels, int pixels_are_f32, int n_crops, void* workspace,

@@ -28,10 +28,27 @@ class InternVisionConfig:
     hidden_act: str = "gelu"
     layer_norm_eps: float = 1e-6
     initializer_factor: float = 0.1
+    norm_type: str = "rms_norm"  # 'layer_norm' for the InternViT-300M variant (intern_vit_300m/modeling_intern_vit.py:61-64)
+
+    def __post_init__(self):
+        if self.norm_type not in ("rms_norm", "layer_norm"):
+            raise ValueError(f"unknown norm_type {self.norm_type!r}")
+
+    @classmethod
+    def intern_vit_300m(cls, **overrides) -> "InternVisionConfig":
+        """intern_vit_300m/configuration_intern_vit.py:60-80 defaults: the lighter tower (LayerNorm, no QK-norm, 16 heads of 64)."""
+        kw = dict(hidden_size=1024, num_attention_heads=16, intermediate_size=4096, qk_normalization=False, num_hidden_layers=24,
+                  norm_type="layer_norm", initializer_factor=1.0)
+        kw.update(overrides)
+        return cls(**kw)
 
     @property
     def num_patches(self) -> int:
         return (self.image_size // self.patch_size) ** 2
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_attention_heads
 
 
 @dataclass
@@ -67,6 +84,15 @@ class OmChatQwen2Config:
     kv_page_size: int = 64
     tp_size: int = 1
     vision_config: InternVisionConfig = field(default_factory=InternVisionConfig)
+
+    def __post_init__(self):
+        # build_vision_tower (multimodal_encoder/builder.py:11-14) picks the tower class from the NAME: a config that names the
+        # 300M tower and leaves vision_config at the 6B defaults gets the 300M defaults
+        name = (self.mm_vision_tower or "").lower()
+        if "internvit-300m" in name and self.vision_config == InternVisionConfig():
+            self.vision_config = InternVisionConfig.intern_vit_300m()
+            if self.mm_hidden_size == 3200:
+                self.mm_hidden_size = self.vision_config.hidden_size
 
     @property
     def head_dim(self) -> int:

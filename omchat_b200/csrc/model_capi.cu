@@ -46,8 +46,9 @@ static void vit_sizes(const omc_vit_desc* d, int n, long long* rows, long long* 
   sizes[1] = (long long)n * P * d->hidden * 2;                   // patch embeddings
   sizes[2] = *rows * d->hidden * 2;                              // residual stream h
   sizes[3] = *rows * d->hidden * 2;                              // normed rows
-  sizes[4] = *rows * 3 * d->hidden * 2;                          // qkv
-  sizes[5] = *rows * d->hidden * 2;                              // attention output
+  const long long Ca = (long long)d->heads * 128;                // attention width (= hidden for 128-dim heads; padded otherwise)
+  sizes[4] = *rows * 3 * Ca * 2;                                 // qkv
+  sizes[5] = *rows * Ca * 2;                                     // attention output
   sizes[6] = *rows * d->inter * 2;                               // MLP activation
   sizes[7] = (long long)n * L * d->hidden * down * down * 2;     // selected (+ shuffled) features
   sizes[8] = (long long)n * L * d->proj_hidden * 2;              // projector hidden
@@ -73,8 +74,15 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
   if (d == nullptr || pixels == nullptr || workspace == nullptr || feats_out == nullptr)
     return set_error(OMC_ERR_ARG, "omc_vit_forward: null argument");
   if (n_crops <= 0) return OMC_OK;
-  if (d->image_size % d->patch_size != 0 || d->hidden % d->heads != 0 || d->hidden / d->heads != 128)
-    return set_error(OMC_ERR_SHAPE, "omc_vit_forward: head_dim must be 128 and the image a whole number of patches");
+  if (d->image_size % d->patch_size != 0 || d->heads <= 0 || d->hidden % d->heads != 0)
+    return set_error(OMC_ERR_SHAPE, "omc_vit_forward: the image must be a whole number of patches, hidden a multiple of heads");
+  const int Dh = d->hidden / d->heads;
+  if (Dh != 128 && (d->attn_head_dim != 128 || Dh > 128 || d->qk_norm))
+    return set_error(OMC_ERR_SHAPE, "omc_vit_forward: head_dim < 128 needs qkv_w / proj_w zero-padded to attn_head_dim = 128 and no QK-norm");
+  const bool layer_norm = d->norm_type == 1;
+  if (d->norm_type != 0 && d->norm_type != 1) return set_error(OMC_ERR_ARG, "omc_vit_forward: norm_type must be 0 (rms) or 1 (layer)");
+  if (layer_norm && (d->norm_folded || d->norm1_b == nullptr || d->norm2_b == nullptr))
+    return set_error(OMC_ERR_ARG, "omc_vit_forward: layer_norm needs norm1_b / norm2_b and norm_folded = 0");
   const int G = d->image_size / d->patch_size, P = G * G, C = d->hidden, S = P + 1;
   const int down = d->pixel_shuffle_down;
   if (down < 1 || G % down != 0) return set_error(OMC_ERR_SHAPE, "omc_vit_forward: bad pixel_shuffle_down");
@@ -101,8 +109,14 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
   OMC_TRY(omc_gemm_bf16(cols, d->patch_k, d->patch_w, d->patch_k, patch, C, n_crops * P, C, d->patch_k, d->patch_b, nullptr,
                         nullptr, 0, OMC_EPI_NONE, 0, 0, stream));
   OMC_TRY(omc_vit_assemble(patch, d->cls, d->pos, h, n_crops, P, C, stream));
-  const float scale = 1.0f / sqrtf(128.0f);
+  const float scale = 1.0f / sqrtf((float)Dh);
   const int M = (int)rows;
+  const int Ca = d->heads * 128;  // attention width
+  auto qkv_bias = [&](int li) -> const void* { return d->qkv_b != nullptr ? d->qkv_b[li] : nullptr; };
+  auto pre_norm = [&](const void* const* w, const void* const* b, int li) {
+    return layer_norm ? omc_layernorm(h, C, w[li], b[li], xn, C, M, C, d->eps, stream)
+                      : omc_rmsnorm(h, C, w[li], xn, C, M, C, d->eps, stream);
+  };
   const bool fold = d->norm_folded != 0;
   int parts_a = 1, parts_b = 1;  // sums-of-squares partials the last producer of each buffer wrote
   if (fold) OMC_TRY(omc_row_ssq_rows(h, C, rows, C, ssq_a, stream));
@@ -120,11 +134,12 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
     // h += ls1 * proj(attn(qk_norm(qkv(norm1(h)))));  h += ls2 * fc2(gelu(fc1(norm2(h))))   (:138-155, 187-191, 218-220)
     if (fold) {
       omc_gemm_norm nf = norm_in(ssq_a, parts_a);
-      OMC_TRY(omc_gemm_bf16_norm(h, C, d->qkv_w[li], C, qkv, 3LL * C, M, 3 * C, C, nullptr, nullptr, nullptr, 0, OMC_EPI_NONE, 0, 0,
-                                 &nf, stream));
+      OMC_TRY(omc_gemm_bf16_norm(h, C, d->qkv_w[li], C, qkv, 3LL * Ca, M, 3 * Ca, C, qkv_bias(li), nullptr, nullptr, 0, OMC_EPI_NONE,
+                                 0, 0, &nf, stream));
     } else {
-      OMC_TRY(omc_rmsnorm(h, C, d->norm1[li], xn, C, M, C, d->eps, stream));
-      OMC_TRY(omc_gemm_bf16(xn, C, d->qkv_w[li], C, qkv, 3LL * C, M, 3 * C, C, nullptr, nullptr, nullptr, 0, OMC_EPI_NONE, 0, 0, stream));
+      OMC_TRY(pre_norm(d->norm1, d->norm1_b, li));
+      OMC_TRY(omc_gemm_bf16(xn, C, d->qkv_w[li], C, qkv, 3LL * Ca, M, 3 * Ca, C, qkv_bias(li), nullptr, nullptr, 0, OMC_EPI_NONE, 0,
+                            0, stream));
     }
     if (d->qk_norm) {
       if (fold) {
@@ -134,11 +149,11 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
         OMC_TRY(omc_rmsnorm(qkv + C, 3LL * C, d->k_norm[li], qkv + C, 3LL * C, M, C, d->eps, stream));
       }
     }
-    OMC_TRY(omc_attention_fwd(qkv, 3LL * C, qkv + C, 3LL * C, qkv + 2 * C, 3LL * C, attn, C, cu, n_crops, S, rows, d->heads,
+    OMC_TRY(omc_attention_fwd(qkv, 3LL * Ca, qkv + Ca, 3LL * Ca, qkv + 2 * Ca, 3LL * Ca, attn, Ca, cu, n_crops, S, rows, d->heads,
                               d->heads, 0, scale, stream));
     if (fold) {
       omc_gemm_norm no = norm_out(ssq_b);
-      OMC_TRY(omc_gemm_bf16_norm(attn, C, d->proj_w[li], C, h, C, M, C, C, d->proj_b[li], d->ls1[li], h, C, OMC_EPI_RES, 0, 0, &no, stream));
+      OMC_TRY(omc_gemm_bf16_norm(attn, Ca, d->proj_w[li], Ca, h, C, M, C, Ca, d->proj_b[li], d->ls1[li], h, C, OMC_EPI_RES, 0, 0, &no, stream));
       parts_b = no.ssq_out_parts;
       omc_gemm_norm nf = norm_in(ssq_b, parts_b);
       OMC_TRY(omc_gemm_bf16_norm(h, C, d->fc1_w[li], C, act, d->inter, M, d->inter, C, d->fc1_b[li], nullptr, nullptr, 0,
@@ -148,8 +163,8 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
                                  OMC_EPI_RES, 0, 0, &no2, stream));
       parts_a = no2.ssq_out_parts;
     } else {
-      OMC_TRY(omc_gemm_bf16(attn, C, d->proj_w[li], C, h, C, M, C, C, d->proj_b[li], d->ls1[li], h, C, OMC_EPI_RES, 0, 0, stream));
-      OMC_TRY(omc_rmsnorm(h, C, d->norm2[li], xn, C, M, C, d->eps, stream));
+      OMC_TRY(omc_gemm_bf16(attn, Ca, d->proj_w[li], Ca, h, C, M, C, Ca, d->proj_b[li], d->ls1[li], h, C, OMC_EPI_RES, 0, 0, stream));
+      OMC_TRY(pre_norm(d->norm2, d->norm2_b, li));
       OMC_TRY(omc_gemm_bf16(xn, C, d->fc1_w[li], C, act, d->inter, M, d->inter, C, d->fc1_b[li], nullptr, nullptr, 0, OMC_EPI_GELU,
                             0, 0, stream));
       OMC_TRY(omc_gemm_bf16(act, d->inter, d->fc2_w[li], d->inter, h, C, M, C, d->inter, d->fc2_b[li], d->ls2[li], h, C, OMC_EPI_RES,

@@ -72,6 +72,85 @@ __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const bf16* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// out = bf16((x - mean) * rsqrt(var + eps) * w + b), statistics and the affine map in fp32, ONE rounding (torch.nn.LayerNorm on
+// bf16 rows) - the norm_type = 'layer_norm' option of the InternViT-300M tower (intern_vit_300m/modeling_intern_vit.py:61-64,
+// 209-210). Two-pass variance from the registers the row already sits in (no E[x^2] - mean^2 cancellation).
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNormThreads / 32; ++i) tot += red[i];
+  __syncthreads();
+  return tot;
+}
+
+__global__ void __launch_bounds__(kNormThreads) layernorm_kernel(const bf16* __restrict__ x, long long ldx,
+                                                                 const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                                                 bf16* __restrict__ out, long long ldo, int rows, int C,
+                                                                 float eps) {
+  __shared__ float red[kNormThreads / 32];
+  const int nvec = C >> 3;
+  const float inv_c = 1.f / (float)C;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+    float f[kNormMaxVec][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kNormMaxVec; ++j) {
+      int i = threadIdx.x + j * kNormThreads;
+      if (i < nvec) {
+        uint4 v = xr[i];
+        uint32_t xi[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float2 a = unpack_bf16(xi[q]);
+          f[j][2 * q] = a.x;
+          f[j][2 * q + 1] = a.y;
+          s += a.x + a.y;
+        }
+      }
+    }
+    const float mean = block_sum_128(s, red) * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kNormMaxVec; ++j) {
+      int i = threadIdx.x + j * kNormThreads;
+      if (i < nvec) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float dlt = f[j][q] - mean;
+          ss += dlt * dlt;
+        }
+      }
+    }
+    const float rstd = rsqrtf(block_sum_128(ss, red) * inv_c + eps);
+    uint4* orow = reinterpret_cast<uint4*>(out + (long long)row * ldo);
+    const uint4* wv = reinterpret_cast<const uint4*>(w);
+    const uint4* bv = reinterpret_cast<const uint4*>(b);
+#pragma unroll
+    for (int j = 0; j < kNormMaxVec; ++j) {
+      int i = threadIdx.x + j * kNormThreads;
+      if (i < nvec) {
+        uint4 ww = wv[i];
+        uint4 bb = b != nullptr ? bv[i] : make_uint4(0u, 0u, 0u, 0u);
+        uint32_t wi[4] = {ww.x, ww.y, ww.z, ww.w};
+        uint32_t bi[4] = {bb.x, bb.y, bb.z, bb.w};
+        uint32_t oo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float2 g = unpack_bf16(wi[q]);
+          float2 c = unpack_bf16(bi[q]);
+          oo[q] = pack_bf16((f[j][2 * q] - mean) * rstd * g.x + c.x, (f[j][2 * q + 1] - mean) * rstd * g.y + c.y);
+        }
+        orow[i] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ patch im2col
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ pix, bf16* __restrict__ cols, long long ldc, int B, int H, int W) {
@@ -403,6 +482,19 @@ extern "C" int omc_rmsnorm(const void* x, long long ldx, const void* w, void* ou
   rmsnorm_kernel<<<grid, kNormThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, nullptr, (bf16*)out,
                                                                    ldo, rows, C, eps, 1);
   return check_launch("rmsnorm");
+}
+
+extern "C" int omc_layernorm(const void* x, long long ldx, const void* w, const void* b, void* out, long long ldo, int rows,
+                             int C, float eps, void* stream) {
+  if (rows <= 0) return OMC_OK;
+  if (x == nullptr || w == nullptr || out == nullptr) return set_error(OMC_ERR_ARG, "omc_layernorm: null argument");
+  if (C <= 0 || C % 8 != 0 || C > kNormThreads * kNormMaxVec * 8)
+    return set_error(OMC_ERR_SHAPE, "omc_layernorm: C must be a multiple of 8 and <= 4096");
+  if (ldx % 8 != 0 || ldo % 8 != 0) return set_error(OMC_ERR_ALIGN, "omc_layernorm: leading dims must be multiples of 8");
+  int grid = rows < num_sms() * 16 ? rows : num_sms() * 16;
+  layernorm_kernel<<<grid, kNormThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b,
+                                                                     (bf16*)out, ldo, rows, C, eps);
+  return check_launch("layernorm");
 }
 
 extern "C" int omc_rmsnorm_pair(void* x, long long ldx, const void* w_a, const void* w_b, int rows, int C, float eps,

@@ -39,6 +39,7 @@ SIGNATURES = {
     "omc_gemv_bf16": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _L, _I, _I, _P]),
     "omc_rmsnorm": (_I, [_P, _L, _P, _P, _L, _I, _I, _F, _P]),
     "omc_rmsnorm_pair": (_I, [_P, _L, _P, _P, _I, _I, _F, _P]),
+    "omc_layernorm": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _F, _P]),
     "omc_vit_im2col": (_I, [_P, _I, _P, _L, _I, _I, _I, _P]),
     "omc_vit_assemble": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "omc_select_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _P]),
@@ -396,6 +397,19 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Te
     return out
 
 
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], eps: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """torch.nn.LayerNorm over the last dim of bf16 rows (InternViT-300M norm_type = 'layer_norm')."""
+    _need_cuda(x, w) if b is None else _need_cuda(x, w, b)
+    assert x.dim() == 2 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    rc = load().omc_layernorm(_ptr(x), x.stride(0), _ptr(w), _ptr(b) if b is not None else None, _ptr(out), out.stride(0),
+                              x.shape[0], x.shape[1], eps, _stream())
+    _check(rc, "omc_layernorm")
+    return out
+
+
 def rmsnorm_pair(x: torch.Tensor, w_a: torch.Tensor, w_b: torch.Tensor, C: int, eps: float) -> torch.Tensor:
     """In place: x[:, :C] normalised with w_a, x[:, C:2C] with w_b (q_norm / k_norm on packed qkv rows), one launch."""
     _need_cuda(x, w_a, w_b)
@@ -739,19 +753,26 @@ class VitDesc(ctypes.Structure):
                 + [("eps", c_float), ("norm_folded", ctypes.c_int32)]
                 + [(n, c_void_p) for n in ("patch_w", "patch_b", "cls", "pos", "norm1", "qkv_w", "q_norm", "k_norm", "proj_w",
                                            "proj_b", "ls1", "norm2", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2", "p_w0", "p_b0",
-                                           "p_w2", "p_b2")])
+                                           "p_w2", "p_b2")]
+                + [("norm_type", ctypes.c_int32), ("attn_head_dim", ctypes.c_int32), ("norm1_b", c_void_p), ("norm2_b", c_void_p),
+                   ("qkv_b", c_void_p)])
 
 
 class VitForward:
     """omc_vit_forward on a model's weights: the whole encode_images (tower + select / pixel shuffle + projector) as ONE
     C call - what a non-Python host binds. `vit` / `proj` are weights.VitW / ProjW, vc an InternVisionConfig."""
 
-    def __init__(self, vit, proj, vc, pixel_shuffle_down: int = 1, folded=None):
+    def __init__(self, vit, proj, vc, pixel_shuffle_down: int = 1, folded=None, mats=None, mats_folded: bool = False):
         """folded: [(qkv * norm1, fc1 * norm2)] per layer (InternVITVisionTower._folded()) -> the norm-folded loop the
-        product runs by default; None -> plain weights + stand-alone RMSNorm kernels."""
+        product runs by default; None -> plain weights + stand-alone norm kernels. mats: the tower's _layer_mats() - per layer
+        (qkv_w, qkv_b, proj_w, fc1_w) with heads zero-padded to 128 dims - required when head_dim < 128 (InternViT-300M)."""
         n = len(vit.layers)
+        if mats is not None:
+            folded = None
+        elif vc.head_dim != 128:
+            raise ValueError("head_dim < 128: pass mats=tower._layer_mats() (zero-padded heads)")
         d = VitDesc()
-        d.norm_folded = 1 if folded is not None else 0
+        d.norm_folded = 1 if (folded is not None or (mats is not None and mats_folded)) else 0
         self._folded = folded
         d.n_layers, d.hidden, d.heads, d.inter = n, vc.hidden_size, vc.num_attention_heads, vc.intermediate_size
         d.image_size, d.patch_size, d.patch_k, d.qk_norm = vc.image_size, vc.patch_size, vit.patch_w.shape[1], int(vc.qk_normalization)
@@ -760,9 +781,19 @@ class VitForward:
         names = {"norm1": "norm1", "qkv_w": "qkv", "q_norm": "q_norm", "k_norm": "k_norm", "proj_w": "proj_w", "proj_b": "proj_b",
                  "ls1": "ls1", "norm2": "norm2", "fc1_w": "fc1_w", "fc1_b": "fc1_b", "fc2_w": "fc2_w", "fc2_b": "fc2_b", "ls2": "ls2"}
         self._arrays = {}
-        for field, attr in names.items():
+        self._mats = mats
+        extra = {"norm1_b": "norm1_b", "norm2_b": "norm2_b"} if vc.norm_type == "layer_norm" else {}
+        if any(l.qkv_b is not None for l in vit.layers):
+            extra["qkv_b"] = "qkv_b"
+        d.norm_type = 1 if vc.norm_type == "layer_norm" else 0
+        d.attn_head_dim = 128 if vc.head_dim != 128 else 0
+        for field, attr in {**names, **extra}.items():
+            if field in ("q_norm", "k_norm") and not vc.qk_normalization:
+                continue
             if folded is not None and field in ("qkv_w", "fc1_w"):
                 ptrs = [f[0 if field == "qkv_w" else 1].data_ptr() for f in folded]
+            elif mats is not None and field in ("qkv_w", "qkv_b", "proj_w", "fc1_w"):
+                ptrs = [m[("qkv_w", "qkv_b", "proj_w", "fc1_w").index(field)].data_ptr() for m in mats]
             else:
                 ptrs = [getattr(l, attr).data_ptr() for l in vit.layers]
             arr = (c_void_p * max(n, 1))(*ptrs)

@@ -24,7 +24,7 @@ import torch
 from .. import lib
 from ..config import IGNORE_INDEX, IMAGE_TOKEN_INDEX, OmChatQwen2Config
 from .decoder import PagedKVCache, Qwen2Decoder, TPInfo
-from .vision import InternVITVisionTower, MMProjector
+from .vision import InternVITVisionTower, MMProjector, build_vision_tower
 from .weights import OmChatWeights, from_state_dict, random_init
 
 
@@ -69,7 +69,7 @@ class OmChatQwen2Model:
 
     def __init__(self, config: OmChatQwen2Config, weights: OmChatWeights, tp: TPInfo):
         self.config = config
-        self.vision_tower = InternVITVisionTower(config, weights.vit) if config.mm_vision_tower is not None else None
+        self.vision_tower = build_vision_tower(config, weights.vit) if config.mm_vision_tower is not None else None
         self.mm_projector = MMProjector(weights.proj) if weights.proj is not None else None
         self.decoder = Qwen2Decoder(config, weights.llm, tp)
         self.embed_weight = weights.llm.embed

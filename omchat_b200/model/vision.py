@@ -1,4 +1,4 @@
-"""InternViT-6B vision tower + mm_projector on the C-ABI kernels.
+"""InternViT-6B (and the lighter InternViT-300M) vision tower + mm_projector on the C-ABI kernels.
 
 Mirrors InternVITVisionTower (omchat/model/multimodal_encoder/internVIT_encoder.py:10-56) and the projector of
 omchat/model/multimodal_projector/builder.py:54-61. Per layer (intern_vit_6b/modeling_intern_vit.py:218-220):
@@ -15,7 +15,9 @@ import torch
 
 from .. import lib
 from ..config import OmChatQwen2Config
-from .weights import ProjW, VitW, fold_norm
+from .weights import ProjW, VitW, fold_norm, pad_head_cols, pad_head_rows
+
+ATTN_HEAD_DIM = 128  # the attention kernels' head_dim; narrower heads (InternViT-300M: 64) run zero-padded to it
 
 
 class InternVITVisionTower:
@@ -32,10 +34,16 @@ class InternVITVisionTower:
         self.image_processor = None  # CPU preprocessing (CLIPImageProcessor) is outside the hot path
         self.max_crops_per_pass = 64
         self._cu_cache = {}
-        # norm1 / norm2 folded into the GEMMs that follow them (0 = stand-alone RMSNorm kernels, the round-1 path)
-        self.fold_norms = os.environ.get("OMCHAT_B200_FOLD_NORMS", "1") != "0"
-        self._folded_w = None
+        # norm1 / norm2 folded into the GEMMs that follow them (0 = stand-alone RMSNorm kernels, the round-1 path); RMSNorm only:
+        # the 'layer_norm' variant (InternViT-300M) keeps its stand-alone LayerNorm kernel
+        self.fold_norms = os.environ.get("OMCHAT_B200_FOLD_NORMS", "1") != "0" and self.vc.norm_type == "rms_norm"
+        self._mats = {}
         self._ssq_bufs = None
+        D = self.vc.head_dim
+        if D > ATTN_HEAD_DIM or ATTN_HEAD_DIM % D != 0 or D % 8 != 0:
+            raise ValueError(f"vision head_dim {D} not supported (must divide {ATTN_HEAD_DIM})")
+        if D != ATTN_HEAD_DIM and self.vc.qk_normalization:
+            raise NotImplementedError("qk_normalization over zero-padded heads")
 
     def load_model(self):
         if self.w is None:
@@ -85,51 +93,76 @@ class InternVITVisionTower:
         states = [h.clone()] if collect else None
         cu = self._cu_seqlens(n, S, h.device)
         rows = n * S
+        Ca = H * ATTN_HEAD_DIM  # attention width: = C for the 6B tower, heads zero-padded to 128 dims otherwise
         xn = torch.empty(rows, C, device=h.device, dtype=torch.bfloat16)
-        qkv = torch.empty(rows, 3 * C, device=h.device, dtype=torch.bfloat16)
-        attn = torch.empty(rows, C, device=h.device, dtype=torch.bfloat16)
+        qkv = torch.empty(rows, 3 * Ca, device=h.device, dtype=torch.bfloat16)
+        attn = torch.empty(rows, Ca, device=h.device, dtype=torch.bfloat16)
         act = torch.empty(rows, vc.intermediate_size, device=h.device, dtype=torch.bfloat16)
         scale = (C // H) ** -0.5
         eps = vc.layer_norm_eps
+        mats = self._layer_mats()
         if self.fold_norms:
             # norm1 / norm2 folded into the qkv / fc1 GEMMs (omc_gemm_bf16_norm): the residual epilogues of proj / fc2 leave
             # the rows' sums of squares behind, the next GEMM scales its rows by rstd - no stand-alone RMSNorm pass
-            folded = self._folded()
             ssq_a, ssq_b = self._ssq(rows, h.device)
             ssq_a.from_rows(h)
             for li in range(n_layers):
-                l, (qkv_f, fc1_f) = w.layers[li], folded[li]
-                lib.gemm(h, qkv_f, out=qkv, ssq_in=ssq_a, norm_dim=C, eps=eps)
+                l, (qkv_f, qkv_b, proj_w, fc1_f) = w.layers[li], mats[li]
+                lib.gemm(h, qkv_f, out=qkv, bias=qkv_b, ssq_in=ssq_a, norm_dim=C, eps=eps)
                 if vc.qk_normalization:
                     lib.rmsnorm_pair(qkv, l.q_norm, l.k_norm, C, eps)
-                lib.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], attn, cu, S, H, H, False, scale)
-                lib.gemm(attn, l.proj_w, out=h, bias=l.proj_b, scale=l.ls1, res=h, epi=lib.EPI_RES, ssq_out=ssq_b)
+                lib.attention(qkv[:, :Ca], qkv[:, Ca:2 * Ca], qkv[:, 2 * Ca:], attn, cu, S, H, H, False, scale)
+                lib.gemm(attn, proj_w, out=h, bias=l.proj_b, scale=l.ls1, res=h, epi=lib.EPI_RES, ssq_out=ssq_b)
                 lib.gemm(h, fc1_f, out=act, bias=l.fc1_b, epi=lib.EPI_GELU, ssq_in=ssq_b, norm_dim=C, eps=eps)
                 lib.gemm(act, l.fc2_w, out=h, bias=l.fc2_b, scale=l.ls2, res=h, epi=lib.EPI_RES, ssq_out=ssq_a)
                 if collect:
                     states.append(h.clone())
             return (h, states) if collect else h
+        layer_norm = vc.norm_type == "layer_norm"
         for li in range(n_layers):
-            l = w.layers[li]
-            lib.rmsnorm(h, l.norm1, eps, out=xn)
-            lib.gemm(xn, l.qkv, out=qkv)
+            l, (qkv_w, qkv_b, proj_w, fc1_w) = w.layers[li], mats[li]
+            if layer_norm:
+                lib.layernorm(h, l.norm1, l.norm1_b, eps, out=xn)
+            else:
+                lib.rmsnorm(h, l.norm1, eps, out=xn)
+            lib.gemm(xn, qkv_w, out=qkv, bias=qkv_b)
             if vc.qk_normalization:
                 lib.rmsnorm(qkv[:, :C], l.q_norm, eps, out=qkv[:, :C])
                 lib.rmsnorm(qkv[:, C:2 * C], l.k_norm, eps, out=qkv[:, C:2 * C])
-            lib.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], attn, cu, S, H, H, False, scale)
-            lib.gemm(attn, l.proj_w, out=h, bias=l.proj_b, scale=l.ls1, res=h, epi=lib.EPI_RES)
-            lib.rmsnorm(h, l.norm2, eps, out=xn)
-            lib.gemm(xn, l.fc1_w, out=act, bias=l.fc1_b, epi=lib.EPI_GELU)
+            lib.attention(qkv[:, :Ca], qkv[:, Ca:2 * Ca], qkv[:, 2 * Ca:], attn, cu, S, H, H, False, scale)
+            lib.gemm(attn, proj_w, out=h, bias=l.proj_b, scale=l.ls1, res=h, epi=lib.EPI_RES)
+            if layer_norm:
+                lib.layernorm(h, l.norm2, l.norm2_b, eps, out=xn)
+            else:
+                lib.rmsnorm(h, l.norm2, eps, out=xn)
+            lib.gemm(xn, fc1_w, out=act, bias=l.fc1_b, epi=lib.EPI_GELU)
             lib.gemm(act, l.fc2_w, out=h, bias=l.fc2_b, scale=l.ls2, res=h, epi=lib.EPI_RES)
             if collect:
                 states.append(h.clone())
         return (h, states) if collect else h
 
+    def _layer_mats(self):
+        """Per layer (qkv_w, qkv_b, proj_w, fc1_w) as the GEMMs take them, built once: norm1 / norm2 folded into qkv / fc1 when
+        fold_norms (6.5 GB more for InternViT-6B), heads zero-padded to the attention kernels' 128 dims when narrower."""
+        if self.fold_norms not in self._mats:
+            vc = self.vc
+            H, D = vc.num_attention_heads, vc.head_dim
+            mats = []
+            for l in self.w.layers:
+                qkv_w = fold_norm(l.qkv, l.norm1) if self.fold_norms else l.qkv
+                fc1_w = fold_norm(l.fc1_w, l.norm2) if self.fold_norms else l.fc1_w
+                qkv_b, proj_w = l.qkv_b, l.proj_w
+                if D != ATTN_HEAD_DIM:
+                    qkv_w = pad_head_rows(qkv_w, 3, H, D, ATTN_HEAD_DIM)
+                    qkv_b = pad_head_rows(qkv_b, 3, H, D, ATTN_HEAD_DIM) if qkv_b is not None else None
+                    proj_w = pad_head_cols(proj_w, H, D, ATTN_HEAD_DIM)
+                mats.append((qkv_w, qkv_b, proj_w, fc1_w))
+            self._mats[self.fold_norms] = mats
+        return self._mats[self.fold_norms]
+
     def _folded(self):
-        """(qkv * norm1, fc1 * norm2) per layer, built once (6.5 GB more for InternViT-6B)."""
-        if self._folded_w is None:
-            self._folded_w = [(fold_norm(l.qkv, l.norm1), fold_norm(l.fc1_w, l.norm2)) for l in self.w.layers]
-        return self._folded_w
+        """(qkv * norm1, fc1 * norm2) per layer for the model-level C entry (lib.VitForward)."""
+        return [(m[0], m[3]) for m in self._layer_mats()]
 
     def _ssq(self, rows: int, device):
         if self._ssq_bufs is None or self._ssq_bufs[0].rows < rows:
@@ -154,6 +187,25 @@ class InternVITVisionTower:
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     forward = __call__
+
+
+class InternVIT300mVisionTower(InternVITVisionTower):
+    """The lighter tower (multimodal_encoder/internVIT300m_encoder.py:10-56, intern_vit_300m/modeling_intern_vit.py): LayerNorm
+    instead of RMSNorm (norm_type = 'layer_norm', :61-64,209-210), no QK-norm, 16 heads of 64 dims, 24 layers. Same kernels; the
+    64-dim heads run zero-padded to the attention kernels' 128 (weights padded once at load)."""
+
+    def __init__(self, cfg: OmChatQwen2Config, weights: Optional[VitW]):
+        super().__init__(cfg, weights)
+        if self.vc.norm_type != "layer_norm" and self.vc.head_dim == ATTN_HEAD_DIM:
+            raise ValueError("InternVIT300mVisionTower expects the 300M vision_config (InternVisionConfig.intern_vit_300m())")
+
+
+def build_vision_tower(cfg: OmChatQwen2Config, weights: Optional[VitW]) -> InternVITVisionTower:
+    """multimodal_encoder/builder.py:7-18: the tower class follows the NAME in mm_vision_tower."""
+    name = (cfg.mm_vision_tower or "").lower()
+    if "internvit-300m" in name:
+        return InternVIT300mVisionTower(cfg, weights)
+    return InternVITVisionTower(cfg, weights)
 
 
 class MMProjector:

@@ -55,6 +55,24 @@ def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     return torch.stack([gate, up], dim=1).reshape(2 * I, K)
 
 
+def pad_head_rows(w: torch.Tensor, groups: int, heads: int, D: int, Dp: int) -> torch.Tensor:
+    """[groups * heads * D, ...] -> [groups * heads * Dp, ...], every head's D rows followed by Dp - D zero rows: a tower whose
+    head_dim is below the attention kernels' 128 (InternViT-300M: 64) runs on zero-padded heads - q.k and P.V are unchanged by
+    the zero dims, the scale stays D^-0.5."""
+    rest = w.shape[1:]
+    out = torch.zeros(groups, heads, Dp, *rest, device=w.device, dtype=w.dtype)
+    out[:, :, :D] = w.reshape(groups, heads, D, *rest)
+    return out.reshape(groups * heads * Dp, *rest).contiguous()
+
+
+def pad_head_cols(w: torch.Tensor, heads: int, D: int, Dp: int) -> torch.Tensor:
+    """proj weight [N, heads * D] -> [N, heads * Dp] with zero columns under the padded dims of the attention output."""
+    N = w.shape[0]
+    out = torch.zeros(N, heads, Dp, device=w.device, dtype=w.dtype)
+    out[:, :, :D] = w.reshape(N, heads, D)
+    return out.reshape(N, heads * Dp).contiguous()
+
+
 def fold_norm(w: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """W'[n, k] = W[n, k] * g[k]: the RMSNorm weight in front of a linear layer folded into its columns (fp32 product, one
     bf16 rounding). The GEMM then runs on the raw residual stream and scales rows by rstd in its epilogue."""
@@ -76,6 +94,10 @@ class VitLayerW:
     fc2_w: torch.Tensor
     fc2_b: torch.Tensor
     ls2: torch.Tensor
+    # InternViT-300M variant: LayerNorm biases (norm_type = 'layer_norm') and the optional qkv bias (config.qkv_bias)
+    norm1_b: Optional[torch.Tensor] = None
+    norm2_b: Optional[torch.Tensor] = None
+    qkv_b: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -208,9 +230,13 @@ def from_state_dict(sd: Dict[str, torch.Tensor], cfg: OmChatQwen2Config, device=
         layers = []
         for li in range(vc.num_hidden_layers):
             p = f"{VT}encoder.layers.{li}."
+            opt = lambda k: _dev(sd[k], device) if k in sd else None  # noqa: E731
+            if vc.norm_type == "layer_norm" and (p + "norm1.bias") not in sd:
+                raise KeyError(f"norm_type 'layer_norm' needs {p}norm1.bias")
             layers.append(VitLayerW(
                 norm1=_dev(sd[p + "norm1.weight"], device), qkv=_dev(sd[p + "attn.qkv.weight"], device),
-                q_norm=_dev(sd[p + "attn.q_norm.weight"], device), k_norm=_dev(sd[p + "attn.k_norm.weight"], device),
+                q_norm=opt(p + "attn.q_norm.weight"), k_norm=opt(p + "attn.k_norm.weight"),
+                norm1_b=opt(p + "norm1.bias"), norm2_b=opt(p + "norm2.bias"), qkv_b=opt(p + "attn.qkv.bias"),
                 proj_w=_dev(sd[p + "attn.proj.weight"], device), proj_b=_dev(sd[p + "attn.proj.bias"], device),
                 ls1=_dev(sd[p + "ls1"], device), norm2=_dev(sd[p + "norm2.weight"], device),
                 fc1_w=_dev(sd[p + "mlp.fc1.weight"], device), fc1_b=_dev(sd[p + "mlp.fc1.bias"], device),
@@ -258,10 +284,14 @@ def random_init(cfg: OmChatQwen2Config, device="cuda", seed: int = 0, vision: bo
         C, I = vc.hidden_size, vc.intermediate_size
         patch_w = torch.zeros(C, PATCH_K, device=device, dtype=torch.bfloat16)
         patch_w[:, :588] = rn(C, 588)
-        layers = [VitLayerW(norm1=rn(C, std=0.02, mean=1.0), qkv=rn(3 * C, C), q_norm=rn(C, std=0.02, mean=1.0),
-                            k_norm=rn(C, std=0.02, mean=1.0), proj_w=rn(C, C), proj_b=rn(C), ls1=rn(C, std=0.01, mean=0.1),
+        ln = vc.norm_type == "layer_norm"
+        layers = [VitLayerW(norm1=rn(C, std=0.02, mean=1.0), qkv=rn(3 * C, C),
+                            q_norm=rn(C, std=0.02, mean=1.0) if vc.qk_normalization else None,
+                            k_norm=rn(C, std=0.02, mean=1.0) if vc.qk_normalization else None,
+                            proj_w=rn(C, C), proj_b=rn(C), ls1=rn(C, std=0.01, mean=0.1),
                             norm2=rn(C, std=0.02, mean=1.0), fc1_w=rn(I, C), fc1_b=rn(I), fc2_w=rn(C, I), fc2_b=rn(C),
-                            ls2=rn(C, std=0.01, mean=0.1)) for _ in range(vc.num_hidden_layers)]
+                            ls2=rn(C, std=0.01, mean=0.1), norm1_b=rn(C) if ln else None, norm2_b=rn(C) if ln else None,
+                            qkv_b=rn(3 * C) if vc.qkv_bias else None) for _ in range(vc.num_hidden_layers)]
         vit = VitW(patch_w=patch_w, patch_b=rn(C), cls=rn(C, std=1.0), pos=rn(vc.num_patches + 1, C, std=1.0), layers=layers)
         H = cfg.hidden_size
         Cin = C * cfg.pixel_shuffle_down ** 2
@@ -299,8 +329,12 @@ def to_reference_state_dict(w: OmChatWeights, cfg: OmChatQwen2Config) -> Dict[st
         sd[VT + "embeddings.patch_embedding.bias"] = w.vit.patch_b
         for li, l in enumerate(w.vit.layers):
             p = f"{VT}encoder.layers.{li}."
-            sd.update({p + "norm1.weight": l.norm1, p + "attn.qkv.weight": l.qkv, p + "attn.q_norm.weight": l.q_norm,
-                       p + "attn.k_norm.weight": l.k_norm, p + "attn.proj.weight": l.proj_w, p + "attn.proj.bias": l.proj_b,
+            for k, v in (("attn.q_norm.weight", l.q_norm), ("attn.k_norm.weight", l.k_norm), ("norm1.bias", l.norm1_b),
+                         ("norm2.bias", l.norm2_b), ("attn.qkv.bias", l.qkv_b)):
+                if v is not None:
+                    sd[p + k] = v
+            sd.update({p + "norm1.weight": l.norm1, p + "attn.qkv.weight": l.qkv,
+                       p + "attn.proj.weight": l.proj_w, p + "attn.proj.bias": l.proj_b,
                        p + "ls1": l.ls1, p + "norm2.weight": l.norm2, p + "mlp.fc1.weight": l.fc1_w,
                        p + "mlp.fc1.bias": l.fc1_b, p + "mlp.fc2.weight": l.fc2_w, p + "mlp.fc2.bias": l.fc2_b, p + "ls2": l.ls2})
         sd.update({"model.mm_projector.0.weight": w.proj.w0, "model.mm_projector.0.bias": w.proj.b0,

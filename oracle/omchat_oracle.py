@@ -45,6 +45,9 @@ class OracleConfig:
     vit_inter: int = 12800
     vit_layers: int = 45
     vit_eps: float = 1e-6
+    # InternViT-300M variant (intern_vit_300m/configuration_intern_vit.py:60-80): 'layer_norm', no QK-norm, optional qkv bias
+    vit_norm_type: str = "rms_norm"
+    vit_qk_norm: bool = True
     image_size: int = 448
     patch_size: int = 14
     select_layer: int = -1
@@ -78,6 +81,14 @@ def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
     return w * h.to(dt)
 
 
+def vit_norm(x: torch.Tensor, sd: Dict[str, torch.Tensor], name: str, cfg: OracleConfig) -> torch.Tensor:
+    """norm1 / norm2 of an encoder layer: NORM2FN[config.norm_type] (intern_vit_300m/modeling_intern_vit.py:61-64,209-210) -
+    InternRMSNorm, or torch.nn.LayerNorm (weight + bias, biased variance) for the 300M tower."""
+    if cfg.vit_norm_type == "layer_norm":
+        return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], cfg.vit_eps)
+    return rms_norm(x, sd[name + ".weight"], cfg.vit_eps)
+
+
 def vit_embeddings(pixels: torch.Tensor, sd: Dict[str, torch.Tensor], cfg: OracleConfig) -> torch.Tensor:
     """InternVisionEmbeddings.forward modeling_intern_vit.py:90-102. The bicubic resize of the position grid (:82-88)
     is applied like the reference does (identity at the native 32x32 grid)."""
@@ -102,10 +113,12 @@ def vit_attention(x: torch.Tensor, sd: Dict[str, torch.Tensor], pre: str, cfg: O
     flattened (:143-146), non-causal softmax attention, proj + bias."""
     B, N, C = x.shape
     H = cfg.vit_heads
-    qkv = F.linear(x, sd[pre + "attn.qkv.weight"]).reshape(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
+    qkv = F.linear(x, sd[pre + "attn.qkv.weight"], sd.get(pre + "attn.qkv.bias"))  # bias iff config.qkv_bias (:131)
+    qkv = qkv.reshape(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
     q, k, v = qkv.unbind(0)
-    q = rms_norm(q.transpose(1, 2).flatten(-2, -1), sd[pre + "attn.q_norm.weight"], cfg.vit_eps).view(B, N, H, C // H).transpose(1, 2)
-    k = rms_norm(k.transpose(1, 2).flatten(-2, -1), sd[pre + "attn.k_norm.weight"], cfg.vit_eps).view(B, N, H, C // H).transpose(1, 2)
+    if cfg.vit_qk_norm:  # config.qk_normalization (:136-140,143-146): off in the 300M tower
+        q = rms_norm(q.transpose(1, 2).flatten(-2, -1), sd[pre + "attn.q_norm.weight"], cfg.vit_eps).view(B, N, H, C // H).transpose(1, 2)
+        k = rms_norm(k.transpose(1, 2).flatten(-2, -1), sd[pre + "attn.k_norm.weight"], cfg.vit_eps).view(B, N, H, C // H).transpose(1, 2)
     scale = (C // H) ** -0.5
     attn = (q * scale) @ k.transpose(-2, -1)
     attn = attn.softmax(dim=-1)
@@ -123,8 +136,8 @@ def vit_mlp(x: torch.Tensor, sd: Dict[str, torch.Tensor], pre: str) -> torch.Ten
 def vit_layer(x: torch.Tensor, sd: Dict[str, torch.Tensor], li: int, cfg: OracleConfig) -> torch.Tensor:
     """InternVisionEncoderLayer.forward modeling_intern_vit.py:218-220 (drop_path is Identity at rate 0, :207-208)."""
     pre = f"{VT}encoder.layers.{li}."
-    x = x + vit_attention(rms_norm(x, sd[pre + "norm1.weight"], cfg.vit_eps), sd, pre, cfg) * sd[pre + "ls1"]
-    x = x + vit_mlp(rms_norm(x, sd[pre + "norm2.weight"], cfg.vit_eps), sd, pre) * sd[pre + "ls2"]
+    x = x + vit_attention(vit_norm(x, sd, pre + "norm1", cfg), sd, pre, cfg) * sd[pre + "ls1"]
+    x = x + vit_mlp(vit_norm(x, sd, pre + "norm2", cfg), sd, pre) * sd[pre + "ls2"]
     return x
 
 

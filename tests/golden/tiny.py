@@ -80,3 +80,22 @@ def tiny_inputs(seed: int = 1):
     pixels = torch.randn(4, 3, TINY["image_size"], TINY["image_size"], generator=g)
     ids = torch.randint(0, TINY["vocab"] - 10, (3, 24), generator=g)
     return pixels, ids
+
+
+# ---- InternViT-300M variant (intern_vit_300m/): LayerNorm with bias, no QK-norm, 64-dim heads, qkv bias on (the published
+# InternViT-300M-448px checkpoint has qkv_bias = true; the reference config default is false - the bias path is the superset)
+TINY_300M = dict(TINY, vit_heads=4, vit_norm_type="layer_norm", vit_qk_norm=False, vit_qkv_bias=True)
+
+
+def tiny_state_dict_300m(seed: int = 0) -> dict:
+    sd = tiny_state_dict(seed)
+    g = torch.Generator().manual_seed(seed + 1000)
+    vt = "model.vision_tower.vision_tower."
+    C = TINY_300M["vit_hidden"]
+    for li in range(TINY_300M["vit_layers"]):
+        p = f"{vt}encoder.layers.{li}."
+        del sd[p + "attn.q_norm.weight"], sd[p + "attn.k_norm.weight"]
+        sd[p + "norm1.bias"] = torch.randn(C, generator=g) * 0.1
+        sd[p + "norm2.bias"] = torch.randn(C, generator=g) * 0.1
+        sd[p + "attn.qkv.bias"] = torch.randn(3 * C, generator=g) * 0.1
+    return sd
