@@ -62,6 +62,12 @@ class OracleConfig:
     vocab: int = 152064
     rms_eps: float = 1e-6
     rope_theta: float = 1e6
+    # Qwen2-MoE language model (omchat_qwen2_moe.py:14-17 = transformers Qwen2MoeConfig); num_experts 0 = the dense Qwen2
+    num_experts: int = 0
+    top_k: int = 4
+    norm_topk_prob: bool = False
+    decoder_sparse_step: int = 1
+    mlp_only_layers: Tuple[int, ...] = ()
     max_len: Optional[int] = None  # tokenizer_model_max_length
     padding_side: str = "right"
 
@@ -309,6 +315,44 @@ def qwen2_mlp(x: torch.Tensor, sd, pre: str) -> torch.Tensor:
                     sd[pre + "mlp.down_proj.weight"])
 
 
+def moe_layer_is_sparse(li: int, cfg: OracleConfig) -> bool:
+    """Qwen2MoeDecoderLayer.__init__ transformers modeling_qwen2_moe.py:381-386."""
+    return (li not in cfg.mlp_only_layers) and cfg.num_experts > 0 and (li + 1) % cfg.decoder_sparse_step == 0
+
+
+def moe_route(x: torch.Tensor, sd, pre: str, cfg: OracleConfig):
+    """Qwen2MoeTopKRouter.forward modeling_qwen2_moe.py:343-352: softmax over ALL experts in fp32, top-k, optional
+    renormalisation of the k weights. x [T, C] -> (weights [T, k], expert ids [T, k])."""
+    probs = torch.softmax(F.linear(x, sd[pre + "mlp.gate.weight"]), dim=-1, dtype=torch.float32)
+    w, idx = torch.topk(probs, cfg.top_k, dim=-1)
+    if cfg.norm_topk_prob:
+        w = w / w.sum(dim=-1, keepdim=True)
+    return w.to(x.dtype), idx
+
+
+def qwen2_moe_block(x: torch.Tensor, sd, pre: str, cfg: OracleConfig) -> torch.Tensor:
+    """Qwen2MoeSparseMoeBlock.forward modeling_qwen2_moe.py:363-374 with Qwen2MoeExperts.forward :307-331: every token goes
+    through its k routed experts (SwiGLU MLPs of moe_intermediate_size, weighted by the routing weights) plus the shared
+    expert scaled by sigmoid(shared_expert_gate(x)). Expert weights under their checkpoint names (one matrix per expert)."""
+    shp = x.shape
+    x = x.reshape(-1, shp[-1])
+    w, idx = moe_route(x, sd, pre, cfg)
+    out = torch.zeros_like(x)
+    for e in range(cfg.num_experts):
+        tok, slot = torch.where(idx == e)
+        if tok.numel() == 0:
+            continue
+        q = f"{pre}mlp.experts.{e}."
+        y = F.linear(F.silu(F.linear(x[tok], sd[q + "gate_proj.weight"])) * F.linear(x[tok], sd[q + "up_proj.weight"]),
+                     sd[q + "down_proj.weight"])
+        out.index_add_(0, tok, y * w[tok, slot, None])
+    q = pre + "mlp.shared_expert."
+    shared = F.linear(F.silu(F.linear(x, sd[q + "gate_proj.weight"])) * F.linear(x, sd[q + "up_proj.weight"]),
+                      sd[q + "down_proj.weight"])
+    out = out + torch.sigmoid(F.linear(x, sd[pre + "mlp.shared_expert_gate.weight"])) * shared
+    return out.reshape(shp)
+
+
 def qwen2_forward(embeds: torch.Tensor, position_ids: torch.Tensor, sd, cfg: OracleConfig,
                   past: Optional[List[Tuple[torch.Tensor, torch.Tensor]]] = None,
                   key_mask: Optional[torch.Tensor] = None, return_hidden: bool = False):
@@ -325,7 +369,8 @@ def qwen2_forward(embeds: torch.Tensor, position_ids: torch.Tensor, sd, cfg: Ora
                                 None if past is None else past[li], key_mask)
         new_past.append(kv)
         h = h + a
-        h = h + qwen2_mlp(rms_norm(h, sd[pre + "post_attention_layernorm.weight"], cfg.rms_eps), sd, pre)
+        xn = rms_norm(h, sd[pre + "post_attention_layernorm.weight"], cfg.rms_eps)
+        h = h + (qwen2_moe_block(xn, sd, pre, cfg) if moe_layer_is_sparse(li, cfg) else qwen2_mlp(xn, sd, pre))
         hiddens.append(h)
     h = rms_norm(h, sd["model.norm.weight"], cfg.rms_eps)
     logits = F.linear(h, sd["lm_head.weight"])

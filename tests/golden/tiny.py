@@ -99,3 +99,49 @@ def tiny_state_dict_300m(seed: int = 0) -> dict:
         sd[p + "norm2.bias"] = torch.randn(C, generator=g) * 0.1
         sd[p + "attn.qkv.bias"] = torch.randn(3 * C, generator=g) * 0.1
     return sd
+
+
+# ---- Qwen2-MoE language model variant (omchat/model/language_model/omchat_qwen2_moe.py over transformers Qwen2MoeForCausalLM)
+TINY_MOE = dict(TINY, num_experts=8, top_k=2, moe_inter=128, shared_inter=256)
+
+
+def tiny_state_dict_moe(seed: int = 0, dense_layers=()) -> dict:
+    """Checkpoint-format names (one gate/up/down matrix per expert, as the published Qwen-MoE safetensors hold them). Layers in
+    `dense_layers` (config.mlp_only_layers) keep the dense MLP of tiny_state_dict; the others get router + experts + shared expert."""
+    sd = tiny_state_dict(seed)
+    g = torch.Generator().manual_seed(seed + 2000)
+    c = TINY_MOE
+    H = c["hidden"]
+
+    def rn(*shape, std=0.05):
+        return torch.randn(*shape, generator=g) * std
+
+    for li in range(c["layers"]):
+        if li in dense_layers:
+            continue
+        p = f"model.layers.{li}.mlp."
+        for k in ("gate_proj", "up_proj", "down_proj"):
+            del sd[p + k + ".weight"]
+        sd[p + "gate.weight"] = rn(c["num_experts"], H, std=0.5)  # wide router logits: top-k margins well above bf16 noise
+        for e in range(c["num_experts"]):
+            sd[p + f"experts.{e}.gate_proj.weight"] = rn(c["moe_inter"], H)
+            sd[p + f"experts.{e}.up_proj.weight"] = rn(c["moe_inter"], H)
+            sd[p + f"experts.{e}.down_proj.weight"] = rn(H, c["moe_inter"])
+        sd[p + "shared_expert.gate_proj.weight"] = rn(c["shared_inter"], H)
+        sd[p + "shared_expert.up_proj.weight"] = rn(c["shared_inter"], H)
+        sd[p + "shared_expert.down_proj.weight"] = rn(H, c["shared_inter"])
+        sd[p + "shared_expert_gate.weight"] = rn(1, H, std=0.3)
+    return sd
+
+
+def fuse_experts_for_transformers5(sd: dict, num_experts: int) -> dict:
+    """transformers >= 5 keeps the experts as 3-D parameters (modeling_qwen2_moe.py:298-305): experts.gate_up_proj
+    [E, 2 I, H] = cat(gate, up) per expert, experts.down_proj [E, H, I]."""
+    out = {k: v for k, v in sd.items() if ".mlp.experts." not in k}
+    layers = sorted({k.split(".mlp.experts.")[0] for k in sd if ".mlp.experts." in k})
+    for p in layers:
+        gu = [torch.cat([sd[f"{p}.mlp.experts.{e}.gate_proj.weight"], sd[f"{p}.mlp.experts.{e}.up_proj.weight"]], 0)
+              for e in range(num_experts)]
+        out[p + ".mlp.experts.gate_up_proj"] = torch.stack(gu)
+        out[p + ".mlp.experts.down_proj"] = torch.stack([sd[f"{p}.mlp.experts.{e}.down_proj.weight"] for e in range(num_experts)])
+    return out
