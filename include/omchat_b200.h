@@ -369,6 +369,35 @@ int omc_decoder_prefill(const omc_decode_desc* desc, const float* inv_freq, void
 /* norm_folded = 1: desc->qkv_w / gate_up_w carry the input / post-attention RMSNorm weights in their columns (ln1 / ln2 are
  * then unused); final_norm + lm_head stay separate. */
 
+/* ---- Qwen2-MoE sparse MLP block --------------------------------------------------------------------------------------
+ * The language model behind omchat/model/language_model/omchat_qwen2_moe.py:28-117 is transformers' Qwen2MoeForCausalLM; its
+ * sparse block (modeling_qwen2_moe.py:295-374) is: router softmax over all experts (fp32) -> top-k (optionally renormalised)
+ * -> every token through its k expert SwiGLU MLPs, weighted -> + sigmoid(shared_expert_gate(x)) * shared_expert(x).
+ * Device-side plan, no host synchronisation (capturable in a CUDA graph):
+ *   omc_moe_route    x [T, C] bf16 (the post-attention-normed rows), router_w [E, C], shared_gate_w [C] or NULL ->
+ *                    topk_ids int32 [T, k], topk_w fp32 [T, k], shared_gate fp32 [T] (sigmoid), counts int32 [E] += histogram
+ *                    (counts must be zero on entry: zero it once, omc_moe_plan re-zeroes it). E <= 128, k <= 8.
+ *   omc_moe_plan     counts -> seg_start int32 [E] (first row of every expert's segment, segments padded to whole 128-row
+ *                    tiles), tile_expert int32 [max_tiles] (expert of every 128-row tile, -1 = unused), cursor [E] = 0,
+ *                    counts = 0. max_tiles >= omc_moe_max_tiles(T, k, E) = T * k / 128 + E.
+ *   omc_moe_scatter  copies row t of x to its k slots of xperm [max_tiles * 128, ldp] and records them in slot_of int32 [T, k]
+ *   omc_gemm_bf16_grouped   out[r, :] = epi(xperm[r, :] . W[tile_expert[r / 128]]^T) for W = [n_experts * N, K] stacked expert
+ *                    matrices on the tcgen05 GEMM (epi OMC_EPI_SWIGLU on interleaved gate/up rows, or OMC_EPI_NONE); tiles
+ *                    with tile_expert < 0 are skipped without touching the weights. M_max = max_tiles * 128, N % 128 == 0.
+ *   omc_moe_combine  h[t] += sum_j topk_w[t, j] * yperm[slot_of[t, j]] + shared_gate[t] * shared_y[t]  (shared_y may be NULL),
+ *                    fp32 accumulate, one bf16 rounding: the block's output + the decoder layer's residual add. */
+int omc_moe_max_tiles(int T, int top_k, int n_experts);
+int omc_moe_route(const void* x, long long ldx, int T, int C, const void* router_w, const void* shared_gate_w, int n_experts,
+                  int top_k, int norm_topk, int32_t* topk_ids, float* topk_w, float* shared_gate, int32_t* counts, void* stream);
+int omc_moe_plan(int32_t* counts, int n_experts, int max_tiles, int32_t* seg_start, int32_t* cursor, int32_t* tile_expert,
+                 void* stream);
+int omc_moe_scatter(const void* x, long long ldx, int T, int C, const int32_t* topk_ids, int top_k, const int32_t* seg_start,
+                    int32_t* cursor, void* xperm, long long ldp, int32_t* slot_of, void* stream);
+int omc_gemm_bf16_grouped(const void* X, long long ldx, int M_max, const void* W, long long ldw, int n_experts, int N, int K,
+                          const int32_t* tile_expert, void* out, long long ldo, int epi, void* stream);
+int omc_moe_combine(void* h, long long ldh, int T, int C, const void* yperm, long long ldy, const int32_t* slot_of,
+                    const float* topk_w, int top_k, const void* shared_y, long long lds, const float* shared_gate, void* stream);
+
 /* ---- peer (NVLink) memory for the tensor-parallel decode step ------------------------------------------------------
  * Replaces the NCCL communicator a Megatron-style decoder would hand to its all-reduce: one exchange buffer per rank,
  * visible to every rank of the node. omc_peer_alloc: cudaMalloc + zero-fill on the current device and export a 64-byte

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "_lib"
 LIB = LIBDIR / "libomchat_b200.so"
-SOURCES = ["capi.cu", "gemm_sm100.cu", "gemm_skinny.cu", "gemm_stream.cu", "gemv.cu", "rowops.cu", "attention.cu", "attention_sm100.cu", "decode_mega.cu", "preprocess.cu", "model_capi.cu"]
+SOURCES = ["capi.cu", "gemm_sm100.cu", "gemm_skinny.cu", "gemm_stream.cu", "gemv.cu", "rowops.cu", "attention.cu", "attention_sm100.cu", "decode_mega.cu", "preprocess.cu", "model_capi.cu", "moe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v",

@@ -112,3 +112,26 @@ class OmChatQwen2Config:
 
     def to_dict(self):
         return asdict(self)
+
+
+@dataclass
+class OmChatQwen2MoeConfig(OmChatQwen2Config):
+    """omchat_qwen2_moe.py:14-17: transformers Qwen2MoeConfig fields + the mm_* attributes. Defaults = Qwen1.5-MoE-A2.7B's
+    language model (Qwen2MoeConfig defaults) under the same vision tower."""
+    model_type: str = "omchat_qwen2_moe"
+    hidden_size: int = 2048
+    intermediate_size: int = 5632
+    num_hidden_layers: int = 24
+    num_attention_heads: int = 16
+    num_key_value_heads: int = 16
+    num_experts: int = 60
+    num_experts_per_tok: int = 4
+    moe_intermediate_size: int = 1408
+    shared_expert_intermediate_size: int = 5632
+    norm_topk_prob: bool = False
+    decoder_sparse_step: int = 1
+    mlp_only_layers: List[int] = field(default_factory=list)
+
+    def layer_is_sparse(self, li: int) -> bool:
+        """Qwen2MoeDecoderLayer.__init__ (transformers modeling_qwen2_moe.py:381-386)."""
+        return li not in self.mlp_only_layers and self.num_experts > 0 and (li + 1) % self.decoder_sparse_step == 0

@@ -38,6 +38,9 @@ struct GemmParams {
   float inv_norm_dim, eps;
   float* ssq_out;        // [num_n_tiles][ssq_out_ld]: sums of squares of the bf16 rows written, per N tile, or null
   long long ssq_out_ld;
+  // grouped (mixture-of-experts) mode, CG = 1 only: X's rows are sorted by expert with every expert's segment padded to whole
+  // 128-row tiles; grp_tile[mt] = expert whose weights [N, K] (rows grp * N ... of the stacked W) tile mt multiplies, < 0 = skip
+  const int32_t* grp_tile;
 };
 
 constexpr int kBM = 128;
@@ -128,8 +131,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int mt, nt;
         tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
+        const int grp = p.grp_tile != nullptr ? __ldg(p.grp_tile + mt) : 0;
+        if (grp < 0) continue;
         const int row_a = (mt * CG + (int)cta_rank) * kBM;
-        const int row_b = nt * BN + (int)cta_rank * Cfg::kBLoadRows;
+        const int row_b = grp * p.N + nt * BN + (int)cta_rank * Cfg::kBLoadRows;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -152,8 +157,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (leader && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(kBM * CG, BN);
       uint32_t it = 0, lt = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        if (p.grp_tile != nullptr) {
+          int mt, nt;
+          tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
+          if (__ldg(p.grp_tile + mt) < 0) continue;
+        }
         const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
+        ++lt;
         mbar_wait_cluster(&tempty_bar[acc], acc_ph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
@@ -179,10 +190,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;
     const int lane = lane_id();
     uint32_t lt = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       int mt, nt;
       tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
+      if (p.grp_tile != nullptr && __ldg(p.grp_tile + mt) < 0) continue;
       const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
+      ++lt;
       const long long row = (long long)(mt * CG + (int)cta_rank) * kBM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       // folded RMSNorm: this row's scale, fetched while the MMAs of the tile are still running
@@ -363,12 +376,12 @@ int num_sms() {
 
 template <int BN, int CG>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, GemmParams p, int max_ctas,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int groups = 1) {
   using Cfg = GemmCfg<BN, CG>;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(&tmA, A, p.M, p.K, lda, kBM);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmB, W, p.N, p.K, ldw, Cfg::kBLoadRows);
+  rc = make_tmap_2d(&tmB, W, (long long)p.N * groups, p.K, ldw, Cfg::kBLoadRows);
   if (rc) return rc;
   p.num_m_tiles = (p.M + kBM * CG - 1) / (kBM * CG);
   p.num_n_tiles = (p.N + BN - 1) / BN;
@@ -421,6 +434,28 @@ extern "C" int omc_gemm_bf16_norm(const void* X, long long ldx, const void* W, l
                                   long long ldr, int epi, int out_is_f32, int tile_cfg, omc_gemm_norm* nf, void* stream) {
   if (nf == nullptr) return set_error(OMC_ERR_ARG, "omc_gemm_bf16_norm: null norm description");
   return gemm_impl(X, ldx, W, ldw, out, ldo, M, N, K, bias, scale, res, ldr, epi, out_is_f32, tile_cfg, nf, stream);
+}
+
+// Grouped GEMM for the routed experts of a mixture-of-experts MLP (transformers Qwen2MoeExperts.forward,
+// modeling_qwen2_moe.py:307-331): out[r, :] = epi( X[r, :] . W[e(r)]^T ) where the rows of X are sorted by expert, every expert's
+// segment starts on a 128-row tile and tile_expert[r / 128] names the expert (< 0: the tile holds no rows, skipped without
+// touching the weights). W is the experts' matrices stacked, [n_experts * N, K]. One launch, no host knowledge of the routing.
+extern "C" int omc_gemm_bf16_grouped(const void* X, long long ldx, int M_max, const void* W, long long ldw, int n_experts, int N,
+                                     int K, const int32_t* tile_expert, void* out, long long ldo, int epi, void* stream) {
+  if (X == nullptr || W == nullptr || tile_expert == nullptr || out == nullptr)
+    return set_error(OMC_ERR_ARG, "omc_gemm_bf16_grouped: null argument");
+  if (M_max <= 0 || M_max % kBM != 0 || n_experts <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % 8 != 0)
+    return set_error(OMC_ERR_SHAPE, "omc_gemm_bf16_grouped: M_max must be whole 128-row tiles, N a multiple of 128, K of 8");
+  if (epi != EPI_NONE && epi != EPI_SWIGLU) return set_error(OMC_ERR_ARG, "omc_gemm_bf16_grouped: epilogue NONE or SWIGLU");
+  GemmParams p{};
+  p.M = M_max; p.N = N; p.K = K;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.epi = epi;
+  p.grp_tile = tile_expert;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N % 256 == 0) return launch_gemm<256, 1>(X, ldx, W, ldw, p, 0, st, n_experts);
+  return launch_gemm<128, 1>(X, ldx, W, ldw, p, 0, st, n_experts);
 }
 
 static int gemm_impl(const void* X, long long ldx, const void* W, long long ldw, void* out, long long ldo, int M, int N, int K,

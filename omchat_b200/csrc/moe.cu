@@ -1,0 +1,312 @@
+// Routing side of the Qwen2-MoE sparse MLP block (transformers modeling_qwen2_moe.py:295-374, the language model behind the
+// reference's omchat/model/language_model/omchat_qwen2_moe.py): router softmax + top-k, the sort of the (token, expert) pairs
+// into expert-contiguous 128-row tiles for the grouped tcgen05 GEMM (omc_gemm_bf16_grouped), and the weighted combine of the
+// expert outputs with the sigmoid-gated shared expert and the residual stream. All of it is HBM/L2-bound row work:
+//   omc_moe_route    one warp per token: E + 1 dot products against the (L2-resident) router / shared-gate rows, fp32 softmax,
+//                    k rounds of warp arg-max, per-expert histogram
+//   omc_moe_plan     one CTA: padded segment starts, the tile -> expert table, counters reset for the next call
+//   omc_moe_scatter  one CTA per token: the normed row is copied to its k slots (slot = segment start + atomic cursor)
+//   omc_moe_combine  one CTA per token: h += sum_j w_j * y[slot_j] + sigmoid_gate * shared_y, fp32 accumulate, one rounding
+// No host synchronisation anywhere: the block can be captured in a CUDA graph; the host sizes buffers for the worst case
+// (T * k / 128 + E tiles).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "omc_internal.h"
+#include "ptx.cuh"
+
+namespace omc {
+
+typedef __nv_bfloat16 bf16;
+constexpr int kMoeMaxExperts = 128;  // 4 router logits per lane
+constexpr int kMoeMaxTopK = 8;
+constexpr int kMoeTile = 128;        // rows per GEMM tile = padding unit of an expert's segment
+constexpr int kRouteWarps = 4;
+
+__device__ __forceinline__ float dot8(uint4 a, uint4 b) {
+  float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+  float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+  return a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+}
+
+// Qwen2MoeTopKRouter.forward (modeling_qwen2_moe.py:343-352) + the shared expert's sigmoid gate (:371).
+__global__ void __launch_bounds__(kRouteWarps * 32) moe_route_kernel(const bf16* __restrict__ x, long long ldx, int T, int C,
+                                                                     const bf16* __restrict__ router_w,
+                                                                     const bf16* __restrict__ shared_gate_w, int E, int top_k,
+                                                                     int norm_topk, int32_t* __restrict__ topk_ids,
+                                                                     float* __restrict__ topk_w, float* __restrict__ shared_gate,
+                                                                     int32_t* __restrict__ counts) {
+  extern __shared__ uint4 s_rows[];  // [kRouteWarps][C / 8]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  uint4* srow = s_rows + warp * nvec;
+  for (int t = blockIdx.x * kRouteWarps + warp; t < T; t += gridDim.x * kRouteWarps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)t * ldx);
+    for (int i = lane; i < nvec; i += 32) srow[i] = xr[i];
+    __syncwarp();
+    float logit[kMoeMaxExperts / 32];
+#pragma unroll
+    for (int j = 0; j < kMoeMaxExperts / 32; ++j) logit[j] = -INFINITY;
+    for (int e = 0; e < E; ++e) {
+      const uint4* wr = reinterpret_cast<const uint4*>(router_w + (long long)e * C);
+      float acc = 0.f;
+      for (int i = lane; i < nvec; i += 32) acc += dot8(srow[i], __ldg(wr + i));
+      acc = warp_sum(acc);
+      if ((e & 31) == lane) {
+#pragma unroll
+        for (int j = 0; j < kMoeMaxExperts / 32; ++j)
+          if (j == (e >> 5)) logit[j] = acc;
+      }
+    }
+    if (shared_gate_w != nullptr) {
+      const uint4* wr = reinterpret_cast<const uint4*>(shared_gate_w);
+      float acc = 0.f;
+      for (int i = lane; i < nvec; i += 32) acc += dot8(srow[i], __ldg(wr + i));
+      acc = warp_sum(acc);
+      if (lane == 0) shared_gate[t] = 1.f / (1.f + __expf(-acc));
+    }
+    // softmax over all E experts in fp32
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kMoeMaxExperts / 32; ++j) mx = fmaxf(mx, logit[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float prob[kMoeMaxExperts / 32], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
+      prob[j] = (j * 32 + lane < E) ? expf(logit[j] - mx) : 0.f;
+      sum += prob[j];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    // top-k: k rounds of warp arg-max (ties -> lowest expert index)
+    float sel_w[kMoeMaxTopK];
+    int sel_e[kMoeMaxTopK];
+    float wsum = 0.f;
+#pragma unroll
+    for (int r = 0; r < kMoeMaxTopK; ++r) {
+      if (r >= top_k) break;
+      float bv = -1.f;
+      int be = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
+        const int e = j * 32 + lane;
+        if (e < E && prob[j] > bv) {
+          bv = prob[j];
+          be = e;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oe = __shfl_xor_sync(0xffffffffu, be, o);
+        if (ov > bv || (ov == bv && oe < be)) {
+          bv = ov;
+          be = oe;
+        }
+      }
+      sel_w[r] = bv * inv;
+      sel_e[r] = be;
+      wsum += sel_w[r];
+      if ((be & 31) == lane) {
+#pragma unroll
+        for (int j = 0; j < kMoeMaxExperts / 32; ++j)
+          if (j == (be >> 5)) prob[j] = -2.f;  // taken
+      }
+    }
+    if (lane == 0) {
+      const float rn = norm_topk ? 1.f / wsum : 1.f;
+#pragma unroll
+      for (int r = 0; r < kMoeMaxTopK; ++r) {
+        if (r >= top_k) break;
+        topk_ids[(long long)t * top_k + r] = sel_e[r];
+        topk_w[(long long)t * top_k + r] = sel_w[r] * rn;
+        atomicAdd(counts + sel_e[r], 1);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(128) moe_plan_kernel(int32_t* __restrict__ counts, int E, int max_tiles,
+                                                       int32_t* __restrict__ seg_start, int32_t* __restrict__ cursor,
+                                                       int32_t* __restrict__ tile_expert) {
+  __shared__ int s_start[kMoeMaxExperts + 1];
+  if (threadIdx.x == 0) {
+    int at = 0;
+    for (int e = 0; e < E; ++e) {
+      s_start[e] = at;
+      at += (counts[e] + kMoeTile - 1) / kMoeTile;  // in tiles
+    }
+    s_start[E] = at;
+  }
+  __syncthreads();
+  for (int mt = threadIdx.x; mt < max_tiles; mt += blockDim.x) {
+    int owner = -1;
+    if (mt < s_start[E]) {
+      int lo = 0, hi = E;  // last e with s_start[e] <= mt (empty experts share a start with their successor: take the last)
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_start[mid] <= mt) lo = mid; else hi = mid;
+      }
+      owner = lo;
+    }
+    tile_expert[mt] = owner;
+  }
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    seg_start[e] = s_start[e] * kMoeTile;
+    cursor[e] = 0;
+    counts[e] = 0;  // ready for the next omc_moe_route
+  }
+}
+
+__global__ void __launch_bounds__(128) moe_scatter_kernel(const bf16* __restrict__ x, long long ldx, int T, int C,
+                                                          const int32_t* __restrict__ topk_ids, int top_k,
+                                                          const int32_t* __restrict__ seg_start, int32_t* __restrict__ cursor,
+                                                          bf16* __restrict__ xperm, long long ldp, int32_t* __restrict__ slot_of) {
+  __shared__ int s_slot[kMoeMaxTopK];
+  const int nvec = C >> 3;
+  for (int t = blockIdx.x; t < T; t += gridDim.x) {
+    if (threadIdx.x < top_k) {
+      const int e = topk_ids[(long long)t * top_k + threadIdx.x];
+      const int slot = seg_start[e] + atomicAdd(cursor + e, 1);
+      s_slot[threadIdx.x] = slot;
+      slot_of[(long long)t * top_k + threadIdx.x] = slot;
+    }
+    __syncthreads();
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)t * ldx);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const uint4 v = xr[i];
+      for (int r = 0; r < top_k; ++r) reinterpret_cast<uint4*>(xperm + (long long)s_slot[r] * ldp)[i] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// Qwen2MoeSparseMoeBlock.forward :363-374 + the decoder layer's residual add (:420): fp32 accumulate, one rounding.
+__global__ void __launch_bounds__(128) moe_combine_kernel(bf16* __restrict__ h, long long ldh, int T, int C,
+                                                          const bf16* __restrict__ yperm, long long ldy,
+                                                          const int32_t* __restrict__ slot_of, const float* __restrict__ topk_w,
+                                                          int top_k, const bf16* __restrict__ shared_y, long long lds,
+                                                          const float* __restrict__ shared_gate) {
+  __shared__ int s_slot[kMoeMaxTopK];
+  __shared__ float s_w[kMoeMaxTopK];
+  const int nvec = C >> 3;
+  for (int t = blockIdx.x; t < T; t += gridDim.x) {
+    if (threadIdx.x < top_k) {
+      s_slot[threadIdx.x] = slot_of[(long long)t * top_k + threadIdx.x];
+      s_w[threadIdx.x] = topk_w[(long long)t * top_k + threadIdx.x];
+    }
+    __syncthreads();
+    const float sg = shared_y != nullptr ? shared_gate[t] : 0.f;
+    uint4* hr = reinterpret_cast<uint4*>(h + (long long)t * ldh);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      float moe[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < top_k; ++r) {
+        const uint4 v = reinterpret_cast<const uint4*>(yperm + (long long)s_slot[r] * ldy)[i];
+        const uint32_t vi[4] = {v.x, v.y, v.z, v.w};
+        const float w = s_w[r];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a = unpack_bf16(vi[q]);
+          moe[2 * q] += w * a.x;
+          moe[2 * q + 1] += w * a.y;
+        }
+      }
+      if (shared_y != nullptr) {
+        const uint4 v = reinterpret_cast<const uint4*>(shared_y + (long long)t * lds)[i];
+        const uint32_t vi[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a = unpack_bf16(vi[q]);
+          moe[2 * q] += sg * a.x;
+          moe[2 * q + 1] += sg * a.y;
+        }
+      }
+      const uint4 hv = hr[i];
+      const uint32_t hi[4] = {hv.x, hv.y, hv.z, hv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 a = unpack_bf16(hi[q]);
+        o[q] = pack_bf16(a.x + moe[2 * q], a.y + moe[2 * q + 1]);
+      }
+      hr[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace omc
+
+using namespace omc;
+
+extern "C" int omc_moe_max_tiles(int T, int top_k, int n_experts) {
+  if (T <= 0 || top_k <= 0 || n_experts <= 0) return 0;
+  return (int)(((long long)T * top_k) / kMoeTile) + n_experts;  // sum_e ceil(c_e / 128) <= floor(sum c_e / 128) + E
+}
+
+extern "C" int omc_moe_route(const void* x, long long ldx, int T, int C, const void* router_w, const void* shared_gate_w,
+                             int n_experts, int top_k, int norm_topk, int32_t* topk_ids, float* topk_w, float* shared_gate,
+                             int32_t* counts, void* stream) {
+  if (T <= 0) return OMC_OK;
+  if (x == nullptr || router_w == nullptr || topk_ids == nullptr || topk_w == nullptr || counts == nullptr ||
+      (shared_gate_w != nullptr && shared_gate == nullptr))
+    return set_error(OMC_ERR_ARG, "omc_moe_route: null argument");
+  if (n_experts < 1 || n_experts > kMoeMaxExperts || top_k < 1 || top_k > kMoeMaxTopK || top_k > n_experts)
+    return set_error(OMC_ERR_SHAPE, "omc_moe_route: at most 128 experts and top-8 routing");
+  if (C <= 0 || C % 8 != 0 || C > 8192 || ldx % 8 != 0)
+    return set_error(OMC_ERR_SHAPE, "omc_moe_route: C must be a multiple of 8 and <= 8192, ldx a multiple of 8");
+  const int smem = kRouteWarps * (C / 8) * 16;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[cur_device()];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(moe_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRouteWarps * 1024 * 16);
+    if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int need = (T + kRouteWarps - 1) / kRouteWarps;
+  const int grid = need < num_sms() * 8 ? need : num_sms() * 8;
+  moe_route_kernel<<<grid, kRouteWarps * 32, smem, (cudaStream_t)stream>>>(
+      (const bf16*)x, ldx, T, C, (const bf16*)router_w, (const bf16*)shared_gate_w, n_experts, top_k, norm_topk, topk_ids, topk_w,
+      shared_gate, counts);
+  return check_launch("moe_route");
+}
+
+extern "C" int omc_moe_plan(int32_t* counts, int n_experts, int max_tiles, int32_t* seg_start, int32_t* cursor,
+                            int32_t* tile_expert, void* stream) {
+  if (counts == nullptr || seg_start == nullptr || cursor == nullptr || tile_expert == nullptr)
+    return set_error(OMC_ERR_ARG, "omc_moe_plan: null argument");
+  if (n_experts < 1 || n_experts > kMoeMaxExperts || max_tiles < 1) return set_error(OMC_ERR_SHAPE, "omc_moe_plan: bad sizes");
+  moe_plan_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(counts, n_experts, max_tiles, seg_start, cursor, tile_expert);
+  return check_launch("moe_plan");
+}
+
+extern "C" int omc_moe_scatter(const void* x, long long ldx, int T, int C, const int32_t* topk_ids, int top_k,
+                               const int32_t* seg_start, int32_t* cursor, void* xperm, long long ldp, int32_t* slot_of,
+                               void* stream) {
+  if (T <= 0) return OMC_OK;
+  if (x == nullptr || topk_ids == nullptr || seg_start == nullptr || cursor == nullptr || xperm == nullptr || slot_of == nullptr)
+    return set_error(OMC_ERR_ARG, "omc_moe_scatter: null argument");
+  if (C % 8 != 0 || ldx % 8 != 0 || ldp % 8 != 0 || top_k < 1 || top_k > kMoeMaxTopK)
+    return set_error(OMC_ERR_SHAPE, "omc_moe_scatter: C / leading dims must be multiples of 8, top_k <= 8");
+  const int grid = T < num_sms() * 16 ? T : num_sms() * 16;
+  moe_scatter_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, T, C, topk_ids, top_k, seg_start, cursor,
+                                                             (bf16*)xperm, ldp, slot_of);
+  return check_launch("moe_scatter");
+}
+
+extern "C" int omc_moe_combine(void* h, long long ldh, int T, int C, const void* yperm, long long ldy, const int32_t* slot_of,
+                               const float* topk_w, int top_k, const void* shared_y, long long lds, const float* shared_gate,
+                               void* stream) {
+  if (T <= 0) return OMC_OK;
+  if (h == nullptr || yperm == nullptr || slot_of == nullptr || topk_w == nullptr || (shared_y != nullptr && shared_gate == nullptr))
+    return set_error(OMC_ERR_ARG, "omc_moe_combine: null argument");
+  if (C % 8 != 0 || ldh % 8 != 0 || ldy % 8 != 0 || lds % 8 != 0 || top_k < 1 || top_k > kMoeMaxTopK)
+    return set_error(OMC_ERR_SHAPE, "omc_moe_combine: C / leading dims must be multiples of 8, top_k <= 8");
+  const int grid = T < num_sms() * 16 ? T : num_sms() * 16;
+  moe_combine_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((bf16*)h, ldh, T, C, (const bf16*)yperm, ldy, slot_of, topk_w, top_k,
+                                                             (const bf16*)shared_y, lds, shared_gate);
+  return check_launch("moe_combine");
+}

@@ -31,6 +31,8 @@ from transformers import AutoConfig, AutoModel, AutoModelForCausalLM, AutoProces
 
 from .config import InternVisionConfig as NativeVisionConfig
 from .config import OmChatQwen2Config as NativeConfig
+from .config import OmChatQwen2MoeConfig as NativeMoeConfig
+from .model import moe as native_moe
 from .model import omchat as native
 from .model.checkpoint import config_from_dict
 from .processing import OmChatImageProcessor, OmChatProcessor
@@ -56,6 +58,21 @@ class OmChatQwen2Config(PretrainedConfig):
 
     def to_native(self) -> NativeConfig:
         return config_from_dict(self.to_dict())
+
+
+class OmChatQwen2MoeConfig(OmChatQwen2Config):
+    """`OmChatQwen2MoeConfig(Qwen2MoeConfig)` of omchat_qwen2_moe.py:14-17: the flat config + the mixture-of-experts fields."""
+    model_type = "omchat_qwen2_moe"
+
+    def __init__(self, **kwargs):
+        base, moe = NativeConfig().to_dict(), NativeMoeConfig().to_dict()
+        for k, v in moe.items():
+            if k not in ("model_type", "vision_config") and (k not in base or base[k] != v):
+                kwargs.setdefault(k, v)  # the MoE defaults (Qwen1.5-MoE-A2.7B sizes) where they differ from the dense model's
+        extra = {k: kwargs.pop(k) for k in list(kwargs) if k in moe and k not in base}
+        super().__init__(**kwargs)
+        for k, v in extra.items():
+            setattr(self, k, v)
 
 
 class OmChatConfig(PretrainedConfig):
@@ -124,6 +141,10 @@ class OmChatQwen2ForCausalLM(_AutoLoadable, native.OmChatQwen2ForCausalLM):
     config_class = OmChatQwen2Config
 
 
+class OmChatQwen2MoeForCausalLM(_AutoLoadable, native_moe.OmChatQwen2MoeForCausalLM):
+    config_class = OmChatQwen2MoeConfig
+
+
 class OmChatForConditionalGeneration(_AutoLoadable, native.OmChatForConditionalGeneration):
     config_class = OmChatConfig
 
@@ -158,6 +179,9 @@ OmChatProcessor.from_pretrained = classmethod(_processor_from_pretrained)
 def register_auto_classes() -> None:
     AutoConfig.register("omchat_qwen2", OmChatQwen2Config, exist_ok=True)
     AutoModelForCausalLM.register(OmChatQwen2Config, OmChatQwen2ForCausalLM, exist_ok=True)
+    # omchat_qwen2_moe.py:116-117
+    AutoConfig.register("omchat_qwen2_moe", OmChatQwen2MoeConfig, exist_ok=True)
+    AutoModelForCausalLM.register(OmChatQwen2MoeConfig, OmChatQwen2MoeForCausalLM, exist_ok=True)
     AutoConfig.register("omchat", OmChatConfig, exist_ok=True)
     AutoModel.register(OmChatConfig, OmChatForConditionalGeneration, exist_ok=True)
     AutoProcessor.register(OmChatConfig, OmChatProcessor, exist_ok=True)

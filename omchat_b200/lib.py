@@ -40,6 +40,12 @@ SIGNATURES = {
     "omc_rmsnorm": (_I, [_P, _L, _P, _P, _L, _I, _I, _F, _P]),
     "omc_rmsnorm_pair": (_I, [_P, _L, _P, _P, _I, _I, _F, _P]),
     "omc_layernorm": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _F, _P]),
+    "omc_moe_max_tiles": (_I, [_I, _I, _I]),
+    "omc_moe_route": (_I, [_P, _L, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "omc_moe_plan": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "omc_moe_scatter": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _P, _L, _P, _P]),
+    "omc_gemm_bf16_grouped": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P]),
+    "omc_moe_combine": (_I, [_P, _L, _I, _I, _P, _L, _P, _P, _I, _P, _L, _P, _P]),
     "omc_vit_im2col": (_I, [_P, _I, _P, _L, _I, _I, _I, _P]),
     "omc_vit_assemble": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "omc_select_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _P]),
@@ -743,6 +749,66 @@ class DecodePlan:
             self.epoch += 1
         rc = load().omc_decode_step(self.host, self.dev.data_ptr(), epoch & 0xFFFFFF, _stream())
         _check(rc, "omc_decode_step")
+
+
+# ----------------------------------------------------------------------------------------------- Qwen2-MoE sparse block
+class MoeWorkspace:
+    """Device buffers of one sparse-MoE block call for up to T tokens (sized for the worst-case routing, reused by every
+    layer): routing results, the expert-sorted copies of the rows, the experts' activations and outputs."""
+
+    def __init__(self, T: int, C: int, n_experts: int, top_k: int, moe_inter: int, shared_inter: int, device):
+        self.T, self.C, self.E, self.k = T, C, n_experts, top_k
+        self.max_tiles = load().omc_moe_max_tiles(T, top_k, n_experts)
+        M = self.max_tiles * 128
+        i32 = dict(device=device, dtype=torch.int32)
+        self.topk_ids = torch.zeros(T, top_k, **i32)
+        self.topk_w = torch.zeros(T, top_k, device=device, dtype=torch.float32)
+        self.shared_gate = torch.zeros(T, device=device, dtype=torch.float32)
+        self.counts = torch.zeros(n_experts, **i32)  # zero on entry of every route call (omc_moe_plan re-zeroes it)
+        self.seg_start = torch.zeros(n_experts, **i32)
+        self.cursor = torch.zeros(n_experts, **i32)
+        self.tile_expert = torch.full((self.max_tiles,), -1, **i32)
+        self.slot_of = torch.zeros(T, top_k, **i32)
+        bf = dict(device=device, dtype=torch.bfloat16)
+        self.xperm = torch.zeros(M, C, **bf)  # zero once: padding rows are multiplied (never read back) - keep them finite
+        self.aperm = torch.zeros(M, moe_inter, **bf)
+        self.yperm = torch.zeros(M, C, **bf)
+        self.shared_act = torch.empty(T, shared_inter, **bf) if shared_inter > 0 else None
+        self.shared_y = torch.empty(T, C, **bf) if shared_inter > 0 else None
+
+
+def moe_block(h: torch.Tensor, xn: torch.Tensor, ws: MoeWorkspace, router_w: torch.Tensor, shared_gate_w: Optional[torch.Tensor],
+              experts_gate_up: torch.Tensor, experts_down: torch.Tensor, shared_gate_up: Optional[torch.Tensor],
+              shared_down: Optional[torch.Tensor], norm_topk: bool) -> torch.Tensor:
+    """h[T, C] += SparseMoeBlock(xn[T, C]) (transformers modeling_qwen2_moe.py:363-374), in place. experts_gate_up
+    [E * 2 I, C] with every expert's gate / up rows interleaved (the SwiGLU epilogue's layout), experts_down [E * C, I]."""
+    _need_cuda(h, xn, router_w, experts_gate_up, experts_down)
+    T, C = xn.shape
+    assert T <= ws.T and C == ws.C and h.shape == xn.shape and xn.stride(1) == 1 and h.stride(1) == 1
+    E, k, L, st = ws.E, ws.k, load(), _stream()
+    I2 = experts_gate_up.shape[0] // E
+    M = ws.max_tiles * 128
+    max_tiles = L.omc_moe_max_tiles(T, k, E)  # tiles this call can touch (<= the workspace's)
+    _check(L.omc_moe_route(_ptr(xn), xn.stride(0), T, C, _ptr(router_w), _ptr(shared_gate_w), E, k, int(norm_topk),
+                           _ptr(ws.topk_ids), _ptr(ws.topk_w), _ptr(ws.shared_gate), _ptr(ws.counts), st), "omc_moe_route")
+    _check(L.omc_moe_plan(_ptr(ws.counts), E, ws.max_tiles, _ptr(ws.seg_start), _ptr(ws.cursor), _ptr(ws.tile_expert), st),
+           "omc_moe_plan")
+    _check(L.omc_moe_scatter(_ptr(xn), xn.stride(0), T, C, _ptr(ws.topk_ids), k, _ptr(ws.seg_start), _ptr(ws.cursor),
+                             _ptr(ws.xperm), C, _ptr(ws.slot_of), st), "omc_moe_scatter")
+    Mc = max_tiles * 128
+    _check(L.omc_gemm_bf16_grouped(_ptr(ws.xperm), C, Mc, _ptr(experts_gate_up), C, E, I2, C, _ptr(ws.tile_expert),
+                                   _ptr(ws.aperm), I2 // 2, EPI_SWIGLU, st), "omc_gemm_bf16_grouped")
+    _check(L.omc_gemm_bf16_grouped(_ptr(ws.aperm), I2 // 2, Mc, _ptr(experts_down), I2 // 2, E, C, I2 // 2,
+                                   _ptr(ws.tile_expert), _ptr(ws.yperm), C, EPI_NONE, st), "omc_gemm_bf16_grouped")
+    add_launches(5)
+    shared_y = None
+    if shared_gate_up is not None:
+        gemm(xn, shared_gate_up, out=ws.shared_act[:T], epi=EPI_SWIGLU)
+        shared_y = gemm(ws.shared_act[:T], shared_down, out=ws.shared_y[:T])
+    _check(L.omc_moe_combine(_ptr(h), h.stride(0), T, C, _ptr(ws.yperm), C, _ptr(ws.slot_of), _ptr(ws.topk_w), k,
+                             _ptr(shared_y), C, _ptr(ws.shared_gate), st), "omc_moe_combine")
+    add_launches(1)
+    return h
 
 
 # ----------------------------------------------------------------------------------------------- model-level entry points

@@ -21,7 +21,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from ..config import InternVisionConfig, OmChatQwen2Config
+from ..config import InternVisionConfig, OmChatQwen2Config, OmChatQwen2MoeConfig
 
 _TEXT_KEYS = ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
               "num_key_value_heads", "rms_norm_eps", "rope_theta", "max_position_embeddings")
@@ -29,6 +29,8 @@ _MM_KEYS = ("mm_vision_tower", "mm_projector_type", "mm_hidden_size", "mm_vision
             "mm_vision_select_feature", "image_grid_pinpoints", "tokenizer_model_max_length", "tokenizer_padding_side",
             "tune_mm_mlp_adapter", "mm_use_im_start_end", "eos_token_id", "pad_token_id", "mm_pixel_shuffle_ratio",
             "kv_page_size")
+_MOE_KEYS = ("num_experts", "num_experts_per_tok", "moe_intermediate_size", "shared_expert_intermediate_size", "norm_topk_prob",
+             "decoder_sparse_step", "mlp_only_layers")
 
 
 def config_from_dict(d: dict) -> OmChatQwen2Config:
@@ -50,6 +52,11 @@ def config_from_dict(d: dict) -> OmChatQwen2Config:
         names = {f.name for f in fields(InternVisionConfig)}
         kw["vision_config"] = InternVisionConfig(**{k: v for k, v in vd.items() if k in names})
         kw.setdefault("mm_hidden_size", kw["vision_config"].hidden_size)
+    if d.get("model_type") == "omchat_qwen2_moe" or text.get("model_type") in ("omchat_qwen2_moe", "qwen2_moe"):
+        for k in _MOE_KEYS:  # omchat_qwen2_moe.py:14-17 (transformers Qwen2MoeConfig)
+            if text.get(k) is not None:
+                kw[k] = text[k]
+        return OmChatQwen2MoeConfig(**kw)
     return OmChatQwen2Config(**kw)
 
 

@@ -121,7 +121,8 @@ class Qwen2Decoder:
         # local (per TP rank) head counts are read off the sharded weights
         self.Hkv = w.kv_heads_local
         self.Hq = w.q_heads_local
-        self.I_local = w.layers[0].gate_up_w.shape[0] // 2 if w.layers else cfg.intermediate_size
+        dense = [l for l in w.layers if l.gate_up_w is not None]
+        self.I_local = dense[0].gate_up_w.shape[0] // 2 if dense else 8  # 8: placeholder width when every layer is sparse
         self.V_local = w.lm_head.shape[0]
         self.scale = cfg.head_dim ** -0.5
         self.eps = cfg.rms_norm_eps
@@ -294,10 +295,9 @@ class Qwen2Decoder:
             self._row_parallel(attn, l.o_w, h, use_gemv=False, ssq_out=ssq_b if fold else None)
             if fold:
                 lib.gemm(h, folded[li][1], out=act, epi=lib.EPI_SWIGLU, ssq_in=ssq_b, norm_dim=C, eps=self.eps)
+                self._row_parallel(act, l.down_w, h, use_gemv=False, ssq_out=ssq_a)
             else:
-                lib.rmsnorm(h, l.ln2, self.eps, out=xn)
-                lib.gemm(xn, l.gate_up_w, out=act, epi=lib.EPI_SWIGLU)
-            self._row_parallel(act, l.down_w, h, use_gemv=False, ssq_out=ssq_a if fold else None)
+                self._mlp_rows(li, l, h, xn, act)
             if collect_hidden:
                 hiddens.append(h.clone())
         if slots is None:
@@ -315,6 +315,22 @@ class Qwen2Decoder:
         elif logits == "all":
             out = self.lm_head(h)
         return (out, hiddens) if collect_hidden else out
+
+    # the MLP half of a layer on the per-op paths (overridden by the mixture-of-experts decoder, model/moe.py)
+    def _mlp_rows(self, li: int, l, h, xn, act):
+        """prefill: h += down(silu(gate(norm(h))) * up(norm(h)))   (modeling_qwen2.py:46-48,300-303)"""
+        lib.rmsnorm(h, l.ln2, self.eps, out=xn)
+        lib.gemm(xn, l.gate_up_w, out=act, epi=lib.EPI_SWIGLU)
+        self._row_parallel(act, l.down_w, h, use_gemv=False)
+
+    def _mlp_step(self, li: int, l, h, st, gv_c: bool, gv_i: bool):
+        """decode step (B rows): same, on the GEMV kernels (RMSNorm fused) when the batch is small enough"""
+        if gv_c:
+            lib.gemv(h, l.gate_up_w, out=st.act, norm_w=l.ln2, eps=self.eps, epi=lib.EPI_SWIGLU)
+        else:
+            lib.rmsnorm(h, l.ln2, self.eps, out=st.xn)
+            lib.gemm(st.xn, l.gate_up_w, out=st.act, epi=lib.EPI_SWIGLU)
+        self._row_parallel(st.act, l.down_w, h, use_gemv=gv_i)
 
     @torch.no_grad()
     def lm_head(self, h: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -441,12 +457,7 @@ class Qwen2Decoder:
             lib.paged_decode_attn(st.qkv, self.inv_freq, cache.pool[li], cache.block_table, cache.page_size,
                                   cache.ctx_lens, self.Hq, self.Hkv, st.splits, self.scale, st.attn, st.attn_ws)
             self._row_parallel(st.attn, l.o_w, h, use_gemv=gv_a)
-            if gv_c:
-                lib.gemv(h, l.gate_up_w, out=st.act, norm_w=l.ln2, eps=self.eps, epi=lib.EPI_SWIGLU)
-            else:
-                lib.rmsnorm(h, l.ln2, self.eps, out=st.xn)
-                lib.gemm(st.xn, l.gate_up_w, out=st.act, epi=lib.EPI_SWIGLU)
-            self._row_parallel(st.act, l.down_w, h, use_gemv=gv_i)
+            self._mlp_step(li, l, h, st, gv_c, gv_i)
         self.lm_head(h, out=st.logits)
         if sample:
             self._greedy(st)

@@ -66,12 +66,13 @@ class _GenerationConfig:
 class OmChatQwen2Model:
     """Holder object mirroring OmChatQwen2Model(OmChatMetaModel, Qwen2Model) (omchat_qwen2.py:22-26,
     omchat_arch.py:21-34): .vision_tower, .mm_projector, .embed_tokens, .layers live here."""
+    decoder_class = Qwen2Decoder
 
     def __init__(self, config: OmChatQwen2Config, weights: OmChatWeights, tp: TPInfo):
         self.config = config
         self.vision_tower = build_vision_tower(config, weights.vit) if config.mm_vision_tower is not None else None
         self.mm_projector = MMProjector(weights.proj) if weights.proj is not None else None
-        self.decoder = Qwen2Decoder(config, weights.llm, tp)
+        self.decoder = self.decoder_class(config, weights.llm, tp)
         self.embed_weight = weights.llm.embed
 
     def get_vision_tower(self):
@@ -84,6 +85,7 @@ class OmChatQwen2Model:
 
 class OmChatQwen2ForCausalLM:
     config_class = OmChatQwen2Config
+    model_class = OmChatQwen2Model
 
     def __init__(self, config: OmChatQwen2Config, weights: Optional[OmChatWeights] = None, device="cuda", seed: int = 0,
                  tp_rank: int = 0, tp_size: int = 1, tp_group=None):
@@ -100,7 +102,7 @@ class OmChatQwen2ForCausalLM:
         self.weights = weights
         self.tp = TPInfo(rank=tp_rank, size=tp_size, group=tp_group)
         self.vision_dp = True  # under tensor parallelism: crops data-parallel over the ranks + one feature all-gather
-        self.model = OmChatQwen2Model(config, weights, self.tp)
+        self.model = self.model_class(config, weights, self.tp)
         self.vocab_size = config.vocab_size
         self.generation_config = _GenerationConfig(config)
 

@@ -118,14 +118,26 @@ class ProjW:
 
 
 @dataclass
+class MoeLayerW:
+    """Sparse MLP block of a Qwen2-MoE layer (transformers modeling_qwen2_moe.py:295-374) in the grouped GEMM's layout."""
+    router_w: torch.Tensor        # [E, C]           mlp.gate.weight
+    shared_gate_w: torch.Tensor   # [C]              mlp.shared_expert_gate.weight
+    experts_gate_up: torch.Tensor  # [E * 2 I, C]     per expert: gate / up rows interleaved (SwiGLU epilogue layout)
+    experts_down: torch.Tensor    # [E * C, I]
+    shared_gate_up: torch.Tensor  # [2 Is, C]        interleaved
+    shared_down: torch.Tensor     # [C, Is]
+
+
+@dataclass
 class LlmLayerW:
     ln1: torch.Tensor
     qkv_w: torch.Tensor
     qkv_b: torch.Tensor
     o_w: torch.Tensor
     ln2: torch.Tensor
-    gate_up_w: torch.Tensor
-    down_w: torch.Tensor
+    gate_up_w: Optional[torch.Tensor]  # None in a sparse (mixture-of-experts) layer
+    down_w: Optional[torch.Tensor]
+    moe: Optional[MoeLayerW] = None
 
 
 @dataclass
@@ -253,6 +265,9 @@ def from_state_dict(sd: Dict[str, torch.Tensor], cfg: OmChatQwen2Config, device=
     for li in range(cfg.num_hidden_layers):
         p = f"model.layers.{li}."
         a = p + "self_attn."
+        if getattr(cfg, "num_experts", 0) > 0 and cfg.layer_is_sparse(li):
+            layers.append(_moe_layer_from_sd(sd, p, cfg, tp_size, device))
+            continue
         qkv_w, qkv_b, o_w, gu, down = shard_llm_layer(
             sd[a + "q_proj.weight"], sd[a + "q_proj.bias"], sd[a + "k_proj.weight"], sd[a + "k_proj.bias"],
             sd[a + "v_proj.weight"], sd[a + "v_proj.bias"], sd[a + "o_proj.weight"], sd[p + "mlp.gate_proj.weight"],
@@ -265,6 +280,36 @@ def from_state_dict(sd: Dict[str, torch.Tensor], cfg: OmChatQwen2Config, device=
                norm=_dev(sd["model.norm.weight"], device), lm_head=_dev(sd["lm_head.weight"][plan.v_lo:plan.v_hi], device),
                q_heads_local=len(plan.q_heads), kv_heads_local=len(plan.kv_heads))
     return OmChatWeights(vit=vit, proj=proj, llm=llm)
+
+
+def moe_experts(sd: Dict[str, torch.Tensor], p: str, E: int):
+    """Per-expert (gate, up, down) matrices of layer prefix `p` from either checkpoint layout: one matrix per expert
+    (`mlp.experts.{e}.gate_proj.weight` ..., the published safetensors) or transformers >= 5's fused 3-D parameters
+    (`mlp.experts.gate_up_proj` [E, 2 I, C] = cat(gate, up), `mlp.experts.down_proj` [E, C, I]; modeling_qwen2_moe.py:298-305)."""
+    if (p + "mlp.experts.gate_up_proj") in sd:
+        gu, dn = sd[p + "mlp.experts.gate_up_proj"], sd[p + "mlp.experts.down_proj"]
+        I = gu.shape[1] // 2
+        return [(gu[e, :I], gu[e, I:], dn[e]) for e in range(E)]
+    return [(sd[f"{p}mlp.experts.{e}.gate_proj.weight"], sd[f"{p}mlp.experts.{e}.up_proj.weight"],
+             sd[f"{p}mlp.experts.{e}.down_proj.weight"]) for e in range(E)]
+
+
+def _moe_layer_from_sd(sd, p: str, cfg, tp_size: int, device) -> "LlmLayerW":
+    if tp_size != 1:
+        raise NotImplementedError("tensor parallelism is not built for the Qwen2-MoE variant")
+    a = p + "self_attn."
+    qkv_w = torch.cat([sd[a + "q_proj.weight"], sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0)
+    qkv_b = torch.cat([sd[a + "q_proj.bias"], sd[a + "k_proj.bias"], sd[a + "v_proj.bias"]], 0)
+    ex = moe_experts(sd, p, cfg.num_experts)
+    moe = MoeLayerW(
+        router_w=_dev(sd[p + "mlp.gate.weight"], device), shared_gate_w=_dev(sd[p + "mlp.shared_expert_gate.weight"].reshape(-1), device),
+        experts_gate_up=_dev(torch.cat([interleave_gate_up(g, u) for g, u, _ in ex], 0), device),
+        experts_down=_dev(torch.cat([d for _, _, d in ex], 0), device),
+        shared_gate_up=_dev(interleave_gate_up(sd[p + "mlp.shared_expert.gate_proj.weight"], sd[p + "mlp.shared_expert.up_proj.weight"]), device),
+        shared_down=_dev(sd[p + "mlp.shared_expert.down_proj.weight"], device))
+    return LlmLayerW(ln1=_dev(sd[p + "input_layernorm.weight"], device), qkv_w=_dev(qkv_w, device), qkv_b=_dev(qkv_b, device),
+                     o_w=_dev(sd[a + "o_proj.weight"], device), ln2=_dev(sd[p + "post_attention_layernorm.weight"], device),
+                     gate_up_w=None, down_w=None, moe=moe)
 
 
 def random_init(cfg: OmChatQwen2Config, device="cuda", seed: int = 0, vision: bool = True, text: bool = True,
@@ -301,8 +346,18 @@ def random_init(cfg: OmChatQwen2Config, device="cuda", seed: int = 0, vision: bo
     plan = tp_plan(cfg, tp_rank, tp_size)
     layers = []
     if text:
-        for _ in range(cfg.num_hidden_layers):
+        for li in range(cfg.num_hidden_layers):
             ln1, ln2 = rn(H, std=0.02, mean=1.0), rn(H, std=0.02, mean=1.0)
+            if getattr(cfg, "num_experts", 0) > 0 and cfg.layer_is_sparse(li):
+                if tp_size != 1:
+                    raise NotImplementedError("tensor parallelism is not built for the Qwen2-MoE variant")
+                E, Im, Is = cfg.num_experts, cfg.moe_intermediate_size, cfg.shared_expert_intermediate_size
+                moe = MoeLayerW(router_w=rn(E, H, std=0.3), shared_gate_w=rn(H, std=0.1),
+                                experts_gate_up=rn(E * 2 * Im, H), experts_down=rn(E * H, Im),
+                                shared_gate_up=rn(2 * Is, H), shared_down=rn(H, Is))
+                layers.append(LlmLayerW(ln1=ln1, qkv_w=rn((nq + 2 * nkv) * D, H), qkv_b=rn((nq + 2 * nkv) * D), o_w=rn(H, nq * D),
+                                        ln2=ln2, gate_up_w=None, down_w=None, moe=moe))
+                continue
             qkv_w, qkv_b, o_w, gu, down = shard_llm_layer(
                 rn(nq * D, H), rn(nq * D), rn(nkv * D, H), rn(nkv * D), rn(nkv * D, H), rn(nkv * D), rn(H, nq * D),
                 rn(I, H), rn(I, H), rn(H, I), plan, D)
@@ -343,6 +398,24 @@ def to_reference_state_dict(w: OmChatWeights, cfg: OmChatQwen2Config) -> Dict[st
     nq, nkv = cfg.num_attention_heads * D, cfg.num_key_value_heads * D
     for li, l in enumerate(w.llm.layers):
         p = f"model.layers.{li}."
+        if l.moe is not None:
+            m, E = l.moe, l.moe.router_w.shape[0]
+            K = m.router_w.shape[1]
+            egu = m.experts_gate_up.view(E, -1, 2, K)
+            edn = m.experts_down.view(E, K, -1)
+            for e in range(E):
+                sd.update({f"{p}mlp.experts.{e}.gate_proj.weight": egu[e, :, 0], f"{p}mlp.experts.{e}.up_proj.weight": egu[e, :, 1],
+                           f"{p}mlp.experts.{e}.down_proj.weight": edn[e]})
+            sgu = m.shared_gate_up.view(-1, 2, K)
+            sd.update({p + "mlp.gate.weight": m.router_w, p + "mlp.shared_expert_gate.weight": m.shared_gate_w.view(1, K),
+                       p + "mlp.shared_expert.gate_proj.weight": sgu[:, 0], p + "mlp.shared_expert.up_proj.weight": sgu[:, 1],
+                       p + "mlp.shared_expert.down_proj.weight": m.shared_down})
+            sd.update({p + "input_layernorm.weight": l.ln1, p + "post_attention_layernorm.weight": l.ln2,
+                       p + "self_attn.q_proj.weight": l.qkv_w[:nq], p + "self_attn.k_proj.weight": l.qkv_w[nq:nq + nkv],
+                       p + "self_attn.v_proj.weight": l.qkv_w[nq + nkv:], p + "self_attn.q_proj.bias": l.qkv_b[:nq],
+                       p + "self_attn.k_proj.bias": l.qkv_b[nq:nq + nkv], p + "self_attn.v_proj.bias": l.qkv_b[nq + nkv:],
+                       p + "self_attn.o_proj.weight": l.o_w})
+            continue
         I2, K = l.gate_up_w.shape
         gu = l.gate_up_w.view(I2 // 2, 2, K)
         sd.update({p + "input_layernorm.weight": l.ln1, p + "post_attention_layernorm.weight": l.ln2,

@@ -320,11 +320,18 @@ def moe_layer_is_sparse(li: int, cfg: OracleConfig) -> bool:
     return (li not in cfg.mlp_only_layers) and cfg.num_experts > 0 and (li + 1) % cfg.decoder_sparse_step == 0
 
 
+ROUTE_TRACE: Optional[list] = None  # tests set this to a list: every moe_route call appends log(p_k / p_(k+1)) per row
+
+
 def moe_route(x: torch.Tensor, sd, pre: str, cfg: OracleConfig):
     """Qwen2MoeTopKRouter.forward modeling_qwen2_moe.py:343-352: softmax over ALL experts in fp32, top-k, optional
     renormalisation of the k weights. x [T, C] -> (weights [T, k], expert ids [T, k])."""
     probs = torch.softmax(F.linear(x, sd[pre + "mlp.gate.weight"]), dim=-1, dtype=torch.float32)
     w, idx = torch.topk(probs, cfg.top_k, dim=-1)
+    if ROUTE_TRACE is not None and cfg.top_k < cfg.num_experts:
+        # how far the routing decision is from flipping: a bf16 run may legitimately pick the other expert when this is ~ 0
+        srt = torch.sort(probs, dim=-1, descending=True).values
+        ROUTE_TRACE.append(torch.log(srt[:, cfg.top_k - 1] / srt[:, cfg.top_k].clamp_min(1e-30)))
     if cfg.norm_topk_prob:
         w = w / w.sum(dim=-1, keepdim=True)
     return w.to(x.dtype), idx

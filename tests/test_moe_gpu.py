@@ -1,0 +1,277 @@
+"""GPU parity of the Qwen2-MoE language-model variant (omchat_qwen2_moe.py over transformers Qwen2MoeForCausalLM).
+
+Kernel level: router / plan / scatter / grouped tcgen05 GEMM / combine against a plain torch fp32 restatement on the same
+bf16 inputs - routing decisions bit-exact wherever the k-th / (k+1)-th probabilities differ by more than fp32 summation noise,
+outputs within bf16 tolerance (rel 2 %), empty experts, experts with more than one tile, T = 1.
+Model level: prefill logits / greedy ids / padded batch against golden vectors of the REAL reference (tests/golden/
+golden_tiny_moe.pt, two variants) and the fp32 oracle on bf16-rounded weights; one layer at Qwen1.5-MoE-A2.7B width
+(hidden 2048, 60 experts, top-4, expert width 1408, shared 5632) against the oracle.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import omchat_oracle as O  # noqa: E402  (checker only)
+from tiny import TINY_MOE as T, tiny_inputs, tiny_state_dict_moe  # noqa: E402
+from test_model_gpu import check  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _moe_ref(xn, h, router_w, sg_w, egu, edn, sgu, sdn, k, norm):
+    """fp32 torch restatement of the sparse block on the kernel's own weight layout (interleaved gate/up)."""
+    E, C = router_w.shape
+    x = xn.float()
+    probs = torch.softmax(x @ router_w.float().t(), dim=-1)
+    w, idx = torch.topk(probs, k, dim=-1)
+    if norm:
+        w = w / w.sum(-1, keepdim=True)
+    gu = egu.float().view(E, -1, 2, C)
+    dn = edn.float().view(E, C, -1)
+    out = torch.zeros_like(x)
+    for e in range(E):
+        tok, slot = torch.where(idx == e)
+        if tok.numel():
+            a = torch.nn.functional.silu(x[tok] @ gu[e, :, 0].t()) * (x[tok] @ gu[e, :, 1].t())
+            a = a.to(torch.bfloat16).float()  # the grouped GEMM stores the activation in bf16
+            y = (a @ dn[e].t()).to(torch.bfloat16).float()
+            out.index_add_(0, tok, y * w[tok, slot, None])
+    s = sgu.float().view(-1, 2, C)
+    a = (torch.nn.functional.silu(x @ s[:, 0].t()) * (x @ s[:, 1].t())).to(torch.bfloat16).float()
+    shared = (a @ sdn.float().t()).to(torch.bfloat16).float()
+    out = out + torch.sigmoid(x @ sg_w.float())[:, None] * shared
+    return h.float() + out, probs, idx, w
+
+
+@pytest.mark.parametrize("Tn,C,E,k,I,Is,norm", [(1, 256, 8, 2, 128, 256, False), (37, 256, 8, 2, 128, 256, True),
+                                                 (700, 512, 60, 4, 128, 384, False), (300, 2048, 64, 8, 256, 512, False),
+                                                 (1500, 256, 4, 2, 128, 128, True)])
+def test_moe_block_kernels_vs_torch(Tn, C, E, k, I, Is, norm):
+    from omchat_b200 import lib
+    g = torch.Generator(device="cuda").manual_seed(Tn * 7 + E)
+
+    def rn(*shape, std=0.05):
+        return (torch.randn(*shape, generator=g, device="cuda") * std).to(torch.bfloat16)
+
+    xn, h = rn(Tn, C, std=1.0), rn(Tn, C, std=1.0)
+    router_w, sg_w = rn(E, C, std=0.2), rn(C, std=0.1)
+    if E == 60:
+        router_w[7] = -1.0  # an expert nobody picks: empty segment between two used ones
+    egu, edn, sgu, sdn = rn(E * 2 * I, C), rn(E * C, I), rn(2 * Is, C), rn(C, Is)
+    ws = lib.MoeWorkspace(Tn, C, E, k, I, Is, "cuda")
+    want, probs, idx, w = _moe_ref(xn, h, router_w, sg_w, egu, edn, sgu, sdn, k, norm)
+    got = h.clone()
+    for _ in range(2):  # twice through the same workspace: the counters must come back to zero
+        got.copy_(h)
+        lib.moe_block(got, xn, ws, router_w, sg_w, egu, edn, sgu, sdn, norm)
+    torch.cuda.synchronize()
+    assert int(ws.counts.abs().sum()) == 0 and int(ws.cursor.sum()) == Tn * k
+    # routing: same expert sets wherever the k-th and (k+1)-th probabilities are not a near-tie
+    srt = torch.sort(probs, dim=-1, descending=True).values
+    clear = (srt[:, k - 1] - srt[:, k]) > 1e-5 * srt[:, 0] if E > k else torch.ones(Tn, dtype=torch.bool, device="cuda")
+    ids = ws.topk_ids[:Tn].long()
+    assert torch.equal(torch.sort(ids[clear], -1).values, torch.sort(idx[clear], -1).values)
+    gw = torch.gather(probs / (torch.gather(probs, 1, ids).sum(-1, keepdim=True) if norm else 1.0), 1, ids)
+    assert (ws.topk_w[:Tn] - gw).abs().max().item() <= 1e-4
+    # plan: every slot lies in its expert's padded segment, slots are unique, tiles name the right expert
+    slots = ws.slot_of[:Tn].long()
+    assert slots.unique().numel() == Tn * k
+    assert torch.equal(ws.tile_expert.long()[slots // 128], ids)
+    counts = torch.bincount(ids.flatten(), minlength=E)
+    used = int(((counts + 127) // 128).sum())
+    assert int((ws.tile_expert >= 0).sum()) == used and int((ws.tile_expert[used:] != -1).sum()) == 0
+    # rows landed where the plan says
+    assert torch.equal(ws.xperm[slots[:, 0]], xn)
+    err = (got.float() - want).abs().max().item()
+    scale = want.abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(got.float()[clear], want[clear], dim=-1).min().item()
+    print(f"T {Tn} C {C} E {E} k {k}: max-abs err {err:.4g} (scale {scale:.4g}), min cosine {cos:.6f}, clear rows {int(clear.sum())}/{Tn}")
+    assert (got.float() - want)[clear].abs().max().item() <= 0.02 * scale and cos >= 0.9995
+
+
+def test_grouped_gemm_skips_unused_tiles():
+    """tile_expert < 0 tiles are never written; used tiles multiply their own expert's matrix."""
+    from omchat_b200 import lib
+    g = torch.Generator(device="cuda").manual_seed(0)
+    E, N, K, tiles = 5, 256, 192, 7
+    x = torch.randn(tiles * 128, K, generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(E * N, K, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    te = torch.tensor([3, -1, 0, 0, 4, -1, -1], device="cuda", dtype=torch.int32)
+    out = torch.full((tiles * 128, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    rc = lib.load().omc_gemm_bf16_grouped(x.data_ptr(), K, tiles * 128, w.data_ptr(), K, E, N, K, te.data_ptr(), out.data_ptr(), N,
+                                          lib.EPI_NONE, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    for t, e in enumerate(te.tolist()):
+        rows = slice(t * 128, (t + 1) * 128)
+        if e < 0:
+            assert (out[rows] == 7.0).all()
+        else:
+            ref = x[rows].float() @ w[e * N:(e + 1) * N].float().t()
+            assert (out[rows].float() - ref).abs().max().item() <= 0.02 * ref.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------ model level
+def moe_cfgs(g):
+    from omchat_b200.config import InternVisionConfig, OmChatQwen2MoeConfig
+    vc = InternVisionConfig(hidden_size=T["vit_hidden"], num_attention_heads=T["vit_heads"], intermediate_size=T["vit_inter"],
+                            num_hidden_layers=T["vit_layers"], image_size=T["image_size"])
+    return OmChatQwen2MoeConfig(
+        vocab_size=T["vocab"], hidden_size=T["hidden"], intermediate_size=T["inter"], num_hidden_layers=T["layers"],
+        num_attention_heads=T["heads"], num_key_value_heads=T["kv_heads"], rope_theta=T["rope_theta"],
+        mm_hidden_size=T["vit_hidden"], kv_page_size=16, vision_config=vc, eos_token_id=-1, num_experts=T["num_experts"],
+        num_experts_per_tok=T["top_k"], moe_intermediate_size=T["moe_inter"], shared_expert_intermediate_size=T["shared_inter"],
+        norm_topk_prob=g["norm_topk_prob"], mlp_only_layers=list(g["dense_layers"]))
+
+
+def oracle_cfg(g):
+    return O.OracleConfig(
+        vit_hidden=T["vit_hidden"], vit_heads=T["vit_heads"], vit_inter=T["vit_inter"], vit_layers=T["vit_layers"],
+        image_size=T["image_size"], hidden=T["hidden"], heads=T["heads"], kv_heads=T["kv_heads"], inter=T["inter"],
+        layers=T["layers"], vocab=T["vocab"], rope_theta=T["rope_theta"], num_experts=T["num_experts"], top_k=T["top_k"],
+        norm_topk_prob=g["norm_topk_prob"], mlp_only_layers=tuple(g["dense_layers"]))
+
+
+@pytest.fixture(scope="module")
+def golden_moe():
+    return torch.load(os.path.join(HERE, "golden", "golden_tiny_moe.pt"), weights_only=False)
+
+
+ROUTE_GAP = 0.3  # log(p_k / p_(k+1)) below this: the bf16 run may legitimately route the token to the other expert (router
+# logits have std ~ 8 here; bf16 activations entering the router are off by ~ 0.5 %, i.e. ~ 0.05-0.1 per logit difference)
+
+
+def traced(fn):
+    """Run an oracle call with routing-margin tracing: (result, [per moe_route call: log-gap per row])."""
+    O.ROUTE_TRACE = []
+    try:
+        out = fn()
+    finally:
+        tr, O.ROUTE_TRACE = O.ROUTE_TRACE, None
+    return out, tr
+
+
+def check_routed(got, ref, gap, what, rel=0.04, cos_min=0.999, max_flipped=0.1):
+    """Every row must meet the usual bf16 tolerance (cosine >= 0.999, max-abs <= 4 % of the tensor's scale) UNLESS the oracle says
+    its routing sits on a tie in some sparse layer (gap < ROUTE_GAP) - such a row may have gone to the other expert: it must still
+    be finite and point the same way (cosine >= 0.9), and such rows must stay below max_flipped of all rows. Returns their count."""
+    got, ref, gap = got.float().cpu(), ref.float().cpu(), gap.float().cpu()
+    assert got.shape == ref.shape and torch.isfinite(got).all(), what
+    scale = ref.abs().max().item() + 1e-6
+    err = (got - ref).abs().amax(-1)
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=-1)
+    bad = (err > rel * scale) | (cos < cos_min)
+    ok = ~bad
+    print(f"{what}: {int(ok.sum())}/{ok.numel()} rows within tolerance (max-abs err {err[ok].max().item() if ok.any() else 0:.4g}, "
+          f"scale {scale:.4g}, min cosine {cos[ok].min().item() if ok.any() else 1:.6f}); {int(bad.sum())} re-routed rows "
+          f"(their routing gaps {[round(float(x), 3) for x in gap[bad]]}, min cosine {cos[bad].min().item() if bad.any() else 1:.4f})")
+    assert (gap[bad] < ROUTE_GAP).all(), f"{what}: rows out of tolerance although their routing is clear: gaps {gap[bad].tolist()}"
+    assert int(bad.sum()) <= max(1, int(max_flipped * bad.numel())), f"{what}: too many re-routed rows"
+    assert not bad.any() or cos[bad].min().item() >= 0.9, what
+    return int(bad.sum())
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_moe_model_vs_reference_golden_and_oracle(golden_moe, variant):
+    from omchat_b200.model.moe import OmChatQwen2MoeForCausalLM, Qwen2MoeDecoder
+    g = golden_moe[variant]
+    sd = {k: v.to(torch.bfloat16).float() for k, v in tiny_state_dict_moe(0, g["dense_layers"]).items()}
+    model = OmChatQwen2MoeForCausalLM.from_state_dict(sd, moe_cfgs(g), device="cuda")
+    assert isinstance(model.get_model().decoder, Qwen2MoeDecoder)
+    pixels, _ = tiny_inputs(1)
+    ids = g["prefill_ids"]
+    # the checker on the SAME bf16-rounded weights: differences are compute-only. A token whose k-th / (k+1)-th router
+    # probabilities are closer than bf16 noise may go to the other expert - the oracle's routing margins say which rows those are
+    (ref_logits, _, _, _), tr = traced(lambda: O.forward_multimodal(ids, pixels[:1], sd, oracle_cfg(g)))
+    gap = torch.stack(tr).min(0).values
+    res = model(input_ids=ids, images=pixels[:1], use_cache=True)
+    check_routed(res.logits[0], ref_logits[0], gap, f"moe {variant} prefill logits vs oracle")
+    check_routed(res.logits[0, ::16, :], g["prefill_logits_sub"], gap[::16], f"moe {variant} prefill logits vs reference golden")
+    n = len(g["greedy_tokens"])
+    out = model.generate(ids, images=pixels[:1], max_new_tokens=n, do_sample=False, eos_token_id=-1)
+    got = out[0, ids.shape[1]:].tolist()
+    (want, step_logits), tr = traced(lambda: O.greedy_generate(ids, pixels[:1], sd, oracle_cfg(g), max_new_tokens=n))
+    n_sparse = len(tr) // n  # moe_route calls per forward: prefill first, then one forward per further token
+    step_gap = [float(torch.stack(tr[i * n_sparse:(i + 1) * n_sparse])[:, -1].min()) for i in range(n)]
+    print("cuda:", got, "oracle:", want, "reference:", g["greedy_tokens"], "routing gaps:", [round(x, 3) for x in step_gap])
+    for i in range(n):
+        if got[i] != want[i]:  # free-running greedy: only a near-tie (of the logits, or of the routing) may flip a token
+            top2 = torch.topk(step_logits[i], 2).values
+            margin, scale = float(top2[0] - top2[1]), float(step_logits[i].abs().max())
+            assert margin < 0.02 * scale or step_gap[i] < ROUTE_GAP, \
+                f"greedy token {i}: {got[i]} vs {want[i]} (margin {margin:.4g}, scale {scale:.4g}, routing gap {step_gap[i]:.3g})"
+            break
+    # padded batch of 3 with 2 / 0 / 1 images
+    resb = model(input_ids=g["batch_ids"], attention_mask=g["batch_mask"], images=pixels)
+    (refb, _, mask, _), tr = traced(lambda: O.forward_multimodal(g["batch_ids"], pixels, sd, oracle_cfg(g),
+                                                                 attention_mask=g["batch_mask"]))
+    gapb = torch.stack(tr).min(0).values.view(mask.shape)
+    sel = mask[:, ::32]
+    lb = resb.logits[:, ::32, ::4].float().cpu()
+    check_routed(lb[sel], refb[:, ::32, ::4][sel], gapb[:, ::32][sel], f"moe {variant} batch logits vs oracle")
+    check_routed(lb[sel], g["batch_logits_sub"][sel], gapb[:, ::32][sel], f"moe {variant} batch logits vs reference golden")
+    model.close()
+
+
+def test_moe_teacher_forced_decode_vs_oracle(golden_moe):
+    """5 decode steps (batch 3) teacher-forced with the oracle's tokens: per-step logits."""
+    from omchat_b200.model.moe import OmChatQwen2MoeForCausalLM
+    g = golden_moe["A"]
+    sd = {k: v.to(torch.bfloat16).float() for k, v in tiny_state_dict_moe(0, ()).items()}
+    model = OmChatQwen2MoeForCausalLM.from_state_dict(sd, moe_cfgs(g), device="cuda")
+    _, ids = tiny_inputs(1)
+    ids = ids[:3]
+    toks, step_logits, gaps = [], [], []
+    for b in range(3):
+        (t, sl), tr = traced(lambda: O.greedy_generate(ids[b:b + 1], None, sd, oracle_cfg(g), max_new_tokens=6))
+        n_sparse = len(tr) // 6
+        toks.append(t)
+        step_logits.append(torch.stack(sl))
+        gaps.append(torch.stack([torch.stack(tr[i * n_sparse:(i + 1) * n_sparse])[:, -1].min() for i in range(6)]))
+    gaps = torch.stack(gaps)  # [3, 6]
+    dec = model.get_model().decoder
+    res = model(input_ids=ids, use_cache=True)
+    cache = res.past_key_values
+    cur = torch.tensor([t[0] for t in toks], device="cuda")
+    flipped = 0
+    for i in range(6):
+        lg = res.logits[:, -1] if i == 0 else dec.decode_step(cur, cache).clone()
+        ref = torch.stack([s[i] for s in step_logits])
+        flipped += check_routed(lg, ref, gaps[:, i], f"moe decode step {i} logits", max_flipped=1.0)
+        cur = torch.tensor([t[i] for t in toks], device="cuda")
+    assert flipped <= 3
+    model.close()
+
+
+def test_moe_real_width_layer_vs_oracle():
+    """One sparse layer at Qwen1.5-MoE-A2.7B width: hidden 2048, 16 heads, 60 experts, top-4, expert width 1408 (gate|up N =
+    2816 = 22 tiles of 128), shared expert 5632 - prefill of 2 x 300 tokens + 3 decode steps against the fp32 oracle."""
+    from omchat_b200.config import OmChatQwen2MoeConfig
+    from omchat_b200.model.moe import Qwen2MoeDecoder
+    from omchat_b200.model.weights import random_init, to_reference_state_dict
+    cfg = OmChatQwen2MoeConfig(num_hidden_layers=1, vocab_size=2048, mm_vision_tower=None)
+    w = random_init(cfg, device="cuda", seed=3, vision=False)
+    dec = Qwen2MoeDecoder(cfg, w.llm)
+    sd = {k: v.float().cpu() for k, v in to_reference_state_dict(w, cfg).items()}
+    oc = O.OracleConfig(hidden=2048, heads=16, kv_heads=16, inter=5632, layers=1, vocab=2048, num_experts=60, top_k=4,
+                        rope_theta=cfg.rope_theta)
+    g = torch.Generator().manual_seed(4)
+    lens = [300, 211]
+    emb = (torch.randn(sum(lens), 2048, generator=g) * 0.5).to(torch.bfloat16)
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens])
+    seq = torch.cat([torch.full((n,), i, dtype=torch.int32) for i, n in enumerate(lens)])
+    offs = [0, lens[0], sum(lens)]
+    cache = dec.new_cache(2, 400)
+    logits = dec.prefill(emb.cuda(), pos.cuda(), seq.cuda(), offs, cache, logits="all")
+    at = 0
+    for b, n in enumerate(lens):
+        ref, _ = O.qwen2_forward(emb[at:at + n].float()[None], torch.arange(n)[None], sd, oc)
+        # a routing flip (k-th vs (k+1)-th expert within bf16 noise of each other) changes ONE token's MLP output: allow a few
+        got = logits[at:at + n].float().cpu()
+        cos = torch.nn.functional.cosine_similarity(got, ref[0], dim=-1)
+        print(f"seq {b}: min cosine {cos.min().item():.6f}, rows below 0.999: {int((cos < 0.999).sum())}/{n}")
+        assert int((cos < 0.999).sum()) <= max(1, n // 50) and cos.median().item() >= 0.9995
+        at += n
