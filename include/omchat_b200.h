@@ -374,9 +374,12 @@ int omc_decoder_prefill(const omc_decode_desc* desc, const float* inv_freq, void
  * sparse block (modeling_qwen2_moe.py:295-374) is: router softmax over all experts (fp32) -> top-k (optionally renormalised)
  * -> every token through its k expert SwiGLU MLPs, weighted -> + sigmoid(shared_expert_gate(x)) * shared_expert(x).
  * Device-side plan, no host synchronisation (capturable in a CUDA graph):
- *   omc_moe_route    x [T, C] bf16 (the post-attention-normed rows), router_w [E, C], shared_gate_w [C] or NULL ->
- *                    topk_ids int32 [T, k], topk_w fp32 [T, k], shared_gate fp32 [T] (sigmoid), counts int32 [E] += histogram
- *                    (counts must be zero on entry: zero it once, omc_moe_plan re-zeroes it). E <= 128, k <= 8.
+ *   omc_moe_route    x [T, C] bf16, router_w [E, C], shared_gate_w [C] or NULL -> topk_ids int32 [T, k], topk_w fp32 [T, k],
+ *                    shared_gate fp32 [T] (sigmoid), counts int32 [E] += histogram (counts must be zero on entry: zero it
+ *                    once, omc_moe_plan re-zeroes it). E <= 128, k <= 8. norm_w == NULL: x holds the post-attention-normed
+ *                    rows; norm_w != NULL: x is the raw residual stream, the kernel applies post_attention_layernorm
+ *                    (Qwen2MoeRMSNorm, modeling_qwen2_moe.py:70-75, same rounding as omc_rmsnorm) itself and also writes the
+ *                    normed rows to xn_out [T, ldn] for omc_moe_scatter / the shared expert.
  *   omc_moe_plan     counts -> seg_start int32 [E] (first row of every expert's segment, segments padded to whole 128-row
  *                    tiles), tile_expert int32 [max_tiles] (expert of every 128-row tile, -1 = unused), cursor [E] = 0,
  *                    counts = 0. max_tiles >= omc_moe_max_tiles(T, k, E) = T * k / 128 + E.
@@ -387,8 +390,9 @@ int omc_decoder_prefill(const omc_decode_desc* desc, const float* inv_freq, void
  *   omc_moe_combine  h[t] += sum_j topk_w[t, j] * yperm[slot_of[t, j]] + shared_gate[t] * shared_y[t]  (shared_y may be NULL),
  *                    fp32 accumulate, one bf16 rounding: the block's output + the decoder layer's residual add. */
 int omc_moe_max_tiles(int T, int top_k, int n_experts);
-int omc_moe_route(const void* x, long long ldx, int T, int C, const void* router_w, const void* shared_gate_w, int n_experts,
-                  int top_k, int norm_topk, int32_t* topk_ids, float* topk_w, float* shared_gate, int32_t* counts, void* stream);
+int omc_moe_route(const void* x, long long ldx, int T, int C, const void* norm_w, float eps, void* xn_out, long long ldn,
+                  const void* router_w, const void* shared_gate_w, int n_experts, int top_k, int norm_topk, int32_t* topk_ids,
+                  float* topk_w, float* shared_gate, int32_t* counts, void* stream);
 int omc_moe_plan(int32_t* counts, int n_experts, int max_tiles, int32_t* seg_start, int32_t* cursor, int32_t* tile_expert,
                  void* stream);
 int omc_moe_scatter(const void* x, long long ldx, int T, int C, const int32_t* topk_ids, int top_k, const int32_t* seg_start,

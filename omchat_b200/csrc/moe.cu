@@ -2,8 +2,8 @@
 // reference's omchat/model/language_model/omchat_qwen2_moe.py): router softmax + top-k, the sort of the (token, expert) pairs
 // into expert-contiguous 128-row tiles for the grouped tcgen05 GEMM (omc_gemm_bf16_grouped), and the weighted combine of the
 // expert outputs with the sigmoid-gated shared expert and the residual stream. All of it is HBM/L2-bound row work:
-//   omc_moe_route    one warp per token: E + 1 dot products against the (L2-resident) router / shared-gate rows, fp32 softmax,
-//                    k rounds of warp arg-max, per-expert histogram
+//   omc_moe_route    one CTA per token: (optional RMSNorm of the row,) E + 1 dot products against the L2-resident router /
+//                    shared-gate rows spread over 8 warps, fp32 softmax, k rounds of warp arg-max, per-expert histogram
 //   omc_moe_plan     one CTA: padded segment starts, the tile -> expert table, counters reset for the next call
 //   omc_moe_scatter  one CTA per token: the normed row is copied to its k slots (slot = segment start + atomic cursor)
 //   omc_moe_combine  one CTA per token: h += sum_j w_j * y[slot_j] + sigmoid_gate * shared_y, fp32 accumulate, one rounding
@@ -22,7 +22,6 @@ typedef __nv_bfloat16 bf16;
 constexpr int kMoeMaxExperts = 128;  // 4 router logits per lane
 constexpr int kMoeMaxTopK = 8;
 constexpr int kMoeTile = 128;        // rows per GEMM tile = padding unit of an expert's segment
-constexpr int kRouteWarps = 4;
 
 __device__ __forceinline__ float dot8(uint4 a, uint4 b) {
   float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
@@ -30,102 +29,138 @@ __device__ __forceinline__ float dot8(uint4 a, uint4 b) {
   return a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
 }
 
-// Qwen2MoeTopKRouter.forward (modeling_qwen2_moe.py:343-352) + the shared expert's sigmoid gate (:371).
-__global__ void __launch_bounds__(kRouteWarps * 32) moe_route_kernel(const bf16* __restrict__ x, long long ldx, int T, int C,
-                                                                     const bf16* __restrict__ router_w,
-                                                                     const bf16* __restrict__ shared_gate_w, int E, int top_k,
-                                                                     int norm_topk, int32_t* __restrict__ topk_ids,
-                                                                     float* __restrict__ topk_w, float* __restrict__ shared_gate,
-                                                                     int32_t* __restrict__ counts) {
-  extern __shared__ uint4 s_rows[];  // [kRouteWarps][C / 8]
+// Qwen2MoeTopKRouter.forward (modeling_qwen2_moe.py:343-352) + the shared expert's sigmoid gate (:371). One CTA per token:
+// the row is staged in shared memory (optionally RMS-normalised on the way in - the decode step hands over the raw residual
+// row and gets the normed row back in xn_out), the E + 1 dot products are spread over the 8 warps (independent 128-bit loads of
+// the L2-resident router rows in flight per lane), warp 0 finishes with the fp32 softmax and k rounds of arg-max.
+constexpr int kRouteThreads = 256;
+__global__ void __launch_bounds__(kRouteThreads) moe_route_kernel(const bf16* __restrict__ x, long long ldx, int T, int C,
+                                                                  const bf16* __restrict__ norm_w, float eps,
+                                                                  bf16* __restrict__ xn_out, long long ldn,
+                                                                  const bf16* __restrict__ router_w,
+                                                                  const bf16* __restrict__ shared_gate_w, int E, int top_k,
+                                                                  int norm_topk, int32_t* __restrict__ topk_ids,
+                                                                  float* __restrict__ topk_w, float* __restrict__ shared_gate,
+                                                                  int32_t* __restrict__ counts) {
+  extern __shared__ uint4 s_row[];  // [C / 8]
+  __shared__ float s_logit[kMoeMaxExperts + 1];
+  __shared__ float s_red[kRouteThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 3;
-  uint4* srow = s_rows + warp * nvec;
-  for (int t = blockIdx.x * kRouteWarps + warp; t < T; t += gridDim.x * kRouteWarps) {
+  for (int t = blockIdx.x; t < T; t += gridDim.x) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)t * ldx);
-    for (int i = lane; i < nvec; i += 32) srow[i] = xr[i];
-    __syncwarp();
-    float logit[kMoeMaxExperts / 32];
-#pragma unroll
-    for (int j = 0; j < kMoeMaxExperts / 32; ++j) logit[j] = -INFINITY;
-    for (int e = 0; e < E; ++e) {
-      const uint4* wr = reinterpret_cast<const uint4*>(router_w + (long long)e * C);
-      float acc = 0.f;
-      for (int i = lane; i < nvec; i += 32) acc += dot8(srow[i], __ldg(wr + i));
-      acc = warp_sum(acc);
-      if ((e & 31) == lane) {
-#pragma unroll
-        for (int j = 0; j < kMoeMaxExperts / 32; ++j)
-          if (j == (e >> 5)) logit[j] = acc;
+    if (norm_w != nullptr) {
+      // Qwen2MoeRMSNorm (:70-75) exactly as omc_rmsnorm does it: bf16(x * rstd) * w
+      float ss = 0.f;
+      for (int i = threadIdx.x; i < nvec; i += kRouteThreads) {
+        const uint4 v = xr[i];
+        s_row[i] = v;
+        float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+        ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
       }
+      ss = warp_sum(ss);
+      if (lane == 0) s_red[warp] = ss;
+      __syncthreads();
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < kRouteThreads / 32; ++i) tot += s_red[i];
+      const float rstd = rsqrtf(tot / (float)C + eps);
+      uint4* on = reinterpret_cast<uint4*>(xn_out + (long long)t * ldn);
+      for (int i = threadIdx.x; i < nvec; i += kRouteThreads) {
+        const uint4 v = s_row[i], ww = reinterpret_cast<const uint4*>(norm_w)[i];
+        const uint32_t xi[4] = {v.x, v.y, v.z, v.w}, wi[4] = {ww.x, ww.y, ww.z, ww.w};
+        uint32_t oo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a = unpack_bf16(xi[q]), g = unpack_bf16(wi[q]);
+          const float2 n = unpack_bf16(pack_bf16(a.x * rstd, a.y * rstd));
+          oo[q] = pack_bf16(n.x * g.x, n.y * g.y);
+        }
+        const uint4 o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+        s_row[i] = o;
+        on[i] = o;
+      }
+    } else {
+      for (int i = threadIdx.x; i < nvec; i += kRouteThreads) s_row[i] = xr[i];
     }
-    if (shared_gate_w != nullptr) {
-      const uint4* wr = reinterpret_cast<const uint4*>(shared_gate_w);
+    __syncthreads();
+    // rows 0..E-1: router, row E: the shared expert's gate
+    const int n_rows = E + (shared_gate_w != nullptr ? 1 : 0);
+    for (int e = warp; e < n_rows; e += kRouteThreads / 32) {
+      const uint4* wr = reinterpret_cast<const uint4*>(e < E ? router_w + (long long)e * C : shared_gate_w);
       float acc = 0.f;
-      for (int i = lane; i < nvec; i += 32) acc += dot8(srow[i], __ldg(wr + i));
+#pragma unroll 4
+      for (int i = lane; i < nvec; i += 32) acc += dot8(s_row[i], __ldg(wr + i));
       acc = warp_sum(acc);
-      if (lane == 0) shared_gate[t] = 1.f / (1.f + __expf(-acc));
+      if (lane == 0) s_logit[e] = acc;
     }
-    // softmax over all E experts in fp32
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < kMoeMaxExperts / 32; ++j) mx = fmaxf(mx, logit[j]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float prob[kMoeMaxExperts / 32], sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
-      prob[j] = (j * 32 + lane < E) ? expf(logit[j] - mx) : 0.f;
-      sum += prob[j];
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    // top-k: k rounds of warp arg-max (ties -> lowest expert index)
-    float sel_w[kMoeMaxTopK];
-    int sel_e[kMoeMaxTopK];
-    float wsum = 0.f;
-#pragma unroll
-    for (int r = 0; r < kMoeMaxTopK; ++r) {
-      if (r >= top_k) break;
-      float bv = -1.f;
-      int be = 0x7fffffff;
+    __syncthreads();
+    if (warp == 0) {
+      if (shared_gate_w != nullptr && lane == 0) shared_gate[t] = 1.f / (1.f + __expf(-s_logit[E]));
+      float logit[kMoeMaxExperts / 32];
+      float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
-        const int e = j * 32 + lane;
-        if (e < E && prob[j] > bv) {
-          bv = prob[j];
-          be = e;
-        }
+        logit[j] = (j * 32 + lane < E) ? s_logit[j * 32 + lane] : -INFINITY;
+        mx = fmaxf(mx, logit[j]);
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oe = __shfl_xor_sync(0xffffffffu, be, o);
-        if (ov > bv || (ov == bv && oe < be)) {
-          bv = ov;
-          be = oe;
-        }
-      }
-      sel_w[r] = bv * inv;
-      sel_e[r] = be;
-      wsum += sel_w[r];
-      if ((be & 31) == lane) {
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float prob[kMoeMaxExperts / 32], sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < kMoeMaxExperts / 32; ++j)
-          if (j == (be >> 5)) prob[j] = -2.f;  // taken
+      for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
+        prob[j] = (j * 32 + lane < E) ? expf(logit[j] - mx) : 0.f;
+        sum += prob[j];
       }
-    }
-    if (lane == 0) {
-      const float rn = norm_topk ? 1.f / wsum : 1.f;
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
+      // top-k: k rounds of warp arg-max (ties -> lowest expert index)
+      float sel_w[kMoeMaxTopK];
+      int sel_e[kMoeMaxTopK];
+      float wsum = 0.f;
 #pragma unroll
       for (int r = 0; r < kMoeMaxTopK; ++r) {
         if (r >= top_k) break;
-        topk_ids[(long long)t * top_k + r] = sel_e[r];
-        topk_w[(long long)t * top_k + r] = sel_w[r] * rn;
-        atomicAdd(counts + sel_e[r], 1);
+        float bv = -1.f;
+        int be = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
+          const int e = j * 32 + lane;
+          if (e < E && prob[j] > bv) {
+            bv = prob[j];
+            be = e;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oe = __shfl_xor_sync(0xffffffffu, be, o);
+          if (ov > bv || (ov == bv && oe < be)) {
+            bv = ov;
+            be = oe;
+          }
+        }
+        sel_w[r] = bv * inv;
+        sel_e[r] = be;
+        wsum += sel_w[r];
+        if ((be & 31) == lane) {
+#pragma unroll
+          for (int j = 0; j < kMoeMaxExperts / 32; ++j)
+            if (j == (be >> 5)) prob[j] = -2.f;  // taken
+        }
+      }
+      if (lane == 0) {
+        const float rn = norm_topk ? 1.f / wsum : 1.f;
+#pragma unroll
+        for (int r = 0; r < kMoeMaxTopK; ++r) {
+          if (r >= top_k) break;
+          topk_ids[(long long)t * top_k + r] = sel_e[r];
+          topk_w[(long long)t * top_k + r] = sel_w[r] * rn;
+          atomicAdd(counts + sel_e[r], 1);
+        }
       }
     }
-    __syncwarp();
+    __syncthreads();
   }
 }
 
@@ -247,30 +282,22 @@ extern "C" int omc_moe_max_tiles(int T, int top_k, int n_experts) {
   return (int)(((long long)T * top_k) / kMoeTile) + n_experts;  // sum_e ceil(c_e / 128) <= floor(sum c_e / 128) + E
 }
 
-extern "C" int omc_moe_route(const void* x, long long ldx, int T, int C, const void* router_w, const void* shared_gate_w,
-                             int n_experts, int top_k, int norm_topk, int32_t* topk_ids, float* topk_w, float* shared_gate,
-                             int32_t* counts, void* stream) {
+extern "C" int omc_moe_route(const void* x, long long ldx, int T, int C, const void* norm_w, float eps, void* xn_out,
+                             long long ldn, const void* router_w, const void* shared_gate_w, int n_experts, int top_k,
+                             int norm_topk, int32_t* topk_ids, float* topk_w, float* shared_gate, int32_t* counts, void* stream) {
   if (T <= 0) return OMC_OK;
   if (x == nullptr || router_w == nullptr || topk_ids == nullptr || topk_w == nullptr || counts == nullptr ||
-      (shared_gate_w != nullptr && shared_gate == nullptr))
+      (shared_gate_w != nullptr && shared_gate == nullptr) || (norm_w != nullptr && xn_out == nullptr))
     return set_error(OMC_ERR_ARG, "omc_moe_route: null argument");
   if (n_experts < 1 || n_experts > kMoeMaxExperts || top_k < 1 || top_k > kMoeMaxTopK || top_k > n_experts)
     return set_error(OMC_ERR_SHAPE, "omc_moe_route: at most 128 experts and top-8 routing");
-  if (C <= 0 || C % 8 != 0 || C > 8192 || ldx % 8 != 0)
-    return set_error(OMC_ERR_SHAPE, "omc_moe_route: C must be a multiple of 8 and <= 8192, ldx a multiple of 8");
-  const int smem = kRouteWarps * (C / 8) * 16;
-  static bool attr_set_dev[kMaxDevices] = {};
-  bool& attr_set = attr_set_dev[cur_device()];
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(moe_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRouteWarps * 1024 * 16);
-    if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
-    attr_set = true;
-  }
-  const int need = (T + kRouteWarps - 1) / kRouteWarps;
-  const int grid = need < num_sms() * 8 ? need : num_sms() * 8;
-  moe_route_kernel<<<grid, kRouteWarps * 32, smem, (cudaStream_t)stream>>>(
-      (const bf16*)x, ldx, T, C, (const bf16*)router_w, (const bf16*)shared_gate_w, n_experts, top_k, norm_topk, topk_ids, topk_w,
-      shared_gate, counts);
+  if (C <= 0 || C % 8 != 0 || C > 8192 || ldx % 8 != 0 || (norm_w != nullptr && ldn % 8 != 0))
+    return set_error(OMC_ERR_SHAPE, "omc_moe_route: C must be a multiple of 8 and <= 8192, leading dims multiples of 8");
+  const int smem = (C / 8) * 16;
+  const int grid = T < num_sms() * 8 ? T : num_sms() * 8;
+  moe_route_kernel<<<grid, kRouteThreads, smem, (cudaStream_t)stream>>>(
+      (const bf16*)x, ldx, T, C, (const bf16*)norm_w, eps, (bf16*)xn_out, ldn, (const bf16*)router_w, (const bf16*)shared_gate_w,
+      n_experts, top_k, norm_topk, topk_ids, topk_w, shared_gate, counts);
   return check_launch("moe_route");
 }
 

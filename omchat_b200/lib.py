@@ -41,7 +41,7 @@ SIGNATURES = {
     "omc_rmsnorm_pair": (_I, [_P, _L, _P, _P, _I, _I, _F, _P]),
     "omc_layernorm": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _F, _P]),
     "omc_moe_max_tiles": (_I, [_I, _I, _I]),
-    "omc_moe_route": (_I, [_P, _L, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "omc_moe_route": (_I, [_P, _L, _I, _I, _P, _F, _P, _L, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "omc_moe_plan": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "omc_moe_scatter": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _P, _L, _P, _P]),
     "omc_gemm_bf16_grouped": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P]),
@@ -779,9 +779,11 @@ class MoeWorkspace:
 
 def moe_block(h: torch.Tensor, xn: torch.Tensor, ws: MoeWorkspace, router_w: torch.Tensor, shared_gate_w: Optional[torch.Tensor],
               experts_gate_up: torch.Tensor, experts_down: torch.Tensor, shared_gate_up: Optional[torch.Tensor],
-              shared_down: Optional[torch.Tensor], norm_topk: bool) -> torch.Tensor:
+              shared_down: Optional[torch.Tensor], norm_topk: bool, norm_w: Optional[torch.Tensor] = None,
+              eps: float = 1e-6) -> torch.Tensor:
     """h[T, C] += SparseMoeBlock(xn[T, C]) (transformers modeling_qwen2_moe.py:363-374), in place. experts_gate_up
-    [E * 2 I, C] with every expert's gate / up rows interleaved (the SwiGLU epilogue's layout), experts_down [E * C, I]."""
+    [E * 2 I, C] with every expert's gate / up rows interleaved (the SwiGLU epilogue's layout), experts_down [E * C, I].
+    norm_w given: xn is an OUTPUT - the router kernel computes xn = RMSNorm(h) * norm_w itself (one launch less)."""
     _need_cuda(h, xn, router_w, experts_gate_up, experts_down)
     T, C = xn.shape
     assert T <= ws.T and C == ws.C and h.shape == xn.shape and xn.stride(1) == 1 and h.stride(1) == 1
@@ -789,8 +791,10 @@ def moe_block(h: torch.Tensor, xn: torch.Tensor, ws: MoeWorkspace, router_w: tor
     I2 = experts_gate_up.shape[0] // E
     M = ws.max_tiles * 128
     max_tiles = L.omc_moe_max_tiles(T, k, E)  # tiles this call can touch (<= the workspace's)
-    _check(L.omc_moe_route(_ptr(xn), xn.stride(0), T, C, _ptr(router_w), _ptr(shared_gate_w), E, k, int(norm_topk),
-                           _ptr(ws.topk_ids), _ptr(ws.topk_w), _ptr(ws.shared_gate), _ptr(ws.counts), st), "omc_moe_route")
+    src = h if norm_w is not None else xn
+    _check(L.omc_moe_route(_ptr(src), src.stride(0), T, C, _ptr(norm_w), eps, _ptr(xn) if norm_w is not None else None,
+                           xn.stride(0), _ptr(router_w), _ptr(shared_gate_w), E, k, int(norm_topk), _ptr(ws.topk_ids),
+                           _ptr(ws.topk_w), _ptr(ws.shared_gate), _ptr(ws.counts), st), "omc_moe_route")
     _check(L.omc_moe_plan(_ptr(ws.counts), E, ws.max_tiles, _ptr(ws.seg_start), _ptr(ws.cursor), _ptr(ws.tile_expert), st),
            "omc_moe_plan")
     _check(L.omc_moe_scatter(_ptr(xn), xn.stride(0), T, C, _ptr(ws.topk_ids), k, _ptr(ws.seg_start), _ptr(ws.cursor),

@@ -2,7 +2,7 @@
 the same multimodal glue over transformers' Qwen2MoeForCausalLM instead of Qwen2ForCausalLM.
 
 Attention, RMSNorm, RoPE, the paged cache and lm_head are the dense decoder's kernels; only the MLP half of a *sparse* layer
-differs (transformers modeling_qwen2_moe.py:295-374). It runs as: RMSNorm -> omc_moe_route (router softmax, top-k, histogram) ->
+differs (transformers modeling_qwen2_moe.py:295-374). It runs as: omc_moe_route (RMSNorm, router softmax, top-k, histogram) ->
 omc_moe_plan -> omc_moe_scatter (rows sorted by expert into 128-row tiles) -> two grouped tcgen05 GEMMs over the stacked expert
 matrices (gate|up with the SwiGLU epilogue, down) -> the shared expert's two GEMMs -> omc_moe_combine (weighted sum + sigmoid-gated
 shared expert + residual). Everything stays on the device (no host look at the routing), so decode steps capture into a CUDA
@@ -48,9 +48,9 @@ class Qwen2MoeDecoder(Qwen2Decoder):
 
     def _moe(self, l, h, xn):
         m = l.moe
-        lib.rmsnorm(h, l.ln2, self.eps, out=xn)
-        lib.moe_block(h, xn, self._workspace(h.shape[0]), m.router_w, m.shared_gate_w, m.experts_gate_up, m.experts_down,
-                      m.shared_gate_up, m.shared_down, self.cfg.norm_topk_prob)
+        # post_attention_layernorm is applied by the router kernel (it needs the normed row anyway) and left in xn
+        lib.moe_block(h, xn[:h.shape[0]], self._workspace(h.shape[0]), m.router_w, m.shared_gate_w, m.experts_gate_up,
+                      m.experts_down, m.shared_gate_up, m.shared_down, self.cfg.norm_topk_prob, norm_w=l.ln2, eps=self.eps)
 
     def _mlp_rows(self, li, l, h, xn, act):
         if l.moe is None:
