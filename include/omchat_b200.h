@@ -387,8 +387,13 @@ int omc_decoder_prefill(const omc_decode_desc* desc, const float* inv_freq, void
  *   omc_gemm_bf16_grouped   out[r, :] = epi(xperm[r, :] . W[tile_expert[r / 128]]^T) for W = [n_experts * N, K] stacked expert
  *                    matrices on the tcgen05 GEMM (epi OMC_EPI_SWIGLU on interleaved gate/up rows, or OMC_EPI_NONE); tiles
  *                    with tile_expert < 0 are skipped without touching the weights. M_max = max_tiles * 128, N % 128 == 0.
+ *                    active_tiles_hint: an upper bound of the tiles that can be active (min(max_tiles, T * k); 0 = M_max / 128),
+ *                    used only to pick the tile width (narrower tiles when few experts' weights are streamed).
  *   omc_moe_combine  h[t] += sum_j topk_w[t, j] * yperm[slot_of[t, j]] + shared_gate[t] * shared_y[t]  (shared_y may be NULL),
- *                    fp32 accumulate, one bf16 rounding: the block's output + the decoder layer's residual add. */
+ *                    fp32 accumulate, one bf16 rounding: the block's output + the decoder layer's residual add. ssq_out != NULL
+ *                    (T <= 64): also leaves the new rows' sums of squares in omc_row_ssq's [ssq_parts][64] layout for the
+ *                    folded RMSNorm of the next omc_gemm_stream.
+ *   omc_moe_plan_scatter   omc_moe_plan + omc_moe_scatter; for T * top_k <= 16 (small decode steps) as ONE single-CTA launch. */
 int omc_moe_max_tiles(int T, int top_k, int n_experts);
 int omc_moe_route(const void* x, long long ldx, int T, int C, const void* norm_w, float eps, void* xn_out, long long ldn,
                   const void* router_w, const void* shared_gate_w, int n_experts, int top_k, int norm_topk, int32_t* topk_ids,
@@ -398,9 +403,13 @@ int omc_moe_plan(int32_t* counts, int n_experts, int max_tiles, int32_t* seg_sta
 int omc_moe_scatter(const void* x, long long ldx, int T, int C, const int32_t* topk_ids, int top_k, const int32_t* seg_start,
                     int32_t* cursor, void* xperm, long long ldp, int32_t* slot_of, void* stream);
 int omc_gemm_bf16_grouped(const void* X, long long ldx, int M_max, const void* W, long long ldw, int n_experts, int N, int K,
-                          const int32_t* tile_expert, void* out, long long ldo, int epi, void* stream);
+                          const int32_t* tile_expert, int active_tiles_hint, void* out, long long ldo, int epi, void* stream);
 int omc_moe_combine(void* h, long long ldh, int T, int C, const void* yperm, long long ldy, const int32_t* slot_of,
-                    const float* topk_w, int top_k, const void* shared_y, long long lds, const float* shared_gate, void* stream);
+                    const float* topk_w, int top_k, const void* shared_y, long long lds, const float* shared_gate, float* ssq_out,
+                    int ssq_parts, void* stream);
+int omc_moe_plan_scatter(int32_t* counts, int n_experts, int max_tiles, int32_t* seg_start, int32_t* cursor, int32_t* tile_expert,
+                         const void* x, long long ldx, int T, int C, const int32_t* topk_ids, int top_k, void* xperm, long long ldp,
+                         int32_t* slot_of, void* stream);
 
 /* ---- peer (NVLink) memory for the tensor-parallel decode step ------------------------------------------------------
  * Replaces the NCCL communicator a Megatron-style decoder would hand to its all-reduce: one exchange buffer per rank,

@@ -441,7 +441,8 @@ extern "C" int omc_gemm_bf16_norm(const void* X, long long ldx, const void* W, l
 // segment starts on a 128-row tile and tile_expert[r / 128] names the expert (< 0: the tile holds no rows, skipped without
 // touching the weights). W is the experts' matrices stacked, [n_experts * N, K]. One launch, no host knowledge of the routing.
 extern "C" int omc_gemm_bf16_grouped(const void* X, long long ldx, int M_max, const void* W, long long ldw, int n_experts, int N,
-                                     int K, const int32_t* tile_expert, void* out, long long ldo, int epi, void* stream) {
+                                     int K, const int32_t* tile_expert, int active_tiles_hint, void* out, long long ldo, int epi,
+                                     void* stream) {
   if (X == nullptr || W == nullptr || tile_expert == nullptr || out == nullptr)
     return set_error(OMC_ERR_ARG, "omc_gemm_bf16_grouped: null argument");
   if (M_max <= 0 || M_max % kBM != 0 || n_experts <= 0 || N <= 0 || K <= 0 || N % 128 != 0 || K % 8 != 0)
@@ -454,7 +455,11 @@ extern "C" int omc_gemm_bf16_grouped(const void* X, long long ldx, int M_max, co
   p.epi = epi;
   p.grp_tile = tile_expert;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (N % 256 == 0) return launch_gemm<256, 1>(X, ldx, W, ldw, p, 0, st, n_experts);
+  // 256-wide tiles unless even the worst case (active_tiles_hint 128-row tiles active) leaves SMs idle: decode steps stream the weights of
+  // a few experts, and more, narrower CTAs put more of them in flight
+  const int m_tiles = (active_tiles_hint > 0 && active_tiles_hint < M_max / kBM) ? active_tiles_hint : M_max / kBM;
+  const long long tiles256 = (long long)m_tiles * ((N + 255) / 256);
+  if (N % 256 == 0 && tiles256 >= 2LL * num_sms()) return launch_gemm<256, 1>(X, ldx, W, ldw, p, 0, st, n_experts);
   return launch_gemm<128, 1>(X, ldx, W, ldw, p, 0, st, n_experts);
 }
 

@@ -33,7 +33,9 @@ __device__ __forceinline__ float dot8(uint4 a, uint4 b) {
 // the row is staged in shared memory (optionally RMS-normalised on the way in - the decode step hands over the raw residual
 // row and gets the normed row back in xn_out), the E + 1 dot products are spread over the 8 warps (independent 128-bit loads of
 // the L2-resident router rows in flight per lane), warp 0 finishes with the fp32 softmax and k rounds of arg-max.
-constexpr int kRouteThreads = 256;
+// kRouteThreads = 256 for prefill-sized T (many CTAs in flight); 1024 for decode steps, where a handful of CTAs must pull the
+// whole router matrix themselves and only more warps put more loads in flight (T = 1: 31 us with 8 warps).
+template <int kRouteThreads>
 __global__ void __launch_bounds__(kRouteThreads) moe_route_kernel(const bf16* __restrict__ x, long long ldx, int T, int C,
                                                                   const bf16* __restrict__ norm_w, float eps,
                                                                   bf16* __restrict__ xn_out, long long ldn,
@@ -219,14 +221,68 @@ __global__ void __launch_bounds__(128) moe_scatter_kernel(const bf16* __restrict
   }
 }
 
+// Decode steps with at most 16 (token, expert) pairs: plan + scatter in ONE single-CTA launch.
+__global__ void __launch_bounds__(128) moe_plan_scatter_small_kernel(int32_t* __restrict__ counts, int E, int max_tiles,
+                                                                     int32_t* __restrict__ seg_start, int32_t* __restrict__ cursor,
+                                                                     int32_t* __restrict__ tile_expert, const bf16* __restrict__ x,
+                                                                     long long ldx, int T, int C,
+                                                                     const int32_t* __restrict__ topk_ids, int top_k,
+                                                                     bf16* __restrict__ xperm, long long ldp,
+                                                                     int32_t* __restrict__ slot_of) {
+  __shared__ int s_start[kMoeMaxExperts + 1];
+  __shared__ int s_slot[16];
+  if (threadIdx.x == 0) {
+    int at = 0;
+    for (int e = 0; e < E; ++e) {
+      s_start[e] = at;
+      at += (counts[e] + kMoeTile - 1) / kMoeTile;
+    }
+    s_start[E] = at;
+    // slots in (token, rank) order: with <= 64 pairs a serial pass is cheaper than atomics + a second launch
+    for (int p = 0; p < T * top_k; ++p) {
+      const int e = topk_ids[p];
+      int n = 0;  // pairs before this one that went to the same expert
+      for (int q = 0; q < p; ++q) n += (topk_ids[q] == e);
+      s_slot[p] = s_start[e] * kMoeTile + n;
+      slot_of[p] = s_slot[p];
+    }
+  }
+  __syncthreads();
+  for (int mt = threadIdx.x; mt < max_tiles; mt += blockDim.x) {
+    int owner = -1;
+    if (mt < s_start[E]) {
+      int lo = 0, hi = E;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_start[mid] <= mt) lo = mid; else hi = mid;
+      }
+      owner = lo;
+    }
+    tile_expert[mt] = owner;
+  }
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    seg_start[e] = s_start[e] * kMoeTile;
+    cursor[e] = counts[e];  // what omc_moe_scatter would have left behind
+    counts[e] = 0;
+  }
+  const int nvec = C >> 3;
+  for (int p = 0; p < T * top_k; ++p) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)(p / top_k) * ldx);
+    uint4* dst = reinterpret_cast<uint4*>(xperm + (long long)s_slot[p] * ldp);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = xr[i];
+  }
+}
+
 // Qwen2MoeSparseMoeBlock.forward :363-374 + the decoder layer's residual add (:420): fp32 accumulate, one rounding.
 __global__ void __launch_bounds__(128) moe_combine_kernel(bf16* __restrict__ h, long long ldh, int T, int C,
                                                           const bf16* __restrict__ yperm, long long ldy,
                                                           const int32_t* __restrict__ slot_of, const float* __restrict__ topk_w,
                                                           int top_k, const bf16* __restrict__ shared_y, long long lds,
-                                                          const float* __restrict__ shared_gate) {
+                                                          const float* __restrict__ shared_gate, float* __restrict__ ssq_out,
+                                                          int ssq_parts) {
   __shared__ int s_slot[kMoeMaxTopK];
   __shared__ float s_w[kMoeMaxTopK];
+  __shared__ float s_red[4];
   const int nvec = C >> 3;
   for (int t = blockIdx.x; t < T; t += gridDim.x) {
     if (threadIdx.x < top_k) {
@@ -236,6 +292,7 @@ __global__ void __launch_bounds__(128) moe_combine_kernel(bf16* __restrict__ h, 
     __syncthreads();
     const float sg = shared_y != nullptr ? shared_gate[t] : 0.f;
     uint4* hr = reinterpret_cast<uint4*>(h + (long long)t * ldh);
+    float ssq = 0.f;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
       float moe[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int r = 0; r < top_k; ++r) {
@@ -266,8 +323,20 @@ __global__ void __launch_bounds__(128) moe_combine_kernel(bf16* __restrict__ h, 
       for (int q = 0; q < 4; ++q) {
         const float2 a = unpack_bf16(hi[q]);
         o[q] = pack_bf16(a.x + moe[2 * q], a.y + moe[2 * q + 1]);
+        const float2 r = unpack_bf16(o[q]);  // of the bf16 values actually stored, like the GEMM epilogues' partials
+        ssq += r.x * r.x + r.y * r.y;
       }
       hr[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (ssq_out != nullptr) {
+      // the row's sum of squares for the folded RMSNorm of the next weight-streaming GEMM (layout of omc_row_ssq: [parts][64])
+      ssq = warp_sum(ssq);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ssq;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        ssq_out[t] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+        for (int q = 1; q < ssq_parts; ++q) ssq_out[q * 64 + t] = 0.f;
+      }
     }
     __syncthreads();
   }
@@ -295,9 +364,14 @@ extern "C" int omc_moe_route(const void* x, long long ldx, int T, int C, const v
     return set_error(OMC_ERR_SHAPE, "omc_moe_route: C must be a multiple of 8 and <= 8192, leading dims multiples of 8");
   const int smem = (C / 8) * 16;
   const int grid = T < num_sms() * 8 ? T : num_sms() * 8;
-  moe_route_kernel<<<grid, kRouteThreads, smem, (cudaStream_t)stream>>>(
-      (const bf16*)x, ldx, T, C, (const bf16*)norm_w, eps, (bf16*)xn_out, ldn, (const bf16*)router_w, (const bf16*)shared_gate_w,
-      n_experts, top_k, norm_topk, topk_ids, topk_w, shared_gate, counts);
+  if (T <= 32)
+    moe_route_kernel<1024><<<grid, 1024, smem, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, T, C, (const bf16*)norm_w, eps, (bf16*)xn_out, ldn, (const bf16*)router_w,
+        (const bf16*)shared_gate_w, n_experts, top_k, norm_topk, topk_ids, topk_w, shared_gate, counts);
+  else
+    moe_route_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, T, C, (const bf16*)norm_w, eps, (bf16*)xn_out, ldn, (const bf16*)router_w,
+        (const bf16*)shared_gate_w, n_experts, top_k, norm_topk, topk_ids, topk_w, shared_gate, counts);
   return check_launch("moe_route");
 }
 
@@ -324,16 +398,39 @@ extern "C" int omc_moe_scatter(const void* x, long long ldx, int T, int C, const
   return check_launch("moe_scatter");
 }
 
+extern "C" int omc_moe_plan_scatter(int32_t* counts, int n_experts, int max_tiles, int32_t* seg_start, int32_t* cursor,
+                                    int32_t* tile_expert, const void* x, long long ldx, int T, int C, const int32_t* topk_ids,
+                                    int top_k, void* xperm, long long ldp, int32_t* slot_of, void* stream) {
+  if (T * top_k > 16) {
+    const int rc = omc_moe_plan(counts, n_experts, max_tiles, seg_start, cursor, tile_expert, stream);
+    if (rc != OMC_OK) return rc;
+    return omc_moe_scatter(x, ldx, T, C, topk_ids, top_k, seg_start, cursor, xperm, ldp, slot_of, stream);
+  }
+  if (T <= 0) return OMC_OK;
+  if (counts == nullptr || seg_start == nullptr || cursor == nullptr || tile_expert == nullptr || x == nullptr ||
+      topk_ids == nullptr || xperm == nullptr || slot_of == nullptr)
+    return set_error(OMC_ERR_ARG, "omc_moe_plan_scatter: null argument");
+  if (n_experts < 1 || n_experts > kMoeMaxExperts || max_tiles < 1 || C % 8 != 0 || ldx % 8 != 0 || ldp % 8 != 0 || top_k < 1 ||
+      top_k > kMoeMaxTopK)
+    return set_error(OMC_ERR_SHAPE, "omc_moe_plan_scatter: bad sizes");
+  moe_plan_scatter_small_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(counts, n_experts, max_tiles, seg_start, cursor, tile_expert,
+                                                                      (const bf16*)x, ldx, T, C, topk_ids, top_k, (bf16*)xperm, ldp,
+                                                                      slot_of);
+  return check_launch("moe_plan_scatter");
+}
+
 extern "C" int omc_moe_combine(void* h, long long ldh, int T, int C, const void* yperm, long long ldy, const int32_t* slot_of,
                                const float* topk_w, int top_k, const void* shared_y, long long lds, const float* shared_gate,
-                               void* stream) {
+                               float* ssq_out, int ssq_parts, void* stream) {
   if (T <= 0) return OMC_OK;
   if (h == nullptr || yperm == nullptr || slot_of == nullptr || topk_w == nullptr || (shared_y != nullptr && shared_gate == nullptr))
     return set_error(OMC_ERR_ARG, "omc_moe_combine: null argument");
   if (C % 8 != 0 || ldh % 8 != 0 || ldy % 8 != 0 || lds % 8 != 0 || top_k < 1 || top_k > kMoeMaxTopK)
     return set_error(OMC_ERR_SHAPE, "omc_moe_combine: C / leading dims must be multiples of 8, top_k <= 8");
+  if (ssq_out != nullptr && (T > 64 || ssq_parts < 1))
+    return set_error(OMC_ERR_SHAPE, "omc_moe_combine: sums of squares are for decode steps of <= 64 rows (omc_row_ssq layout)");
   const int grid = T < num_sms() * 16 ? T : num_sms() * 16;
   moe_combine_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((bf16*)h, ldh, T, C, (const bf16*)yperm, ldy, slot_of, topk_w, top_k,
-                                                             (const bf16*)shared_y, lds, shared_gate);
+                                                             (const bf16*)shared_y, lds, shared_gate, ssq_out, ssq_parts);
   return check_launch("moe_combine");
 }

@@ -44,8 +44,9 @@ SIGNATURES = {
     "omc_moe_route": (_I, [_P, _L, _I, _I, _P, _F, _P, _L, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "omc_moe_plan": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "omc_moe_scatter": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _P, _L, _P, _P]),
-    "omc_gemm_bf16_grouped": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _P, _P, _L, _I, _P]),
-    "omc_moe_combine": (_I, [_P, _L, _I, _I, _P, _L, _P, _P, _I, _P, _L, _P, _P]),
+    "omc_gemm_bf16_grouped": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _P, _I, _P, _L, _I, _P]),
+    "omc_moe_combine": (_I, [_P, _L, _I, _I, _P, _L, _P, _P, _I, _P, _L, _P, _P, _I, _P]),
+    "omc_moe_plan_scatter": (_I, [_P, _I, _I, _P, _P, _P, _P, _L, _I, _I, _P, _I, _P, _L, _P, _P]),
     "omc_vit_im2col": (_I, [_P, _I, _P, _L, _I, _I, _I, _P]),
     "omc_vit_assemble": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "omc_select_pixel_shuffle": (_I, [_P, _P, _I, _I, _I, _I, _P]),
@@ -780,10 +781,13 @@ class MoeWorkspace:
 def moe_block(h: torch.Tensor, xn: torch.Tensor, ws: MoeWorkspace, router_w: torch.Tensor, shared_gate_w: Optional[torch.Tensor],
               experts_gate_up: torch.Tensor, experts_down: torch.Tensor, shared_gate_up: Optional[torch.Tensor],
               shared_down: Optional[torch.Tensor], norm_topk: bool, norm_w: Optional[torch.Tensor] = None,
-              eps: float = 1e-6) -> torch.Tensor:
+              eps: float = 1e-6, shared_y: Optional[torch.Tensor] = None, ssq_out: Optional[torch.Tensor] = None,
+              ssq_parts: int = 1) -> torch.Tensor:
     """h[T, C] += SparseMoeBlock(xn[T, C]) (transformers modeling_qwen2_moe.py:363-374), in place. experts_gate_up
     [E * 2 I, C] with every expert's gate / up rows interleaved (the SwiGLU epilogue's layout), experts_down [E * C, I].
-    norm_w given: xn is an OUTPUT - the router kernel computes xn = RMSNorm(h) * norm_w itself (one launch less)."""
+    norm_w given: xn is an OUTPUT - the router kernel computes xn = RMSNorm(h) * norm_w itself (one launch less).
+    shared_y given: the shared expert's output [T, C], already computed by the caller (the decode step runs it on the
+    weight-streaming GEMMs); shared_gate_up / shared_down are then unused."""
     _need_cuda(h, xn, router_w, experts_gate_up, experts_down)
     T, C = xn.shape
     assert T <= ws.T and C == ws.C and h.shape == xn.shape and xn.stride(1) == 1 and h.stride(1) == 1
@@ -795,23 +799,23 @@ def moe_block(h: torch.Tensor, xn: torch.Tensor, ws: MoeWorkspace, router_w: tor
     _check(L.omc_moe_route(_ptr(src), src.stride(0), T, C, _ptr(norm_w), eps, _ptr(xn) if norm_w is not None else None,
                            xn.stride(0), _ptr(router_w), _ptr(shared_gate_w), E, k, int(norm_topk), _ptr(ws.topk_ids),
                            _ptr(ws.topk_w), _ptr(ws.shared_gate), _ptr(ws.counts), st), "omc_moe_route")
-    _check(L.omc_moe_plan(_ptr(ws.counts), E, ws.max_tiles, _ptr(ws.seg_start), _ptr(ws.cursor), _ptr(ws.tile_expert), st),
-           "omc_moe_plan")
-    _check(L.omc_moe_scatter(_ptr(xn), xn.stride(0), T, C, _ptr(ws.topk_ids), k, _ptr(ws.seg_start), _ptr(ws.cursor),
-                             _ptr(ws.xperm), C, _ptr(ws.slot_of), st), "omc_moe_scatter")
+    _check(L.omc_moe_plan_scatter(_ptr(ws.counts), E, ws.max_tiles, _ptr(ws.seg_start), _ptr(ws.cursor), _ptr(ws.tile_expert),
+                                  _ptr(xn), xn.stride(0), T, C, _ptr(ws.topk_ids), k, _ptr(ws.xperm), C, _ptr(ws.slot_of), st),
+           "omc_moe_plan_scatter")
     Mc = max_tiles * 128
-    _check(L.omc_gemm_bf16_grouped(_ptr(ws.xperm), C, Mc, _ptr(experts_gate_up), C, E, I2, C, _ptr(ws.tile_expert),
+    hint = min(max_tiles, T * k)
+    _check(L.omc_gemm_bf16_grouped(_ptr(ws.xperm), C, Mc, _ptr(experts_gate_up), C, E, I2, C, _ptr(ws.tile_expert), hint,
                                    _ptr(ws.aperm), I2 // 2, EPI_SWIGLU, st), "omc_gemm_bf16_grouped")
     _check(L.omc_gemm_bf16_grouped(_ptr(ws.aperm), I2 // 2, Mc, _ptr(experts_down), I2 // 2, E, C, I2 // 2,
-                                   _ptr(ws.tile_expert), _ptr(ws.yperm), C, EPI_NONE, st), "omc_gemm_bf16_grouped")
-    add_launches(5)
-    shared_y = None
-    if shared_gate_up is not None:
+                                   _ptr(ws.tile_expert), hint, _ptr(ws.yperm), C, EPI_NONE, st), "omc_gemm_bf16_grouped")
+    add_launches(3)
+    if shared_y is None and shared_gate_up is not None:
         gemm(xn, shared_gate_up, out=ws.shared_act[:T], epi=EPI_SWIGLU)
         shared_y = gemm(ws.shared_act[:T], shared_down, out=ws.shared_y[:T])
     _check(L.omc_moe_combine(_ptr(h), h.stride(0), T, C, _ptr(ws.yperm), C, _ptr(ws.slot_of), _ptr(ws.topk_w), k,
-                             _ptr(shared_y), C, _ptr(ws.shared_gate), st), "omc_moe_combine")
-    add_launches(1)
+                             _ptr(shared_y), shared_y.stride(0) if shared_y is not None else C, _ptr(ws.shared_gate),
+                             _ptr(ssq_out), ssq_parts, st), "omc_moe_combine")
+    add_launches(1 if T * k <= 16 else 2)
     return h
 
 

@@ -8,8 +8,9 @@ matrices (gate|up with the SwiGLU epilogue, down) -> the shared expert's two GEM
 shared expert + residual). Everything stays on the device (no host look at the routing), so decode steps capture into a CUDA
 graph like the dense model's. Layers listed in mlp_only_layers (or skipped by decoder_sparse_step) keep the dense MLP.
 
-Not built for this variant: tensor parallelism, the persistent decode kernel and the weight-streaming GEMMs (their layer loops
-are dense-MLP specific) - every batch size decodes on the per-op path.
+Decode steps of 1..64 rows run the attention projections, the shared expert and lm_head on the weight-streaming GEMMs of
+csrc/gemm_stream.cu (RMSNorms folded in) around the routed block. Not built for this variant: tensor parallelism (expert
+parallelism is the natural sharding) and the persistent decode kernel.
 """
 from __future__ import annotations
 
@@ -30,8 +31,10 @@ class Qwen2MoeDecoder(Qwen2Decoder):
         if self.tp.size != 1:
             raise NotImplementedError("tensor parallelism is not built for the Qwen2-MoE variant")
         self.mega_enabled = False
-        self.stream_enabled = False
         self.fold_norms = False
+        # decode steps of 1..64 rows: attention projections, the shared expert and lm_head on the weight-streaming GEMMs
+        # (csrc/gemm_stream.cu, RMSNorms folded in); the routed experts on the grouped GEMM. OMCHAT_B200_NO_STREAM=1: per-op path
+        self.stream_min_b = 1
         self._moe_ws = {}
 
     def _workspace(self, T: int) -> lib.MoeWorkspace:
@@ -61,6 +64,53 @@ class Qwen2MoeDecoder(Qwen2Decoder):
         if l.moe is None:
             return super()._mlp_step(li, l, h, st, gv_c, gv_i)
         self._moe(l, h, st.xn)
+
+    def packed_weights(self):
+        """As the dense decoder's, with a sparse layer's SHARED expert in the gate_up / down places (the routed experts stay in
+        the grouped GEMM's stacked layout)."""
+        if self._packed is None:
+            P = Qwen2Decoder._Packed()
+            P.layers = []
+            for l in self.w.layers:
+                e = Qwen2Decoder._Packed()
+                e.qkv = lib.PackedWeight(l.qkv_w, col_scale=l.ln1)
+                e.o = lib.PackedWeight(l.o_w)
+                gu, dn = (l.gate_up_w, l.down_w) if l.moe is None else (l.moe.shared_gate_up, l.moe.shared_down)
+                e.gate_up = lib.PackedWeight(gu, col_scale=l.ln2)
+                e.down = lib.PackedWeight(dn)
+                P.layers.append(e)
+            P.lm_head = lib.PackedWeight(self.w.lm_head, col_scale=self.w.norm)
+            self._packed = P
+        return self._packed
+
+    def _decode_body_stream(self, st, cache):
+        """Decode step (1..64 rows): per layer qkv -> paged attention -> o_proj (+residual, leaves the rows' sums of squares) ->
+        [sparse layer: shared expert gate|up, down on the streaming GEMMs -> route (RMSNorm fused) -> plan -> scatter ->
+        grouped gate|up, down -> combine -> sums of squares] or [dense layer: gate|up, down]."""
+        P = self.packed_weights()
+        C, eps, B = self.C, self.eps, st.B
+        parts = lib.ssq_parts(C)
+        cache.ctx_lens.add_(1)
+        lib.embed_lookup(st.tokens, self.w.embed, out=st.h)
+        lib.row_ssq(st.h, st.ssq_a, parts=parts, pdl=False)
+        h = st.h
+        for li, (l, p) in enumerate(zip(self.w.layers, P.layers)):
+            lib.gemm_stream(h, p.qkv, out=st.qkv, bias=l.qkv_b, ssq_in=st.ssq_a, ssq_in_parts=parts, norm_dim=C, eps=eps)
+            lib.paged_decode_attn(st.qkv, self.inv_freq, cache.pool[li], cache.block_table, cache.page_size,
+                                  cache.ctx_lens, self.Hq, self.Hkv, st.splits, self.scale, st.attn, st.attn_ws)
+            lib.gemm_stream(st.attn, p.o, out=h, res=h, epi=lib.EPI_RES, ssq_out=st.ssq_b)
+            if l.moe is None:
+                lib.gemm_stream(h, p.gate_up, out=st.act, epi=lib.EPI_SWIGLU, ssq_in=st.ssq_b, ssq_in_parts=parts, norm_dim=C,
+                                eps=eps)
+                lib.gemm_stream(st.act, p.down, out=h, res=h, epi=lib.EPI_RES, ssq_out=st.ssq_a)
+                continue
+            m, ws = l.moe, self._workspace(B)
+            lib.gemm_stream(h, p.gate_up, out=ws.shared_act[:B], epi=lib.EPI_SWIGLU, ssq_in=st.ssq_b, ssq_in_parts=parts,
+                            norm_dim=C, eps=eps)
+            shared_y = lib.gemm_stream(ws.shared_act[:B], p.down, out=ws.shared_y[:B])
+            lib.moe_block(h, st.xn, ws, m.router_w, m.shared_gate_w, m.experts_gate_up, m.experts_down, None, None,
+                          self.cfg.norm_topk_prob, norm_w=l.ln2, eps=eps, shared_y=shared_y, ssq_out=st.ssq_a, ssq_parts=parts)
+        lib.gemm_stream(h, P.lm_head, out=st.logits, out_f32=True, ssq_in=st.ssq_a, ssq_in_parts=parts, norm_dim=C, eps=eps)
 
     def release(self):
         super().release()

@@ -92,7 +92,8 @@ def test_moe_block_kernels_vs_torch(Tn, C, E, k, I, Is, norm):
     assert (got.float() - want)[clear].abs().max().item() <= 0.02 * scale and cos >= 0.9995
 
 
-def test_grouped_gemm_skips_unused_tiles():
+@pytest.mark.parametrize("hint", [0, 4])
+def test_grouped_gemm_skips_unused_tiles(hint):
     """tile_expert < 0 tiles are never written; used tiles multiply their own expert's matrix."""
     from omchat_b200 import lib
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -101,7 +102,7 @@ def test_grouped_gemm_skips_unused_tiles():
     w = (torch.randn(E * N, K, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
     te = torch.tensor([3, -1, 0, 0, 4, -1, -1], device="cuda", dtype=torch.int32)
     out = torch.full((tiles * 128, N), 7.0, device="cuda", dtype=torch.bfloat16)
-    rc = lib.load().omc_gemm_bf16_grouped(x.data_ptr(), K, tiles * 128, w.data_ptr(), K, E, N, K, te.data_ptr(), out.data_ptr(), N,
+    rc = lib.load().omc_gemm_bf16_grouped(x.data_ptr(), K, tiles * 128, w.data_ptr(), K, E, N, K, te.data_ptr(), hint, out.data_ptr(), N,
                                           lib.EPI_NONE, torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
@@ -216,8 +217,10 @@ def test_moe_model_vs_reference_golden_and_oracle(golden_moe, variant):
     model.close()
 
 
-def test_moe_teacher_forced_decode_vs_oracle(golden_moe):
-    """5 decode steps (batch 3) teacher-forced with the oracle's tokens: per-step logits."""
+@pytest.mark.parametrize("stream", [True, False])
+def test_moe_teacher_forced_decode_vs_oracle(golden_moe, stream):
+    """5 decode steps (batch 3) teacher-forced with the oracle's tokens: per-step logits - on the weight-streaming GEMMs around
+    the routed block (the default) and on the per-op path."""
     from omchat_b200.model.moe import OmChatQwen2MoeForCausalLM
     g = golden_moe["A"]
     sd = {k: v.to(torch.bfloat16).float() for k, v in tiny_state_dict_moe(0, ()).items()}
@@ -233,6 +236,8 @@ def test_moe_teacher_forced_decode_vs_oracle(golden_moe):
         gaps.append(torch.stack([torch.stack(tr[i * n_sparse:(i + 1) * n_sparse])[:, -1].min() for i in range(6)]))
     gaps = torch.stack(gaps)  # [3, 6]
     dec = model.get_model().decoder
+    dec.stream_enabled = stream
+    assert dec.use_stream(3) == stream and not dec.use_mega(3)
     res = model(input_ids=ids, use_cache=True)
     cache = res.past_key_values
     cur = torch.tensor([t[0] for t in toks], device="cuda")
@@ -266,12 +271,26 @@ def test_moe_real_width_layer_vs_oracle():
     offs = [0, lens[0], sum(lens)]
     cache = dec.new_cache(2, 400)
     logits = dec.prefill(emb.cuda(), pos.cuda(), seq.cuda(), offs, cache, logits="all")
-    at = 0
+    at, pasts = 0, []
     for b, n in enumerate(lens):
-        ref, _ = O.qwen2_forward(emb[at:at + n].float()[None], torch.arange(n)[None], sd, oc)
+        ref, past = O.qwen2_forward(emb[at:at + n].float()[None], torch.arange(n)[None], sd, oc)
+        pasts.append(past)
         # a routing flip (k-th vs (k+1)-th expert within bf16 noise of each other) changes ONE token's MLP output: allow a few
         got = logits[at:at + n].float().cpu()
         cos = torch.nn.functional.cosine_similarity(got, ref[0], dim=-1)
         print(f"seq {b}: min cosine {cos.min().item():.6f}, rows below 0.999: {int((cos < 0.999).sum())}/{n}")
         assert int((cos < 0.999).sum()) <= max(1, n // 50) and cos.median().item() >= 0.9995
         at += n
+    # 3 decode steps (batch 2) on the weight-streaming GEMMs at the real widths (qkv N 6144, shared expert N 11264 / K 5632)
+    assert dec.use_stream(2)
+    table = sd["model.embed_tokens.weight"]
+    for step in range(3):
+        toks = torch.tensor([17 + step, 1203 - step])
+        lg = dec.decode_step(toks.cuda(), cache).float().cpu()
+        for b, n in enumerate(lens):
+            (ref, pasts[b]), tr = traced(lambda: O.qwen2_forward(table[toks[b]].view(1, 1, -1), torch.tensor([[n + step]]), sd, oc,
+                                                                 past=pasts[b]))
+            cos = torch.nn.functional.cosine_similarity(lg[b], ref[0, 0], dim=-1).item()
+            gap = float(tr[0][0])
+            print(f"decode step {step} seq {b}: cosine {cos:.6f} (routing gap {gap:.3f})")
+            assert cos >= 0.999 or (gap < ROUTE_GAP and cos >= 0.9)

@@ -8,5 +8,5 @@ hdr=rows[0]; ki=hdr.index("Kernel Name"); vi=hdr.index("Metric Value"); ui=hdr.i
 seq=[(r[ki], float(r[vi].replace(",",""))/ (1000.0 if r[ui]=="ns" else 1.0)) for r in rows[1:]]
 print(len(seq),"launches")
 # last decode step = last ~45 launches
-for n,t in seq[-48:]: print(f"{t:8.2f} us  {n[:90]}")
+for n,t in seq[-34:]: print(f"{t:8.2f} us  {n[:90]}")
 PY
