@@ -29,12 +29,158 @@ __device__ __forceinline__ float dot8(uint4 a, uint4 b) {
   return a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
 }
 
+// One warp: fp32 softmax over the E router logits of token t (logit[E] = the shared expert's gate logit), k rounds of warp
+// arg-max (ties -> lowest expert index), optional renormalisation, histogram.
+__device__ __forceinline__ void route_select(const float* logit_row, int E, int top_k, int norm_topk, bool has_gate, int t,
+                                             int32_t* __restrict__ topk_ids, float* __restrict__ topk_w,
+                                             float* __restrict__ shared_gate, int32_t* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  if (has_gate && lane == 0) shared_gate[t] = 1.f / (1.f + __expf(-logit_row[E]));
+  float logit[kMoeMaxExperts / 32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
+    logit[j] = (j * 32 + lane < E) ? logit_row[j * 32 + lane] : -INFINITY;
+    mx = fmaxf(mx, logit[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float prob[kMoeMaxExperts / 32], sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
+    prob[j] = (j * 32 + lane < E) ? expf(logit[j] - mx) : 0.f;
+    sum += prob[j];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  float sel_w[kMoeMaxTopK];
+  int sel_e[kMoeMaxTopK];
+  float wsum = 0.f;
+#pragma unroll
+  for (int r = 0; r < kMoeMaxTopK; ++r) {
+    if (r >= top_k) break;
+    float bv = -1.f;
+    int be = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
+      const int e = j * 32 + lane;
+      if (e < E && prob[j] > bv) {
+        bv = prob[j];
+        be = e;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oe = __shfl_xor_sync(0xffffffffu, be, o);
+      if (ov > bv || (ov == bv && oe < be)) {
+        bv = ov;
+        be = oe;
+      }
+    }
+    sel_w[r] = bv * inv;
+    sel_e[r] = be;
+    wsum += sel_w[r];
+    if ((be & 31) == lane) {
+#pragma unroll
+      for (int j = 0; j < kMoeMaxExperts / 32; ++j)
+        if (j == (be >> 5)) prob[j] = -2.f;  // taken
+    }
+  }
+  if (lane == 0) {
+    const float rn = norm_topk ? 1.f / wsum : 1.f;
+#pragma unroll
+    for (int r = 0; r < kMoeMaxTopK; ++r) {
+      if (r >= top_k) break;
+      topk_ids[(long long)t * top_k + r] = sel_e[r];
+      topk_w[(long long)t * top_k + r] = sel_w[r] * rn;
+      atomicAdd(counts + sel_e[r], 1);
+    }
+  }
+}
+
+// Prefill-sized T: TOK tokens per CTA (one warp each for the row staging / RMSNorm and for the selection), so that every router
+// row fetched from L2 is used for TOK dot products - a CTA per token re-reads the whole router matrix (E x C x 2 B = 245 KB)
+// per token: 2 GB of L2 traffic per layer at T = 8192, 48 us per 1024 tokens.
+template <int TOK>
+__global__ void __launch_bounds__(TOK * 32) moe_route_rows_kernel(const bf16* __restrict__ x, long long ldx, int T, int C,
+                                                                  const bf16* __restrict__ norm_w, float eps,
+                                                                  bf16* __restrict__ xn_out, long long ldn,
+                                                                  const bf16* __restrict__ router_w,
+                                                                  const bf16* __restrict__ shared_gate_w, int E, int top_k,
+                                                                  int norm_topk, int32_t* __restrict__ topk_ids,
+                                                                  float* __restrict__ topk_w, float* __restrict__ shared_gate,
+                                                                  int32_t* __restrict__ counts) {
+  extern __shared__ uint4 s_rows[];  // [TOK][C / 8]
+  __shared__ float s_logit[TOK][kMoeMaxExperts + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  for (int t0 = blockIdx.x * TOK; t0 < T; t0 += gridDim.x * TOK) {
+    const int t = t0 + warp;
+    uint4* srow = s_rows + warp * nvec;
+    if (t < T) {
+      const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)t * ldx);
+      if (norm_w != nullptr) {
+        float ss = 0.f;
+        for (int i = lane; i < nvec; i += 32) {
+          const uint4 v = xr[i];
+          srow[i] = v;
+          float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+          ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+        }
+        ss = warp_sum(ss);
+        const float rstd = rsqrtf(ss / (float)C + eps);
+        uint4* on = reinterpret_cast<uint4*>(xn_out + (long long)t * ldn);
+        for (int i = lane; i < nvec; i += 32) {
+          const uint4 v = srow[i], ww = __ldg(reinterpret_cast<const uint4*>(norm_w) + i);
+          const uint32_t xi[4] = {v.x, v.y, v.z, v.w}, wi[4] = {ww.x, ww.y, ww.z, ww.w};
+          uint32_t oo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 a = unpack_bf16(xi[q]), g = unpack_bf16(wi[q]);
+            const float2 n = unpack_bf16(pack_bf16(a.x * rstd, a.y * rstd));
+            oo[q] = pack_bf16(n.x * g.x, n.y * g.y);
+          }
+          const uint4 o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+          srow[i] = o;
+          on[i] = o;
+        }
+      } else {
+        for (int i = lane; i < nvec; i += 32) srow[i] = xr[i];
+      }
+    } else {
+      for (int i = lane; i < nvec; i += 32) srow[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    const int n_rows = E + (shared_gate_w != nullptr ? 1 : 0);
+    for (int e = warp; e < n_rows; e += TOK) {
+      const uint4* wr = reinterpret_cast<const uint4*>(e < E ? router_w + (long long)e * C : shared_gate_w);
+      float acc[TOK];
+#pragma unroll
+      for (int j = 0; j < TOK; ++j) acc[j] = 0.f;
+      for (int i = lane; i < nvec; i += 32) {
+        const uint4 wv = __ldg(wr + i);
+#pragma unroll
+        for (int j = 0; j < TOK; ++j) acc[j] += dot8(s_rows[j * nvec + i], wv);
+      }
+#pragma unroll
+      for (int j = 0; j < TOK; ++j) {
+        const float a = warp_sum(acc[j]);
+        if (lane == 0) s_logit[j][e] = a;
+      }
+    }
+    __syncthreads();
+    if (t < T) route_select(s_logit[warp], E, top_k, norm_topk, shared_gate_w != nullptr, t, topk_ids, topk_w, shared_gate, counts);
+    __syncthreads();
+  }
+}
+
 // Qwen2MoeTopKRouter.forward (modeling_qwen2_moe.py:343-352) + the shared expert's sigmoid gate (:371). One CTA per token:
 // the row is staged in shared memory (optionally RMS-normalised on the way in - the decode step hands over the raw residual
 // row and gets the normed row back in xn_out), the E + 1 dot products are spread over the 8 warps (independent 128-bit loads of
 // the L2-resident router rows in flight per lane), warp 0 finishes with the fp32 softmax and k rounds of arg-max.
-// kRouteThreads = 256 for prefill-sized T (many CTAs in flight); 1024 for decode steps, where a handful of CTAs must pull the
-// whole router matrix themselves and only more warps put more loads in flight (T = 1: 31 us with 8 warps).
+// Used for decode steps (T <= 32) with 1024 threads: a handful of CTAs must pull the whole router matrix themselves and only
+// more warps put more loads in flight (T = 1: 31 us with 8 warps). Larger T: moe_route_rows_kernel.
 template <int kRouteThreads>
 __global__ void __launch_bounds__(kRouteThreads) moe_route_kernel(const bf16* __restrict__ x, long long ldx, int T, int C,
                                                                   const bf16* __restrict__ norm_w, float eps,
@@ -97,71 +243,8 @@ __global__ void __launch_bounds__(kRouteThreads) moe_route_kernel(const bf16* __
       if (lane == 0) s_logit[e] = acc;
     }
     __syncthreads();
-    if (warp == 0) {
-      if (shared_gate_w != nullptr && lane == 0) shared_gate[t] = 1.f / (1.f + __expf(-s_logit[E]));
-      float logit[kMoeMaxExperts / 32];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
-        logit[j] = (j * 32 + lane < E) ? s_logit[j * 32 + lane] : -INFINITY;
-        mx = fmaxf(mx, logit[j]);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float prob[kMoeMaxExperts / 32], sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
-        prob[j] = (j * 32 + lane < E) ? expf(logit[j] - mx) : 0.f;
-        sum += prob[j];
-      }
-      sum = warp_sum(sum);
-      const float inv = 1.f / sum;
-      // top-k: k rounds of warp arg-max (ties -> lowest expert index)
-      float sel_w[kMoeMaxTopK];
-      int sel_e[kMoeMaxTopK];
-      float wsum = 0.f;
-#pragma unroll
-      for (int r = 0; r < kMoeMaxTopK; ++r) {
-        if (r >= top_k) break;
-        float bv = -1.f;
-        int be = 0x7fffffff;
-#pragma unroll
-        for (int j = 0; j < kMoeMaxExperts / 32; ++j) {
-          const int e = j * 32 + lane;
-          if (e < E && prob[j] > bv) {
-            bv = prob[j];
-            be = e;
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int oe = __shfl_xor_sync(0xffffffffu, be, o);
-          if (ov > bv || (ov == bv && oe < be)) {
-            bv = ov;
-            be = oe;
-          }
-        }
-        sel_w[r] = bv * inv;
-        sel_e[r] = be;
-        wsum += sel_w[r];
-        if ((be & 31) == lane) {
-#pragma unroll
-          for (int j = 0; j < kMoeMaxExperts / 32; ++j)
-            if (j == (be >> 5)) prob[j] = -2.f;  // taken
-        }
-      }
-      if (lane == 0) {
-        const float rn = norm_topk ? 1.f / wsum : 1.f;
-#pragma unroll
-        for (int r = 0; r < kMoeMaxTopK; ++r) {
-          if (r >= top_k) break;
-          topk_ids[(long long)t * top_k + r] = sel_e[r];
-          topk_w[(long long)t * top_k + r] = sel_w[r] * rn;
-          atomicAdd(counts + sel_e[r], 1);
-        }
-      }
-    }
+    if (warp == 0)
+      route_select(s_logit, E, top_k, norm_topk, shared_gate_w != nullptr, t, topk_ids, topk_w, shared_gate, counts);
     __syncthreads();
   }
 }
@@ -362,16 +445,28 @@ extern "C" int omc_moe_route(const void* x, long long ldx, int T, int C, const v
     return set_error(OMC_ERR_SHAPE, "omc_moe_route: at most 128 experts and top-8 routing");
   if (C <= 0 || C % 8 != 0 || C > 8192 || ldx % 8 != 0 || (norm_w != nullptr && ldn % 8 != 0))
     return set_error(OMC_ERR_SHAPE, "omc_moe_route: C must be a multiple of 8 and <= 8192, leading dims multiples of 8");
-  const int smem = (C / 8) * 16;
-  const int grid = T < num_sms() * 8 ? T : num_sms() * 8;
-  if (T <= 32)
-    moe_route_kernel<1024><<<grid, 1024, smem, (cudaStream_t)stream>>>(
+  cudaStream_t st = (cudaStream_t)stream;
+  if (T <= 32) {
+    const int grid = T;
+    moe_route_kernel<1024><<<grid, 1024, (C / 8) * 16, st>>>(
         (const bf16*)x, ldx, T, C, (const bf16*)norm_w, eps, (bf16*)xn_out, ldn, (const bf16*)router_w,
         (const bf16*)shared_gate_w, n_experts, top_k, norm_topk, topk_ids, topk_w, shared_gate, counts);
-  else
-    moe_route_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(
+  } else {
+    constexpr int TOK = 8;
+    const int smem = TOK * (C / 8) * 16;  // 32 KB at C = 2048, 128 KB at C = 8192
+    static bool attr_set_dev[kMaxDevices] = {};
+    bool& attr_set = attr_set_dev[cur_device()];
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(moe_route_rows_kernel<TOK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOK * 1024 * 16);
+      if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
+      attr_set = true;
+    }
+    const int need = (T + TOK - 1) / TOK;
+    const int grid = need < num_sms() * 4 ? need : num_sms() * 4;
+    moe_route_rows_kernel<TOK><<<grid, TOK * 32, smem, st>>>(
         (const bf16*)x, ldx, T, C, (const bf16*)norm_w, eps, (bf16*)xn_out, ldn, (const bf16*)router_w,
         (const bf16*)shared_gate_w, n_experts, top_k, norm_topk, topk_ids, topk_w, shared_gate, counts);
+  }
   return check_launch("moe_route");
 }
 
