@@ -147,3 +147,68 @@ def test_auto_model_generate_with_stopping_criteria(tmp_path, golden):
     out3 = model.generate(ids, images=pixels[:1], max_new_tokens=20, do_sample=False, eos_token_id=want[3])
     assert out3[0, ids.shape[1]:].tolist() == want[:want.index(want[3]) + 1]
     assert tok is not None and tiny_inputs is not None
+
+
+# ------------------------------------------------------------------------------------------------ the lighter families
+def _moe_cfg():
+    from test_moe_gpu import moe_cfgs
+    return moe_cfgs({"norm_topk_prob": True, "dense_layers": [0]})
+
+
+def test_moe_and_300m_config_round_trips(tmp_path):
+    """omchat_qwen2_moe.py:116-117 (AutoConfig / AutoModelForCausalLM registration of the MoE family), the config.json of a MoE
+    checkpoint and of a checkpoint whose vision_config says norm_type = 'layer_norm' (InternViT-300M)."""
+    from transformers import AutoConfig, AutoModelForCausalLM
+    import omchat_b200.hf as H
+    from omchat_b200.config import InternVisionConfig, OmChatQwen2Config, OmChatQwen2MoeConfig
+    from omchat_b200.model import OmChatQwen2MoeForCausalLM as NativeMoe
+    from omchat_b200.model.checkpoint import config_from_dict, save_checkpoint
+    from tiny import tiny_state_dict_moe
+    assert issubclass(H.OmChatQwen2MoeForCausalLM, NativeMoe)
+    assert type(AutoConfig.for_model("omchat_qwen2_moe")) is H.OmChatQwen2MoeConfig
+    assert AutoModelForCausalLM._model_mapping[H.OmChatQwen2MoeConfig] is H.OmChatQwen2MoeForCausalLM
+    cfg = _moe_cfg()
+    d = str(tmp_path / "moe")
+    save_checkpoint({k: v.to(torch.bfloat16) for k, v in tiny_state_dict_moe(0, (0,)).items()}, cfg, d)
+    c = AutoConfig.from_pretrained(d)
+    assert type(c) is H.OmChatQwen2MoeConfig and c.num_experts == 8 and c.mlp_only_layers == [0]
+    n = c.to_native()
+    assert type(n) is OmChatQwen2MoeConfig and n == cfg and n.layer_is_sparse(1) and not n.layer_is_sparse(0)
+    # a dense config never becomes a MoE one and vice versa
+    assert type(config_from_dict(OmChatQwen2Config().to_dict())) is OmChatQwen2Config
+    # the 300M tower: picked by NAME (multimodal_encoder/builder.py:11-14); vision_config survives config.json
+    c300 = OmChatQwen2Config(mm_vision_tower="OpenGVLab/InternViT-300M-448px")
+    assert c300.vision_config == InternVisionConfig.intern_vit_300m() and c300.mm_hidden_size == 1024
+    back = config_from_dict(json.loads(json.dumps(c300.to_dict())))
+    assert back == c300 and back.vision_config.norm_type == "layer_norm" and not back.vision_config.qk_normalization
+    with pytest.raises(ValueError):
+        InternVisionConfig(norm_type="batch_norm")
+
+
+@pytest.mark.gpu
+def test_auto_model_loads_moe_checkpoint_both_expert_layouts(tmp_path):
+    """AutoModelForCausalLM.from_pretrained on a saved MoE checkpoint - with one matrix per expert (the published safetensors
+    layout) and with transformers >= 5's fused 3-D expert parameters - gives the same logits as the model built directly."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from transformers import AutoModelForCausalLM
+    import omchat_b200.hf as H
+    from omchat_b200.model.checkpoint import save_checkpoint
+    from omchat_b200.model.moe import OmChatQwen2MoeForCausalLM
+    from tiny import fuse_experts_for_transformers5, tiny_state_dict_moe
+    cfg = _moe_cfg()
+    sd = {k: v.to(torch.bfloat16) for k, v in tiny_state_dict_moe(0, (0,)).items()}
+    pixels, ids = tiny_inputs(1)
+    ids = ids[:1].clone()
+    ids[0, 5] = -200
+    direct = OmChatQwen2MoeForCausalLM.from_state_dict(sd, cfg, device="cuda")
+    want = direct(input_ids=ids, images=pixels[:1]).logits.clone()
+    direct.close()
+    for name, state in (("per_expert", sd), ("fused", fuse_experts_for_transformers5(sd, cfg.num_experts))):
+        d = str(tmp_path / name)
+        save_checkpoint(state, cfg, d)
+        model = AutoModelForCausalLM.from_pretrained(d)
+        assert type(model) is H.OmChatQwen2MoeForCausalLM
+        got = model(input_ids=ids, images=pixels[:1]).logits
+        assert torch.equal(got, want), name
+        model.close()
