@@ -291,6 +291,7 @@ def main():
                     "feature all-gather -> decoder-TP over all GPUs")
     ap.add_argument("--c5-mb", type=int, default=0, help="c5: prompts per mini-batch (0 = default of the mode)")
     ap.add_argument("--no-workloads", action="store_true", help="skip the c3 / c4 legs of the main line (`workloads`)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the Qwen2-MoE / InternViT-300M legs (`variants`, N = 1 only)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--pixel-shuffle", type=float, default=1.0, help="mm_pixel_shuffle_ratio (1.0 = reference behaviour)")
     args = ap.parse_args()
@@ -497,6 +498,26 @@ def main():
         wl["c4"] = measure_c4(args, rank, world, local, cfg, dec)
         keep = ("metric", "value", "unit", "ms_per_step", "scaling", "config", "phases", "e2e", "gpu_launches", "roofline")
         line["workloads"] = {k: {kk: v[kk] for kk in keep if kk in v} for k, v in wl.items()}
+    # ---- the reference's two lighter model families on one GPU, each in its own right:
+    # random-init Qwen1.5-MoE-A2.7B-sized decoder (prefill + decode steps) and the InternViT-300M tower. Never allowed to
+    # break the headline line.
+    if world == 1 and not args.no_workloads and not args.no_variants:
+        var = {}
+        try:
+            torch.cuda.empty_cache()
+            from tools.bench_moe import measure as measure_moe
+            recs = measure_moe(batches=(1, 32), steps=32)
+            var["qwen2_moe_a2.7b"] = {"prefill": recs[0], "decode": recs[1:],
+                                      "config": "24 layers, hidden 2048, 60 experts top-4 x 1408, shared 5632, random init, bf16"}
+        except Exception as e:  # noqa: BLE001
+            var["qwen2_moe_a2.7b"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        try:
+            torch.cuda.empty_cache()
+            from tools.bench_vit300m import measure as measure_300m
+            var["internvit_300m"] = measure_300m(crops=64, iters=3)
+        except Exception as e:  # noqa: BLE001
+            var["internvit_300m"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        line["variants"] = var
     if world > 1:
         dist.barrier()
     if rank == 0:

@@ -294,3 +294,39 @@ def test_moe_real_width_layer_vs_oracle():
             gap = float(tr[0][0])
             print(f"decode step {step} seq {b}: cosine {cos:.6f} (routing gap {gap:.3f})")
             assert cos >= 0.999 or (gap < ROUTE_GAP and cos >= 0.9)
+
+
+def test_moe_continuous_batching_bookkeeping(golden_moe):
+    """The serving loop (omchat_b200/serving.py) over the MoE decoder: 5 requests through 3 slots. Integer bookkeeping must be
+    exact (lengths, pages returned, slots freed); each request's FIRST token comes from its own prefill and must equal
+    generate()'s; later tokens are checked against generate() up to the first near-tie (batch composition changes GEMM shapes)."""
+    from omchat_b200.model.moe import OmChatQwen2MoeForCausalLM
+    from omchat_b200.serving import ContinuousBatcher
+    g = golden_moe["A"]
+    sd = {k: v.to(torch.bfloat16).float() for k, v in tiny_state_dict_moe(0, ()).items()}
+    model = OmChatQwen2MoeForCausalLM.from_state_dict(sd, moe_cfgs(g), device="cuda")
+    gen = torch.Generator().manual_seed(5)
+    S = T["image_size"]
+    reqs = []
+    for n_text, n_img, max_new in [(20, 1, 6), (33, 0, 4), (12, 0, 8), (25, 1, 5), (18, 0, 3)]:
+        ids = torch.randint(1, T["vocab"], (1, n_text + n_img), generator=gen)
+        for j in range(n_img):
+            ids[0, 3 + 5 * j] = -200
+        px = torch.randn(n_img, 3, S, S, generator=gen).to(torch.bfloat16).float() if n_img else None
+        reqs.append((ids, px, max_new))
+    cb = ContinuousBatcher(model, slots=3, max_ctx=400, chunk=4)
+    total_free = len(cb.free_pages)
+    rids = [cb.submit(ids, px, max_new_tokens=mn) for ids, px, mn in reqs]
+    out = cb.run()
+    assert sorted(out) == rids and len(cb.free_pages) == total_free and all(r is None for r in cb.active)
+    agree = 0
+    for rid, (ids, px, mn) in zip(rids, reqs):
+        got = out[rid].view(-1).tolist()
+        alone = model.generate(ids, images=px, max_new_tokens=mn, do_sample=False, eos_token_id=-1)[0, ids.shape[1]:].tolist()
+        assert len(got) == mn == len(alone)
+        assert got[0] == alone[0], (rid, got, alone)
+        agree += sum(1 for a, b in zip(got, alone) if a == b)
+    total = sum(mn for _, _, mn in reqs)
+    print(f"serving vs stand-alone generate: {agree}/{total} tokens equal")
+    assert agree >= total // 2
+    model.close()

@@ -29,6 +29,16 @@ def main():
     ap.add_argument("--prefill", type=int, default=8)
     a = ap.parse_args()
     torch.cuda.set_device(0)
+    for rec in measure(a.layers, a.batch or [1, 32], a.ctx, a.steps, a.prefill):
+        print(json.dumps(rec))
+
+
+def measure(layers=24, batches=(1, 32), ctx=1024, steps=64, prefill=8):
+    """-> list of records (one for the prefill, one per decode batch size); see the module docstring."""
+    class a:  # noqa: N801
+        pass
+    a.layers, a.batch, a.ctx, a.steps, a.prefill = layers, list(batches), ctx, steps, prefill
+    out = []
     lib.load()
     cfg = OmChatQwen2MoeConfig(num_hidden_layers=a.layers, mm_vision_tower=None)
     w = random_init(cfg, device="cuda:0", vision=False)
@@ -65,8 +75,8 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     flops = 2.0 * T * a.layers * (attn_w + k * expert_w + 3 * Is * C) + 4.0 * n * a.layers * Hq * 128 * L * L / 2
-    print(json.dumps({"phase": "prefill", "tokens": T, "ms": ms, "tokens_per_sec": T / ms * 1e3, "tflops": flops / ms / 1e9,
-                      "frac_tensor": flops / ms / 1e9 / peak_tf, "launches": (lib.launch_count() - n0) // 3}))
+    out.append({"phase": "prefill", "tokens": T, "ms": ms, "tokens_per_sec": T / ms * 1e3, "tflops": flops / ms / 1e9,
+                "frac_tensor": flops / ms / 1e9 / peak_tf, "launches": (lib.launch_count() - n0) // 3})
     del cache, emb
     # ---- decode
     for B in a.batch or [1, 32]:
@@ -88,11 +98,12 @@ def main():
         wbytes = 2.0 * (a.layers * (attn_w + shared_w + distinct * expert_w) + w.llm.lm_head.numel())
         kv = B * (a.ctx + 8 + a.steps / 2.0) * 2 * a.layers * Hkv * 128 * 2
         gbs = (wbytes + kv) / (ms * 1e-3) / 1e9
-        print(json.dumps({"phase": "decode", "batch": B, "ctx": a.ctx, "ms_per_step": ms, "tokens_per_sec": B / ms * 1e3,
-                          "algorithmic_gb": (wbytes + kv) / 1e9, "gbs": gbs, "frac_hbm": gbs / peak_hbm,
-                          "launches_per_step": (lib.launch_count() - n0) // a.steps}))
+        out.append({"phase": "decode", "batch": B, "ctx": a.ctx, "ms_per_step": ms, "tokens_per_sec": B / ms * 1e3,
+                    "algorithmic_gb": (wbytes + kv) / 1e9, "gbs": gbs, "frac_hbm": gbs / peak_hbm,
+                    "launches_per_step": (lib.launch_count() - n0) // a.steps})
         del cache
     dec.release()
+    return out
 
 
 if __name__ == "__main__":

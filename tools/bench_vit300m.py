@@ -22,6 +22,13 @@ def main():
     ap.add_argument("--crops", type=int, default=64)
     ap.add_argument("--iters", type=int, default=5)
     a = ap.parse_args()
+    print(json.dumps(measure(a.crops, a.iters)))
+
+
+def measure(crops=64, iters=5):
+    class a:  # noqa: N801
+        pass
+    a.crops, a.iters = crops, iters
     lib.load()
     vc = InternVisionConfig.intern_vit_300m()
     cfg = OmChatQwen2Config(vision_config=vc, mm_vision_tower="InternViT-300M-448px", mm_hidden_size=1024, hidden_size=256,
@@ -42,8 +49,8 @@ def main():
     ms = e0.elapsed_time(e1) / a.iters
     S, C, I, L = 1025, 1024, 4096, 24
     flops = a.crops * L * (2.0 * S * (4 * C * C + 2 * C * I) + 4.0 * S * S * C) + a.crops * 2.0 * 1024 * 588 * C
-    print(json.dumps({"tower": "InternViT-300M-448px", "crops": a.crops, "ms": ms, "crops_per_sec": a.crops / ms * 1e3,
-                      "algorithmic_tflops": flops / ms / 1e9, "launches": (lib.launch_count() - n0) // a.iters}))
+    return {"tower": "InternViT-300M-448px", "crops": a.crops, "ms": ms, "crops_per_sec": a.crops / ms * 1e3,
+            "algorithmic_tflops": flops / ms / 1e9, "launches": (lib.launch_count() - n0) // a.iters}
 
 
 if __name__ == "__main__":
