@@ -291,6 +291,7 @@ def main():
                     "feature all-gather -> decoder-TP over all GPUs")
     ap.add_argument("--c5-mb", type=int, default=0, help="c5: prompts per mini-batch (0 = default of the mode)")
     ap.add_argument("--no-workloads", action="store_true", help="skip the c3 / c4 legs of the main line (`workloads`)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the c5 leg of the main line (N > 1 only)")
     ap.add_argument("--no-variants", action="store_true", help="skip the Qwen2-MoE / InternViT-300M legs (`variants`, N = 1 only)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--pixel-shuffle", type=float, default=1.0, help="mm_pixel_shuffle_ratio (1.0 = reference behaviour)")
@@ -496,7 +497,12 @@ def main():
         wl["c3"] = measure_c3(args, rank, world, local, cfg, model.get_vision_tower(), model.get_model().mm_projector)
         torch.cuda.empty_cache()
         wl["c4"] = measure_c4(args, rank, world, local, cfg, dec)
-        keep = ("metric", "value", "unit", "ms_per_step", "scaling", "config", "phases", "e2e", "gpu_launches", "roofline")
+        if world > 1 and not args.no_c5:
+            # c5 (16 multi-image 4k-context requests) as data-parallel replicas over the N GPUs, through the public generate()
+            from tools.bench_workloads import measure_c5
+            torch.cuda.empty_cache()
+            wl["c5"] = measure_c5(args, rank, world, local)
+        keep = ("metric", "value", "unit", "ms_per_step", "scaling", "config", "phases", "e2e", "gpu_launches", "roofline", "error")
         line["workloads"] = {k: {kk: v[kk] for kk in keep if kk in v} for k, v in wl.items()}
     # ---- the reference's two lighter model families on one GPU, each in its own right:
     # random-init Qwen1.5-MoE-A2.7B-sized decoder (prefill + decode steps) and the InternViT-300M tower. Never allowed to

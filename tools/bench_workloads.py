@@ -258,7 +258,22 @@ def measure_c4(args, rank, world, local, cfg, dec, n_seq: int = 32, text_tokens:
 
 
 # ------------------------------------------------------------------------------------------------------------ c5
-def run_c5(args, rank, world, local, n_prompts: int = 16, images_per_prompt: int = 8, text_tokens: int = 2048, mb: int = 2):
+def run_c5(args, rank, world, local, **kw):
+    import torch
+    import torch.distributed as dist
+    line, model = measure_c5(args, rank, world, local, keep_model=True, **kw)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        _finish(torch, dist, model.model.decoder if model is not None else None)
+
+
+def measure_c5(args, rank, world, local, n_prompts: int = 16, images_per_prompt: int = 8, text_tokens: int = 2048, mb: int = 2,
+               keep_model: bool = False):
+    """-> the c5 JSON line as a dict (and the model when keep_model). Builds its own model (pixel-shuffle 0.5 projector). In the
+    data-parallel mode everything up to and including the warm-up runs without a collective, so a rank that fails there (out of
+    memory next to another workload's buffers) is caught, agreed on by ONE all-reduce, and every rank returns {"error": ...}
+    instead of leaving its peers in a barrier."""
     import torch
     import torch.distributed as dist
     from bench import ClockSampler
@@ -269,40 +284,57 @@ def run_c5(args, rank, world, local, n_prompts: int = 16, images_per_prompt: int
     dev = torch.device("cuda", local)
     cfg = OmChatQwen2Config(mm_pixel_shuffle_ratio=0.5, eos_token_id=-1)
     tp_mode = getattr(args, "c5_mode", "dp") == "tp" and world > 1
-    if tp_mode:
-        # SURVEY.md §8e row 3, second variant: ONE model over all GPUs - the 128 crops data-parallel over the N towers, one
-        # all-gather of the projected features, then the decoder tensor-parallel N ways over all 16 prompts
-        model = OmChatQwen2ForCausalLM(cfg, device=f"cuda:{local}", seed=0, tp_rank=rank, tp_size=world,
-                                       tp_group=dist.group.WORLD)
-        mb = getattr(args, "c5_mb", 0) or 8
-    else:
-        model = OmChatQwen2ForCausalLM(cfg, device=f"cuda:{local}", seed=0)
-    new_tokens = min(args.new_tokens, 64)
-    L = cfg.image_tokens_per_crop  # 256
-    T = text_tokens + images_per_prompt * L
-    mine = list(range(n_prompts)) if tp_mode else list(range(rank, n_prompts, world))
-    g = torch.Generator().manual_seed(2)
-    ids = torch.randint(0, 151643, (n_prompts, text_tokens + images_per_prompt), generator=g)
-    step = (text_tokens + images_per_prompt) // images_per_prompt
-    for j in range(images_per_prompt):
-        ids[:, 8 + j * step] = IMAGE_TOKEN_INDEX  # placeholders evenly spaced
-    g1 = torch.Generator().manual_seed(1)
-    pixels = torch.randn(len(mine) * images_per_prompt, 3, 448, 448, generator=g1).to(torch.bfloat16)
-    ids_host, px_host = ids[mine].contiguous().pin_memory(), pixels.pin_memory()
-    groups = [list(range(i, min(i + mb, len(mine)))) for i in range(0, len(mine), mb)]
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    err, model = None, None
+    try:
+        if tp_mode:
+            # SURVEY.md §8e row 3, second variant: ONE model over all GPUs - the 128 crops data-parallel over the N towers, one
+            # all-gather of the projected features, then the decoder tensor-parallel N ways over all 16 prompts
+            model = OmChatQwen2ForCausalLM(cfg, device=f"cuda:{local}", seed=0, tp_rank=rank, tp_size=world,
+                                           tp_group=dist.group.WORLD)
+            mb = getattr(args, "c5_mb", 0) or 8
+        else:
+            model = OmChatQwen2ForCausalLM(cfg, device=f"cuda:{local}", seed=0)
+        new_tokens = min(args.new_tokens, 64)
+        L = cfg.image_tokens_per_crop  # 256
+        T = text_tokens + images_per_prompt * L
+        mine = list(range(n_prompts)) if tp_mode else list(range(rank, n_prompts, world))
+        g = torch.Generator().manual_seed(2)
+        ids = torch.randint(0, 151643, (n_prompts, text_tokens + images_per_prompt), generator=g)
+        step = (text_tokens + images_per_prompt) // images_per_prompt
+        for j in range(images_per_prompt):
+            ids[:, 8 + j * step] = IMAGE_TOKEN_INDEX  # placeholders evenly spaced
+        g1 = torch.Generator().manual_seed(1)
+        pixels = torch.randn(len(mine) * images_per_prompt, 3, 448, 448, generator=g1).to(torch.bfloat16)
+        ids_host, px_host = ids[mine].contiguous().pin_memory(), pixels.pin_memory()
+        groups = [list(range(i, min(i + mb, len(mine)))) for i in range(0, len(mine), mb)]
+        ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def serve(ids_src, px_src):
-        outs = []
-        for grp in groups:
-            i_d = ids_src[grp[0]:grp[-1] + 1].to(dev, non_blocking=True)
-            p_d = px_src[grp[0] * images_per_prompt:(grp[-1] + 1) * images_per_prompt].to(dev, non_blocking=True)
-            outs.append(model.generate(i_d, images=p_d, max_new_tokens=new_tokens, do_sample=False))
-        return outs
+        def serve(ids_src, px_src):
+            outs = []
+            for grp in groups:
+                i_d = ids_src[grp[0]:grp[-1] + 1].to(dev, non_blocking=True)
+                p_d = px_src[grp[0] * images_per_prompt:(grp[-1] + 1) * images_per_prompt].to(dev, non_blocking=True)
+                outs.append(model.generate(i_d, images=p_d, max_new_tokens=new_tokens, do_sample=False))
+            return outs
 
-    ids_dev, px_dev = ids_host.to(dev), px_host.to(dev)
-    for _ in range(max(args.warmup, 3) if len(groups) <= 2 else 1):
-        serve(ids_dev, px_dev)
+        ids_dev, px_dev = ids_host.to(dev), px_host.to(dev)
+        for _ in range(max(args.warmup, 3) if len(groups) <= 2 else 1):
+            serve(ids_dev, px_dev)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        if tp_mode:
+            raise
+        err = f"{type(e).__name__}: {e}"[:300]
+    if world > 1 and not tp_mode:
+        flag = torch.tensor([0 if err else 1], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and err is None:
+            err = "another rank failed to set the workload up"
+    if err is not None:
+        if model is not None:
+            model.close()
+        line = {"error": err}
+        return (line, None) if keep_model else line
     _barrier(torch, dist, world)
     n0 = lib.launch_count()
     t0e, t1e, v0, v1 = ev(), ev(), ev(), ev()
@@ -345,7 +377,9 @@ def run_c5(args, rank, world, local, n_prompts: int = 16, images_per_prompt: int
                 "d2h_bytes_per_step": sum(o.numel() for o in out_host) * 8},
         "gpu_launches": launches, "clocks": clocks.summary(),
     }
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        _finish(torch, dist, model.model.decoder)
+    if keep_model:
+        return line, model
+    model.close()
+    del model
+    torch.cuda.empty_cache()
+    return line
