@@ -145,6 +145,12 @@ int omc_anyres_pack(const void* thumb, const void* resized, int new_w, int new_h
 int omc_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                       void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
                       long long total_rows, int Hq, int Hkv, int causal, float scale, void* stream);
+/* The same with an explicit head_dim: 128, or 64 - the 16 x 64 heads of the InternViT-300M tower
+ * (intern_vit_300m/configuration_intern_vit.py:66-67; InternAttention, modeling_intern_vit.py:138-172) on the default tcgen05
+ * kernel (one 64-column TMA box per tile, 4 k-steps for S = Q K^T, N = 64 for O += P V). q / k / v / out rows are [total, H, head_dim]. */
+int omc_attention_fwd_hd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                         void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
+                         long long total_rows, int Hq, int Hkv, int head_dim, int causal, float scale, void* stream);
 int omc_attention_set_impl(int impl);
 /* diagnostic: device buffer of 12 x 8 uint64 filled by CTA (0,0,0) of the tcgen05 kernel with per-warp clock accumulators
  * (tools/attn_check.py prof-clocks); NULL = off */
@@ -351,7 +357,7 @@ typedef struct omc_vit_desc {
   const void* p_b2;
   /* InternViT-300M variant (intern_vit_300m/modeling_intern_vit.py:61-64,131,209-210); all zero / NULL for the 6B tower */
   int32_t norm_type;     /* 0: InternRMSNorm; 1: nn.LayerNorm with norm1_b / norm2_b (requires norm_folded = 0) */
-  int32_t attn_head_dim; /* 0: hidden / heads (must be 128). 128 with hidden / heads < 128: every head of qkv_w's rows (and of
+  int32_t attn_head_dim; /* 0: hidden / heads (128, or 64 = the 300M tower, native). 128 with hidden / heads < 128: every head of qkv_w's rows (and of
                             qkv_b) and of proj_w's columns is zero-padded to 128 dims by the caller, qkv_w is [3 * heads * 128,
                             hidden], proj_w [hidden, heads * 128]; q.k and P.V are unchanged, the softmax scale stays
                             (hidden / heads)^-0.5 */

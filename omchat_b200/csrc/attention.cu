@@ -503,7 +503,7 @@ using namespace omc;
 namespace omc {
 int launch_fa_sm100(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                     long long ldo, const int32_t* cu, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv,
-                    int causal, float scale_log2, cudaStream_t stream);
+                    int head_dim, int causal, float scale_log2, cudaStream_t stream);
 }
 
 namespace omc { void set_fa_prof(void* ptr); void set_fa_version(int v); }
@@ -522,10 +522,22 @@ extern "C" int omc_attention_set_impl(int impl) {
   return OMC_OK;
 }
 
+extern "C" int omc_attention_fwd_hd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                                    void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
+                                    long long total_rows, int Hq, int Hkv, int head_dim, int causal, float scale, void* stream);
+
 extern "C" int omc_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                                  void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
                                  long long total_rows, int Hq, int Hkv, int causal, float scale, void* stream) {
+  return omc_attention_fwd_hd(q, ldq, k, ldk, v, ldv, out, ldo, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv, 128, causal,
+                              scale, stream);
+}
+
+extern "C" int omc_attention_fwd_hd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                                    void* out, long long ldo, const int32_t* cu_seqlens, int num_seqs, int max_seqlen,
+                                    long long total_rows, int Hq, int Hkv, int head_dim, int causal, float scale, void* stream) {
   if (num_seqs <= 0 || max_seqlen <= 0) return OMC_OK;
+  if (head_dim != 128 && head_dim != 64) return set_error(OMC_ERR_SHAPE, "omc_attention_fwd: head_dim must be 128 or 64");
   if (Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0) return set_error(OMC_ERR_SHAPE, "omc_attention_fwd: Hq must be a multiple of Hkv");
   if ((ldq | ldk | ldv | ldo) % 8 != 0) return set_error(OMC_ERR_ALIGN, "omc_attention_fwd: row strides must be multiples of 8");
   static bool attr_set_dev[kMaxDevices] = {};
@@ -547,7 +559,8 @@ extern "C" int omc_attention_fwd(const void* q, long long ldq, const void* k, lo
   }
   if (g_attn_impl == 0 && total_rows > 0)  // tcgen05 / TMEM kernel (attention_sm100.cu)
     return launch_fa_sm100(q, ldq, k, ldk, v, ldv, out, ldo, cu_seqlens, num_seqs, max_seqlen, total_rows, Hq, Hkv,
-                           causal, p.scale_log2, (cudaStream_t)stream);
+                           head_dim, causal, p.scale_log2, (cudaStream_t)stream);
+  if (head_dim != 128) return set_error(OMC_ERR_SHAPE, "omc_attention_fwd: the mma.sync baseline kernel is head_dim 128 only");
   dim3 grid((max_seqlen + kAttM - 1) / kAttM, Hq, num_seqs);
   attention_fwd_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(p);
   return check_launch("attention_fwd");

@@ -1,4 +1,5 @@
-// Flash attention forward for sm_100a on the 5th-generation tensor cores (tcgen05 + TMEM), head_dim 128, bf16.
+// Flash attention forward for sm_100a on the 5th-generation tensor cores (tcgen05 + TMEM), head_dim 128 (and 64 in the v2
+// kernel: the InternViT-300M tower), bf16.
 //
 // Serves the same call sites as the mma.sync kernel of attention.cu (InternAttention._flash_attn
 // intern_vit_6b/modeling_intern_vit.py:157-172 — non-causal, 1025 tokens, 25 heads — and the causal GQA attention of the
@@ -459,14 +460,24 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // step (at its end, when the previous P.V has long finished), which also orders the rare lazy rescale of O.
 constexpr uint32_t kFaPolyMask = 0x52;             // pairs (of every 8) whose exp2 runs on the FMA pipe: {1, 4, 6} = 3/8
 constexpr int kKv2 = 64;                          // keys per K/V tile
-constexpr int kKv2Bytes = kKv2 * 128 * 2;         // 16 KB: two [64 keys x 64 dims] swizzled boxes
-constexpr int kKv2Half = kKv2Bytes / 2;
+constexpr int kKv2Half = kKv2 * 64 * 2;           // 8 KB: one [64 keys x 64 dims] 128B-swizzled box
 constexpr int kFa2Stages = 4;
-constexpr int kFa2Smem = 2 * kFaTileBytes + 2 * kFa2Stages * kKv2Bytes + 1024 + 1024;
+// HD = head_dim: 128 (InternViT-6B, Qwen2) = two 64-column boxes per tile, or 64 (InternViT-300M) = one. Everything that is a
+// function of it - tile bytes, boxes per tile, k-steps of S = Q K^T, the N of O += P V, the O columns - hangs off this struct.
+template <int HD>
+struct Fa2Cfg {
+  static_assert(HD == 64 || HD == 128, "head_dim 64 or 128");
+  static constexpr int kBoxes = HD / 64;
+  static constexpr int kQBytes = kFaTile * HD * 2;   // 32 / 16 KB
+  static constexpr int kKvBytes = kKv2 * HD * 2;     // 16 / 8 KB
+  static constexpr int kSmem = 2 * kQBytes + 2 * kFa2Stages * kKvBytes + 1024 + 1024;
+};
 
+template <int HD>
 __global__ void __launch_bounds__(kFaThreads, 1)
 fa_fwd_sm100_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+  using C = Fa2Cfg<HD>;
   const int seq = blockIdx.z, head = blockIdx.y;
   const int row0 = p.cu[seq], len = p.cu[seq + 1] - row0;
   const int n_tiles = (len + kFaTile - 1) / kFaTile;
@@ -488,9 +499,9 @@ fa_fwd_sm100_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t raw_addr = smem_u32(fa_smem_raw);
   uint8_t* smem = fa_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + 2 * kFaTileBytes;
-  uint8_t* sV = sK + kFa2Stages * kKv2Bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kFa2Stages * kKv2Bytes);
+  uint8_t* sK = smem + 2 * C::kQBytes;
+  uint8_t* sV = sK + kFa2Stages * C::kKvBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kFa2Stages * C::kKvBytes);
   uint64_t* q_full = bars;                  // 1
   uint64_t* k_full = bars + 1;              // [4]
   uint64_t* k_empty = bars + 5;             // [4]
@@ -538,23 +549,23 @@ fa_fwd_sm100_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 0) {
     // ============================================ TMA producer ============================================
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, (uint32_t)(ntile * kFaTileBytes));
+      mbar_arrive_expect_tx(q_full, (uint32_t)(ntile * C::kQBytes));
       for (int t = 0; t < ntile; ++t)
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(sQ + t * kFaTileBytes + h * kFaHalfBytes, &tmQ, q_full, head * 128 + h * 64,
+        for (int h = 0; h < C::kBoxes; ++h)
+          tma_load_2d(sQ + t * C::kQBytes + h * kFaHalfBytes, &tmQ, q_full, head * HD + h * 64,
                       row0 + q0 + t * kFaTile, kEvictNormal);
       for (int j = 0; j < nkv_max; ++j) {
         const int s = j % kFa2Stages;
         const uint32_t ph = (uint32_t)(j / kFa2Stages) & 1u;
         const int krow = row0 + j * kKv2;
         mbar_wait(&k_empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&k_full[s], (uint32_t)kKv2Bytes);
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(sK + s * kKv2Bytes + h * kKv2Half, &tmK, &k_full[s], kvh * 128 + h * 64, krow, kEvictLast);
+        mbar_arrive_expect_tx(&k_full[s], (uint32_t)C::kKvBytes);
+        for (int h = 0; h < C::kBoxes; ++h)
+          tma_load_2d(sK + s * C::kKvBytes + h * kKv2Half, &tmK, &k_full[s], kvh * HD + h * 64, krow, kEvictLast);
         mbar_wait(&v_empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&v_full[s], (uint32_t)kKv2Bytes);
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(sV + s * kKv2Bytes + h * kKv2Half, &tmV, &v_full[s], kvh * 128 + h * 64, krow, kEvictLast);
+        mbar_arrive_expect_tx(&v_full[s], (uint32_t)C::kKvBytes);
+        for (int h = 0; h < C::kBoxes; ++h)
+          tma_load_2d(sV + s * C::kKvBytes + h * kKv2Half, &tmV, &v_full[s], kvh * HD + h * 64, krow, kEvictLast);
       }
     }
   } else if (warp == 1) {
@@ -566,10 +577,10 @@ fa_fwd_sm100_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       };
       auto issue_s = [&](int t, int j) {
         const uint32_t idesc = make_idesc_bf16_major(128, keys_padded(t, j), 0, 0);
-        const uint32_t qa = smem_u32(sQ + t * kFaTileBytes), ka = smem_u32(sK + (j % kFa2Stages) * kKv2Bytes);
+        const uint32_t qa = smem_u32(sQ + t * C::kQBytes), ka = smem_u32(sK + (j % kFa2Stages) * C::kKvBytes);
         const uint32_t d = tmem_base + (uint32_t)(t * 128 + (j & 1) * 64);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < HD / 16; ++kk) {  // 16 head dims per instruction
           const uint64_t da = make_sw128_kmajor_desc(qa + (kk >> 2) * kFaHalfBytes) + (uint64_t)(2 * (kk & 3));
           const uint64_t db = make_sw128_kmajor_desc(ka + (kk >> 2) * kKv2Half) + (uint64_t)(2 * (kk & 3));
           umma_bf16<1>(d, da, db, idesc, kk > 0 ? 1u : 0u);
@@ -577,8 +588,8 @@ fa_fwd_sm100_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         umma_commit(&s_full[t * 2 + (j & 1)]);
       };
       auto issue_pv = [&](int t, int j) {
-        constexpr uint32_t idesc = make_idesc_bf16_major(128, 128, 0, 1);
-        const uint32_t va = smem_u32(sV + (j % kFa2Stages) * kKv2Bytes);
+        constexpr uint32_t idesc = make_idesc_bf16_major(128, HD, 0, 1);  // N = head dims of O; B = V is MN-major
+        const uint32_t va = smem_u32(sV + (j % kFa2Stages) * C::kKvBytes);
         const uint32_t d = tmem_base + 256u + (uint32_t)(t * 128), pt = tmem_base + (uint32_t)(t * 128 + (j & 1) * 64);
         const int ksteps = keys_padded(t, j) >> 4;
         for (int kk = 0; kk < ksteps; ++kk) {
@@ -755,7 +766,7 @@ fa_fwd_sm100_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           if (rescale) {
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            for (int c0 = 0; c0 < HD; c0 += 32) {
               uint32_t o[32];
               tmem_ld32(tO + (uint32_t)c0, o);
               tmem_ld_wait();
@@ -778,10 +789,10 @@ fa_fwd_sm100_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait(&o_done[t], (uint32_t)(nkv[t] - 1) & 1u);
       tc_fence_after();
       const float inv = 1.0f / l_sum;
-      bf16* orow = p.out + (long long)(row0 + qi) * p.ldo + head * 128;
+      bf16* orow = p.out + (long long)(row0 + qi) * p.ldo + head * HD;
       const bool row_ok = qi < len;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < HD; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tO + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -814,23 +825,27 @@ void set_fa_version(int v) { g_fa_version = v; }
 // host launcher (called by omc_attention_fwd in attention.cu): full 128-row query tiles of every sequence
 int launch_fa_sm100(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* out,
                     long long ldo, const int32_t* cu, int num_seqs, int max_seqlen, long long total_rows, int Hq, int Hkv,
-                    int causal, float scale_log2, cudaStream_t stream) {
+                    int head_dim, int causal, float scale_log2, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(out) & 15) || (ldo % 8) != 0)
     return set_error(OMC_ERR_ALIGN, "omc_attention_fwd: output must be 16-byte aligned with a row stride multiple of 8");
+  if (head_dim != 128 && !(head_dim == 64 && g_fa_version == 2))
+    return set_error(OMC_ERR_SHAPE, "omc_attention_fwd: head_dim must be 128, or 64 on the default (64-key tile) kernel");
   CUtensorMap tmQ, tmK, tmV;
-  int rc = make_tmap_2d(&tmQ, q, total_rows, (long long)Hq * 128, ldq, kFaTile);
+  int rc = make_tmap_2d(&tmQ, q, total_rows, (long long)Hq * head_dim, ldq, kFaTile);
   if (rc) return rc;
   const int kv_box = g_fa_version == 2 ? kKv2 : kFaTile;
-  rc = make_tmap_2d(&tmK, k, total_rows, (long long)Hkv * 128, ldk, kv_box);
+  rc = make_tmap_2d(&tmK, k, total_rows, (long long)Hkv * head_dim, ldk, kv_box);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmV, v, total_rows, (long long)Hkv * 128, ldv, kv_box);
+  rc = make_tmap_2d(&tmV, v, total_rows, (long long)Hkv * head_dim, ldv, kv_box);
   if (rc) return rc;
   static bool attr_set_dev[kMaxDevices] = {};
   bool& attr_set = attr_set_dev[cur_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(fa_fwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(fa_fwd_sm100_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFa2Smem);
+      e = cudaFuncSetAttribute(fa_fwd_sm100_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa2Cfg<128>::kSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fa_fwd_sm100_v2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa2Cfg<64>::kSmem);
     if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -839,7 +854,8 @@ int launch_fa_sm100(const void* q, long long ldq, const void* k, long long ldk, 
   p.scale_log2 = scale_log2;
   p.prof = g_fa_prof;
   dim3 grid(((max_seqlen + kFaTile - 1) / kFaTile + 1) / 2, Hq, num_seqs);
-  if (g_fa_version == 2) fa_fwd_sm100_v2_kernel<<<grid, kFaThreads, kFa2Smem, stream>>>(tmQ, tmK, tmV, p);
+  if (head_dim == 64) fa_fwd_sm100_v2_kernel<64><<<grid, kFaThreads, Fa2Cfg<64>::kSmem, stream>>>(tmQ, tmK, tmV, p);
+  else if (g_fa_version == 2) fa_fwd_sm100_v2_kernel<128><<<grid, kFaThreads, Fa2Cfg<128>::kSmem, stream>>>(tmQ, tmK, tmV, p);
   else fa_fwd_sm100_kernel<<<grid, kFaThreads, kFaSmem, stream>>>(tmQ, tmK, tmV, p);
   return check_launch("fa_fwd_sm100");
 }

@@ -46,7 +46,8 @@ static void vit_sizes(const omc_vit_desc* d, int n, long long* rows, long long* 
   sizes[1] = (long long)n * P * d->hidden * 2;                   // patch embeddings
   sizes[2] = *rows * d->hidden * 2;                              // residual stream h
   sizes[3] = *rows * d->hidden * 2;                              // normed rows
-  const long long Ca = (long long)d->heads * 128;                // attention width (= hidden for 128-dim heads; padded otherwise)
+  // attention width: heads * 128 when the caller zero-padded narrower heads (attn_head_dim = 128), else hidden
+  const long long Ca = d->attn_head_dim == 128 ? (long long)d->heads * 128 : (long long)d->hidden;
   sizes[4] = *rows * 3 * Ca * 2;                                 // qkv
   sizes[5] = *rows * Ca * 2;                                     // attention output
   sizes[6] = *rows * d->inter * 2;                               // MLP activation
@@ -77,8 +78,12 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
   if (d->image_size % d->patch_size != 0 || d->heads <= 0 || d->hidden % d->heads != 0)
     return set_error(OMC_ERR_SHAPE, "omc_vit_forward: the image must be a whole number of patches, hidden a multiple of heads");
   const int Dh = d->hidden / d->heads;
-  if (Dh != 128 && (d->attn_head_dim != 128 || Dh > 128 || d->qk_norm))
-    return set_error(OMC_ERR_SHAPE, "omc_vit_forward: head_dim < 128 needs qkv_w / proj_w zero-padded to attn_head_dim = 128 and no QK-norm");
+  const bool padded = d->attn_head_dim == 128 && Dh < 128;  // heads zero-padded to 128 by the caller
+  if (d->attn_head_dim != 0 && d->attn_head_dim != 128) return set_error(OMC_ERR_ARG, "omc_vit_forward: attn_head_dim must be 0 or 128");
+  if (!padded && Dh != 128 && Dh != 64)
+    return set_error(OMC_ERR_SHAPE, "omc_vit_forward: head_dim must be 128 or 64 (or zero-padded to attn_head_dim = 128)");
+  if (padded && d->qk_norm) return set_error(OMC_ERR_SHAPE, "omc_vit_forward: no QK-norm over zero-padded heads");
+  const int Da = padded ? 128 : Dh;  // head width the attention kernel runs at
   const bool layer_norm = d->norm_type == 1;
   if (d->norm_type != 0 && d->norm_type != 1) return set_error(OMC_ERR_ARG, "omc_vit_forward: norm_type must be 0 (rms) or 1 (layer)");
   if (layer_norm && (d->norm_folded || d->norm1_b == nullptr || d->norm2_b == nullptr))
@@ -111,7 +116,7 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
   OMC_TRY(omc_vit_assemble(patch, d->cls, d->pos, h, n_crops, P, C, stream));
   const float scale = 1.0f / sqrtf((float)Dh);
   const int M = (int)rows;
-  const int Ca = d->heads * 128;  // attention width
+  const int Ca = d->heads * Da;  // attention width
   auto qkv_bias = [&](int li) -> const void* { return d->qkv_b != nullptr ? d->qkv_b[li] : nullptr; };
   auto pre_norm = [&](const void* const* w, const void* const* b, int li) {
     return layer_norm ? omc_layernorm(h, C, w[li], b[li], xn, C, M, C, d->eps, stream)
@@ -149,8 +154,8 @@ extern "C" int omc_vit_forward(const omc_vit_desc* d, const void* pixels, int pi
         OMC_TRY(omc_rmsnorm(qkv + C, 3LL * C, d->k_norm[li], qkv + C, 3LL * C, M, C, d->eps, stream));
       }
     }
-    OMC_TRY(omc_attention_fwd(qkv, 3LL * Ca, qkv + Ca, 3LL * Ca, qkv + 2 * Ca, 3LL * Ca, attn, Ca, cu, n_crops, S, rows, d->heads,
-                              d->heads, 0, scale, stream));
+    OMC_TRY(omc_attention_fwd_hd(qkv, 3LL * Ca, qkv + Ca, 3LL * Ca, qkv + 2 * Ca, 3LL * Ca, attn, Ca, cu, n_crops, S, rows, d->heads,
+                                 d->heads, Da, 0, scale, stream));
     if (fold) {
       omc_gemm_norm no = norm_out(ssq_b);
       OMC_TRY(omc_gemm_bf16_norm(attn, Ca, d->proj_w[li], Ca, h, C, M, C, Ca, d->proj_b[li], d->ls1[li], h, C, OMC_EPI_RES, 0, 0, &no, stream));

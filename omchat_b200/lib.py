@@ -53,6 +53,7 @@ SIGNATURES = {
     "omc_resample_u8": (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _I, _I, _P]),
     "omc_anyres_pack": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "omc_attention_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _L, _I, _I, _I, _F, _P]),
+    "omc_attention_fwd_hd": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _L, _I, _I, _I, _I, _F, _P]),
     "omc_attention_set_impl": (_I, [_I]),
     "omc_attention_set_prof": (_I, [_P]),
     "omc_rope_kv_store": (_I, [_P, _L, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
@@ -480,14 +481,16 @@ def anyres_pack(thumb, resized, target_w, target_h, paste_x, paste_y, crop, lut,
     return out
 
 
-def attention(q, k, v, out, cu_seqlens: torch.Tensor, max_seqlen: int, Hq: int, Hkv: int, causal: bool, scale: float):
-    """q/k/v/out: 2-D row views [total, H*128] (possibly slices of a packed qkv buffer: row stride = parent's)."""
+def attention(q, k, v, out, cu_seqlens: torch.Tensor, max_seqlen: int, Hq: int, Hkv: int, causal: bool, scale: float,
+              head_dim: int = 128):
+    """q/k/v/out: 2-D row views [total, H*head_dim] (possibly slices of a packed qkv buffer: row stride = parent's);
+    head_dim 128, or 64 (the InternViT-300M tower)."""
     _need_cuda(q, k, v, out, cu_seqlens)
     assert cu_seqlens.dtype == torch.int32
-    rc = load().omc_attention_fwd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
-                                  out.stride(0), _ptr(cu_seqlens), cu_seqlens.numel() - 1, max_seqlen,
-                                  min(q.shape[0], k.shape[0], v.shape[0], out.shape[0]), Hq, Hkv,
-                                  1 if causal else 0, scale, _stream())
+    rc = load().omc_attention_fwd_hd(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                     out.stride(0), _ptr(cu_seqlens), cu_seqlens.numel() - 1, max_seqlen,
+                                     min(q.shape[0], k.shape[0], v.shape[0], out.shape[0]), Hq, Hkv, head_dim,
+                                     1 if causal else 0, scale, _stream())
     _check(rc, "omc_attention_fwd")
     return out
 
@@ -843,8 +846,9 @@ class VitForward:
         n = len(vit.layers)
         if mats is not None:
             folded = None
-        elif vc.head_dim != 128:
-            raise ValueError("head_dim < 128: pass mats=tower._layer_mats() (zero-padded heads)")
+        elif vc.head_dim not in (64, 128):
+            raise ValueError("head_dim other than 64 / 128: pass mats=tower._layer_mats() (zero-padded heads)")
+        padded = mats is not None and mats[0][2].shape[1] != vc.hidden_size  # proj_w widened: heads zero-padded to 128
         d = VitDesc()
         d.norm_folded = 1 if (folded is not None or (mats is not None and mats_folded)) else 0
         self._folded = folded
@@ -860,7 +864,7 @@ class VitForward:
         if any(l.qkv_b is not None for l in vit.layers):
             extra["qkv_b"] = "qkv_b"
         d.norm_type = 1 if vc.norm_type == "layer_norm" else 0
-        d.attn_head_dim = 128 if vc.head_dim != 128 else 0
+        d.attn_head_dim = 128 if padded else 0
         for field, attr in {**names, **extra}.items():
             if field in ("q_norm", "k_norm") and not vc.qk_normalization:
                 continue

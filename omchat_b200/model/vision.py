@@ -17,7 +17,8 @@ from .. import lib
 from ..config import OmChatQwen2Config
 from .weights import ProjW, VitW, fold_norm, pad_head_cols, pad_head_rows
 
-ATTN_HEAD_DIM = 128  # the attention kernels' head_dim; narrower heads (InternViT-300M: 64) run zero-padded to it
+ATTN_HEAD_DIM = 128       # the attention kernels' head_dim ...
+ATTN_NATIVE_DIMS = (64, 128)  # ... and the ones the tcgen05 kernel is instantiated for; other widths run zero-padded to 128
 
 
 class InternVITVisionTower:
@@ -42,8 +43,15 @@ class InternVITVisionTower:
         D = self.vc.head_dim
         if D > ATTN_HEAD_DIM or ATTN_HEAD_DIM % D != 0 or D % 8 != 0:
             raise ValueError(f"vision head_dim {D} not supported (must divide {ATTN_HEAD_DIM})")
-        if D != ATTN_HEAD_DIM and self.vc.qk_normalization:
+        # head width the attention kernel runs at: D itself when there is an instantiation for it (64: InternViT-300M), else 128
+        # with every head zero-padded (pad_heads = True forces that path; the tests keep it alive)
+        self.pad_heads = D not in ATTN_NATIVE_DIMS
+        if self.attn_dim != D and self.vc.qk_normalization:
             raise NotImplementedError("qk_normalization over zero-padded heads")
+
+    @property
+    def attn_dim(self) -> int:
+        return ATTN_HEAD_DIM if self.pad_heads else self.vc.head_dim
 
     def load_model(self):
         if self.w is None:
@@ -93,7 +101,8 @@ class InternVITVisionTower:
         states = [h.clone()] if collect else None
         cu = self._cu_seqlens(n, S, h.device)
         rows = n * S
-        Ca = H * ATTN_HEAD_DIM  # attention width: = C for the 6B tower, heads zero-padded to 128 dims otherwise
+        Da = self.attn_dim
+        Ca = H * Da  # attention width: = C unless the heads run zero-padded to 128 dims
         xn = torch.empty(rows, C, device=h.device, dtype=torch.bfloat16)
         qkv = torch.empty(rows, 3 * Ca, device=h.device, dtype=torch.bfloat16)
         attn = torch.empty(rows, Ca, device=h.device, dtype=torch.bfloat16)
@@ -111,7 +120,7 @@ class InternVITVisionTower:
                 lib.gemm(h, qkv_f, out=qkv, bias=qkv_b, ssq_in=ssq_a, norm_dim=C, eps=eps)
                 if vc.qk_normalization:
                     lib.rmsnorm_pair(qkv, l.q_norm, l.k_norm, C, eps)
-                lib.attention(qkv[:, :Ca], qkv[:, Ca:2 * Ca], qkv[:, 2 * Ca:], attn, cu, S, H, H, False, scale)
+                lib.attention(qkv[:, :Ca], qkv[:, Ca:2 * Ca], qkv[:, 2 * Ca:], attn, cu, S, H, H, False, scale, head_dim=Da)
                 lib.gemm(attn, proj_w, out=h, bias=l.proj_b, scale=l.ls1, res=h, epi=lib.EPI_RES, ssq_out=ssq_b)
                 lib.gemm(h, fc1_f, out=act, bias=l.fc1_b, epi=lib.EPI_GELU, ssq_in=ssq_b, norm_dim=C, eps=eps)
                 lib.gemm(act, l.fc2_w, out=h, bias=l.fc2_b, scale=l.ls2, res=h, epi=lib.EPI_RES, ssq_out=ssq_a)
@@ -129,7 +138,7 @@ class InternVITVisionTower:
             if vc.qk_normalization:
                 lib.rmsnorm(qkv[:, :C], l.q_norm, eps, out=qkv[:, :C])
                 lib.rmsnorm(qkv[:, C:2 * C], l.k_norm, eps, out=qkv[:, C:2 * C])
-            lib.attention(qkv[:, :Ca], qkv[:, Ca:2 * Ca], qkv[:, 2 * Ca:], attn, cu, S, H, H, False, scale)
+            lib.attention(qkv[:, :Ca], qkv[:, Ca:2 * Ca], qkv[:, 2 * Ca:], attn, cu, S, H, H, False, scale, head_dim=Da)
             lib.gemm(attn, proj_w, out=h, bias=l.proj_b, scale=l.ls1, res=h, epi=lib.EPI_RES)
             if layer_norm:
                 lib.layernorm(h, l.norm2, l.norm2_b, eps, out=xn)
@@ -144,7 +153,8 @@ class InternVITVisionTower:
     def _layer_mats(self):
         """Per layer (qkv_w, qkv_b, proj_w, fc1_w) as the GEMMs take them, built once: norm1 / norm2 folded into qkv / fc1 when
         fold_norms (6.5 GB more for InternViT-6B), heads zero-padded to the attention kernels' 128 dims when narrower."""
-        if self.fold_norms not in self._mats:
+        key = (self.fold_norms, self.pad_heads)
+        if key not in self._mats:
             vc = self.vc
             H, D = vc.num_attention_heads, vc.head_dim
             mats = []
@@ -152,13 +162,13 @@ class InternVITVisionTower:
                 qkv_w = fold_norm(l.qkv, l.norm1) if self.fold_norms else l.qkv
                 fc1_w = fold_norm(l.fc1_w, l.norm2) if self.fold_norms else l.fc1_w
                 qkv_b, proj_w = l.qkv_b, l.proj_w
-                if D != ATTN_HEAD_DIM:
+                if self.attn_dim != D:
                     qkv_w = pad_head_rows(qkv_w, 3, H, D, ATTN_HEAD_DIM)
                     qkv_b = pad_head_rows(qkv_b, 3, H, D, ATTN_HEAD_DIM) if qkv_b is not None else None
                     proj_w = pad_head_cols(proj_w, H, D, ATTN_HEAD_DIM)
                 mats.append((qkv_w, qkv_b, proj_w, fc1_w))
-            self._mats[self.fold_norms] = mats
-        return self._mats[self.fold_norms]
+            self._mats[key] = mats
+        return self._mats[key]
 
     def _folded(self):
         """(qkv * norm1, fc1 * norm2) per layer for the model-level C entry (lib.VitForward)."""
@@ -191,8 +201,8 @@ class InternVITVisionTower:
 
 class InternVIT300mVisionTower(InternVITVisionTower):
     """The lighter tower (multimodal_encoder/internVIT300m_encoder.py:10-56, intern_vit_300m/modeling_intern_vit.py): LayerNorm
-    instead of RMSNorm (norm_type = 'layer_norm', :61-64,209-210), no QK-norm, 16 heads of 64 dims, 24 layers. Same kernels; the
-    64-dim heads run zero-padded to the attention kernels' 128 (weights padded once at load)."""
+    instead of RMSNorm (norm_type = 'layer_norm', :61-64,209-210), no QK-norm, 16 heads of 64 dims, 24 layers. Same kernels, the
+    attention kernel in its head_dim-64 instantiation."""
 
     def __init__(self, cfg: OmChatQwen2Config, weights: Optional[VitW]):
         super().__init__(cfg, weights)

@@ -380,6 +380,32 @@ def test_attention_fwd(L, causal, Hq, Hkv, lens, legacy):
     L.attention_set_impl(False)
 
 
+@pytest.mark.parametrize("causal,Hq,Hkv,lens", [(False, 16, 16, [1025]), (False, 4, 4, [1025, 1025, 300]), (False, 2, 2, [64, 1, 129]),
+                                                 (True, 4, 2, [700, 77]), (False, 3, 3, [2000])])
+def test_attention_fwd_head_dim_64(L, causal, Hq, Hkv, lens):
+    """The head_dim-64 instantiation of the tcgen05 kernel (InternViT-300M: 16 heads of 64, 1025 tokens) against the fp32
+    reference: full and ragged query / key tiles, several sequences, GQA + causal for completeness."""
+    g = torch.Generator().manual_seed(sum(lens) + 64)
+    total, D = sum(lens), 64
+    q = bf(torch.randn(total, Hq, D, generator=g))
+    k = bf(torch.randn(total, Hkv, D, generator=g))
+    v = bf(torch.randn(total, Hkv, D, generator=g))
+    qkv = torch.cat([q.flatten(1), k.flatten(1), v.flatten(1)], dim=1).cuda()
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    out = torch.zeros(total, Hq * D, device="cuda", dtype=torch.bfloat16)
+    scale = D ** -0.5
+    L.attention(qkv[:, :Hq * D], qkv[:, Hq * D:(Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:], out, cu, max(lens), Hq, Hkv, causal, scale,
+                head_dim=D)
+    o = 0
+    for n in lens:
+        want = _ref_attention(q[o:o + n].float(), k[o:o + n].float(), v[o:o + n].float(), causal, scale)
+        assert_close(out[o:o + n].view(n * Hq, D), want.reshape(n * Hq, D), rel=2 ** -6, what=f"attention D=64 len {n}")
+        o += n
+    with pytest.raises(L.OmcError):
+        L.attention(qkv[:, :Hq * D], qkv[:, Hq * D:(Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:], out, cu, max(lens), Hq, Hkv, causal,
+                    scale, head_dim=32)
+
+
 def _make_paged(B, Hkv, ctx_max, page, g):
     pages_per = (ctx_max + page - 1) // page
     n_pages = B * pages_per + 3

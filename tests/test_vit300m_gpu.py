@@ -1,5 +1,6 @@
-"""GPU parity of the InternViT-300M tower variant (LayerNorm + bias, no QK-norm, qkv bias, 16 x 64-dim heads run zero-padded
-to the attention kernels' 128) through the same drop-in boundary, against (1) golden vectors of the REAL reference's 300M
+"""GPU parity of the InternViT-300M tower variant (LayerNorm + bias, no QK-norm, qkv bias, 16 x 64-dim heads on the head_dim-64
+instantiation of the attention kernel; the zero-padded-to-128 path that serves other head widths is kept alive by one test)
+through the same drop-in boundary, against (1) golden vectors of the REAL reference's 300M
 tower (tests/golden/golden_tiny_300m.pt, fp32) and (2) the CPU oracle on bf16-rounded weights - at the tiny size and at the
 real 300M width (hidden 1024, 16 heads, inter 4096, 448 px; reduced depth).
 
@@ -81,7 +82,7 @@ def test_tower_class_follows_the_name(model):
     from omchat_b200.model.vision import InternVIT300mVisionTower
     tower = model.get_vision_tower()
     assert isinstance(tower, InternVIT300mVisionTower) and not tower.fold_norms
-    assert tower.hidden_size == T["vit_hidden"] and tower.vc.head_dim == 64
+    assert tower.hidden_size == T["vit_hidden"] and tower.vc.head_dim == 64 and tower.attn_dim == 64 and not tower.pad_heads
 
 
 def test_300m_tower_vs_reference_golden(model, golden300):
@@ -94,6 +95,21 @@ def test_300m_tower_vs_reference_golden(model, golden300):
         check(mine.view(2, S, -1)[:, ::16, ::4], ref, f"300m hidden state {li}")
     check(tower(pixels[:2].cuda())[:, ::8, :], golden300["vit_features_sub"], "300m features")
     check(model.encode_images(pixels[:2])[:, ::8, :], golden300["encode_images_sub"], "300m encode_images")
+
+
+def test_300m_tower_zero_padded_heads_path(model, golden300):
+    """pad_heads = True: the heads run zero-padded to 128 dims (the path a tower with, say, 32-dim heads takes) - same golden."""
+    pixels, _ = tiny_inputs(1)
+    tower = model.get_vision_tower()
+    native = tower(pixels[:2].cuda()).clone()
+    tower.pad_heads = True
+    try:
+        assert tower.attn_dim == 128
+        padded = tower(pixels[:2].cuda())
+        check(padded[:, ::8, :], golden300["vit_features_sub"], "300m features (zero-padded heads)")
+        check(padded, native, "zero-padded vs native head_dim 64", rel=2 ** -6)
+    finally:
+        tower.pad_heads = False
 
 
 def test_300m_prefill_and_greedy_vs_reference_golden(model, golden300, sd_bf16):
@@ -116,8 +132,8 @@ def test_300m_prefill_and_greedy_vs_reference_golden(model, golden300, sd_bf16):
 
 
 def test_300m_real_width_tower_vs_oracle():
-    """hidden 1024 / 16 heads of 64 / inter 4096 / 448 px (1025 rows per crop), 3 of the 24 layers, 2 crops: the padded-head
-    attention and the N = 6144 (padded qkv) / K = 2048 (padded proj) GEMM shapes of the real 300M tower against the fp32 oracle."""
+    """hidden 1024 / 16 heads of 64 / inter 4096 / 448 px (1025 rows per crop), 3 of the 24 layers, 2 crops: the head_dim-64
+    attention and the GEMM shapes of the real 300M tower against the fp32 oracle."""
     from omchat_b200.config import InternVisionConfig, OmChatQwen2Config
     from omchat_b200.model.vision import build_vision_tower
     from omchat_b200.model.weights import random_init, to_reference_state_dict
@@ -147,7 +163,18 @@ def test_300m_model_level_c_entry_equals_host_path(model, monkeypatch):
     want = model.encode_images(pixels[:3])
     fwd = lib.VitForward(model.weights.vit, model.weights.proj, model.config.vision_config, 1, mats=tower._layer_mats(),
                          mats_folded=tower.fold_norms)
+    assert fwd.desc.attn_head_dim == 0 and fwd.desc.norm_type == 1
     got = fwd(pixels[:3].cuda().contiguous())
     assert got.shape == want.shape and torch.equal(got, want)
-    with pytest.raises(ValueError):
-        lib.VitForward(model.weights.vit, model.weights.proj, model.config.vision_config, 1)
+    # plain weights (no mats): the native head_dim-64 path needs no padded copies
+    got2 = lib.VitForward(model.weights.vit, model.weights.proj, model.config.vision_config, 1)(pixels[:3].cuda().contiguous())
+    assert torch.equal(got2, want)
+    # and the zero-padded layout through the same entry (attn_head_dim = 128)
+    tower.pad_heads = True
+    try:
+        fwd_p = lib.VitForward(model.weights.vit, model.weights.proj, model.config.vision_config, 1, mats=tower._layer_mats())
+        assert fwd_p.desc.attn_head_dim == 128
+        got_p = fwd_p(pixels[:3].cuda().contiguous())
+        assert torch.equal(got_p, model.encode_images(pixels[:3]))
+    finally:
+        tower.pad_heads = False
