@@ -10,6 +10,9 @@
 //                                 TMEM accumulator; tcgen05.commit releases smem slots / publishes accumulators
 //   warps 2..5  : epilogue      - tcgen05.ld TMEM->registers, bias / GELU / layer-scale+residual / SwiGLU, bf16 stores
 // Three mbarrier pipelines: smem full/empty, TMEM full/empty, and a static persistent tile schedule.
+#include <functional>
+#include <mutex>
+#include <unordered_map>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -348,11 +351,44 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] (leading dim ld elements), box = [box_rows, 64 cols], 128-byte swizzle.
+// A tensor map is a pure function of (base, rows, cols, ld, box_rows): encoded once and kept (weights and the activation
+// buffers of a steady-state loop come back with the same key every call - a prefill issues ~900 of these).
+namespace {
+struct TmapKey {
+  const void* base;
+  long long rows, cols, ld;
+  int box_rows, device;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && device == o.device;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.base);
+    auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix((size_t)k.rows); mix((size_t)k.cols); mix((size_t)k.ld); mix((size_t)k.box_rows); mix((size_t)k.device);
+    return h;
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+constexpr size_t kTmapCacheMax = 16384;
+}  // namespace
+
 int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error(OMC_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15))
     return set_error(OMC_ERR_ALIGN, "GEMM operand must be 16-byte aligned with a leading dim multiple of 8");
+  const TmapKey key{base, rows, cols, ld, box_rows, cur_device()};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *tm = it->second;
+      return OMC_OK;
+    }
+  }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
@@ -361,6 +397,11 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long long co
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(OMC_ERR_DRIVER, "cuTensorMapEncodeTiled failed");
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() >= kTmapCacheMax) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *tm);
+  }
   return OMC_OK;
 }
 
