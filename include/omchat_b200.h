@@ -386,6 +386,10 @@ int omc_decoder_prefill(const omc_decode_desc* desc, const float* inv_freq, void
  *                    rows; norm_w != NULL: x is the raw residual stream, the kernel applies post_attention_layernorm
  *                    (Qwen2MoeRMSNorm, modeling_qwen2_moe.py:70-75, same rounding as omc_rmsnorm) itself and also writes the
  *                    normed rows to xn_out [T, ldn] for omc_moe_scatter / the shared expert.
+ *   omc_moe_select   the selection alone, for logits computed elsewhere: logits fp32 [T, ld], columns 0..E-1 = router logits,
+ *                    column E = the shared expert's gate logit when has_gate. At prefill sizes the host computes them with
+ *                    omc_gemm_bf16 (fp32 out) against [router_w; shared_gate_w; zero rows up to a multiple of 128] - the 61 dot
+ *                    products per token cost 170 us per 8192 tokens on the CUDA cores and ~10 us on the tensor cores.
  *   omc_moe_plan     counts -> seg_start int32 [E] (first row of every expert's segment, segments padded to whole 128-row
  *                    tiles), tile_expert int32 [max_tiles] (expert of every 128-row tile, -1 = unused), cursor [E] = 0,
  *                    counts = 0. max_tiles >= omc_moe_max_tiles(T, k, E) = T * k / 128 + E.
@@ -404,6 +408,8 @@ int omc_moe_max_tiles(int T, int top_k, int n_experts);
 int omc_moe_route(const void* x, long long ldx, int T, int C, const void* norm_w, float eps, void* xn_out, long long ldn,
                   const void* router_w, const void* shared_gate_w, int n_experts, int top_k, int norm_topk, int32_t* topk_ids,
                   float* topk_w, float* shared_gate, int32_t* counts, void* stream);
+int omc_moe_select(const float* logits, long long ld, int T, int n_experts, int top_k, int norm_topk, int has_gate,
+                   int32_t* topk_ids, float* topk_w, float* shared_gate, int32_t* counts, void* stream);
 int omc_moe_plan(int32_t* counts, int n_experts, int max_tiles, int32_t* seg_start, int32_t* cursor, int32_t* tile_expert,
                  void* stream);
 int omc_moe_scatter(const void* x, long long ldx, int T, int C, const int32_t* topk_ids, int top_k, const int32_t* seg_start,

@@ -4,6 +4,8 @@
 // expert outputs with the sigmoid-gated shared expert and the residual stream. All of it is HBM/L2-bound row work:
 //   omc_moe_route    one CTA per token: (optional RMSNorm of the row,) E + 1 dot products against the L2-resident router /
 //                    shared-gate rows spread over 8 warps, fp32 softmax, k rounds of warp arg-max, per-expert histogram
+//   omc_moe_select   prefill sizes: the logits come from the tcgen05 GEMM (router rows stacked with the gate row); one warp per
+//                    token does the softmax / top-k / histogram
 //   omc_moe_plan     one CTA: padded segment starts, the tile -> expert table, counters reset for the next call
 //   omc_moe_scatter  one CTA per token: the normed row is copied to its k slots (slot = segment start + atomic cursor)
 //   omc_moe_combine  one CTA per token: h += sum_j w_j * y[slot_j] + sigmoid_gate * shared_y, fp32 accumulate, one rounding
@@ -249,6 +251,17 @@ __global__ void __launch_bounds__(kRouteThreads) moe_route_kernel(const bf16* __
   }
 }
 
+// Prefill sizes: the E + 1 logits per token come out of the tcgen05 GEMM ([T, C] x [router rows | shared-gate row | zero
+// padding]^T, fp32 out); this kernel is only the selection - one warp per token.
+__global__ void __launch_bounds__(256) moe_select_kernel(const float* __restrict__ logits, long long ld, int T, int E, int top_k,
+                                                         int norm_topk, int has_gate, int32_t* __restrict__ topk_ids,
+                                                         float* __restrict__ topk_w, float* __restrict__ shared_gate,
+                                                         int32_t* __restrict__ counts) {
+  const int warps = blockDim.x >> 5;
+  for (int t = blockIdx.x * warps + (threadIdx.x >> 5); t < T; t += gridDim.x * warps)
+    route_select(logits + (long long)t * ld, E, top_k, norm_topk, has_gate != 0, t, topk_ids, topk_w, shared_gate, counts);
+}
+
 __global__ void __launch_bounds__(128) moe_plan_kernel(int32_t* __restrict__ counts, int E, int max_tiles,
                                                        int32_t* __restrict__ seg_start, int32_t* __restrict__ cursor,
                                                        int32_t* __restrict__ tile_expert) {
@@ -468,6 +481,21 @@ extern "C" int omc_moe_route(const void* x, long long ldx, int T, int C, const v
         (const bf16*)shared_gate_w, n_experts, top_k, norm_topk, topk_ids, topk_w, shared_gate, counts);
   }
   return check_launch("moe_route");
+}
+
+extern "C" int omc_moe_select(const float* logits, long long ld, int T, int n_experts, int top_k, int norm_topk, int has_gate,
+                              int32_t* topk_ids, float* topk_w, float* shared_gate, int32_t* counts, void* stream) {
+  if (T <= 0) return OMC_OK;
+  if (logits == nullptr || topk_ids == nullptr || topk_w == nullptr || counts == nullptr || (has_gate && shared_gate == nullptr))
+    return set_error(OMC_ERR_ARG, "omc_moe_select: null argument");
+  if (n_experts < 1 || n_experts > kMoeMaxExperts || top_k < 1 || top_k > kMoeMaxTopK || top_k > n_experts ||
+      ld < n_experts + (has_gate ? 1 : 0))
+    return set_error(OMC_ERR_SHAPE, "omc_moe_select: at most 128 experts, top-8 routing, ld >= experts (+ 1 with a gate column)");
+  const int need = (T + 7) / 8;
+  const int grid = need < num_sms() * 8 ? need : num_sms() * 8;
+  moe_select_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, ld, T, n_experts, top_k, norm_topk, has_gate, topk_ids, topk_w,
+                                                            shared_gate, counts);
+  return check_launch("moe_select");
 }
 
 extern "C" int omc_moe_plan(int32_t* counts, int n_experts, int max_tiles, int32_t* seg_start, int32_t* cursor,

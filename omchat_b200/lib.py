@@ -42,6 +42,7 @@ SIGNATURES = {
     "omc_layernorm": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _F, _P]),
     "omc_moe_max_tiles": (_I, [_I, _I, _I]),
     "omc_moe_route": (_I, [_P, _L, _I, _I, _P, _F, _P, _L, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "omc_moe_select": (_I, [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "omc_moe_plan": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "omc_moe_scatter": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _P, _L, _P, _P]),
     "omc_gemm_bf16_grouped": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _P, _I, _P, _L, _I, _P]),
@@ -777,20 +778,37 @@ class MoeWorkspace:
         self.xperm = torch.zeros(M, C, **bf)  # zero once: padding rows are multiplied (never read back) - keep them finite
         self.aperm = torch.zeros(M, moe_inter, **bf)
         self.yperm = torch.zeros(M, C, **bf)
+        self.logits = None  # fp32 [T, 128 n] router logits of the tensor-core router path (allocated on first use)
         self.shared_act = torch.empty(T, shared_inter, **bf) if shared_inter > 0 else None
         self.shared_y = torch.empty(T, C, **bf) if shared_inter > 0 else None
+
+
+ROUTER_GEMM_MIN_T = 256  # from this many tokens on the router logits are computed on the tensor cores
+
+
+def router_cat(router_w: torch.Tensor, shared_gate_w: Optional[torch.Tensor]) -> torch.Tensor:
+    """[router_w; shared_gate_w; zero rows] padded to a multiple of 128 rows: the B operand of the router-logits GEMM."""
+    E, C = router_w.shape
+    rows = E + (1 if shared_gate_w is not None else 0)
+    out = torch.zeros((rows + 127) // 128 * 128, C, device=router_w.device, dtype=torch.bfloat16)
+    out[:E] = router_w
+    if shared_gate_w is not None:
+        out[E] = shared_gate_w.view(-1)
+    return out
 
 
 def moe_block(h: torch.Tensor, xn: torch.Tensor, ws: MoeWorkspace, router_w: torch.Tensor, shared_gate_w: Optional[torch.Tensor],
               experts_gate_up: torch.Tensor, experts_down: torch.Tensor, shared_gate_up: Optional[torch.Tensor],
               shared_down: Optional[torch.Tensor], norm_topk: bool, norm_w: Optional[torch.Tensor] = None,
               eps: float = 1e-6, shared_y: Optional[torch.Tensor] = None, ssq_out: Optional[torch.Tensor] = None,
-              ssq_parts: int = 1) -> torch.Tensor:
+              ssq_parts: int = 1, router_cat_w: Optional[torch.Tensor] = None) -> torch.Tensor:
     """h[T, C] += SparseMoeBlock(xn[T, C]) (transformers modeling_qwen2_moe.py:363-374), in place. experts_gate_up
     [E * 2 I, C] with every expert's gate / up rows interleaved (the SwiGLU epilogue's layout), experts_down [E * C, I].
     norm_w given: xn is an OUTPUT - the router kernel computes xn = RMSNorm(h) * norm_w itself (one launch less).
     shared_y given: the shared expert's output [T, C], already computed by the caller (the decode step runs it on the
-    weight-streaming GEMMs); shared_gate_up / shared_down are then unused."""
+    weight-streaming GEMMs); shared_gate_up / shared_down are then unused.
+    router_cat_w given (see router_cat()) and T >= ROUTER_GEMM_MIN_T: the E + 1 logits per token are computed on the tensor
+    cores - RMSNorm kernel -> omc_gemm_bf16 with fp32 output -> omc_moe_select - instead of on the CUDA cores."""
     _need_cuda(h, xn, router_w, experts_gate_up, experts_down)
     T, C = xn.shape
     assert T <= ws.T and C == ws.C and h.shape == xn.shape and xn.stride(1) == 1 and h.stride(1) == 1
@@ -798,10 +816,20 @@ def moe_block(h: torch.Tensor, xn: torch.Tensor, ws: MoeWorkspace, router_w: tor
     I2 = experts_gate_up.shape[0] // E
     M = ws.max_tiles * 128
     max_tiles = L.omc_moe_max_tiles(T, k, E)  # tiles this call can touch (<= the workspace's)
-    src = h if norm_w is not None else xn
-    _check(L.omc_moe_route(_ptr(src), src.stride(0), T, C, _ptr(norm_w), eps, _ptr(xn) if norm_w is not None else None,
-                           xn.stride(0), _ptr(router_w), _ptr(shared_gate_w), E, k, int(norm_topk), _ptr(ws.topk_ids),
-                           _ptr(ws.topk_w), _ptr(ws.shared_gate), _ptr(ws.counts), st), "omc_moe_route")
+    if router_cat_w is not None and T >= ROUTER_GEMM_MIN_T:
+        if norm_w is not None:
+            rmsnorm(h, norm_w, eps, out=xn)
+        W = router_cat_w.shape[0]
+        if ws.logits is None or ws.logits.shape[1] != W:
+            ws.logits = torch.empty(ws.T, W, device=xn.device, dtype=torch.float32)
+        gemm(xn, router_cat_w, out=ws.logits[:T], out_f32=True)
+        _check(L.omc_moe_select(_ptr(ws.logits), W, T, E, k, int(norm_topk), 1 if shared_gate_w is not None else 0,
+                                _ptr(ws.topk_ids), _ptr(ws.topk_w), _ptr(ws.shared_gate), _ptr(ws.counts), st), "omc_moe_select")
+    else:
+        src = h if norm_w is not None else xn
+        _check(L.omc_moe_route(_ptr(src), src.stride(0), T, C, _ptr(norm_w), eps, _ptr(xn) if norm_w is not None else None,
+                               xn.stride(0), _ptr(router_w), _ptr(shared_gate_w), E, k, int(norm_topk), _ptr(ws.topk_ids),
+                               _ptr(ws.topk_w), _ptr(ws.shared_gate), _ptr(ws.counts), st), "omc_moe_route")
     _check(L.omc_moe_plan_scatter(_ptr(ws.counts), E, ws.max_tiles, _ptr(ws.seg_start), _ptr(ws.cursor), _ptr(ws.tile_expert),
                                   _ptr(xn), xn.stride(0), T, C, _ptr(ws.topk_ids), k, _ptr(ws.xperm), C, _ptr(ws.slot_of), st),
            "omc_moe_plan_scatter")

@@ -36,6 +36,7 @@ class Qwen2MoeDecoder(Qwen2Decoder):
         # (csrc/gemm_stream.cu, RMSNorms folded in); the routed experts on the grouped GEMM. OMCHAT_B200_NO_STREAM=1: per-op path
         self.stream_min_b = 1
         self._moe_ws = {}
+        self._rcat = {}
 
     def _workspace(self, T: int) -> lib.MoeWorkspace:
         """One workspace per power-of-two token bucket, shared by all layers (allocated outside graph capture: the first,
@@ -49,11 +50,19 @@ class Qwen2MoeDecoder(Qwen2Decoder):
             self._moe_ws[bucket] = ws
         return ws
 
+    def _router_cat(self, m):
+        """Router rows stacked with the shared expert's gate row for the tensor-core logits GEMM of prefill-sized blocks."""
+        key = m.router_w.data_ptr()
+        if key not in self._rcat:
+            self._rcat[key] = lib.router_cat(m.router_w, m.shared_gate_w)
+        return self._rcat[key]
+
     def _moe(self, l, h, xn):
         m = l.moe
         # post_attention_layernorm is applied by the router kernel (it needs the normed row anyway) and left in xn
         lib.moe_block(h, xn[:h.shape[0]], self._workspace(h.shape[0]), m.router_w, m.shared_gate_w, m.experts_gate_up,
-                      m.experts_down, m.shared_gate_up, m.shared_down, self.cfg.norm_topk_prob, norm_w=l.ln2, eps=self.eps)
+                      m.experts_down, m.shared_gate_up, m.shared_down, self.cfg.norm_topk_prob, norm_w=l.ln2, eps=self.eps,
+                      router_cat_w=self._router_cat(m) if h.shape[0] >= lib.ROUTER_GEMM_MIN_T else None)
 
     def _mlp_rows(self, li, l, h, xn, act):
         if l.moe is None:
@@ -115,6 +124,7 @@ class Qwen2MoeDecoder(Qwen2Decoder):
     def release(self):
         super().release()
         self._moe_ws.clear()
+        self._rcat.clear()
 
 
 class OmChatQwen2MoeModel(OmChatQwen2Model):

@@ -64,9 +64,11 @@ def test_moe_block_kernels_vs_torch(Tn, C, E, k, I, Is, norm):
     ws = lib.MoeWorkspace(Tn, C, E, k, I, Is, "cuda")
     want, probs, idx, w = _moe_ref(xn, h, router_w, sg_w, egu, edn, sgu, sdn, k, norm)
     got = h.clone()
+    rcat = lib.router_cat(router_w, sg_w)  # T >= 256: logits on the tensor cores (omc_gemm_bf16 fp32 out -> omc_moe_select)
+    assert rcat.shape[0] % 128 == 0 and torch.equal(rcat[:E], router_w) and torch.equal(rcat[E], sg_w) and not rcat[E + 1:].any()
     for _ in range(2):  # twice through the same workspace: the counters must come back to zero
         got.copy_(h)
-        lib.moe_block(got, xn, ws, router_w, sg_w, egu, edn, sgu, sdn, norm)
+        lib.moe_block(got, xn, ws, router_w, sg_w, egu, edn, sgu, sdn, norm, router_cat_w=rcat)
     torch.cuda.synchronize()
     assert int(ws.counts.abs().sum()) == 0 and int(ws.cursor.sum()) == Tn * k
     # routing: same expert sets wherever the k-th and (k+1)-th probabilities are not a near-tie
