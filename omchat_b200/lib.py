@@ -801,14 +801,15 @@ def moe_block(h: torch.Tensor, xn: torch.Tensor, ws: MoeWorkspace, router_w: tor
               experts_gate_up: torch.Tensor, experts_down: torch.Tensor, shared_gate_up: Optional[torch.Tensor],
               shared_down: Optional[torch.Tensor], norm_topk: bool, norm_w: Optional[torch.Tensor] = None,
               eps: float = 1e-6, shared_y: Optional[torch.Tensor] = None, ssq_out: Optional[torch.Tensor] = None,
-              ssq_parts: int = 1, router_cat_w: Optional[torch.Tensor] = None) -> torch.Tensor:
+              ssq_parts: int = 1, router_cat_w: Optional[torch.Tensor] = None, defer_combine: bool = False) -> torch.Tensor:
     """h[T, C] += SparseMoeBlock(xn[T, C]) (transformers modeling_qwen2_moe.py:363-374), in place. experts_gate_up
     [E * 2 I, C] with every expert's gate / up rows interleaved (the SwiGLU epilogue's layout), experts_down [E * C, I].
     norm_w given: xn is an OUTPUT - the router kernel computes xn = RMSNorm(h) * norm_w itself (one launch less).
     shared_y given: the shared expert's output [T, C], already computed by the caller (the decode step runs it on the
     weight-streaming GEMMs); shared_gate_up / shared_down are then unused.
     router_cat_w given (see router_cat()) and T >= ROUTER_GEMM_MIN_T: the E + 1 logits per token are computed on the tensor
-    cores - RMSNorm kernel -> omc_gemm_bf16 with fp32 output -> omc_moe_select - instead of on the CUDA cores."""
+    cores - RMSNorm kernel -> omc_gemm_bf16 with fp32 output -> omc_moe_select - instead of on the CUDA cores.
+    defer_combine: stop after the routed experts' GEMMs; the caller finishes with moe_combine()."""
     _need_cuda(h, xn, router_w, experts_gate_up, experts_down)
     T, C = xn.shape
     assert T <= ws.T and C == ws.C and h.shape == xn.shape and xn.stride(1) == 1 and h.stride(1) == 1
@@ -840,12 +841,23 @@ def moe_block(h: torch.Tensor, xn: torch.Tensor, ws: MoeWorkspace, router_w: tor
     _check(L.omc_gemm_bf16_grouped(_ptr(ws.aperm), I2 // 2, Mc, _ptr(experts_down), I2 // 2, E, C, I2 // 2,
                                    _ptr(ws.tile_expert), hint, _ptr(ws.yperm), C, EPI_NONE, st), "omc_gemm_bf16_grouped")
     add_launches(3)
+    if defer_combine:
+        return h
     if shared_y is None and shared_gate_up is not None:
         gemm(xn, shared_gate_up, out=ws.shared_act[:T], epi=EPI_SWIGLU)
         shared_y = gemm(ws.shared_act[:T], shared_down, out=ws.shared_y[:T])
-    _check(L.omc_moe_combine(_ptr(h), h.stride(0), T, C, _ptr(ws.yperm), C, _ptr(ws.slot_of), _ptr(ws.topk_w), k,
-                             _ptr(shared_y), shared_y.stride(0) if shared_y is not None else C, _ptr(ws.shared_gate),
-                             _ptr(ssq_out), ssq_parts, st), "omc_moe_combine")
+    return moe_combine(h, ws, shared_y, ssq_out, ssq_parts)
+
+
+def moe_combine(h: torch.Tensor, ws: MoeWorkspace, shared_y: Optional[torch.Tensor], ssq_out: Optional[torch.Tensor] = None,
+                ssq_parts: int = 1) -> torch.Tensor:
+    """The last step of moe_block (for callers that ran it with defer_combine=True and computed the shared expert on another
+    stream meanwhile): h += sum_j w_j * y[slot_j] + sigmoid_gate * shared_y."""
+    T, C = h.shape
+    k = ws.k
+    _check(load().omc_moe_combine(_ptr(h), h.stride(0), T, C, _ptr(ws.yperm), C, _ptr(ws.slot_of), _ptr(ws.topk_w), k,
+                                  _ptr(shared_y), shared_y.stride(0) if shared_y is not None else C, _ptr(ws.shared_gate),
+                                  _ptr(ssq_out), ssq_parts, _stream()), "omc_moe_combine")
     add_launches(1 if T * k <= 16 else 2)
     return h
 

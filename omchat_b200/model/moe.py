@@ -14,6 +14,7 @@ parallelism is the natural sharding) and the persistent decode kernel.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -35,6 +36,8 @@ class Qwen2MoeDecoder(Qwen2Decoder):
         # decode steps of 1..64 rows: attention projections, the shared expert and lm_head on the weight-streaming GEMMs
         # (csrc/gemm_stream.cu, RMSNorms folded in); the routed experts on the grouped GEMM. OMCHAT_B200_NO_STREAM=1: per-op path
         self.stream_min_b = 1
+        self.overlap_shared = os.environ.get("OMCHAT_B200_MOE_OVERLAP", "1") != "0"
+        self._side_stream = torch.cuda.Stream(device=self.device)
         self._moe_ws = {}
         self._rcat = {}
 
@@ -114,11 +117,21 @@ class Qwen2MoeDecoder(Qwen2Decoder):
                 lib.gemm_stream(st.act, p.down, out=h, res=h, epi=lib.EPI_RES, ssq_out=st.ssq_a)
                 continue
             m, ws = l.moe, self._workspace(B)
-            lib.gemm_stream(h, p.gate_up, out=ws.shared_act[:B], epi=lib.EPI_SWIGLU, ssq_in=st.ssq_b, ssq_in_parts=parts,
-                            norm_dim=C, eps=eps)
-            shared_y = lib.gemm_stream(ws.shared_act[:B], p.down, out=ws.shared_y[:B])
+            # the shared expert (two streaming GEMMs) and the routed block (route -> plan/scatter -> two grouped GEMMs) both
+            # read h and are independent until the combine: run them on two streams (a fork / join inside the captured graph)
+            main = torch.cuda.current_stream()
+            side = self._side_stream if self.overlap_shared else main
+            if side is not main:
+                side.wait_stream(main)
+            with torch.cuda.stream(side):
+                lib.gemm_stream(h, p.gate_up, out=ws.shared_act[:B], epi=lib.EPI_SWIGLU, ssq_in=st.ssq_b, ssq_in_parts=parts,
+                                norm_dim=C, eps=eps)
+                shared_y = lib.gemm_stream(ws.shared_act[:B], p.down, out=ws.shared_y[:B])
             lib.moe_block(h, st.xn, ws, m.router_w, m.shared_gate_w, m.experts_gate_up, m.experts_down, None, None,
-                          self.cfg.norm_topk_prob, norm_w=l.ln2, eps=eps, shared_y=shared_y, ssq_out=st.ssq_a, ssq_parts=parts)
+                          self.cfg.norm_topk_prob, norm_w=l.ln2, eps=eps, defer_combine=True)
+            if side is not main:
+                main.wait_stream(side)
+            lib.moe_combine(h, ws, shared_y, st.ssq_a, parts)
         lib.gemm_stream(h, P.lm_head, out=st.logits, out_f32=True, ssq_in=st.ssq_a, ssq_in_parts=parts, norm_dim=C, eps=eps)
 
     def release(self):
