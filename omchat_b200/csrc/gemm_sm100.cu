@@ -126,6 +126,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (the grouped GEMMs of a mixture-of-experts decode step are launched that way): everything
+  // above - barrier init, the TMEM allocation, the descriptor prefetch - overlapped the predecessor's tail; operands, the
+  // tile -> expert table and the epilogue inputs are only touched from here on. No-ops in an ordinary launch.
+  pdl_launch();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -415,6 +420,8 @@ int num_sms() {
   return g_num_sms[dev];
 }
 
+int moe_pdl_enabled();  // moe.cu
+
 template <int BN, int CG>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, GemmParams p, int max_ctas,
                        cudaStream_t stream, int groups = 1) {
@@ -444,13 +451,15 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = CG;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (p.grp_tile != nullptr && moe_pdl_enabled()) ? 2 : 1;  // grouped (expert) GEMMs: programmatic dependents
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG>, tmA, tmB, p);
   if (e != cudaSuccess) return set_error(OMC_ERR_CUDA, cudaGetErrorString(e));
   return OMC_OK;

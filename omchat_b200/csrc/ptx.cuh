@@ -115,6 +115,13 @@ constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// pdl_launch: dependents of this grid that were launched with cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled
+// from now on (they run their own prologue and then sit in pdl_wait); pdl_wait: returns when the grids this one depends on have
+// completed and their memory is visible. Both are no-ops in a grid launched the ordinary way.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {

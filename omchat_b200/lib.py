@@ -41,6 +41,7 @@ SIGNATURES = {
     "omc_rmsnorm_pair": (_I, [_P, _L, _P, _P, _I, _I, _F, _P]),
     "omc_layernorm": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _F, _P]),
     "omc_moe_max_tiles": (_I, [_I, _I, _I]),
+    "omc_moe_set_pdl": (_I, [_I]),
     "omc_moe_route": (_I, [_P, _L, _I, _I, _P, _F, _P, _L, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "omc_moe_select": (_I, [_P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "omc_moe_plan": (_I, [_P, _I, _I, _P, _P, _P, _P]),
