@@ -120,3 +120,34 @@ def test_decode_plan_build_is_host_only(built):
     assert l.omc_decode_plan_build(ctypes.byref(d5), buf) == -2
     dbad, _kb = _fake_desc(lib, hidden=8192)
     assert l.omc_decode_plan_build(ctypes.byref(dbad), buf) == -2
+
+
+def test_header_is_plain_c_and_integration_snippet_compiles(tmp_path):
+    """include/omchat_b200.h must be consumable by a C compiler (the drop-in boundary is a C ABI: plain pointers and sizes),
+    and the MoE / LayerNorm / head_dim-64 calls INTEGRATION.md shows must match the declared signatures."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr_check.c"
+    src.write_text('''
+#include <stddef.h>
+#include "omchat_b200.h"
+int f(void* h, void* xn, void* ln2, void* rw, void* sg, int32_t* ids, float* w, float* g, int32_t* counts, int32_t* seg,
+      int32_t* cur, int32_t* te, void* xperm, void* aperm, void* yperm, int32_t* slot, void* egu, void* edn, void* sy, void* st) {
+  int T = 4, C = 2048, E = 60, k = 4, I = 1408;
+  int tiles = omc_moe_max_tiles(T, k, E);
+  omc_moe_route(h, C, T, C, ln2, 1e-6f, xn, C, rw, sg, E, k, 0, ids, w, g, counts, st);
+  omc_moe_plan_scatter(counts, E, tiles, seg, cur, te, xn, C, T, C, ids, k, xperm, C, slot, st);
+  omc_gemm_bf16_grouped(xperm, C, tiles * 128, egu, C, E, 2 * I, C, te, 0, aperm, I, OMC_EPI_SWIGLU, st);
+  omc_gemm_bf16_grouped(aperm, I, tiles * 128, edn, I, E, C, I, te, 0, yperm, C, OMC_EPI_NONE, st);
+  omc_moe_select((const float*)h, 128, T, E, k, 0, 1, ids, w, g, counts, st);
+  omc_layernorm(h, C, ln2, NULL, xn, C, T, C, 1e-6f, st);
+  omc_attention_fwd_hd(h, C, h, C, h, C, xn, C, ids, 1, T, T, 16, 16, 64, 0, 0.125f, st);
+  return omc_moe_combine(h, C, T, C, yperm, C, slot, w, k, sy, C, g, NULL, 1, st);
+}
+''')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", f"-I{inc}", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
