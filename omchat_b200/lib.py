@@ -816,7 +816,6 @@ def moe_block(h: torch.Tensor, xn: torch.Tensor, ws: MoeWorkspace, router_w: tor
     assert T <= ws.T and C == ws.C and h.shape == xn.shape and xn.stride(1) == 1 and h.stride(1) == 1
     E, k, L, st = ws.E, ws.k, load(), _stream()
     I2 = experts_gate_up.shape[0] // E
-    M = ws.max_tiles * 128
     max_tiles = L.omc_moe_max_tiles(T, k, E)  # tiles this call can touch (<= the workspace's)
     if router_cat_w is not None and T >= ROUTER_GEMM_MIN_T:
         if norm_w is not None:
