@@ -80,6 +80,10 @@ __device__ __forceinline__ void route_select(const float* logit_row, int E, int 
         be = oe;
       }
     }
+    if (be >= E) {  // only with NaN logits (no comparison succeeds): stay inside the expert table, the output is NaN either way
+      be = r % E;
+      bv = 0.f;
+    }
     sel_w[r] = bv * inv;
     sel_e[r] = be;
     wsum += sel_w[r];

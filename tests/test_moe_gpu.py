@@ -94,6 +94,28 @@ def test_moe_block_kernels_vs_torch(Tn, C, E, k, I, Is, norm):
     assert (got.float() - want)[clear].abs().max().item() <= 0.02 * scale and cos >= 0.9995
 
 
+def test_router_survives_nan_rows():
+    """A NaN activation row must not index outside the expert table (torch.topk on NaN returns in-range indices too): the
+    row's output is NaN, the other rows are untouched."""
+    from omchat_b200 import lib
+    g = torch.Generator(device="cuda").manual_seed(1)
+    Tn, C, E, k, I, Is = 5, 256, 8, 2, 128, 128
+    rn = lambda *shape, std=0.05: (torch.randn(*shape, generator=g, device="cuda") * std).to(torch.bfloat16)  # noqa: E731
+    xn, h = rn(Tn, C, std=1.0), rn(Tn, C, std=1.0)
+    xn[2] = float("nan")
+    router_w, sg_w = rn(E, C, std=0.2), rn(C, std=0.1)
+    egu, edn, sgu, sdn = rn(E * 2 * I, C), rn(E * C, I), rn(2 * Is, C), rn(C, Is)
+    ws = lib.MoeWorkspace(Tn, C, E, k, I, Is, "cuda")
+    ref, _, _, _ = _moe_ref(xn, h, router_w, sg_w, egu, edn, sgu, sdn, k, False)
+    out = lib.moe_block(h.clone(), xn, ws, router_w, sg_w, egu, edn, sgu, sdn, False)
+    torch.cuda.synchronize()
+    ids = ws.topk_ids[:Tn]
+    assert int(ids.min()) >= 0 and int(ids.max()) < E
+    good = [0, 1, 3, 4]
+    assert torch.isfinite(out[good]).all() and (out[good].float() - ref[good]).abs().max().item() <= 0.02 * ref[good].abs().max().item()
+    assert torch.isnan(out[2]).any()
+
+
 @pytest.mark.parametrize("hint", [0, 4])
 def test_grouped_gemm_skips_unused_tiles(hint):
     """tile_expert < 0 tiles are never written; used tiles multiply their own expert's matrix."""
