@@ -51,6 +51,17 @@ def test_no_cpu_fallback():
     from omchat_b200 import lib
     with pytest.raises(lib.OmcError):
         lib.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    # the variants' ops refuse host tensors just as loudly: there is no CPU path behind any of them
+    x = torch.zeros(8, 64, dtype=torch.bfloat16)
+    with pytest.raises(lib.OmcError):
+        lib.layernorm(x, torch.ones(64, dtype=torch.bfloat16), None, 1e-6)
+    with pytest.raises(lib.OmcError):
+        lib.attention(x, x, x, x.clone(), torch.tensor([0, 8], dtype=torch.int32), 8, 1, 1, False, 0.125, head_dim=64)
+    if not torch.cuda.is_available():
+        from omchat_b200.config import OmChatQwen2MoeConfig
+        from omchat_b200.model import OmChatQwen2MoeForCausalLM
+        with pytest.raises(lib.OmcError):
+            OmChatQwen2MoeForCausalLM(OmChatQwen2MoeConfig(num_hidden_layers=1))
 
 
 def test_product_does_not_import_oracle():
