@@ -15,6 +15,12 @@ pinned against outputs of the reference itself: tests/golden/make_golden.py impo
 outputs in tests/golden/*.pt; tests/test_oracle.py checks this restatement against those files. The pixel-shuffle
 (ratio 0.5) has NO reference symbol ("parity unpinned" for that one function): it is pinned against the InternVL
 view/permute formulation quoted in SURVEY.md §8 a7.
+The two lighter model families are pinned the same way: the InternViT-300M branch (vit_norm / LayerNorm, no QK-norm, qkv bias)
+on tests/golden/golden_tiny_300m.pt = outputs of the reference's InternVIT300mVisionTower (make_golden_300m.py,
+tests/test_oracle_300m.py); the Qwen2-MoE branch (moe_route / qwen2_moe_block; third-party transformers
+models/qwen2_moe/modeling_qwen2_moe.py, checked copy 5.5.0) on golden_tiny_moe.pt = outputs of the reference's
+OmChatQwen2MoeForCausalLM in two configurations (make_golden_moe.py, tests/test_oracle_moe.py). ROUTE_TRACE exposes the
+routing margins to the GPU tests: a bf16 run may legitimately send a token on a router near-tie to the other expert.
 
 The tower / projector / decoder functions are device- and dtype-agnostic plain torch: the parity tests also run them with
 bf16 CUDA tensors ("what the reference's own 16-bit PyTorch path gives on this box") to calibrate how much of an error
